@@ -1,0 +1,254 @@
+/*
+ * swr.h — C ABI of the B200-native rasterisation hot path (libswr_b200.so).
+ *
+ * This is the drop-in boundary under the reference's `Renderer`
+ * (reference: src/renderer.rs:165 `Renderer::new`, :201 `render_scene`,
+ * :258 `update_auto_exposure`, :293 `blit_to_buffer`).  The reference has no
+ * FFI of its own; the entry points below are what a Rust shim behind
+ * `renderer.rs` binds (see INTEGRATION.md for the `extern "C"` block).
+ *
+ * Conventions
+ *  - plain C99, pointers + sizes only, no C++/torch types;
+ *  - matrices are column-major 16 floats, exactly the bytes of glam `Mat4`;
+ *  - every call returns 0 on success or a negative swr_status; the message is
+ *    available from swr_last_error();
+ *  - one context per GPU, callable from any host thread, one call at a time
+ *    per context (mirrors `&mut self` on the reference's Renderer);
+ *  - there is NO CPU fallback: if no CUDA device is usable swr_create fails.
+ */
+#ifndef SWR_H_
+#define SWR_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWR_ABI_VERSION 1
+
+/* Numerical contract constants (reference: renderer.rs:14, tilerasterizer.rs:10-22). */
+#define SWR_TILE_SIZE 64
+#define SWR_SUBPIXEL_SHIFT 4
+#define SWR_SUBPIXEL_SCALE 16
+#define SWR_COARSE_BLOCK_PIXELS 16
+#define SWR_DEFAULT_EXPOSURE 2.0f
+
+typedef enum swr_status {
+    SWR_OK = 0,
+    SWR_ERR_INVALID = -1,   /* bad argument / inconsistent scene description */
+    SWR_ERR_CUDA = -2,      /* CUDA runtime error (message has the detail) */
+    SWR_ERR_NO_DEVICE = -3, /* no usable sm_100 device: there is no CPU fallback */
+    SWR_ERR_NO_SCENE = -4,  /* render before upload */
+    SWR_ERR_OOM = -5
+} swr_status;
+
+/* texture.rs:19-26 */
+typedef enum swr_texture_type {
+    SWR_TEX_SRGB = 0,
+    SWR_TEX_NORMAL = 1,
+    SWR_TEX_METALLIC_ROUGHNESS = 2,
+    SWR_TEX_CUBEMAP = 3,
+    SWR_TEX_LINEAR = 4
+} swr_texture_type;
+
+/* texture.rs:554-558 */
+typedef enum swr_wrap_mode {
+    SWR_WRAP_REPEAT = 0,
+    SWR_WRAP_MIRRORED_REPEAT = 1,
+    SWR_WRAP_CLAMP_TO_EDGE = 2
+} swr_wrap_mode;
+
+/* scene.rs:94-102 `Primitive`.  All attribute arrays have nverts entries. */
+typedef struct swr_primitive_desc {
+    const float *positions;  /* nverts x 4 (glam Vec4, w = 1.0)            */
+    const float *normals;    /* nverts x 4 (glam Vec3A: 16-byte stride)    */
+    const float *tangents;   /* nverts x 4 (xyz + handedness)              */
+    const float *texcoords;  /* nverts x 2                                  */
+    const uint32_t *indices; /* nindices, triangle list                     */
+    uint32_t nverts;
+    uint32_t nindices;
+    uint32_t material_index;
+    float bounding_sphere[4]; /* centre xyz, radius (scene.rs:31-34)        */
+} swr_primitive_desc;
+
+/* scene.rs:87-92 `Mesh`: a contiguous range of the scene's primitive array.
+ * primitives_opaque / primitives_translucent are derived from the material's
+ * translucent flag in primitive order (scene.rs:276-284). */
+typedef struct swr_mesh_desc {
+    uint32_t first_primitive;
+    uint32_t num_primitives;
+} swr_mesh_desc;
+
+/* scene.rs:79-85 `Node` (hierarchy already flattened). */
+typedef struct swr_node_desc {
+    float transform[16];            /* local -> world */
+    int32_t mesh_index;             /* -1 = none */
+    float bounding_sphere_world[4]; /* centre xyz, radius */
+} swr_node_desc;
+
+/* texture.rs:28-42 `Texture` + :565-570 `Sampler`. RGBA8 with R in bits 31..24. */
+typedef struct swr_texture_desc {
+    const uint32_t *data; /* all mips (and 6 faces for cubemaps) concatenated */
+    uint32_t ntexels;
+    uint32_t width, height;
+    uint32_t texture_type;  /* swr_texture_type */
+    uint32_t max_mip_level; /* number of mips - 1 */
+    const uint32_t *mip_offsets;  /* max_mip_level + 1 entries each */
+    const uint32_t *mip_widths;
+    const uint32_t *mip_heights;
+    const uint32_t *array_stride; /* texels between faces per mip */
+    uint32_t wrap_s, wrap_t;      /* swr_wrap_mode */
+} swr_texture_desc;
+
+#define SWR_MAT_ALPHA_TESTED 1u
+#define SWR_MAT_TRANSLUCENT 2u
+
+/* scene.rs:104-121 `Material`. Texture slots index swr_scene_desc.textures; -1 = None. */
+typedef struct swr_material_desc {
+    float base_color_factor[4];
+    float metallic_factor;
+    float roughness_factor;
+    float emissive_factor[3];
+    float occlusion_strength;
+    float transmission;
+    float alpha_cutoff;
+    uint32_t flags;
+    int32_t base_color_texture;
+    int32_t metallic_roughness_texture;
+    int32_t normal_texture;
+    int32_t emissive_texture;
+    int32_t occlusion_texture;
+    int32_t transmission_texture;
+} swr_material_desc;
+
+/* voxelgrid.rs:6-18. gi_sh4 index = z*w*h + y*w + x, 4 coeffs x Vec4 per voxel. */
+typedef struct swr_voxel_grid_desc {
+    uint32_t dims[3];
+    float world_min[3];
+    float world_max[3];
+    const float *gi_sh4; /* nvoxels x 16 floats */
+} swr_voxel_grid_desc;
+
+/* scene.rs:65-77 `Scene` (immutable after load; uploaded once). */
+typedef struct swr_scene_desc {
+    const swr_primitive_desc *primitives;
+    uint32_t nprimitives;
+    const swr_mesh_desc *meshes;
+    uint32_t nmeshes;
+    const swr_node_desc *nodes;
+    uint32_t nnodes;
+    const swr_material_desc *materials;
+    uint32_t nmaterials;
+    const swr_texture_desc *textures;
+    uint32_t ntextures;
+    swr_voxel_grid_desc voxel_grid;
+    int32_t cubemap;          /* texture index (type CUBEMAP) */
+    int32_t cubemap_specular; /* texture index (prefiltered, all mips full res) */
+    int32_t brdf_lut;         /* texture index */
+    float light_direction[3]; /* scene.rs:236-239 */
+    float light_color[3];
+} swr_scene_desc;
+
+/* rendercamera.rs:5-25: the cached matrices are INPUTS of the path. */
+typedef struct swr_camera {
+    float position[4];
+    float view_matrix[16];
+    float view_project_matrix[16];
+    float skybox_matrix_transposed[16];
+    float view_clip_planes[6][4];
+    float one_over_width;
+    float one_over_height;
+    float reserved[2];
+} swr_camera;
+
+#define SWR_DRAW_CLIP 1u /* primitive sphere intersects the frustum: renderer.rs:453-462 */
+
+/* One (node, opaque primitive) pair that survived the sphere/frustum test, in the
+ * reference's serial submission order (renderer.rs:207 -> :396 -> :490).
+ * `first_triangle` is the running sum of triangle counts of the draws before
+ * it; the fragment tie-break id is seq = (first_triangle + tri) * 8 + fan. */
+typedef struct swr_draw {
+    float model[16];
+    float mvp[16];
+    uint32_t primitive; /* index into swr_scene_desc.primitives */
+    uint32_t flags;
+    uint32_t first_triangle;
+    uint32_t reserved;
+} swr_draw;
+
+typedef struct swr_frame_stats {
+    uint64_t triangles_submitted; /* T: input triangles over all draws       */
+    uint64_t vertices_submitted;  /* V: sum over draws of primitive nverts   */
+    uint64_t triangles_binned;    /* after cull/clip (fan triangles counted) */
+    uint64_t triangles_clipped;   /* polygons that went through the clipper  */
+    uint64_t tile_refs;           /* R: (triangle, tile) references          */
+    uint32_t tiles;
+    uint32_t reserved;
+    float ms_setup_bin;           /* CUDA-event ms: set-up + count + scan + scatter */
+    float ms_raster;              /* tile rasteriser */
+    float ms_shade;               /* vis-buffer shading */
+    float ms_resolve;             /* last swr_resolve */
+} swr_frame_stats;
+
+typedef struct swr_ctx swr_ctx;
+
+int swr_abi_version(void);
+/* sizeof() of the ABI structs as compiled into the library, for binding self-checks:
+ * 0 primitive, 1 mesh, 2 node, 3 texture, 4 material, 5 voxel grid, 6 scene, 7 camera, 8 draw, 9 stats. */
+size_t swr_sizeof(int which);
+const char *swr_last_error(const swr_ctx *ctx); /* ctx may be NULL: last create error */
+
+/* Renderer::new (renderer.rs:165). device = CUDA ordinal. */
+swr_ctx *swr_create(int width, int height, int device);
+void swr_destroy(swr_ctx *ctx);
+
+/* Sort-first partition: this context owns tile rows [row_begin,row_end) only
+ * (default: all rows).  Triangles are binned, rasterised and shaded for owned
+ * tiles; other pixels are left untouched. */
+int swr_set_tile_rows(swr_ctx *ctx, int row_begin, int row_end);
+
+/* Copies the scene to device memory; the descriptor may be freed afterwards. */
+int swr_upload_scene(swr_ctx *ctx, const swr_scene_desc *scene);
+
+/* Device half of render_scene (renderer.rs:201-220): set-up, clip, bin, raster,
+ * shade.  Asynchronous on the context's stream. With shade=0 only the
+ * visibility buffer is produced (used by the sort-last composite). */
+int swr_render(swr_ctx *ctx, const swr_camera *camera, const swr_draw *draws, int ndraws, int shade);
+
+/* Shade the current visibility-key buffer (after an external depth composite). */
+int swr_shade(swr_ctx *ctx, const swr_camera *camera);
+
+/* blit_to_buffer (renderer.rs:293-355): exposure, tonemap, RGBA8 pack into a
+ * row-major W*H u32 image on the device; if out_pixels != NULL it is copied to
+ * that HOST buffer and the call synchronises. */
+int swr_resolve(swr_ctx *ctx, float exposure, uint32_t *out_pixels);
+
+/* Per-tile metering luminance (tilerasterizer.rs:103-106), row-major tiles. */
+int swr_read_tile_luminance(swr_ctx *ctx, float *out_per_tile);
+
+/* Parity read-back: per pixel depth bits, seq id and the two barycentrics, row-major
+ * W*H each (any pointer may be NULL). Uncovered = (+INF bits, 0xFFFFFFFF, 0, 0). */
+int swr_read_visbuffer(swr_ctx *ctx, uint32_t *depth_bits, uint32_t *seq, float *bary1, float *bary2);
+
+/* Linear HDR colour before exposure/tonemap, row-major W*H*3 floats (parity only). */
+int swr_read_color(swr_ctx *ctx, float *rgb);
+
+int swr_synchronize(swr_ctx *ctx);
+int swr_get_stats(swr_ctx *ctx, swr_frame_stats *out);
+
+/* Device pointers for zero-copy interop (NCCL gather / composite from the host
+ * language): RGBA8 image (W*H u32, row-major) and the 64-bit visibility keys
+ * (tile-major: tile (ty*tiles_x+tx) owns 4096 consecutive keys, y*64+x inside the
+ * tile; key = orderable(depth)<<32 | ~record id, empty = all ones). Valid until the
+ * next swr_render that grows buffers, or swr_destroy. */
+void *swr_device_pixels(swr_ctx *ctx);
+void *swr_device_keys(swr_ctx *ctx);
+size_t swr_device_keys_bytes(swr_ctx *ctx);
+void *swr_cuda_stream(swr_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWR_H_ */

@@ -1,0 +1,723 @@
+// swr_api.cu — implementation of the C ABI in include/swr.h on CUDA (sm_100a).
+// Frame = k_setup -> k_scan_tiles -> k_scatter -> k_raster_tiles -> k_shade -> k_luminance, all on one
+// stream, no host synchronisation inside swr_render. Buffer growth (tile refs, clip vertices) is detected
+// from device counters at the next synchronising call and the frame is replayed once.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/swr.h"
+#include "swr_shade.cuh"
+
+static thread_local std::string g_create_error;
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                          \
+            return SWR_ERR_CUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Staging {  // pinned host mirror of the per-frame draw table, rotated so a pending copy is never overwritten
+    void *host = nullptr;
+    size_t bytes = 0;
+    cudaEvent_t done = nullptr;
+};
+
+struct swr_ctx {
+    int device = 0;
+    int W = 0, H = 0, tiles_x = 0, tiles_y = 0, ntiles = 0;
+    int row_begin = 0, row_end = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_res[2] = {nullptr, nullptr};
+    std::string err;
+
+    // scene
+    bool have_scene = false;
+    std::vector<void *> scene_allocs;
+    std::vector<cudaTextureObject_t> tex_objs;
+    DevScene scene{};
+    std::vector<uint32_t> prim_ntris, prim_nverts;
+
+    // frame
+    DevBuf<DevDraw> draws;
+    DevBuf<uint32_t> tri_prefix;
+    DevBuf<TriRecord> records;
+    DevBuf<uint32_t> rects;
+    DevBuf<ClipVertex> clip_verts;
+    DevBuf<uint32_t> tile_count, tile_offset, tile_cursor;
+    DevBuf<uint32_t> refs;
+    DevBuf<unsigned long long> keys;
+    DevBuf<float4> color;
+    DevBuf<uint32_t> pixels;
+    DevBuf<float> lum;
+    DevBuf<FrameCounters> counters;
+    FrameCounters *h_counters = nullptr;  // pinned
+    Staging staging[4];
+    int staging_next = 0;
+
+    // replay info
+    std::vector<swr_draw> last_draws;
+    swr_camera last_cam{};
+    int last_shade = 0;
+    bool frame_pending = false;
+    bool frame_valid = false;
+    uint32_t ndraws = 0, nslots = 0, total_tris = 0;
+    uint64_t total_verts = 0;
+    DevCamera dcam{};
+    swr_frame_stats stats{};
+    bool rendered_once = false;
+};
+
+template <typename T>
+static int upload(swr_ctx *ctx, const T *src, size_t n, T **out) {
+    *out = nullptr;
+    if (n == 0) return SWR_OK;
+    void *d = nullptr;
+    CK(cudaMalloc(&d, n * sizeof(T)));
+    ctx->scene_allocs.push_back(d);
+    CK(cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *out = (T *)d;
+    return SWR_OK;
+}
+
+static size_t raster_smem_bytes() { return SWR_TILE_PIXELS * 8 + RASTER_WARPS * sizeof(WarpPackets); }
+
+extern "C" {
+
+int swr_abi_version(void) { return SWR_ABI_VERSION; }
+
+size_t swr_sizeof(int which) {
+    switch (which) {
+        case 0: return sizeof(swr_primitive_desc);
+        case 1: return sizeof(swr_mesh_desc);
+        case 2: return sizeof(swr_node_desc);
+        case 3: return sizeof(swr_texture_desc);
+        case 4: return sizeof(swr_material_desc);
+        case 5: return sizeof(swr_voxel_grid_desc);
+        case 6: return sizeof(swr_scene_desc);
+        case 7: return sizeof(swr_camera);
+        case 8: return sizeof(swr_draw);
+        case 9: return sizeof(swr_frame_stats);
+        default: return 0;
+    }
+}
+
+const char *swr_last_error(const swr_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+swr_ctx *swr_create(int width, int height, int device) {
+    if (width <= 0 || height <= 0 || (width & 1) || (height & 1)) {
+        g_create_error = "width and height must be positive and even (2x2 quads; renderer.rs:296 processes row pairs)";
+        return nullptr;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        g_create_error = std::string("no usable CUDA device (there is no CPU fallback): ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range");
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+        g_create_error = "device is not sm_100 class: this library carries sm_100a code only";
+        return nullptr;
+    }
+    swr_ctx *ctx = new swr_ctx();
+    ctx->device = device;
+    ctx->W = width;
+    ctx->H = height;
+    ctx->tiles_x = (width + SWR_TILE - 1) / SWR_TILE;
+    ctx->tiles_y = (height + SWR_TILE - 1) / SWR_TILE;
+    ctx->ntiles = ctx->tiles_x * ctx->tiles_y;
+    ctx->row_begin = 0;
+    ctx->row_end = ctx->tiles_y;
+    if (ctx->tiles_x > 255 || ctx->tiles_y > 255) {
+        g_create_error = "resolution above 16320 pixels per axis is not supported (tile rectangles are packed in 8 bits)";
+        delete ctx;
+        return nullptr;
+    }
+    bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < 5; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    for (int i = 0; ok && i < 2; i++) ok = cudaEventCreate(&ctx->ev_res[i]) == cudaSuccess;
+    for (int i = 0; ok && i < 4; i++) ok = cudaEventCreateWithFlags(&ctx->staging[i].done, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMallocHost(&ctx->h_counters, sizeof(FrameCounters)) == cudaSuccess;
+    ok = ok && ctx->tile_count.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_offset.reserve(ctx->ntiles + 1) == cudaSuccess &&
+         ctx->tile_cursor.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->keys.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess &&
+         ctx->color.reserve((size_t)width * height) == cudaSuccess && ctx->pixels.reserve((size_t)width * height) == cudaSuccess &&
+         ctx->lum.reserve(ctx->ntiles) == cudaSuccess && ctx->counters.reserve(1) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_raster_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes()) == cudaSuccess;
+    if (ok) {
+        ok = cudaMemsetAsync(ctx->keys.p, 0xFF, (size_t)ctx->ntiles * SWR_TILE_PIXELS * 8, ctx->stream) == cudaSuccess &&
+             cudaMemsetAsync(ctx->color.p, 0, (size_t)width * height * sizeof(float4), ctx->stream) == cudaSuccess &&
+             cudaMemsetAsync(ctx->pixels.p, 0, (size_t)width * height * 4, ctx->stream) == cudaSuccess &&
+             cudaMemsetAsync(ctx->lum.p, 0, ctx->ntiles * sizeof(float), ctx->stream) == cudaSuccess &&
+             cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    }
+    if (!ok) {
+        g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
+        swr_destroy(ctx);
+        return nullptr;
+    }
+    return ctx;
+}
+
+static void free_scene(swr_ctx *ctx) {
+    for (cudaTextureObject_t t : ctx->tex_objs) cudaDestroyTextureObject(t);
+    ctx->tex_objs.clear();
+    for (void *p : ctx->scene_allocs) cudaFree(p);
+    ctx->scene_allocs.clear();
+    ctx->have_scene = false;
+}
+
+void swr_destroy(swr_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_scene(ctx);
+    ctx->draws.release();
+    ctx->tri_prefix.release();
+    ctx->records.release();
+    ctx->rects.release();
+    ctx->clip_verts.release();
+    ctx->tile_count.release();
+    ctx->tile_offset.release();
+    ctx->tile_cursor.release();
+    ctx->refs.release();
+    ctx->keys.release();
+    ctx->color.release();
+    ctx->pixels.release();
+    ctx->lum.release();
+    ctx->counters.release();
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    for (auto &s : ctx->staging) {
+        if (s.host) cudaFreeHost(s.host);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    for (auto &e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->ev_res)
+        if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int swr_set_tile_rows(swr_ctx *ctx, int row_begin, int row_end) {
+    if (!ctx) return SWR_ERR_INVALID;
+    if (row_begin < 0 || row_end > ctx->tiles_y || row_begin > row_end) {
+        ctx->err = "tile row range out of bounds";
+        return SWR_ERR_INVALID;
+    }
+    ctx->row_begin = row_begin;
+    ctx->row_end = row_end;
+    return SWR_OK;
+}
+
+int swr_upload_scene(swr_ctx *ctx, const swr_scene_desc *s) {
+    if (!ctx || !s) return SWR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_scene(ctx);
+    ctx->frame_valid = false;
+    if (s->nmaterials == 0 || s->cubemap < 0 || s->cubemap_specular < 0 || s->brdf_lut < 0 || (uint32_t)s->cubemap >= s->ntextures ||
+        (uint32_t)s->cubemap_specular >= s->ntextures || (uint32_t)s->brdf_lut >= s->ntextures) {
+        ctx->err = "scene needs at least one material (scene.rs:493) and cubemap / cubemap_specular / brdf_lut textures";
+        return SWR_ERR_INVALID;
+    }
+    int rc;
+    std::vector<DevPrim> prims(s->nprimitives);
+    ctx->prim_ntris.assign(s->nprimitives, 0);
+    ctx->prim_nverts.assign(s->nprimitives, 0);
+    for (uint32_t i = 0; i < s->nprimitives; i++) {
+        const swr_primitive_desc &p = s->primitives[i];
+        if (p.material_index >= s->nmaterials) {
+            ctx->err = "primitive material_index out of range";
+            return SWR_ERR_INVALID;
+        }
+        for (uint32_t k = 0; k < p.nindices; k++)
+            if (p.indices[k] >= p.nverts) {
+                ctx->err = "primitive index out of range";  // the reference would panic on the slice access
+                return SWR_ERR_INVALID;
+            }
+        DevPrim d{};
+        float4 *pos, *nrm, *tan;
+        float2 *uv;
+        uint32_t *idx;
+        if ((rc = upload(ctx, (const float4 *)p.positions, p.nverts, &pos))) return rc;
+        if ((rc = upload(ctx, (const float4 *)p.normals, p.nverts, &nrm))) return rc;
+        if ((rc = upload(ctx, (const float4 *)p.tangents, p.nverts, &tan))) return rc;
+        if ((rc = upload(ctx, (const float2 *)p.texcoords, p.nverts, &uv))) return rc;
+        if ((rc = upload(ctx, p.indices, p.nindices, &idx))) return rc;
+        d.pos = pos;
+        d.nrm = nrm;
+        d.tan = tan;
+        d.uv = uv;
+        d.idx = idx;
+        d.nverts = p.nverts;
+        d.ntris = p.nindices / 3;
+        d.material = p.material_index;
+        prims[i] = d;
+        ctx->prim_ntris[i] = d.ntris;
+        ctx->prim_nverts[i] = p.nverts;
+    }
+    std::vector<DevMat> mats(s->nmaterials);
+    for (uint32_t i = 0; i < s->nmaterials; i++) {
+        const swr_material_desc &m = s->materials[i];
+        DevMat d{};
+        memcpy(d.base, m.base_color_factor, 16);
+        d.metallic = m.metallic_factor;
+        d.roughness = m.roughness_factor;
+        memcpy(d.emissive, m.emissive_factor, 12);
+        d.occlusion_strength = m.occlusion_strength;
+        d.transmission = m.transmission;
+        d.alpha_cutoff = m.alpha_cutoff;
+        d.flags = m.flags;
+        const int32_t t[6] = {m.base_color_texture, m.metallic_roughness_texture, m.normal_texture, m.emissive_texture, m.occlusion_texture, m.transmission_texture};
+        for (int k = 0; k < 6; k++)
+            if (t[k] >= (int32_t)s->ntextures) {
+                ctx->err = "material texture index out of range";
+                return SWR_ERR_INVALID;
+            }
+        d.tex_base = t[0];
+        d.tex_mr = t[1];
+        d.tex_normal = t[2];
+        d.tex_emissive = t[3];
+        d.tex_occlusion = t[4];
+        d.tex_transmission = t[5];
+        if (m.flags & SWR_MAT_ALPHA_TESTED) {
+            ctx->err = "alpha-tested materials are not implemented yet (SURVEY 8f N1)";
+            return SWR_ERR_INVALID;
+        }
+        mats[i] = d;
+    }
+    std::vector<DevTex> texs(s->ntextures);
+    for (uint32_t i = 0; i < s->ntextures; i++) {
+        const swr_texture_desc &t = s->textures[i];
+        if (t.max_mip_level + 1 > SWR_MAX_MIPS) {
+            ctx->err = "texture has more than 16 mip levels";
+            return SWR_ERR_INVALID;
+        }
+        DevTex d{};
+        uint32_t *data;
+        if ((rc = upload(ctx, t.data, t.ntexels, &data))) return rc;
+        d.data = data;
+        d.width = t.width;
+        d.height = t.height;
+        d.type = t.texture_type;
+        d.max_mip = t.max_mip_level;
+        d.wrap_s = t.wrap_s;
+        d.wrap_t = t.wrap_t;
+        for (uint32_t k = 0; k <= t.max_mip_level; k++) {
+            d.mip_off[k] = t.mip_offsets[k];
+            d.mip_w[k] = t.mip_widths[k];
+            d.mip_h[k] = t.mip_heights[k];
+            d.stride[k] = t.array_stride[k];
+        }
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = data;
+        rd.res.linear.desc = cudaCreateChannelDesc<unsigned int>();
+        rd.res.linear.sizeInBytes = (size_t)t.ntexels * 4;
+        cudaTextureDesc td{};
+        td.readMode = cudaReadModeElementType;
+        td.filterMode = cudaFilterModePoint;
+        td.addressMode[0] = cudaAddressModeClamp;
+        cudaTextureObject_t obj = 0;
+        CK(cudaCreateTextureObject(&obj, &rd, &td, nullptr));
+        ctx->tex_objs.push_back(obj);
+        d.obj = obj;
+        texs[i] = d;
+    }
+    DevPrim *dprims;
+    DevMat *dmats;
+    DevTex *dtexs;
+    float4 *gi;
+    if ((rc = upload(ctx, prims.data(), prims.size(), &dprims))) return rc;
+    if ((rc = upload(ctx, mats.data(), mats.size(), &dmats))) return rc;
+    if ((rc = upload(ctx, texs.data(), texs.size(), &dtexs))) return rc;
+    const swr_voxel_grid_desc &g = s->voxel_grid;
+    size_t nvox = (size_t)g.dims[0] * g.dims[1] * g.dims[2];
+    if (nvox == 0 || !g.gi_sh4) {
+        ctx->err = "voxel grid is empty";
+        return SWR_ERR_INVALID;
+    }
+    if ((rc = upload(ctx, (const float4 *)g.gi_sh4, nvox * 4, &gi))) return rc;
+    DevScene &sc = ctx->scene;
+    sc.prims = dprims;
+    sc.mats = dmats;
+    sc.texs = dtexs;
+    sc.gi = gi;
+    for (int k = 0; k < 3; k++) {
+        sc.gdim[k] = g.dims[k];
+        sc.gmin[k] = g.world_min[k];
+        sc.gmax[k] = g.world_max[k];
+        sc.light_dir[k] = s->light_direction[k];
+        sc.light_color[k] = s->light_color[k];
+    }
+    sc.cubemap = s->cubemap;
+    sc.cubemap_specular = s->cubemap_specular;
+    sc.brdf_lut = s->brdf_lut;
+    CK(cudaStreamSynchronize(ctx->stream));  // host staging vectors go out of scope
+    ctx->have_scene = true;
+    return SWR_OK;
+}
+
+// Enqueue one frame from ctx->last_* (no host synchronisation).
+static int launch_frame(swr_ctx *ctx) {
+    const std::vector<swr_draw> &draws = ctx->last_draws;
+    const uint32_t nd = (uint32_t)draws.size();
+    // host-side tables: DevDraw + local triangle prefix + slot bases
+    size_t bytes = (size_t)nd * sizeof(DevDraw) + (size_t)(nd + 1) * sizeof(uint32_t);
+    Staging &st = ctx->staging[ctx->staging_next];
+    ctx->staging_next = (ctx->staging_next + 1) & 3;
+    CK(cudaEventSynchronize(st.done));
+    if (st.bytes < bytes) {
+        if (st.host) cudaFreeHost(st.host);
+        st.host = nullptr;
+        st.bytes = 0;
+        CK(cudaMallocHost(&st.host, bytes + 4096));
+        st.bytes = bytes + 4096;
+    }
+    DevDraw *hd = (DevDraw *)st.host;
+    uint32_t *hp = (uint32_t *)((char *)st.host + (size_t)nd * sizeof(DevDraw));
+    uint64_t tris = 0, slots = 0, verts = 0, clip_tris = 0;
+    for (uint32_t i = 0; i < nd; i++) {
+        const swr_draw &d = draws[i];
+        if (d.primitive >= ctx->prim_ntris.size()) {
+            ctx->err = "draw references a primitive that is not in the uploaded scene";
+            return SWR_ERR_INVALID;
+        }
+        memcpy(hd[i].model, d.model, 64);
+        memcpy(hd[i].mvp, d.mvp, 64);
+        hd[i].prim = d.primitive;
+        hd[i].flags = d.flags;
+        hd[i].first_tri = d.first_triangle;
+        hd[i].slot_base = (uint32_t)slots;
+        hp[i] = (uint32_t)tris;
+        uint32_t nt = ctx->prim_ntris[d.primitive];
+        tris += nt;
+        verts += ctx->prim_nverts[d.primitive];
+        slots += (uint64_t)nt * ((d.flags & SWR_DRAW_CLIP) ? 7 : 1);
+        if (d.flags & SWR_DRAW_CLIP) clip_tris += nt;
+        if ((uint64_t)d.first_triangle + nt > 0x1FFFFFFFull) {
+            ctx->err = "more than 2^29 triangles in one frame: the seq id (tri*8+fan) would overflow";
+            return SWR_ERR_INVALID;
+        }
+    }
+    hp[nd] = (uint32_t)tris;
+    if (slots >= 0xFFFFFFFFull || tris >= 0xFFFFFFFFull) {
+        ctx->err = "frame too large for 32-bit record ids";
+        return SWR_ERR_INVALID;
+    }
+    ctx->ndraws = nd;
+    ctx->total_tris = (uint32_t)tris;
+    ctx->nslots = (uint32_t)slots;
+    ctx->total_verts = verts;
+    if (ctx->draws.reserve(nd + 1) != cudaSuccess || ctx->tri_prefix.reserve(nd + 2) != cudaSuccess || ctx->records.reserve(slots + 1) != cudaSuccess ||
+        ctx->rects.reserve(slots + 1) != cudaSuccess) {
+        ctx->err = "out of device memory for per-frame triangle records";
+        return SWR_ERR_OOM;
+    }
+    size_t want_refs = (size_t)(tris + tris / 2) + (1u << 16);
+    if (ctx->refs.cap < want_refs && !ctx->rendered_once) {
+        if (ctx->refs.reserve(want_refs) != cudaSuccess) {
+            ctx->err = "out of device memory for tile lists";
+            return SWR_ERR_OOM;
+        }
+    }
+    if (ctx->refs.cap == 0 && ctx->refs.reserve(1u << 16) != cudaSuccess) return SWR_ERR_OOM;
+    size_t want_clip = (size_t)clip_tris / 4 + 4096;
+    if (ctx->clip_verts.cap < want_clip && !ctx->rendered_once) {
+        if (ctx->clip_verts.reserve(want_clip) != cudaSuccess) return SWR_ERR_OOM;
+    }
+    if (ctx->clip_verts.cap == 0 && ctx->clip_verts.reserve(4096) != cudaSuccess) return SWR_ERR_OOM;
+
+    cudaStream_t s = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[0], s));
+    if (nd) CK(cudaMemcpyAsync(ctx->draws.p, hd, (size_t)nd * sizeof(DevDraw), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->tri_prefix.p, hp, (size_t)(nd + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(st.done, s));
+    CK(cudaMemsetAsync(ctx->tile_count.p, 0, (ctx->ntiles + 1) * sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(FrameCounters), s));
+
+    const int rb = ctx->row_begin, re = ctx->row_end;
+    if (tris > 0) {
+        SetupParams sp{};
+        sp.draws = ctx->draws.p;
+        sp.tri_prefix = ctx->tri_prefix.p;
+        sp.ndraws = nd;
+        sp.total_tris = (uint32_t)tris;
+        sp.prims = ctx->scene.prims;
+        sp.records = ctx->records.p;
+        sp.rects = ctx->rects.p;
+        sp.clip_verts = ctx->clip_verts.p;
+        sp.clip_capacity = (uint32_t)ctx->clip_verts.cap;
+        sp.tile_count = ctx->tile_count.p;
+        sp.counters = ctx->counters.p;
+        sp.W = ctx->W;
+        sp.H = ctx->H;
+        sp.tiles_x = ctx->tiles_x;
+        sp.tiles_y = ctx->tiles_y;
+        sp.row_begin = rb;
+        sp.row_end = re;
+        k_setup<<<(unsigned)((tris + SETUP_THREADS - 1) / SETUP_THREADS), SETUP_THREADS, 0, s>>>(sp);
+    }
+    k_scan_tiles<<<1, 1024, 0, s>>>(ctx->tile_count.p, ctx->tile_offset.p, ctx->tile_cursor.p, ctx->ntiles, ctx->counters.p, (uint32_t)ctx->refs.cap);
+    if (slots > 0)
+        k_scatter<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(ctx->rects.p, (uint32_t)slots, ctx->tile_cursor.p, ctx->refs.p, (uint32_t)ctx->refs.cap,
+                                                                  ctx->counters.p, ctx->tiles_x);
+    CK(cudaEventRecord(ctx->ev[1], s));
+    if (re > rb) {
+        RasterParams rp{};
+        rp.records = ctx->records.p;
+        rp.refs = ctx->refs.p;
+        rp.tile_offset = ctx->tile_offset.p;
+        rp.keys = ctx->keys.p;
+        rp.counters = ctx->counters.p;
+        rp.W = ctx->W;
+        rp.H = ctx->H;
+        rp.tiles_x = ctx->tiles_x;
+        rp.tiles_y = ctx->tiles_y;
+        rp.row_begin = rb;
+        rp.row_end = re;
+        k_raster_tiles<<<(unsigned)((re - rb) * ctx->tiles_x), RASTER_THREADS, raster_smem_bytes(), s>>>(rp);
+    }
+    CK(cudaEventRecord(ctx->ev[2], s));
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
+    CK(cudaGetLastError());
+    return SWR_OK;
+}
+
+static int launch_shade(swr_ctx *ctx) {
+    cudaStream_t s = ctx->stream;
+    const int rb = ctx->row_begin, re = ctx->row_end;
+    if (re > rb) {
+        ShadeParams sp{};
+        sp.keys = ctx->keys.p;
+        sp.records = ctx->records.p;
+        sp.draws = ctx->draws.p;
+        sp.clip_verts = ctx->clip_verts.p;
+        sp.scene = ctx->scene;
+        sp.cam = ctx->dcam;
+        sp.color = ctx->color.p;
+        sp.W = ctx->W;
+        sp.H = ctx->H;
+        sp.tiles_x = ctx->tiles_x;
+        sp.row_begin = rb;
+        sp.row_end = re;
+        int y0 = rb * SWR_TILE, y1 = re * SWR_TILE < ctx->H ? re * SWR_TILE : ctx->H;
+        dim3 grid((ctx->W + 15) / 16, (y1 - y0 + 15) / 16);
+        k_shade<<<grid, SHADE_BLOCK, 0, s>>>(sp);
+        k_luminance<<<(ctx->ntiles + 127) / 128, 128, 0, s>>>(ctx->color.p, ctx->lum.p, ctx->W, ctx->H, ctx->tiles_x, ctx->ntiles);
+    }
+    CK(cudaEventRecord(ctx->ev[3], s));
+    CK(cudaGetLastError());
+    return SWR_OK;
+}
+
+static void set_camera(swr_ctx *ctx, const swr_camera *cam) {
+    ctx->last_cam = *cam;
+    memcpy(ctx->dcam.position, cam->position, 12);
+    memcpy(ctx->dcam.skybox_T, cam->skybox_matrix_transposed, 64);
+    ctx->dcam.one_over_width = cam->one_over_width;
+    ctx->dcam.one_over_height = cam->one_over_height;
+}
+
+// Synchronise, and if a device-side buffer overflowed grow it and replay the frame.
+static int finish_frame(swr_ctx *ctx) {
+    CK(cudaSetDevice(ctx->device));
+    for (int attempt = 0; attempt < 4; attempt++) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (!ctx->frame_pending) return SWR_OK;
+        const FrameCounters c = *ctx->h_counters;
+        if (!c.overflow_refs && !c.overflow_clip) {
+            ctx->frame_pending = false;
+            ctx->frame_valid = true;
+            ctx->rendered_once = true;
+            swr_frame_stats &st = ctx->stats;
+            st.triangles_submitted = ctx->total_tris;
+            st.vertices_submitted = ctx->total_verts;
+            st.triangles_binned = c.tris_binned;
+            st.triangles_clipped = c.tris_clipped;
+            st.tile_refs = c.tile_refs;
+            st.tiles = (uint32_t)ctx->ntiles;
+            cudaEventElapsedTime(&st.ms_setup_bin, ctx->ev[0], ctx->ev[1]);
+            cudaEventElapsedTime(&st.ms_raster, ctx->ev[1], ctx->ev[2]);
+            st.ms_shade = 0.0f;
+            if (ctx->last_shade) cudaEventElapsedTime(&st.ms_shade, ctx->ev[2], ctx->ev[3]);
+            return SWR_OK;
+        }
+        if (c.overflow_refs) {
+            size_t want = (size_t)c.tile_refs + (size_t)c.tile_refs / 4 + 4096;
+            if (ctx->refs.reserve(want) != cudaSuccess) {
+                ctx->err = "out of device memory growing tile lists";
+                return SWR_ERR_OOM;
+            }
+        }
+        if (c.overflow_clip) {
+            size_t want = (size_t)c.clip_verts + (size_t)c.clip_verts / 4 + 4096;
+            if (ctx->clip_verts.reserve(want) != cudaSuccess) {
+                ctx->err = "out of device memory growing clip vertex buffer";
+                return SWR_ERR_OOM;
+            }
+        }
+        int rc = launch_frame(ctx);
+        if (rc) return rc;
+        if (ctx->last_shade && (rc = launch_shade(ctx))) return rc;
+    }
+    ctx->err = "frame did not fit after growing buffers";
+    return SWR_ERR_OOM;
+}
+
+int swr_render(swr_ctx *ctx, const swr_camera *camera, const swr_draw *draws, int ndraws, int shade) {
+    if (!ctx || !camera || ndraws < 0 || (ndraws > 0 && !draws)) return SWR_ERR_INVALID;
+    if (!ctx->have_scene) {
+        ctx->err = "swr_render called before swr_upload_scene";
+        return SWR_ERR_NO_SCENE;
+    }
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if (ctx->frame_pending && (rc = finish_frame(ctx))) return rc;  // settle a previous frame's growth before reusing buffers
+    ctx->last_draws.assign(draws, draws + ndraws);
+    set_camera(ctx, camera);
+    ctx->last_shade = shade;
+    if ((rc = launch_frame(ctx))) return rc;
+    if (shade && (rc = launch_shade(ctx))) return rc;
+    ctx->frame_pending = true;
+    return SWR_OK;
+}
+
+int swr_shade(swr_ctx *ctx, const swr_camera *camera) {
+    if (!ctx || !camera) return SWR_ERR_INVALID;
+    if (!ctx->have_scene) return SWR_ERR_NO_SCENE;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = finish_frame(ctx))) return rc;
+    set_camera(ctx, camera);
+    ctx->last_shade = 1;
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    return launch_shade(ctx);
+}
+
+int swr_resolve(swr_ctx *ctx, float exposure, uint32_t *out_pixels) {
+    if (!ctx) return SWR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    // a pending frame may still need a replay; only the synchronising form (host output) or an explicit
+    // swr_synchronize settles it, so the device-only form stays asynchronous.
+    if (out_pixels && (rc = finish_frame(ctx))) return rc;
+    cudaStream_t s = ctx->stream;
+    const size_t W = ctx->W;
+    size_t y0 = (size_t)ctx->row_begin * SWR_TILE, y1 = (size_t)ctx->row_end * SWR_TILE;
+    if (y1 > (size_t)ctx->H) y1 = ctx->H;
+    CK(cudaEventRecord(ctx->ev_res[0], s));
+    if (y1 > y0) {
+        size_t first4 = y0 * W / 4, end4 = y1 * W / 4;
+        k_resolve<<<(unsigned)((end4 - first4 + 255) / 256), 256, 0, s>>>(ctx->color.p, ctx->pixels.p, exposure, end4, first4);
+    }
+    CK(cudaEventRecord(ctx->ev_res[1], s));
+    CK(cudaGetLastError());
+    if (out_pixels) {
+        if (y1 > y0) CK(cudaMemcpyAsync(out_pixels + y0 * W, ctx->pixels.p + y0 * W, (y1 - y0) * W * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        cudaEventElapsedTime(&ctx->stats.ms_resolve, ctx->ev_res[0], ctx->ev_res[1]);
+    }
+    return SWR_OK;
+}
+
+int swr_synchronize(swr_ctx *ctx) {
+    if (!ctx) return SWR_ERR_INVALID;
+    return finish_frame(ctx);
+}
+
+int swr_read_tile_luminance(swr_ctx *ctx, float *out) {
+    if (!ctx || !out) return SWR_ERR_INVALID;
+    int rc;
+    if ((rc = finish_frame(ctx))) return rc;
+    CK(cudaMemcpy(out, ctx->lum.p, ctx->ntiles * sizeof(float), cudaMemcpyDeviceToHost));
+    return SWR_OK;
+}
+
+int swr_read_visbuffer(swr_ctx *ctx, uint32_t *depth_bits, uint32_t *seq, float *bary1, float *bary2) {
+    if (!ctx) return SWR_ERR_INVALID;
+    int rc;
+    if ((rc = finish_frame(ctx))) return rc;
+    if (!ctx->frame_valid) {
+        ctx->err = "no frame has been rendered";
+        return SWR_ERR_INVALID;
+    }
+    const size_t n = (size_t)ctx->W * ctx->H;
+    uint32_t *d = nullptr;
+    CK(cudaMalloc(&d, n * 16));
+    VisParams vp{};
+    vp.keys = ctx->keys.p;
+    vp.records = ctx->records.p;
+    vp.draws = ctx->draws.p;
+    vp.ndraws = ctx->ndraws;
+    vp.W = ctx->W;
+    vp.H = ctx->H;
+    vp.tiles_x = ctx->tiles_x;
+    dim3 blk(32, 8), grid((ctx->W + 31) / 32, (ctx->H + 7) / 8);
+    k_read_vis<<<grid, blk, 0, ctx->stream>>>(vp, d, d + n, (float *)(d + 2 * n), (float *)(d + 3 * n));
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && depth_bits) e = cudaMemcpy(depth_bits, d, n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && seq) e = cudaMemcpy(seq, d + n, n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && bary1) e = cudaMemcpy(bary1, d + 2 * n, n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && bary2) e = cudaMemcpy(bary2, d + 3 * n, n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    CK(e);
+    return SWR_OK;
+}
+
+int swr_read_color(swr_ctx *ctx, float *rgb) {
+    if (!ctx || !rgb) return SWR_ERR_INVALID;
+    int rc;
+    if ((rc = finish_frame(ctx))) return rc;
+    const size_t n = (size_t)ctx->W * ctx->H;
+    std::vector<float4> tmp(n);
+    CK(cudaMemcpy(tmp.data(), ctx->color.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; i++) {
+        rgb[i * 3 + 0] = tmp[i].x;
+        rgb[i * 3 + 1] = tmp[i].y;
+        rgb[i * 3 + 2] = tmp[i].z;
+    }
+    return SWR_OK;
+}
+
+int swr_get_stats(swr_ctx *ctx, swr_frame_stats *out) {
+    if (!ctx || !out) return SWR_ERR_INVALID;
+    int rc;
+    if ((rc = finish_frame(ctx))) return rc;
+    ctx->stats.tiles = (uint32_t)ctx->ntiles;
+    *out = ctx->stats;
+    return SWR_OK;
+}
+
+void *swr_device_pixels(swr_ctx *ctx) { return ctx ? ctx->pixels.p : nullptr; }
+void *swr_device_keys(swr_ctx *ctx) { return ctx ? ctx->keys.p : nullptr; }
+size_t swr_device_keys_bytes(swr_ctx *ctx) { return ctx ? (size_t)ctx->ntiles * SWR_TILE_PIXELS * 8 : 0; }
+void *swr_cuda_stream(swr_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,445 @@
+// swr_shade.cuh — K5 visibility-buffer shading and K6 resolve.
+//   k_shade     one thread per pixel, 2x2 quads inside a warp (lanes 4q..4q+3) so that the reference's
+//               quad-coupled mip selection (shader.rs:130: du_dv * w is lane-wise) is reproduced with shuffles.
+//               Reference: tilerasterizer.rs:386-508 (shade_vbuffer, compute_skybox), shader.rs:102-309
+//               (pbr_shader<false>), texture.rs:577-864 (samplers), voxelgrid.rs:264-368, util.rs, math.rs.
+//   k_luminance per-tile metering value (tilerasterizer.rs:103-106)
+//   k_resolve   exposure, tonemap, RGBA8 pack with 128-bit stores (renderer.rs:293-355, util.rs:37-41,98-100)
+// Arithmetic is restated operation for operation (translation unit built with -fmad=false, IEEE div/sqrt);
+// the only deliberate difference is normalize(): the reference uses the 12-bit _mm_rsqrt_ps (math.rs:34-39),
+// here rsqrtf() — inside the +-1 LSB colour tolerance, see DESIGN.md.
+#pragma once
+#include "swr_raster.cuh"
+
+struct ShadeParams {
+    const unsigned long long *keys;
+    const TriRecord *records;
+    const DevDraw *draws;
+    const ClipVertex *clip_verts;
+    DevScene scene;
+    DevCamera cam;
+    float4 *color;  // row-major W*H, linear HDR rgb (+ unused w)
+    int W, H, tiles_x;
+    int row_begin, row_end;
+};
+
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 operator*(V3 a, V3 b) { return V3{a.x * b.x, a.y * b.y, a.z * b.z}; }
+__device__ __forceinline__ V3 operator*(V3 a, float b) { return V3{a.x * b, a.y * b, a.z * b}; }
+__device__ __forceinline__ V3 operator+(V3 a, float b) { return V3{a.x + b, a.y + b, a.z + b}; }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  // math.rs:88-90
+__device__ __forceinline__ V3 normalize(V3 a) {                                                  // math.rs:101-108
+    float r = rsqrtf(dot(a, a));
+    return V3{a.x * r, a.y * r, a.z * r};
+}
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+// _mm_min_ps / _mm_max_ps semantics (second operand on NaN)
+__device__ __forceinline__ float sse_min(float a, float b) { return a < b ? a : b; }
+__device__ __forceinline__ float sse_max(float a, float b) { return a > b ? a : b; }
+__device__ __forceinline__ float sse_clamp(float a, float lo, float hi) { return sse_min(sse_max(a, lo), hi); }
+__device__ __forceinline__ V3 srgb_to_linear_fast(V3 x) { return x * (x * (x * 0.305306011f + 0.682171111f) + 0.012522878f); }
+
+__device__ __forceinline__ float4 fetch_texel(const DevTex &t, uint32_t idx) {  // util.rs:83-89
+    uint32_t p = tex1Dfetch<unsigned int>(t.obj, (int)idx);
+    return make_float4((float)((p >> 24) & 0xFF) / 255.0f, (float)((p >> 16) & 0xFF) / 255.0f, (float)((p >> 8) & 0xFF) / 255.0f,
+                       (float)(p & 0xFF) / 255.0f);
+}
+__device__ __forceinline__ float apply_wrap_mode(float texel, float dim, uint32_t mode) {  // texture.rs:578-589
+    float t2 = texel;
+    if (mode == 0u) {
+        t2 = texel - floorf(texel / dim) * dim;
+    } else if (mode == 1u) {
+        float two = dim * 2.0f;
+        float t = texel - floorf(texel / two) * two;
+        t2 = sse_min(t, two - t);
+    }
+    return sse_min(t2, dim - 1.0f);
+}
+__device__ __forceinline__ uint32_t compute_mip_level(const DevTex &t, const float d[4]) {  // texture.rs:851-863
+    float wf = (float)t.width, hf = (float)t.height;
+    float d0 = d[0] * wf, d1 = d[1] * wf, d2 = d[2] * hf, d3 = d[3] * hf;
+    float dx2 = d0 * d0 + d2 * d2;
+    float dy2 = d1 * d1 + d3 * d3;
+    float fp = (dx2 + dy2) * 0.5f;
+    float fm = fp > 1.0f ? fp : 1.0f;  // f32::max(1.0)
+    uint32_t mip = (31u - (uint32_t)__clz((int)__float2uint_rz(fm))) >> 1;
+    return min(mip, t.max_mip);
+}
+__device__ __forceinline__ float4 sample4(const DevTex &t, float u, float v, const float du_dv[4]) {  // texture.rs:680-714
+    uint32_t mip = compute_mip_level(t, du_dv);
+    float wf = (float)t.mip_w[mip], hf = (float)t.mip_h[mip];
+    uint32_t x = __float2uint_rz(apply_wrap_mode(floorf(u * wf), wf, t.wrap_s));
+    uint32_t y = __float2uint_rz(apply_wrap_mode(floorf(v * hf), hf, t.wrap_t));
+    return fetch_texel(t, t.mip_off[mip] + y * t.mip_w[mip] + x);
+}
+__device__ __forceinline__ V3 sample_cubemap_rgb(const DevTex &t, V3 n, uint32_t mip) {  // texture.rs:593-663
+    float ax = fabsf(n.x), ay = fabsf(n.y), az = fabsf(n.z);
+    bool mx = (ax >= ay) && (ax >= az);
+    bool my = (ay > ax) && (ay >= az);
+    float sx = n.x >= 0.0f ? 1.0f : -1.0f, sy = n.y >= 0.0f ? 1.0f : -1.0f, sz = n.z >= 0.0f ? 1.0f : -1.0f;
+    float u = mx ? (-n.z * sx) : (my ? n.x : n.x * sz);
+    float v = mx ? (-n.y) : (my ? n.z * sy : -n.y);
+    float den = mx ? ax : (my ? ay : az);
+    den = sse_max(den, 1.0e-19f);
+    float uf = 0.5f * (u / den + 1.0f), vf = 0.5f * (v / den + 1.0f);
+    uint32_t slice = mx ? (n.x >= 0.0f ? 0u : 1u) : (my ? (n.y >= 0.0f ? 2u : 3u) : (n.z >= 0.0f ? 4u : 5u));
+    mip = min(mip, t.max_mip);
+    float wf = (float)t.mip_w[mip], hf = (float)t.mip_h[mip];
+    float x = rintf(uf * (wf - 1.0f)), y = rintf(vf * (hf - 1.0f));  // glam Vec4::round: half to even
+    uint32_t xi = __float2uint_rz(sse_clamp(x, 0.0f, wf - 1.0f)), yi = __float2uint_rz(sse_clamp(y, 0.0f, hf - 1.0f));
+    float4 c = fetch_texel(t, t.mip_off[mip] + slice * t.stride[mip] + yi * t.mip_w[mip] + xi);
+    return v3(c.x, c.y, c.z);
+}
+__device__ __forceinline__ V3 sample_cubemap_trilinear_rgb(const DevTex &t, V3 n, float mip_level) {  // texture.rs:665-678
+    float maxm = (float)t.max_mip;
+    float mip = sse_clamp(mip_level, 0.0f, maxm);
+    float m0 = floorf(mip), m1 = sse_min(m0 + 1.0f, maxm), tt = mip - m0;
+    V3 c0 = sample_cubemap_rgb(t, n, __float2uint_rz(m0));
+    V3 c1 = sample_cubemap_rgb(t, n, __float2uint_rz(m1));
+    return v3(c0.x + (c1.x - c0.x) * tt, c0.y + (c1.y - c0.y) * tt, c0.z + (c1.z - c0.z) * tt);
+}
+__device__ __forceinline__ V3 sample_bilinear_rgb0(const DevTex &t, float u, float v) {  // texture.rs:730-790, mip 0 slice 0
+    float wf = (float)t.mip_w[0], hf = (float)t.mip_h[0];
+    uint32_t wi = t.mip_w[0], off = t.mip_off[0];
+    float xf = u * wf - 0.5f, yf = v * hf - 0.5f;
+    float x0 = floorf(xf), y0 = floorf(yf), x1 = x0 + 1.0f, y1 = y0 + 1.0f;
+    float fx = xf - x0, fy = yf - y0, omfx = 1.0f - fx, omfy = 1.0f - fy;
+    uint32_t x0i = __float2uint_rz(apply_wrap_mode(x0, wf, t.wrap_s)), y0i = __float2uint_rz(apply_wrap_mode(y0, hf, t.wrap_t));
+    uint32_t x1i = __float2uint_rz(apply_wrap_mode(x1, wf, t.wrap_s)), y1i = __float2uint_rz(apply_wrap_mode(y1, hf, t.wrap_t));
+    float4 p00 = fetch_texel(t, off + y0i * wi + x0i), p10 = fetch_texel(t, off + y0i * wi + x1i);
+    float4 p01 = fetch_texel(t, off + y1i * wi + x0i), p11 = fetch_texel(t, off + y1i * wi + x1i);
+    float w00 = omfx * omfy, w10 = fx * omfy, w01 = omfx * fy, w11 = fx * fy;
+    return v3(p00.x * w00 + p10.x * w10 + p01.x * w01 + p11.x * w11, p00.y * w00 + p10.y * w10 + p01.y * w01 + p11.y * w11,
+              p00.z * w00 + p10.z * w10 + p01.z * w01 + p11.z * w11);
+}
+
+// voxelgrid.rs:264-368 for one position.
+__device__ __forceinline__ uint32_t f2usize_clamped(float f, uint32_t hi) { return min(__float2uint_rz(f), hi); }
+__device__ __forceinline__ void sample_gi(const DevScene &s, V3 pos, V3 rgb[4], float w[4]) {
+    const uint32_t W = s.gdim[0], H = s.gdim[1], D = s.gdim[2];
+    float vsx = (s.gmax[0] - s.gmin[0]) / (float)W, vsy = (s.gmax[1] - s.gmin[1]) / (float)H, vsz = (s.gmax[2] - s.gmin[2]) / (float)D;
+    float vx = (pos.x - s.gmin[0]) / vsx, vy = (pos.y - s.gmin[1]) / vsy, vz = (pos.z - s.gmin[2]) / vsz;
+    float x0f = floorf(vx), y0f = floorf(vy), z0f = floorf(vz);
+    uint32_t x0 = f2usize_clamped(x0f, W - 1), y0 = f2usize_clamped(y0f, H - 1), z0 = f2usize_clamped(z0f, D - 1);
+    uint32_t x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1), z1 = min(z0 + 1, D - 1);
+    float fx = vx - x0f, fy = vy - y0f, fz = vz - z0f;
+    float ox = 1.0f - fx, oy = 1.0f - fy, oz = 1.0f - fz;
+    const size_t WH = (size_t)W * H;
+    const float4 *g000 = s.gi + ((size_t)z0 * WH + (size_t)y0 * W + x0) * 4, *g001 = s.gi + ((size_t)z1 * WH + (size_t)y0 * W + x0) * 4;
+    const float4 *g010 = s.gi + ((size_t)z0 * WH + (size_t)y1 * W + x0) * 4, *g011 = s.gi + ((size_t)z1 * WH + (size_t)y1 * W + x0) * 4;
+    const float4 *g100 = s.gi + ((size_t)z0 * WH + (size_t)y0 * W + x1) * 4, *g101 = s.gi + ((size_t)z1 * WH + (size_t)y0 * W + x1) * 4;
+    const float4 *g110 = s.gi + ((size_t)z0 * WH + (size_t)y1 * W + x1) * 4, *g111 = s.gi + ((size_t)z1 * WH + (size_t)y1 * W + x1) * 4;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        float4 v000 = __ldg(g000 + c), v001 = __ldg(g001 + c), v010 = __ldg(g010 + c), v011 = __ldg(g011 + c);
+        float4 v100 = __ldg(g100 + c), v101 = __ldg(g101 + c), v110 = __ldg(g110 + c), v111 = __ldg(g111 + c);
+#define SWR_TRI(F)                                                                                   \
+    ({                                                                                               \
+        float v00 = v000.F * ox + v100.F * fx, v01 = v001.F * ox + v101.F * fx;                      \
+        float v10 = v010.F * ox + v110.F * fx, v11 = v011.F * ox + v111.F * fx;                      \
+        float v0 = v00 * oy + v10 * fy, v1 = v01 * oy + v11 * fy;                                    \
+        v0 * oz + v1 * fz;                                                                           \
+    })
+        rgb[c] = v3(SWR_TRI(x), SWR_TRI(y), SWR_TRI(z));
+        w[c] = SWR_TRI(w);
+#undef SWR_TRI
+    }
+}
+
+// Per-packet data the shader interpolates (renderer.rs:697-754, util.rs:149-194).
+struct ShadePacket {
+    V3 n_a, n_da, n_db;
+    V3 t_a, t_da, t_db;
+    float ts_a, ts_da, ts_db;
+    float u_a, u_da, u_db, v_a, v_da, v_db;
+    V3 p_a, p_da, p_db;
+    float du_dv[4];
+    uint32_t material;
+};
+
+__device__ __forceinline__ void build_shade_packet(const ShadeParams &P, const TriRecord &r, ShadePacket &sp) {
+    const DevDraw &dr = P.draws[r.draw];
+    const DevPrim &pr = P.scene.prims[dr.prim];
+    V3 n[3], t[3], pw[3];
+    float tw[3], uu[3], vv[3];
+    if (r.clip == SWR_NO_CLIP) {  // renderer.rs:494-560
+        const uint32_t tri = (r.seq >> 3) - dr.first_tri;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            uint32_t iv = __ldg(pr.idx + 3 * tri + k);
+            float4 wp = mul_vec4(dr.model, __ldg(pr.pos + iv));
+            float4 n4 = __ldg(pr.nrm + iv), t4 = __ldg(pr.tan + iv);
+            float3 nw = mul_mat3(dr.model, make_float3(n4.x, n4.y, n4.z));
+            float3 tv = mul_mat3(dr.model, make_float3(t4.x, t4.y, t4.z));
+            float2 uv = __ldg(pr.uv + iv);
+            pw[k] = v3(wp.x, wp.y, wp.z);
+            n[k] = v3(nw.x, nw.y, nw.z);
+            t[k] = v3(tv.x, tv.y, tv.z);
+            tw[k] = t4.w;
+            uu[k] = uv.x;
+            vv[k] = uv.y;
+        }
+    } else {  // fan (0, j, j+1) of the clipped polygon (renderer.rs:655-664)
+        const uint32_t fan = r.seq & 7u;
+        const uint32_t vi[3] = {r.clip, r.clip + fan + 1u, r.clip + fan + 2u};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float4 *src = reinterpret_cast<const float4 *>(P.clip_verts + vi[k]);
+            float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+            pw[k] = v3(a.x, a.y, a.z);
+            n[k] = v3(a.w, b.x, b.y);
+            t[k] = v3(b.z, b.w, c.x);
+            tw[k] = c.y;
+            uu[k] = c.z;
+            vv[k] = c.w;
+        }
+    }
+    const float iw[3] = {r.iw0, r.iw1, r.iw2};
+    float uw[3], vw[3];
+    V3 pww[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        uw[k] = uu[k] * iw[k];
+        vw[k] = vv[k] * iw[k];
+        pww[k] = pw[k] * iw[k];
+    }
+    sp.n_a = n[0]; sp.n_da = n[1] - n[0]; sp.n_db = n[2] - n[0];
+    sp.t_a = t[0]; sp.t_da = t[1] - t[0]; sp.t_db = t[2] - t[0];
+    sp.ts_a = tw[0]; sp.ts_da = tw[1] - tw[0]; sp.ts_db = tw[2] - tw[0];
+    sp.u_a = uw[0]; sp.u_da = uw[1] - uw[0]; sp.u_db = uw[2] - uw[0];
+    sp.v_a = vw[0]; sp.v_da = vw[1] - vw[0]; sp.v_db = vw[2] - vw[0];
+    sp.p_a = pww[0]; sp.p_da = pww[1] - pww[0]; sp.p_db = pww[2] - pww[0];
+    // renderer.rs:738-754
+    float dx1 = i2f(wsub(r.X1, r.X0)), dx2 = i2f(wsub(r.X2, r.X0)), dy1 = i2f(wsub(r.Y1, r.Y0)), dy2 = i2f(wsub(r.Y2, r.Y0));
+    float du1 = uw[1] - uw[0], du2 = uw[2] - uw[0], dv1 = vw[1] - vw[0], dv2 = vw[2] - vw[0];
+    float s = r.ooa * 16.0f;
+    sp.du_dv[0] = (du1 * dy2 - du2 * dy1) * s;
+    sp.du_dv[1] = (du2 * dx1 - du1 * dx2) * s;
+    sp.du_dv[2] = (dv1 * dy2 - dv2 * dy1) * s;
+    sp.du_dv[3] = (dv2 * dx1 - dv1 * dx2) * s;
+    sp.material = pr.material;
+}
+
+__device__ __forceinline__ float interp1(float a, float da, float db, float b1, float b2) { return a + b1 * da + b2 * db; }
+__device__ __forceinline__ V3 interp3(V3 a, V3 da, V3 db, float b1, float b2) {
+    return v3(a.x + b1 * da.x + b2 * db.x, a.y + b1 * da.y + b2 * db.y, a.z + b1 * da.z + b2 * db.z);
+}
+
+// shader.rs:110-309, TRANSLUCENT = false. `du_dv` is already scaled lane-wise by the quad's w values.
+__device__ __forceinline__ V3 pbr_shader(const ShadeParams &P, const ShadePacket &sp, float b1, float b2, float w, const float du_dv[4]) {
+    const DevScene &sc = P.scene;
+    const DevMat &mat = sc.mats[sp.material];
+    const float EPS = 1e-6f, PI = 3.14159265358979323846f;
+    V3 input_normal = normalize(interp3(sp.n_a, sp.n_da, sp.n_db, b1, b2));
+    V3 input_tangent = normalize(interp3(sp.t_a, sp.t_da, sp.t_db, b1, b2));
+    float tangent_sign = interp1(sp.ts_a, sp.ts_da, sp.ts_db, b1, b2);
+    V3 pos_world = interp3(sp.p_a, sp.p_da, sp.p_db, b1, b2) * w;
+    float uv_x = interp1(sp.u_a, sp.u_da, sp.u_db, b1, b2) * w;
+    float uv_y = interp1(sp.v_a, sp.v_da, sp.v_db, b1, b2) * w;
+
+    V3 tangent_world = normalize(input_tangent - input_normal * dot(input_normal, input_tangent));
+    float handed = tangent_sign >= 0.0f ? 1.0f : -1.0f;
+    V3 bitangent_world = cross(input_normal, tangent_world) * handed;
+    V3 normal_world = normalize(input_normal);
+    if (mat.tex_normal >= 0) {
+        float4 s = sample4(sc.texs[mat.tex_normal], uv_x, uv_y, du_dv);
+        V3 tsn = v3(s.x, s.y, s.z) * 2.0f + (-1.0f);
+        normal_world = tangent_world * tsn.x + bitangent_world * tsn.y + input_normal * tsn.z;
+        normal_world = normalize(normal_world);
+    }
+    V3 light_dir = v3(sc.light_dir[0], sc.light_dir[1], sc.light_dir[2]);
+    V3 light_color = v3(sc.light_color[0], sc.light_color[1], sc.light_color[2]);
+    V3 view_dir = v3(P.cam.position[0], P.cam.position[1], P.cam.position[2]) - pos_world;
+    V3 view_normal = normalize(view_dir);
+
+    float n_dot_l = sse_max(dot(normal_world, light_dir), 0.0f);
+    V3 half_vector = normalize(light_dir + view_normal);
+    float n_dot_h = sse_max(dot(normal_world, half_vector), 0.0f);
+    float n_dot_v = sse_max(dot(normal_world, view_normal), 1.0e-4f);
+    float v_dot_h = sse_max(dot(view_normal, half_vector), 0.0f);
+
+    V3 gi_rgb[4];
+    float gi_w[4];
+    sample_gi(sc, pos_world, gi_rgb, gi_w);
+    float voxel_light_intensity = sse_clamp(gi_w[0], 0.0f, 1.0f);
+    float sky_visibility = sse_clamp(gi_w[1], 0.0f, 1.0f);
+
+    V3 base = v3(mat.base[0], mat.base[1], mat.base[2]);
+    if (mat.tex_base >= 0) {
+        float4 s = sample4(sc.texs[mat.tex_base], uv_x, uv_y, du_dv);
+        base = base * srgb_to_linear_fast(v3(s.x, s.y, s.z));
+    }
+    float roughness = mat.roughness, metallic = mat.metallic;
+    if (mat.tex_mr >= 0) {
+        float4 s = sample4(sc.texs[mat.tex_mr], uv_x, uv_y, du_dv);
+        roughness = roughness * s.y;
+        metallic = metallic * s.z;
+    }
+    roughness = sse_clamp(roughness, 0.045f, 1.0f);
+    metallic = sse_clamp(metallic, 0.0f, 1.0f);
+    float ao = 1.0f;
+    if (mat.tex_occlusion >= 0) {
+        ao = sample4(sc.texs[mat.tex_occlusion], uv_x, uv_y, du_dv).x;
+        ao = 1.0f + (ao - 1.0f) * mat.occlusion_strength;
+    }
+    V3 f0 = v3(0.04f + (base.x - 0.04f) * metallic, 0.04f + (base.y - 0.04f) * metallic, 0.04f + (base.z - 0.04f) * metallic);
+    float omvh = 1.0f - v_dot_h;
+    float omvh2 = omvh * omvh;
+    float omvh4 = omvh2 * omvh2;
+    float omvh5 = omvh4 * omvh;
+    V3 one3 = v3(1.0f, 1.0f, 1.0f);
+    V3 brdf_f_direct = f0 + (one3 - f0) * omvh5;
+
+    float alpha = roughness * roughness;
+    float alpha_2 = alpha * alpha;
+    float ndh_2 = n_dot_h * n_dot_h;
+    float denom_d = ndh_2 * (alpha_2 - 1.0f) + 1.0f;
+    float brdf_d = alpha_2 / (PI * (denom_d * denom_d) + EPS);
+    float k = roughness + 1.0f;
+    k = (k * k) * 0.125f;
+    float gv = n_dot_v / ((n_dot_v * (1.0f - k) + k) + EPS);
+    float gl = n_dot_l / ((n_dot_l * (1.0f - k) + k) + EPS);
+    float brdf_g = gv * gl;
+    float specular_dg = (brdf_d * brdf_g) / (4.0f * n_dot_l * n_dot_v + EPS);
+    V3 k_d_direct = (one3 - brdf_f_direct) * (1.0f - metallic);
+    const float INV_PI = 1.0f / 3.14159265358979323846f;
+    V3 lambert = base * INV_PI;
+    V3 color_direct_diffuse = light_color * k_d_direct * lambert * n_dot_l * voxel_light_intensity;
+    V3 color_direct_specular = light_color * brdf_f_direct * specular_dg * n_dot_l * voxel_light_intensity;
+
+    V3 k_d_indirect = (one3 - f0) * (1.0f - metallic);
+    V3 irr = gi_rgb[0] + gi_rgb[1] * normal_world.y + gi_rgb[2] * normal_world.z + gi_rgb[3] * normal_world.x;  // shader.rs:102-108
+    irr = v3(sse_max(irr.x, 0.0f), sse_max(irr.y, 0.0f), sse_max(irr.z, 0.0f));
+    V3 color_indirect_diffuse = irr * base * k_d_indirect * INV_PI;
+
+    V3 vneg = view_normal * -1.0f;
+    V3 reflect_dir = vneg - normal_world * dot(vneg, normal_world) * 2.0f;  // math.rs:118-120
+    const DevTex &spec = sc.texs[sc.cubemap_specular];
+    V3 prefiltered_env = sample_cubemap_trilinear_rgb(spec, reflect_dir, roughness * (float)spec.max_mip);
+    V3 lut = sample_bilinear_rgb0(sc.texs[sc.brdf_lut], sse_clamp(n_dot_v, 0.0f, 1.0f), sse_clamp(roughness, 0.0f, 1.0f));
+    V3 brdf_spec_factor = f0 * lut.x;
+    brdf_spec_factor = brdf_spec_factor + lut.y;
+    V3 color_indirect_specular = prefiltered_env * brdf_spec_factor;
+    float ao_spec = 1.0f + (ao - 1.0f) * 0.5f;
+    color_indirect_specular = color_indirect_specular * (ao_spec * sky_visibility);
+
+    V3 color = color_direct_diffuse + color_direct_specular + color_indirect_diffuse + color_indirect_specular;
+    V3 emissive_mat = one3;
+    if (mat.tex_emissive >= 0) {
+        float4 s = sample4(sc.texs[mat.tex_emissive], uv_x, uv_y, du_dv);
+        emissive_mat = srgb_to_linear_fast(v3(s.x, s.y, s.z));
+    }
+    color = color + emissive_mat * v3(mat.emissive[0], mat.emissive[1], mat.emissive[2]);
+    return color;
+}
+
+__device__ __forceinline__ V3 compute_skybox(const ShadeParams &P, int px, int py) {  // tilerasterizer.rs:478-508
+    float pixel_x = (float)px + 0.5f, pixel_y = (float)py + 0.5f;
+    float ndc_x = pixel_x * P.cam.one_over_width * 2.0f - 1.0f;
+    float ndc_y = (1.0f - pixel_y * P.cam.one_over_height) * 2.0f - 1.0f;
+    const float *m = P.cam.skybox_T;
+    V3 d = v3(ndc_x * m[0] + ndc_y * m[1] + 1.0f * m[2] + m[3], ndc_x * m[4] + ndc_y * m[5] + 1.0f * m[6] + m[7],
+              ndc_x * m[8] + ndc_y * m[9] + 1.0f * m[10] + m[11]);
+    return srgb_to_linear_fast(sample_cubemap_rgb(P.scene.texs[P.scene.cubemap], normalize(d), 0u));
+}
+
+#define SHADE_BLOCK 256
+__global__ void __launch_bounds__(SHADE_BLOCK) k_shade(ShadeParams P) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int quad = lane >> 2, sub = lane & 3;
+    const int px = blockIdx.x * 16 + quad * 2 + (sub & 1);
+    const int py = P.row_begin * SWR_TILE + blockIdx.y * 16 + warp * 2 + (sub >> 1);
+    const bool inside = px < P.W && py < P.H;
+    const unsigned qmask = 0xFu << (lane & ~3);
+
+    unsigned long long key = inside ? load_key(P.keys, P.tiles_x, px, py) : SWR_KEY_EMPTY;
+    uint32_t slot = 0xFFFFFFFFu;
+    float b1 = 0.0f, b2 = 0.0f;
+    bool covered = false;
+    TriRecord rec;
+    if (key != SWR_KEY_EMPTY) {
+        slot = 0xFFFFFFFFu - (uint32_t)key;
+        rec = P.records[slot];
+        float z;
+        if (resolve_pixel(rec, P.W, P.H, px, py, b1, b2, z)) covered = __float_as_uint(z) != SWR_INF_BITS;  // depth.cmpne(INF)
+    }
+    V3 out = v3(0.0f, 0.0f, 0.0f);
+    // tilerasterizer.rs:419-463: consume the distinct packets of the quad; each evaluation sees all four lanes' barycentrics
+    uint32_t qslot[4];
+    bool qcov[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        qslot[k] = __shfl_sync(qmask, slot, (lane & ~3) + k);
+        qcov[k] = __shfl_sync(qmask, (int)covered, (lane & ~3) + k) != 0;
+    }
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        bool first = qcov[k];
+        for (int j = 0; j < k; j++) first = first && !(qcov[j] && qslot[j] == qslot[k]);
+        if (!first) continue;  // uniform across the quad
+        const uint32_t ps = qslot[k];
+        const bool mine = covered && slot == ps;
+        float iw0, iw1, iw2;
+        if (slot == ps) {
+            iw0 = rec.iw0; iw1 = rec.iw1; iw2 = rec.iw2;
+        } else {
+            const TriRecord *r = P.records + ps;
+            iw0 = __ldg(&r->iw0); iw1 = __ldg(&r->iw1); iw2 = __ldg(&r->iw2);
+        }
+        // shader.rs:123: w of THIS packet at every lane's stored barycentrics (0,0 for never-written lanes)
+        float w = 1.0f / interp1(iw0, iw1 - iw0, iw2 - iw0, b1, b2);
+        float wq[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) wq[j] = __shfl_sync(qmask, w, (lane & ~3) + j);
+        if (mine) {
+            ShadePacket sp;
+            build_shade_packet(P, rec, sp);
+            float dd[4] = {sp.du_dv[0] * wq[0], sp.du_dv[1] * wq[1], sp.du_dv[2] * wq[2], sp.du_dv[3] * wq[3]};  // shader.rs:130
+            out = pbr_shader(P, sp, b1, b2, w, dd);
+        }
+    }
+    if (!covered && inside) out = compute_skybox(P, px, py);
+    if (inside) P.color[(size_t)py * P.W + px] = make_float4(out.x, out.y, out.z, 1.0f);
+}
+
+// tilerasterizer.rs:103-106: quad #512 of the tile = pixels (0..1, 32..33)
+__global__ void k_luminance(const float4 *color, float *lum, int W, int H, int tiles_x, int ntiles) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    int x0 = (t % tiles_x) * SWR_TILE, y0 = (t / tiles_x) * SWR_TILE + 32;
+    float l[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int x = x0 + (k & 1), y = y0 + (k >> 1);
+        float4 c = (x < W && y < H) ? color[(size_t)y * W + x] : make_float4(0, 0, 0, 0);
+        l[k] = c.x * 0.2126f + c.y * 0.7152f + c.z * 0.0722f;
+    }
+    lum[t] = (l[0] + l[1] + l[2] + l[3]) * 0.25f;
+}
+
+// renderer.rs:293-355. One thread = 4 horizontally adjacent pixels -> one 128-bit store.
+__device__ __forceinline__ uint32_t f2u8(float f) { return min(__float2uint_rz(f), 255u); }  // Rust `as u8`
+__device__ __forceinline__ uint32_t resolve_pixel_rgba(float4 c, float exposure) {
+    float r = c.x * exposure, g = c.y * exposure, b = c.z * exposure;
+    const float k = 0.2f, opk = 1.0f + 0.2f;  // util.rs:37-41
+    r = r / (r + k) * opk;
+    g = g / (g + k) * opk;
+    b = b / (b + k) * opk;
+    return (f2u8(r * 255.0f) << 24) | (f2u8(g * 255.0f) << 16) | (f2u8(b * 255.0f) << 8) | 0xFFu;
+}
+__global__ void __launch_bounds__(256) k_resolve(const float4 *color, uint32_t *pixels, float exposure, size_t npix4, size_t first4) {
+    size_t i = first4 + (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= npix4) return;
+    const float4 *c = color + i * 4;
+    uint4 o;
+    o.x = resolve_pixel_rgba(c[0], exposure);
+    o.y = resolve_pixel_rgba(c[1], exposure);
+    o.z = resolve_pixel_rgba(c[2], exposure);
+    o.w = resolve_pixel_rgba(c[3], exposure);
+    reinterpret_cast<uint4 *>(pixels)[i] = o;
+}
