@@ -209,6 +209,14 @@ void swr_destroy(swr_ctx *ctx);
  * tiles; other pixels are left untouched. */
 int swr_set_tile_rows(swr_ctx *ctx, int row_begin, int row_end);
 
+/* normalize() compatibility (math.rs:34-39, :101-108). On x86-64 the reference normalises with the hardware
+ * estimate _mm_rsqrt_ps, whose value is a pure function of the exponent parity and the top `mantissa_bits`
+ * mantissa bits of its input (a table that differs between CPU vendors). Passing that table — 2^(bits+1)
+ * entries: the result bits for inputs (127+p)<<23 | k<<(23-bits), index p<<bits | k — makes the CUDA shading
+ * normalise bit-identically to the reference running on that host. table == NULL (the default) selects
+ * rsqrtf(), which is within the estimate's error envelope but not bit-identical to it. */
+int swr_set_rsqrt_table(swr_ctx *ctx, const uint32_t *table, int mantissa_bits);
+
 /* Copies the scene to device memory; the descriptor may be freed afterwards. */
 int swr_upload_scene(swr_ctx *ctx, const swr_scene_desc *scene);
 

@@ -76,6 +76,9 @@ struct swr_ctx {
     DevBuf<uint32_t> pixels;
     DevBuf<float> lum;
     DevBuf<FrameCounters> counters;
+    DevBuf<uint32_t> rsqrt_tab;
+    int rsqrt_bits = 0;
+    bool rsqrt_on = false;
     FrameCounters *h_counters = nullptr;  // pinned
     Staging staging[4];
     int staging_next = 0;
@@ -166,12 +169,12 @@ swr_ctx *swr_create(int width, int height, int device) {
     ok = ok && cudaMallocHost(&ctx->h_counters, sizeof(FrameCounters)) == cudaSuccess;
     ok = ok && ctx->tile_count.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_offset.reserve(ctx->ntiles + 1) == cudaSuccess &&
          ctx->tile_cursor.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->keys.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess &&
-         ctx->color.reserve((size_t)width * height) == cudaSuccess && ctx->pixels.reserve((size_t)width * height) == cudaSuccess &&
+         ctx->color.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess && ctx->pixels.reserve((size_t)width * height) == cudaSuccess &&
          ctx->lum.reserve(ctx->ntiles) == cudaSuccess && ctx->counters.reserve(1) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_raster_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes()) == cudaSuccess;
     if (ok) {
         ok = cudaMemsetAsync(ctx->keys.p, 0xFF, (size_t)ctx->ntiles * SWR_TILE_PIXELS * 8, ctx->stream) == cudaSuccess &&
-             cudaMemsetAsync(ctx->color.p, 0, (size_t)width * height * sizeof(float4), ctx->stream) == cudaSuccess &&
+             cudaMemsetAsync(ctx->color.p, 0, (size_t)ctx->ntiles * SWR_TILE_PIXELS * sizeof(float4), ctx->stream) == cudaSuccess &&
              cudaMemsetAsync(ctx->pixels.p, 0, (size_t)width * height * 4, ctx->stream) == cudaSuccess &&
              cudaMemsetAsync(ctx->lum.p, 0, ctx->ntiles * sizeof(float), ctx->stream) == cudaSuccess &&
              cudaStreamSynchronize(ctx->stream) == cudaSuccess;
@@ -211,6 +214,7 @@ void swr_destroy(swr_ctx *ctx) {
     ctx->pixels.release();
     ctx->lum.release();
     ctx->counters.release();
+    ctx->rsqrt_tab.release();
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (auto &s : ctx->staging) {
         if (s.host) cudaFreeHost(s.host);
@@ -222,6 +226,27 @@ void swr_destroy(swr_ctx *ctx) {
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+int swr_set_rsqrt_table(swr_ctx *ctx, const uint32_t *table, int mantissa_bits) {
+    if (!ctx) return SWR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = SWR_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (!table) {
+        ctx->rsqrt_on = false;
+        return rc;
+    }
+    if (mantissa_bits < 1 || mantissa_bits > 16) {
+        ctx->err = "rsqrt table: mantissa_bits must be in 1..16";
+        return SWR_ERR_INVALID;
+    }
+    size_t n = (size_t)2 << mantissa_bits;
+    if (ctx->rsqrt_tab.reserve(n) != cudaSuccess) return SWR_ERR_OOM;
+    CK(cudaMemcpy(ctx->rsqrt_tab.p, table, n * 4, cudaMemcpyHostToDevice));
+    ctx->rsqrt_bits = mantissa_bits;
+    ctx->rsqrt_on = true;
+    return rc;
 }
 
 int swr_set_tile_rows(swr_ctx *ctx, int row_begin, int row_end) {
@@ -525,12 +550,16 @@ static int launch_shade(swr_ctx *ctx) {
         sp.W = ctx->W;
         sp.H = ctx->H;
         sp.tiles_x = ctx->tiles_x;
+        sp.Wp = ctx->tiles_x * SWR_TILE;
+        sp.Hp = ctx->tiles_y * SWR_TILE;
         sp.row_begin = rb;
         sp.row_end = re;
-        int y0 = rb * SWR_TILE, y1 = re * SWR_TILE < ctx->H ? re * SWR_TILE : ctx->H;
-        dim3 grid((ctx->W + 15) / 16, (y1 - y0 + 15) / 16);
+        sp.rsqrt_tab = ctx->rsqrt_on ? ctx->rsqrt_tab.p : nullptr;
+        sp.rsqrt_bits = ctx->rsqrt_bits;
+        dim3 grid(sp.Wp / 16, (re - rb) * SWR_TILE / 16);
         k_shade<<<grid, SHADE_BLOCK, 0, s>>>(sp);
-        k_luminance<<<(ctx->ntiles + 127) / 128, 128, 0, s>>>(ctx->color.p, ctx->lum.p, ctx->W, ctx->H, ctx->tiles_x, ctx->ntiles);
+        const int t0 = rb * ctx->tiles_x, t1 = re * ctx->tiles_x;
+        k_luminance<<<(t1 - t0 + 127) / 128, 128, 0, s>>>(ctx->color.p, ctx->lum.p, sp.Wp, sp.Hp, ctx->tiles_x, ctx->ntiles, t0, t1);
     }
     CK(cudaEventRecord(ctx->ev[3], s));
     CK(cudaGetLastError());
@@ -634,8 +663,8 @@ int swr_resolve(swr_ctx *ctx, float exposure, uint32_t *out_pixels) {
     if (y1 > (size_t)ctx->H) y1 = ctx->H;
     CK(cudaEventRecord(ctx->ev_res[0], s));
     if (y1 > y0) {
-        size_t first4 = y0 * W / 4, end4 = y1 * W / 4;
-        k_resolve<<<(unsigned)((end4 - first4 + 255) / 256), 256, 0, s>>>(ctx->color.p, ctx->pixels.p, exposure, end4, first4);
+        dim3 grid((unsigned)((W + 255) / 256), (unsigned)((y1 - y0 + 3) / 4));
+        k_resolve<<<grid, 256, 0, s>>>(ctx->color.p, ctx->tiles_x * SWR_TILE, ctx->pixels.p, ctx->W, (int)y0, (int)y1, exposure);
     }
     CK(cudaEventRecord(ctx->ev_res[1], s));
     CK(cudaGetLastError());
@@ -695,14 +724,17 @@ int swr_read_color(swr_ctx *ctx, float *rgb) {
     if (!ctx || !rgb) return SWR_ERR_INVALID;
     int rc;
     if ((rc = finish_frame(ctx))) return rc;
-    const size_t n = (size_t)ctx->W * ctx->H;
+    const size_t Wp = (size_t)ctx->tiles_x * SWR_TILE, n = Wp * ctx->tiles_y * SWR_TILE;
     std::vector<float4> tmp(n);
     CK(cudaMemcpy(tmp.data(), ctx->color.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < n; i++) {
-        rgb[i * 3 + 0] = tmp[i].x;
-        rgb[i * 3 + 1] = tmp[i].y;
-        rgb[i * 3 + 2] = tmp[i].z;
-    }
+    for (size_t y = 0; y < (size_t)ctx->H; y++)
+        for (size_t x = 0; x < (size_t)ctx->W; x++) {
+            const float4 &c = tmp[y * Wp + x];
+            float *o = rgb + (y * ctx->W + x) * 3;
+            o[0] = c.x;
+            o[1] = c.y;
+            o[2] = c.z;
+        }
     return SWR_OK;
 }
 

@@ -6,8 +6,8 @@
 //   k_luminance per-tile metering value (tilerasterizer.rs:103-106)
 //   k_resolve   exposure, tonemap, RGBA8 pack with 128-bit stores (renderer.rs:293-355, util.rs:37-41,98-100)
 // Arithmetic is restated operation for operation (translation unit built with -fmad=false, IEEE div/sqrt);
-// the only deliberate difference is normalize(): the reference uses the 12-bit _mm_rsqrt_ps (math.rs:34-39),
-// here rsqrtf() — inside the +-1 LSB colour tolerance, see DESIGN.md.
+// normalize(): the reference uses the hardware estimate _mm_rsqrt_ps (math.rs:34-39); with the host's table
+// installed (swr_set_rsqrt_table) it is emulated bit for bit, otherwise rsqrtf() is used.
 #pragma once
 #include "swr_raster.cuh"
 
@@ -18,9 +18,12 @@ struct ShadeParams {
     const ClipVertex *clip_verts;
     DevScene scene;
     DevCamera cam;
-    float4 *color;  // row-major W*H, linear HDR rgb (+ unused w)
+    float4 *color;  // row-major, padded to whole tiles (Wp x Hp): the reference shades every quad of a tile
     int W, H, tiles_x;
+    int Wp, Hp;
     int row_begin, row_end;
+    const uint32_t *rsqrt_tab;  // host _mm_rsqrt_ps table (swr_set_rsqrt_table) or NULL
+    int rsqrt_bits;
 };
 
 struct V3 {
@@ -33,8 +36,27 @@ __device__ __forceinline__ V3 operator*(V3 a, V3 b) { return V3{a.x * b.x, a.y *
 __device__ __forceinline__ V3 operator*(V3 a, float b) { return V3{a.x * b, a.y * b, a.z * b}; }
 __device__ __forceinline__ V3 operator+(V3 a, float b) { return V3{a.x + b, a.y + b, a.z + b}; }
 __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  // math.rs:88-90
-__device__ __forceinline__ V3 normalize(V3 a) {                                                  // math.rs:101-108
-    float r = rsqrtf(dot(a, a));
+// math.rs:34-39 rsqrt_vec. With a host table: exact emulation of _mm_rsqrt_ps (value = table[parity][top mantissa
+// bits] scaled by the even part of the exponent; zero/denormal -> inf, negative -> NaN, inf -> 0).
+struct Rsq {
+    const uint32_t *tab;
+    int bits;
+};
+__device__ __forceinline__ float rsqrt_ref(float x, Rsq q) {
+    if (q.tab == nullptr) return rsqrtf(x);
+    const uint32_t b = __float_as_uint(x);
+    const uint32_t e = (b >> 23) & 0xFFu;
+    if (e == 0u) return __uint_as_float((b & 0x80000000u) | 0x7F800000u);
+    if (e == 255u) return (b & 0x007FFFFFu) ? __uint_as_float(b | 0x00400000u) : ((b >> 31) ? __uint_as_float(0xFFC00000u) : 0.0f);
+    if (b >> 31) return __uint_as_float(0xFFC00000u);
+    const int ue = (int)e - 127;
+    const int p = ue & 1;
+    const int k = (ue - p) >> 1;
+    const uint32_t t = __ldg(q.tab + (((uint32_t)p << q.bits) | ((b & 0x007FFFFFu) >> (23 - q.bits))));
+    return __uint_as_float(t - ((uint32_t)k << 23));
+}
+__device__ __forceinline__ V3 normalize(V3 a, Rsq q) {  // math.rs:101-108
+    float r = rsqrt_ref(dot(a, a), q);
     return V3{a.x * r, a.y * r, a.z * r};
 }
 __device__ __forceinline__ V3 cross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
@@ -235,30 +257,31 @@ __device__ __forceinline__ V3 pbr_shader(const ShadeParams &P, const ShadePacket
     const DevScene &sc = P.scene;
     const DevMat &mat = sc.mats[sp.material];
     const float EPS = 1e-6f, PI = 3.14159265358979323846f;
-    V3 input_normal = normalize(interp3(sp.n_a, sp.n_da, sp.n_db, b1, b2));
-    V3 input_tangent = normalize(interp3(sp.t_a, sp.t_da, sp.t_db, b1, b2));
+    const Rsq rq{P.rsqrt_tab, P.rsqrt_bits};
+    V3 input_normal = normalize(interp3(sp.n_a, sp.n_da, sp.n_db, b1, b2), rq);
+    V3 input_tangent = normalize(interp3(sp.t_a, sp.t_da, sp.t_db, b1, b2), rq);
     float tangent_sign = interp1(sp.ts_a, sp.ts_da, sp.ts_db, b1, b2);
     V3 pos_world = interp3(sp.p_a, sp.p_da, sp.p_db, b1, b2) * w;
     float uv_x = interp1(sp.u_a, sp.u_da, sp.u_db, b1, b2) * w;
     float uv_y = interp1(sp.v_a, sp.v_da, sp.v_db, b1, b2) * w;
 
-    V3 tangent_world = normalize(input_tangent - input_normal * dot(input_normal, input_tangent));
+    V3 tangent_world = normalize(input_tangent - input_normal * dot(input_normal, input_tangent), rq);
     float handed = tangent_sign >= 0.0f ? 1.0f : -1.0f;
     V3 bitangent_world = cross(input_normal, tangent_world) * handed;
-    V3 normal_world = normalize(input_normal);
+    V3 normal_world = normalize(input_normal, rq);
     if (mat.tex_normal >= 0) {
         float4 s = sample4(sc.texs[mat.tex_normal], uv_x, uv_y, du_dv);
         V3 tsn = v3(s.x, s.y, s.z) * 2.0f + (-1.0f);
         normal_world = tangent_world * tsn.x + bitangent_world * tsn.y + input_normal * tsn.z;
-        normal_world = normalize(normal_world);
+        normal_world = normalize(normal_world, rq);
     }
     V3 light_dir = v3(sc.light_dir[0], sc.light_dir[1], sc.light_dir[2]);
     V3 light_color = v3(sc.light_color[0], sc.light_color[1], sc.light_color[2]);
     V3 view_dir = v3(P.cam.position[0], P.cam.position[1], P.cam.position[2]) - pos_world;
-    V3 view_normal = normalize(view_dir);
+    V3 view_normal = normalize(view_dir, rq);
 
     float n_dot_l = sse_max(dot(normal_world, light_dir), 0.0f);
-    V3 half_vector = normalize(light_dir + view_normal);
+    V3 half_vector = normalize(light_dir + view_normal, rq);
     float n_dot_h = sse_max(dot(normal_world, half_vector), 0.0f);
     float n_dot_v = sse_max(dot(normal_world, view_normal), 1.0e-4f);
     float v_dot_h = sse_max(dot(view_normal, half_vector), 0.0f);
@@ -345,7 +368,8 @@ __device__ __forceinline__ V3 compute_skybox(const ShadeParams &P, int px, int p
     const float *m = P.cam.skybox_T;
     V3 d = v3(ndc_x * m[0] + ndc_y * m[1] + 1.0f * m[2] + m[3], ndc_x * m[4] + ndc_y * m[5] + 1.0f * m[6] + m[7],
               ndc_x * m[8] + ndc_y * m[9] + 1.0f * m[10] + m[11]);
-    return srgb_to_linear_fast(sample_cubemap_rgb(P.scene.texs[P.scene.cubemap], normalize(d), 0u));
+    const Rsq rq{P.rsqrt_tab, P.rsqrt_bits};
+    return srgb_to_linear_fast(sample_cubemap_rgb(P.scene.texs[P.scene.cubemap], normalize(d, rq), 0u));
 }
 
 #define SHADE_BLOCK 256
@@ -354,7 +378,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_shade(ShadeParams P) {
     const int quad = lane >> 2, sub = lane & 3;
     const int px = blockIdx.x * 16 + quad * 2 + (sub & 1);
     const int py = P.row_begin * SWR_TILE + blockIdx.y * 16 + warp * 2 + (sub >> 1);
-    const bool inside = px < P.W && py < P.H;
+    const bool inside = px < P.Wp && py < P.Hp;  // off-screen quads of edge tiles are shaded too (metering, tilerasterizer.rs:392-475)
     const unsigned qmask = 0xFu << (lane & ~3);
 
     unsigned long long key = inside ? load_key(P.keys, P.tiles_x, px, py) : SWR_KEY_EMPTY;
@@ -404,13 +428,13 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_shade(ShadeParams P) {
         }
     }
     if (!covered && inside) out = compute_skybox(P, px, py);
-    if (inside) P.color[(size_t)py * P.W + px] = make_float4(out.x, out.y, out.z, 1.0f);
+    if (inside) P.color[(size_t)py * P.Wp + px] = make_float4(out.x, out.y, out.z, 1.0f);
 }
 
 // tilerasterizer.rs:103-106: quad #512 of the tile = pixels (0..1, 32..33)
-__global__ void k_luminance(const float4 *color, float *lum, int W, int H, int tiles_x, int ntiles) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntiles) return;
+__global__ void k_luminance(const float4 *color, float *lum, int W, int H, int tiles_x, int ntiles, int tile_begin, int tile_end) {
+    int t = tile_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tile_end || t >= ntiles) return;
     int x0 = (t % tiles_x) * SWR_TILE, y0 = (t / tiles_x) * SWR_TILE + 32;
     float l[4];
 #pragma unroll
@@ -432,14 +456,20 @@ __device__ __forceinline__ uint32_t resolve_pixel_rgba(float4 c, float exposure)
     b = b / (b + k) * opk;
     return (f2u8(r * 255.0f) << 24) | (f2u8(g * 255.0f) << 16) | (f2u8(b * 255.0f) << 8) | 0xFFu;
 }
-__global__ void __launch_bounds__(256) k_resolve(const float4 *color, uint32_t *pixels, float exposure, size_t npix4, size_t first4) {
-    size_t i = first4 + (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= npix4) return;
-    const float4 *c = color + i * 4;
-    uint4 o;
-    o.x = resolve_pixel_rgba(c[0], exposure);
-    o.y = resolve_pixel_rgba(c[1], exposure);
-    o.z = resolve_pixel_rgba(c[2], exposure);
-    o.w = resolve_pixel_rgba(c[3], exposure);
-    reinterpret_cast<uint4 *>(pixels)[i] = o;
+__global__ void __launch_bounds__(256) k_resolve(const float4 *color, int Wp, uint32_t *pixels, int W, int y0, int y1, float exposure) {
+    const int x = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
+    const int y = y0 + blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (y >= y1 || x >= W) return;
+    const float4 *c = color + (size_t)y * Wp + x;
+    uint32_t *o = pixels + (size_t)y * W + x;
+    if (x + 3 < W && (W & 3) == 0) {
+        uint4 v;
+        v.x = resolve_pixel_rgba(c[0], exposure);
+        v.y = resolve_pixel_rgba(c[1], exposure);
+        v.z = resolve_pixel_rgba(c[2], exposure);
+        v.w = resolve_pixel_rgba(c[3], exposure);
+        *reinterpret_cast<uint4 *>(o) = v;
+    } else {
+        for (int k = 0; k < 4 && x + k < W; k++) o[k] = resolve_pixel_rgba(c[k], exposure);
+    }
 }

@@ -23,6 +23,9 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <immintrin.h>
+#endif
 #include "../../include/swr.h"
 
 namespace swr {
@@ -288,6 +291,42 @@ inline void build_draw_list(const swr_scene_desc &sc, const swr_camera &cam, std
     }
 }
 
+// math.rs:34-39: on x86-64 the reference's rsqrt_vec IS the hardware estimate _mm_rsqrt_ps. Its value depends only on
+// the exponent parity and the top K mantissa bits of the input (K = 10 on Intel parts), i.e. it is a small table that
+// belongs to the CPU the host program runs on. Probe it once and hand it to the device (swr_set_rsqrt_table) so that the
+// CUDA shading normalises exactly as the reference would on this very host. Returns K, or 0 when the estimate has no such
+// structure here (then the device keeps rsqrtf()).
+inline int probe_host_rsqrt_table(std::vector<uint32_t> &table) {
+#if defined(__x86_64__) || defined(_M_X64)
+    auto rs = [](uint32_t b) {
+        float f;
+        std::memcpy(&f, &b, 4);
+        float r = _mm_cvtss_f32(_mm_rsqrt_ss(_mm_set_ss(f)));
+        uint32_t o;
+        std::memcpy(&o, &r, 4);
+        return o;
+    };
+    for (int K = 8; K <= 16; K++) {
+        const size_t n = (size_t)1 << K;
+        table.assign(2 * n, 0);
+        bool ok = true;
+        for (int p = 0; p < 2 && ok; p++) {
+            for (uint32_t k = 0; k < n; k++) table[(size_t)p * n + k] = rs(((127u + p) << 23) | (k << (23 - K)));
+            // every mantissa must agree with its bucket (exhaustive for the accepted K, strided pre-check otherwise)
+            for (uint32_t m = 0; m < (1u << 23) && ok; m += 61) ok = rs(((127u + p) << 23) | m) == table[(size_t)p * n + (m >> (23 - K))];
+        }
+        if (!ok) continue;
+        for (int p = 0; p < 2 && ok; p++)
+            for (uint32_t m = 0; m < (1u << 23) && ok; m++) ok = rs(((127u + p) << 23) | m) == table[(size_t)p * n + (m >> (23 - K))];
+        for (uint32_t e = 1; e < 253 && ok; e += 2)  // exponent scaling: +2 in the exponent halves the result
+            for (uint32_t m = 0; m < (1u << 23) && ok; m += 4099) ok = rs((e << 23) | m) - rs(((e + 2) << 23) | m) == (1u << 23);
+        if (ok) return K;
+    }
+#endif
+    table.clear();
+    return 0;
+}
+
 // ---- renderer.rs:145-355 --------------------------------------------------------------
 class Renderer {
    public:
@@ -297,7 +336,20 @@ class Renderer {
         if (!ctx_) throw std::runtime_error(std::string("swr_create: ") + swr_last_error(nullptr));
         auto_exposure_ = auto_exposure_target_ = SWR_DEFAULT_EXPOSURE;  // renderer.rs:194-196
         auto_exposure_ev_ = std::log2(SWR_DEFAULT_EXPOSURE);
+        set_reference_rsqrt(true);
     }
+    // Match the reference's normalize() on this host (default), or use the device's own rsqrtf().
+    void set_reference_rsqrt(bool on) {
+        static std::vector<uint32_t> table;
+        static int bits = -1;
+        if (bits < 0) bits = probe_host_rsqrt_table(table);
+        if (on && bits > 0)
+            check(swr_set_rsqrt_table(ctx_, table.data(), bits), "swr_set_rsqrt_table");
+        else
+            check(swr_set_rsqrt_table(ctx_, nullptr, 0), "swr_set_rsqrt_table");
+        rsqrt_bits_ = on ? bits : 0;
+    }
+    int reference_rsqrt_bits() const { return rsqrt_bits_; }
     ~Renderer() {
         if (ctx_) swr_destroy(ctx_);
     }
@@ -358,6 +410,7 @@ class Renderer {
         if (rc != 0) throw std::runtime_error(std::string(what) + ": " + swr_last_error(ctx_));
     }
     int width_, height_;
+    int rsqrt_bits_ = 0;
     swr_ctx *ctx_ = nullptr;
     const swr_scene_desc *uploaded_ = nullptr;
     std::vector<swr_draw> draws_;

@@ -41,6 +41,8 @@ void *swrh_renderer_new(int width, int height, int device) {
 void swrh_renderer_free(void *r) { delete (swr::Renderer *)r; }
 void *swrh_renderer_ctx(void *r) { return ((swr::Renderer *)r)->ctx(); }
 
+int swrh_set_reference_rsqrt(void *r, int on) { SWRH_TRY(((swr::Renderer *)r)->set_reference_rsqrt(on != 0)); }
+int swrh_reference_rsqrt_bits(void *r) { return ((swr::Renderer *)r)->reference_rsqrt_bits(); }
 int swrh_set_tile_rows(void *r, int r0, int r1) { SWRH_TRY(((swr::Renderer *)r)->set_tile_rows(r0, r1)); }
 
 int swrh_render_scene(void *r, const swr_scene_desc *scene, const swr_camera *cam, int shade, int shard, int nshards) {

@@ -1,0 +1,73 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed): SURVEY.md 8(e).
+
+sort-first: every rank holds the whole scene, owns a contiguous range of 64-pixel tile rows
+(Renderer.set_tile_rows), and the finished RGBA8 strips are gathered to rank 0. Tiles are independent
+after binning (renderer.rs:216-218), so there is no data-path collective besides that gather.
+
+sort-last: every rank rasterises its own draws at full resolution into the 64-bit key buffer; the keys are
+min-reduced across ranks (depth in the high word, inverted global seq in the low word, so the minimum IS the
+reference's serial `<=` rule, tilerasterizer.rs:516) and the winner is shaded.
+"""
+import numpy as np
+
+
+def tile_row_ranges(tiles_y, world):
+    """Contiguous, balanced [begin, end) tile-row ranges, one per rank."""
+    base, rem = divmod(tiles_y, world)
+    out, r = [], 0
+    for i in range(world):
+        n = base + (1 if i < rem else 0)
+        out.append((r, r + n))
+        r += n
+    return out
+
+
+def gather_strips(image, ranges, height, dst=0):
+    """image: (H, W) int32 torch tensor whose rows [64*r0, 64*r1) are valid on this rank.
+    Returns the assembled image on `dst` (in place in `image`), None elsewhere. Uses send/recv so strips of
+    unequal height need no padding; on NCCL this is one grouped NVLink transfer per peer."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if world == 1:
+        return image
+    ops = []
+    if rank == dst:
+        for src in range(world):
+            if src == dst:
+                continue
+            y0, y1 = ranges[src][0] * 64, min(ranges[src][1] * 64, height)
+            if y1 > y0:
+                ops.append(dist.P2POp(dist.irecv, image[y0:y1], src))
+    else:
+        y0, y1 = ranges[rank][0] * 64, min(ranges[rank][1] * 64, height)
+        if y1 > y0:
+            ops.append(dist.P2POp(dist.isend, image[y0:y1], dst))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return image if rank == dst else None
+
+
+def composite_keys_min(keys):
+    """keys: int64 torch tensor holding the UNSIGNED 64-bit visibility keys of this rank (empty = all ones).
+    All-reduce with unsigned MIN: flip the sign bit so signed order == unsigned order, reduce, flip back."""
+    import torch
+    import torch.distributed as dist
+    sign = torch.tensor(-(2 ** 63), dtype=torch.int64, device=keys.device)
+    keys.bitwise_xor_(sign)
+    dist.all_reduce(keys, op=dist.ReduceOp.MIN)
+    keys.bitwise_xor_(sign)
+    return keys
+
+
+def device_tensor(ptr, nbytes, dtype, device):
+    """Zero-copy torch view of a device buffer owned by the renderer (swr_device_pixels / swr_device_keys)."""
+    import torch
+
+    class _Arr:
+        pass
+    itemsize = torch.empty((), dtype=dtype).element_size()
+    a = _Arr()
+    typestr = {torch.int32: "<i4", torch.int64: "<i8", torch.uint8: "|u1"}[dtype]
+    a.__cuda_array_interface__ = {"shape": (nbytes // itemsize,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(a, device=device)

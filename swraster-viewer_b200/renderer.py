@@ -44,6 +44,7 @@ def load_libraries():
     core.swr_create.argtypes = [i32, i32, i32]
     core.swr_destroy.argtypes = [vp]
     core.swr_set_tile_rows.argtypes = [vp, i32, i32]
+    core.swr_set_rsqrt_table.argtypes = [vp, vp, i32]
     core.swr_upload_scene.argtypes = [vp, C.POINTER(abi.SceneDesc)]
     core.swr_render.argtypes = [vp, C.POINTER(abi.Camera), C.POINTER(abi.Draw), i32, i32]
     core.swr_shade.argtypes = [vp, C.POINTER(abi.Camera)]
@@ -70,6 +71,8 @@ def load_libraries():
     host.swrh_renderer_ctx.restype = vp
     host.swrh_renderer_ctx.argtypes = [vp]
     host.swrh_set_tile_rows.argtypes = [vp, i32, i32]
+    host.swrh_set_reference_rsqrt.argtypes = [vp, i32]
+    host.swrh_reference_rsqrt_bits.argtypes = [vp]
     host.swrh_render_scene.argtypes = [vp, C.POINTER(abi.SceneDesc), C.POINTER(abi.Camera), i32, i32, i32]
     host.swrh_update_auto_exposure.argtypes = [vp, f32]
     host.swrh_auto_exposure.restype = f32
@@ -169,6 +172,14 @@ class Renderer:
     def _check_core(self, rc):
         if rc != 0:
             raise RuntimeError(self.core.swr_last_error(self.ctx).decode())
+
+    def set_reference_rsqrt(self, on):
+        """normalize() as the reference computes it on this host (_mm_rsqrt_ps table; default) or rsqrtf()."""
+        self._check(self.host.swrh_set_reference_rsqrt(self._h, int(on)))
+
+    @property
+    def reference_rsqrt_bits(self):
+        return self.host.swrh_reference_rsqrt_bits(self._h)
 
     def set_tile_rows(self, r0, r1):
         self._check(self.host.swrh_set_tile_rows(self._h, r0, r1))

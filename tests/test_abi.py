@@ -1,0 +1,58 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol
+include/swr.h declares, and its struct layouts match the ctypes mirror. No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import swraster_viewer_b200 as swr
+from swraster_viewer_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_are_exported():
+    core, host = swr.load_libraries()
+    header = open(os.path.join(ROOT, "include", "swr.h")).read()
+    declared = set(re.findall(r"\b(swr_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(abi.EXPORTS), declared ^ set(abi.EXPORTS)
+    for name in declared:
+        assert hasattr(core, name), f"libswr_b200.so does not export {name}"
+    assert core.swr_abi_version() == 1
+
+
+def test_struct_sizes_match_library():
+    core, _ = swr.load_libraries()
+    for which, T in enumerate([abi.PrimitiveDesc, abi.MeshDesc, abi.NodeDesc, abi.TextureDesc, abi.MaterialDesc,
+                               abi.VoxelGridDesc, abi.SceneDesc, abi.Camera, abi.Draw, abi.FrameStats]):
+        assert core.swr_sizeof(which) == C.sizeof(T), (which, T.__name__)
+
+
+def test_library_carries_sm100a_code_only():
+    import subprocess
+    lib = os.path.join(ROOT, "swraster-viewer_b200", "lib", "libswr_b200.so")
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", lib], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_product_package_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under the product package may reference it."""
+    pkg = os.path.join(ROOT, "swraster-viewer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                for needle in ("import oracle", "from oracle", "liboracle", "orc_", "oracle/", "oracle.cpp", "oracle.py"):
+                    assert needle not in text, (os.path.join(dirpath, f), needle)
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback_without_device():
+    core, _ = swr.load_libraries()
+    assert core.swr_create(64, 64, 0) is None
+    assert b"no usable CUDA device" in core.swr_last_error(None) or b"CUDA" in core.swr_last_error(None)
+    with pytest.raises(RuntimeError):
+        swr.Renderer(64, 64)

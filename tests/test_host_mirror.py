@@ -1,0 +1,133 @@
+"""Host-side logic above the C ABI (no GPU): draw-list construction against the oracle's own restatement of
+renderer.rs:357-468, camera construction, rsqrt-table probing, and the sort-first partition maths over gloo."""
+import ctypes as C
+import math
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import swraster_viewer_b200 as swr
+from swraster_viewer_b200 import abi, scenes
+from swraster_viewer_b200.renderer import build_draws
+from swraster_viewer_b200.multigpu import tile_row_ranges
+from helpers import small_configs, SMALL
+
+
+def test_draw_list_matches_oracle_bitwise():
+    import oracle as orc
+    for name, scene, spec, W, H in small_configs():
+        cam = swr.RenderCamera.from_spec(spec, W, H)
+        mine, n = build_draws(scene, cam)
+        o = orc.Oracle(64, 64)
+        ref, m = o.build_draws(scene, cam.abi, abi.Draw)
+        assert n == m and n > 0, name
+        assert bytes(mine)[: n * C.sizeof(abi.Draw)] == bytes(ref)[: n * C.sizeof(abi.Draw)], name
+
+
+def test_draw_list_sharding_keeps_global_ids():
+    _, scene, spec, W, H = small_configs()[2]
+    cam = swr.RenderCamera.from_spec(spec, W, H)
+    full, n = build_draws(scene, cam)
+    got = []
+    for s in range(3):
+        part, m = build_draws(scene, cam, shard=s, nshards=3)
+        got += [(part[i].first_triangle, part[i].primitive, part[i].flags) for i in range(m)]
+    assert sorted(got) == sorted((full[i].first_triangle, full[i].primitive, full[i].flags) for i in range(n))
+
+
+def test_camera_level_matches_reference_construction():
+    """RenderCamera::new towards a level target: view matrix puts the target on -z, projection is glam's perspective_rh."""
+    cam = swr.RenderCamera((1.0, 2.0, 9.0), (1.0, 2.0, 0.0), math.pi / 4, 640, 360, 50.0)
+    V = np.array(cam.abi.view_matrix).reshape(4, 4).T
+    VP = np.array(cam.abi.view_project_matrix).reshape(4, 4).T
+    t = V @ np.array([1.0, 2.0, 0.0, 1.0])
+    np.testing.assert_allclose(t[:3], [0, 0, -9], atol=1e-5)
+    near, far = 0.5, 50.0
+    c_near = VP @ np.array([1.0, 2.0, 9.0 - near, 1.0])
+    c_far = VP @ np.array([1.0, 2.0, 9.0 - far, 1.0])
+    assert abs(c_near[2] / c_near[3]) < 1e-5 and abs(c_far[2] / c_far[3] - 1.0) < 1e-5  # depth 0..1
+    planes = np.array(cam.abi.view_clip_planes)
+    np.testing.assert_allclose(planes[0], [0, 0, -1, near], atol=1e-6)
+    np.testing.assert_allclose(planes[1], [0, 0, 1, far], atol=1e-6)
+    assert cam.abi.one_over_width == pytest.approx(1 / 640)
+
+
+def test_from_spec_aims_at_target():
+    spec = scenes.CameraSpec((0.5, 3.0, 6.5), (0.0, 0.8, 0.0), math.pi / 4, 30.0)
+    cam = swr.RenderCamera.from_spec(spec, 640, 360)
+    VP = np.array(cam.abi.view_project_matrix).reshape(4, 4).T
+    c = VP @ np.array([0.0, 0.8, 0.0, 1.0])
+    assert abs(c[0] / c[3]) < 1e-4 and abs(c[1] / c[3]) < 1e-4
+
+
+def test_tile_row_ranges_partition():
+    for tiles_y in (17, 34, 68, 3):
+        for n in (1, 2, 4, 8):
+            r = tile_row_ranges(tiles_y, n)
+            assert len(r) == n and r[0][0] == 0 and r[-1][1] == tiles_y
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_worker(rank, world, port, W, H, tmp):
+    import torch
+    import torch.distributed as dist
+    from swraster_viewer_b200.multigpu import tile_row_ranges, gather_strips
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tiles_y = (H + 63) // 64
+    ranges = tile_row_ranges(tiles_y, world)
+    full = torch.arange(W * H, dtype=torch.int32).reshape(H, W)
+    mine = torch.zeros(H, W, dtype=torch.int32)
+    y0, y1 = ranges[rank][0] * 64, min(ranges[rank][1] * 64, H)
+    mine[y0:y1] = full[y0:y1]  # this rank "rendered" only its rows
+    out = gather_strips(mine, ranges, H, dst=0)
+    if rank == 0:
+        assert torch.equal(out, full)
+        open(os.path.join(tmp, "ok"), "w").write("1")
+    dist.destroy_process_group()
+
+
+def test_sort_first_gather_gloo_world2(tmp_path):
+    """The N>1 data path (row strips -> rank 0) on CPU with gloo, world_size 2."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_gather_worker, args=(2, port, 192, 200, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").exists()
+
+
+def _composite_worker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    from swraster_viewer_b200.multigpu import composite_keys_min
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(5)
+    allk = torch.randint(0, 2 ** 62, (world, 4096 * 6), generator=g, dtype=torch.int64)
+    allk[:, ::7] = -1  # empty key = all ones
+    mine = allk[rank].clone()
+    out = composite_keys_min(mine)
+    # unsigned minimum across ranks
+    u = allk.numpy().view(np.uint64)
+    assert np.array_equal(out.numpy().view(np.uint64), u.min(axis=0))
+    if rank == 0:
+        open(os.path.join(tmp, "ok"), "w").write("1")
+    dist.destroy_process_group()
+
+
+def test_sort_last_key_composite_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_composite_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").exists()
