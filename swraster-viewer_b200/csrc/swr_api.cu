@@ -69,7 +69,8 @@ struct swr_ctx {
     DevBuf<TriRecord> records;
     DevBuf<uint32_t> rects;
     DevBuf<ClipVertex> clip_verts;
-    DevBuf<uint32_t> tile_count, tile_offset, tile_cursor;
+    DevBuf<uint32_t> tile_count, tile_offset, tile_cursor, tile_order;
+    DevBuf<uint32_t> clip_queue;
     DevBuf<uint32_t> refs;
     DevBuf<unsigned long long> keys;
     DevBuf<float4> color;
@@ -108,7 +109,7 @@ static int upload(swr_ctx *ctx, const T *src, size_t n, T **out) {
     return SWR_OK;
 }
 
-static size_t raster_smem_bytes() { return SWR_TILE_PIXELS * 8 + RASTER_WARPS * sizeof(WarpPackets); }
+static size_t raster_smem_bytes() { return SWR_TILE_PIXELS * 8 + sizeof(TileBatch); }
 
 extern "C" {
 
@@ -168,7 +169,7 @@ swr_ctx *swr_create(int width, int height, int device) {
     for (int i = 0; ok && i < 4; i++) ok = cudaEventCreateWithFlags(&ctx->staging[i].done, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMallocHost(&ctx->h_counters, sizeof(FrameCounters)) == cudaSuccess;
     ok = ok && ctx->tile_count.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_offset.reserve(ctx->ntiles + 1) == cudaSuccess &&
-         ctx->tile_cursor.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->keys.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess &&
+         ctx->tile_cursor.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_order.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->keys.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess &&
          ctx->color.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess && ctx->pixels.reserve((size_t)width * height) == cudaSuccess &&
          ctx->lum.reserve(ctx->ntiles) == cudaSuccess && ctx->counters.reserve(1) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_raster_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes()) == cudaSuccess;
@@ -208,6 +209,8 @@ void swr_destroy(swr_ctx *ctx) {
     ctx->tile_count.release();
     ctx->tile_offset.release();
     ctx->tile_cursor.release();
+    ctx->tile_order.release();
+    ctx->clip_queue.release();
     ctx->refs.release();
     ctx->keys.release();
     ctx->color.release();
@@ -478,6 +481,7 @@ static int launch_frame(swr_ctx *ctx) {
         if (ctx->clip_verts.reserve(want_clip) != cudaSuccess) return SWR_ERR_OOM;
     }
     if (ctx->clip_verts.cap == 0 && ctx->clip_verts.reserve(4096) != cudaSuccess) return SWR_ERR_OOM;
+    if (ctx->clip_queue.reserve(clip_tris + 1) != cudaSuccess) return SWR_ERR_OOM;
 
     cudaStream_t s = ctx->stream;
     CK(cudaEventRecord(ctx->ev[0], s));
@@ -499,6 +503,7 @@ static int launch_frame(swr_ctx *ctx) {
         sp.rects = ctx->rects.p;
         sp.clip_verts = ctx->clip_verts.p;
         sp.clip_capacity = (uint32_t)ctx->clip_verts.cap;
+        sp.clip_queue = ctx->clip_queue.p;
         sp.tile_count = ctx->tile_count.p;
         sp.counters = ctx->counters.p;
         sp.W = ctx->W;
@@ -508,8 +513,13 @@ static int launch_frame(swr_ctx *ctx) {
         sp.row_begin = rb;
         sp.row_end = re;
         k_setup<<<(unsigned)((tris + SETUP_THREADS - 1) / SETUP_THREADS), SETUP_THREADS, 0, s>>>(sp);
+        if (clip_tris > 0) {
+            uint64_t want = (clip_tris + CLIP_GROUPS - 1) / CLIP_GROUPS;
+            k_clip<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), CLIP_THREADS, 0, s>>>(sp);
+        }
     }
-    k_scan_tiles<<<1, 1024, 0, s>>>(ctx->tile_count.p, ctx->tile_offset.p, ctx->tile_cursor.p, ctx->ntiles, ctx->counters.p, (uint32_t)ctx->refs.cap);
+    k_scan_tiles<<<1, 1024, 0, s>>>(ctx->tile_count.p, ctx->tile_offset.p, ctx->tile_cursor.p, ctx->ntiles, ctx->counters.p, (uint32_t)ctx->refs.cap,
+                                    ctx->tile_order.p, rb * ctx->tiles_x, re * ctx->tiles_x);
     if (slots > 0)
         k_scatter<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(ctx->rects.p, (uint32_t)slots, ctx->tile_cursor.p, ctx->refs.p, (uint32_t)ctx->refs.cap,
                                                                   ctx->counters.p, ctx->tiles_x);
@@ -519,6 +529,7 @@ static int launch_frame(swr_ctx *ctx) {
         rp.records = ctx->records.p;
         rp.refs = ctx->refs.p;
         rp.tile_offset = ctx->tile_offset.p;
+        rp.tile_order = ctx->tile_order.p;
         rp.keys = ctx->keys.p;
         rp.counters = ctx->counters.p;
         rp.W = ctx->W;
@@ -556,7 +567,7 @@ static int launch_shade(swr_ctx *ctx) {
         sp.row_end = re;
         sp.rsqrt_tab = ctx->rsqrt_on ? ctx->rsqrt_tab.p : nullptr;
         sp.rsqrt_bits = ctx->rsqrt_bits;
-        dim3 grid(sp.Wp / 16, (re - rb) * SWR_TILE / 16);
+        dim3 grid(sp.Wp / 16, (re - rb) * SWR_TILE / SHADE_ROWS);
         k_shade<<<grid, SHADE_BLOCK, 0, s>>>(sp);
         const int t0 = rb * ctx->tiles_x, t1 = re * ctx->tiles_x;
         k_luminance<<<(t1 - t0 + 127) / 128, 128, 0, s>>>(ctx->color.p, ctx->lum.p, sp.Wp, sp.Hp, ctx->tiles_x, ctx->ntiles, t0, t1);

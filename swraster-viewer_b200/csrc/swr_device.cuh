@@ -97,7 +97,7 @@ struct FrameCounters {
     uint32_t clip_verts;      // bump allocator for ClipVertex
     uint32_t overflow_refs;   // tile_refs exceeded the ref buffer
     uint32_t overflow_clip;   // clip vertex buffer exhausted
-    uint32_t pad;
+    uint32_t clip_queue_n;    // triangles queued for k_clip
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -1,10 +1,12 @@
 // swr_raster.cuh — geometry and visibility kernels:
-//   k_setup        K1 + K2: per-triangle projection, snap, cull, bbox, record write, tile counting, and a
-//                  cooperative Sutherland-Hodgman clipper (16 lanes = 16 polygon vertices) for straddlers
-//                  (reference: renderer.rs:470-574, 579-665, 668-760)
-//   k_scan_tiles   exclusive scan of per-tile counts (replaces bumpqueue.rs block lists)
+//   k_setup        K1: per-triangle projection, snap, cull, bbox, record write, tile counting; triangles of
+//                  clip-flagged draws are classified exactly (all-in / provably empty / needs clipping)
+//                  (reference: renderer.rs:470-574, 668-760)
+//   k_clip         K2: cooperative Sutherland-Hodgman clipper, 16 lanes = 16 polygon vertices, one group per
+//                  straddling triangle (reference: renderer.rs:579-665)
+//   k_scan_tiles   exclusive scan of per-tile counts + heaviest-first tile order (replaces bumpqueue.rs)
 //   k_scatter      K3 pass 2: warp-aggregated scatter of triangle refs into per-tile lists
-//   k_raster_tiles K4: one CTA per 64x64 tile, 64-bit depth|~seq keys in shared memory, atomicMin
+//   k_raster_tiles K4: one CTA per 64x64 tile, 64-bit depth|~id keys in shared memory, atomicMin
 //                  (reference: tilerasterizer.rs:72-81, 114-383, 511-523; shader.rs:32-63)
 //   k_read_vis     parity read-back of (depth bits, seq, bary1, bary2)
 #pragma once
@@ -20,6 +22,7 @@ struct SetupParams {
     uint32_t *rects;
     ClipVertex *clip_verts;
     uint32_t clip_capacity;
+    uint32_t *clip_queue;  // global triangle ids that need the clipper
     uint32_t *tile_count;
     FrameCounters *counters;
     int W, H, tiles_x, tiles_y;
@@ -41,7 +44,8 @@ __device__ __forceinline__ uint32_t find_draw(const uint32_t *prefix, uint32_t n
 }
 
 // Count one triangle's tile rectangle into tile_count. Single-tile rectangles (the common case) are
-// aggregated across the warp with match.any so each distinct tile costs one atomic.
+// aggregated across the warp with match.any so each distinct tile costs one atomic. Must be called by
+// all 32 lanes of the warp.
 __device__ __forceinline__ void count_tiles(uint32_t rect, uint32_t *tile_count, int tiles_x) {
     int tx0 = rect & 0xFF, ty0 = (rect >> 8) & 0xFF, tx1 = (rect >> 16) & 0xFF, ty1 = rect >> 24;
     bool valid = rect != 0;
@@ -106,83 +110,87 @@ __device__ __forceinline__ float plane_dist(int pl, float4 v) {
     return fadd(fadd(fmul(px, v.x), fmul(pz, v.z)), fadd(fmul(py, v.y), fmul(1.0f, v.w)));
 }
 
-struct ClipVtx {  // renderer.rs:31-37 as 16 floats
-    float f[16];  // 0-3 pos_clip, 4-6 pos_world, 7-9 normal, 10-13 tangent, 14-15 uv
-};
-
-#define CLIP_GROUPS (SETUP_THREADS / 16)
-
 __global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams P) {
-    __shared__ uint32_t s_queue[SETUP_THREADS];  // local thread ids of triangles that need the clipper
-    __shared__ uint32_t s_qn;
     __shared__ uint32_t s_draw0;
-    __shared__ float s_poly[CLIP_GROUPS][2][16][17];  // +1 pad: lanes read rows
-
     const uint32_t tid = threadIdx.x;
     const uint32_t g0 = blockIdx.x * SETUP_THREADS;
-    if (tid == 0) {
-        s_qn = 0;
-        s_draw0 = find_draw(P.tri_prefix, P.ndraws, g0);
-    }
+    if (tid == 0) s_draw0 = find_draw(P.tri_prefix, P.ndraws, g0);
     __syncthreads();
     const uint32_t g = g0 + tid;
-    bool active = g < P.total_tris;
-    uint32_t d = s_draw0;
-    uint32_t tri = 0, slot = 0, rect = 0;
-    bool survived = false;
+    uint32_t rect = 0;
     bool queued = false;
-    if (active) {
+    if (g < P.total_tris) {
+        uint32_t d = s_draw0;
         while (g >= P.tri_prefix[d + 1]) d++;
-        tri = g - P.tri_prefix[d];
+        const uint32_t tri = g - P.tri_prefix[d];
         const DevDraw &dr = P.draws[d];
         const DevPrim &pr = P.prims[dr.prim];
         const bool clip = (dr.flags & 1u) != 0;
-        slot = dr.slot_base + tri * (clip ? 7u : 1u);
+        const uint32_t slot = dr.slot_base + tri * (clip ? 7u : 1u);
         uint32_t i0 = __ldg(pr.idx + 3 * tri), i1 = __ldg(pr.idx + 3 * tri + 1), i2 = __ldg(pr.idx + 3 * tri + 2);
         float4 c0 = mul_vec4(dr.mvp, __ldg(pr.pos + i0));
         float4 c1 = mul_vec4(dr.mvp, __ldg(pr.pos + i1));
         float4 c2 = mul_vec4(dr.mvp, __ldg(pr.pos + i2));
-        uint32_t seq = (dr.first_tri + tri) * 8u;
+        const uint32_t seq = (dr.first_tri + tri) * 8u;
         if (clip) {
-            bool all_in = true;
+            // Exact classification against renderer.rs:621-648: planes are visited in order; while all three
+            // vertices are inside the polygon is passed through unchanged, so the first plane with any vertex
+            // outside decides: all three outside -> the polygon becomes empty (nothing is emitted);
+            // mixed -> the real clipper is needed; no such plane -> the triangle goes through untouched.
+            int state = 0;  // 0 all-in, 1 empty, 2 needs clipping
 #pragma unroll
-            for (int pl = 0; pl < 6; pl++)
-                all_in = all_in && (plane_dist(pl, c0) >= 0.0f) && (plane_dist(pl, c1) >= 0.0f) && (plane_dist(pl, c2) >= 0.0f);
-            if (all_in) {
-                rect = emit_triangle(P, c0, c1, c2, slot, d, seq, SWR_NO_CLIP);  // polygon passes S-H unchanged
-            } else {
-                queued = true;
-                s_queue[atomicAdd(&s_qn, 1u)] = tid;
+            for (int pl = 0; pl < 6; pl++) {
+                if (state == 0) {
+                    int in = (plane_dist(pl, c0) >= 0.0f ? 1 : 0) + (plane_dist(pl, c1) >= 0.0f ? 1 : 0) + (plane_dist(pl, c2) >= 0.0f ? 1 : 0);
+                    if (in == 0)
+                        state = 1;
+                    else if (in != 3)
+                        state = 2;
+                }
             }
-            P.rects[slot] = rect;
+            if (state == 0) rect = emit_triangle(P, c0, c1, c2, slot, d, seq, SWR_NO_CLIP);
+            queued = state == 2;
+            uint32_t *rr = P.rects + slot;
+            rr[0] = rect;
 #pragma unroll
-            for (int k = 1; k < 7; k++) P.rects[slot + k] = 0;
+            for (int k = 1; k < 7; k++) rr[k] = 0;
         } else {
             rect = emit_triangle(P, c0, c1, c2, slot, d, seq, SWR_NO_CLIP);
             P.rects[slot] = rect;
         }
-        survived = rect != 0;
     }
     count_tiles(rect, P.tile_count, P.tiles_x);
-    unsigned surv = __ballot_sync(0xFFFFFFFFu, survived);
-    if ((tid & 31) == 0 && surv) atomicAdd(&P.counters->tris_binned, (unsigned long long)__popc(surv));
-    __syncthreads();
+    const unsigned lane = tid & 31;
+    unsigned surv = __ballot_sync(0xFFFFFFFFu, rect != 0);
+    if (lane == 0 && surv) atomicAdd(&P.counters->tris_binned, (unsigned long long)__popc(surv));
+    // warp-aggregated append to the clip queue
+    unsigned qm = __ballot_sync(0xFFFFFFFFu, queued);
+    if (qm) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&P.counters->clip_queue_n, (uint32_t)__popc(qm));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (queued) P.clip_queue[base + __popc(qm & ((1u << lane) - 1u))] = g;
+    }
+}
 
-    // ---- K2: cooperative clipper, one 16-lane group per straddling triangle ------------------------------
-    const uint32_t qn = s_qn;
-    if (qn == 0) return;
+// ---------------------------------------------------------------------------------------------
+// K2: cooperative clipper over the queue written by k_setup
+// ---------------------------------------------------------------------------------------------
+#define CLIP_THREADS 256
+#define CLIP_GROUPS (CLIP_THREADS / 16)
+
+__global__ void __launch_bounds__(CLIP_THREADS) k_clip(SetupParams P) {
+    __shared__ float s_poly[CLIP_GROUPS][2][16][17];  // renderer.rs:31-37 as 16 floats per vertex (+1 pad)
+    const uint32_t qn = P.counters->clip_queue_n;
+    const uint32_t tid = threadIdx.x;
     const uint32_t grp = tid >> 4, lane = tid & 15;
-    const unsigned gmask = 0xFFFFu << ((tid & 16));  // the 16 lanes of my group inside the warp
-    for (uint32_t base = 0; base < qn; base += CLIP_GROUPS) {
+    const unsigned gmask = 0xFFFFu << (tid & 16);  // the 16 lanes of my group inside the warp
+    for (uint32_t base = blockIdx.x * CLIP_GROUPS; base < qn; base += gridDim.x * CLIP_GROUPS) {
         const uint32_t e = base + grp;
-        const bool have = e < qn;  // warp-uniform per half only; all syncs below use gmask
         uint32_t rect_out = 0;
-        bool surv_out = false;
-        if (have) {
-            const uint32_t ltid = s_queue[e];
-            const uint32_t gg = g0 + ltid;
-            uint32_t dd = s_draw0;
-            while (gg >= P.tri_prefix[dd + 1]) dd++;
+        if (e < qn) {
+            const uint32_t gg = P.clip_queue[e];
+            const uint32_t dd = find_draw(P.tri_prefix, P.ndraws, gg);
             const uint32_t ttri = gg - P.tri_prefix[dd];
             const DevDraw &dr = P.draws[dd];
             const DevPrim &pr = P.prims[dr.prim];
@@ -206,22 +214,17 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams P) {
             __syncwarp(gmask);
             int n = 3, cur = 0;
             for (int pl = 0; pl < 6 && n > 0; pl++) {  // renderer.rs:621-648
-                ClipVtx vc, vp;
                 bool cin = false, pin = false;
                 float dc = 0.0f, dp = 0.0f;
+                const float *c = poly[cur][lane], *p = poly[cur][(int)lane < n ? (lane + n - 1) % n : 0];
                 if ((int)lane < n) {
-                    const float *c = poly[cur][lane];
-                    const float *p = poly[cur][(lane + n - 1) % n];
-#pragma unroll
-                    for (int k = 0; k < 16; k++) {
-                        vc.f[k] = c[k];
-                        vp.f[k] = p[k];
-                    }
-                    dc = plane_dist(pl, make_float4(vc.f[0], vc.f[1], vc.f[2], vc.f[3]));
-                    dp = plane_dist(pl, make_float4(vp.f[0], vp.f[1], vp.f[2], vp.f[3]));
+                    dc = plane_dist(pl, make_float4(c[0], c[1], c[2], c[3]));
+                    dp = plane_dist(pl, make_float4(p[0], p[1], p[2], p[3]));
                     cin = dc >= 0.0f;
                     pin = dp >= 0.0f;
                 }
+                const unsigned allin = __ballot_sync(gmask, (int)lane >= n || cin);
+                if (allin == gmask) continue;  // polygon unchanged by this plane
                 int cnt = cin ? (pin ? 1 : 2) : (pin ? 1 : 0);
                 int incl = cnt;  // inclusive scan over the 16-lane group
 #pragma unroll
@@ -229,22 +232,21 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams P) {
                     int t = __shfl_up_sync(gmask, incl, o, 16);
                     if ((int)lane >= o) incl += t;
                 }
-                int total = __shfl_sync(gmask, incl, 15, 16);
-                int off = incl - cnt;
-                __syncwarp(gmask);
+                const int total = __shfl_sync(gmask, incl, 15, 16);
+                const int off = incl - cnt;
                 if (cnt > 0 && off + cnt <= 16) {
                     float(*np)[17] = poly[cur ^ 1];
                     if (cin != pin) {  // intersect(prev, curr): t = d0 / (d0 - d1), v0 + (v1 - v0) * t (renderer.rs:598-609)
-                        float t = fdiv(dp, fsub(dp, dc));
+                        const float t = fdiv(dp, fsub(dp, dc));
 #pragma unroll
-                        for (int k = 0; k < 16; k++) np[off][k] = fadd(vp.f[k], fmul(fsub(vc.f[k], vp.f[k]), t));
+                        for (int k = 0; k < 16; k++) np[off][k] = fadd(p[k], fmul(fsub(c[k], p[k]), t));
                         if (cin) {
 #pragma unroll
-                            for (int k = 0; k < 16; k++) np[off + 1][k] = vc.f[k];
+                            for (int k = 0; k < 16; k++) np[off + 1][k] = c[k];
                         }
                     } else {
 #pragma unroll
-                        for (int k = 0; k < 16; k++) np[off][k] = vc.f[k];
+                        for (int k = 0; k < 16; k++) np[off][k] = c[k];
                     }
                 }
                 __syncwarp(gmask);
@@ -252,9 +254,11 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams P) {
                 cur ^= 1;
             }
             if (n >= 3) {  // renderer.rs:650-664 fan (0, i, i+1)
-                if (lane == 0) atomicAdd(&P.counters->tris_clipped, 1ull);
                 uint32_t vbase = 0;
-                if (lane == 0) vbase = atomicAdd(&P.counters->clip_verts, (uint32_t)n);
+                if (lane == 0) {
+                    atomicAdd(&P.counters->tris_clipped, 1ull);
+                    vbase = atomicAdd(&P.counters->clip_verts, (uint32_t)n);
+                }
                 vbase = __shfl_sync(gmask, vbase, 0, 16);
                 const bool room = vbase + (uint32_t)n <= P.clip_capacity;
                 if (!room && lane == 0) P.counters->overflow_clip = 1;
@@ -267,36 +271,35 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams P) {
                     cv.u = v[14]; cv.v = v[15];
                     P.clip_verts[vbase + lane] = cv;
                 }
-                if (room && lane >= 1 && (int)lane <= n - 2) {
+                if (room && lane >= 1 && (int)lane <= n - 2 && lane <= 7) {
                     const float *v0 = poly[cur][0], *v1 = poly[cur][lane], *v2 = poly[cur][lane + 1];
                     const uint32_t fan = lane - 1;
                     const uint32_t sl = dr.slot_base + ttri * 7u + fan;
-                    if (fan < 7) {
-                        rect_out = emit_triangle(P, make_float4(v0[0], v0[1], v0[2], v0[3]), make_float4(v1[0], v1[1], v1[2], v1[3]),
-                                                 make_float4(v2[0], v2[1], v2[2], v2[3]), sl, dd, (dr.first_tri + ttri) * 8u + fan, vbase);
-                        P.rects[sl] = rect_out;
-                        surv_out = rect_out != 0;
-                    }
+                    rect_out = emit_triangle(P, make_float4(v0[0], v0[1], v0[2], v0[3]), make_float4(v1[0], v1[1], v1[2], v1[3]),
+                                             make_float4(v2[0], v2[1], v2[2], v2[3]), sl, dd, (dr.first_tri + ttri) * 8u + fan, vbase);
+                    P.rects[sl] = rect_out;
                 }
             }
         }
-        // all 32 lanes reconverge here for the warp-aggregated counting
-        __syncwarp();
+        __syncwarp();  // both half-warps reconverge for the warp-aggregated counting
         count_tiles(rect_out, P.tile_count, P.tiles_x);
-        unsigned sv = __ballot_sync(0xFFFFFFFFu, surv_out);
+        unsigned sv = __ballot_sync(0xFFFFFFFFu, rect_out != 0);
         if ((tid & 31) == 0 && sv) atomicAdd(&P.counters->tris_binned, (unsigned long long)__popc(sv));
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// exclusive scan over tiles (<= 65,025): one CTA
+// exclusive scan over tiles (<= 65,025) + heaviest-first order of the owned tiles: one CTA
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count, uint32_t *tile_offset, uint32_t *tile_cursor, int ntiles,
-                                                     FrameCounters *counters, uint32_t ref_capacity) {
+                                                     FrameCounters *counters, uint32_t ref_capacity, uint32_t *tile_order, int tile_begin,
+                                                     int tile_end) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
+    __shared__ uint32_t s_hist[34], s_cur[34];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_carry = 0;
+    if (tid < 34) s_hist[tid] = 0;
     __syncthreads();
     for (int base = 0; base < ntiles; base += 1024) {
         int i = base + tid;
@@ -323,6 +326,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
         if (i < ntiles) {
             tile_offset[i] = excl;
             tile_cursor[i] = excl;
+            if (i >= tile_begin && i < tile_end) atomicAdd(&s_hist[v ? 32 - __clz(v) : 0], 1u);  // bucket = bit length
         }
         __syncthreads();
         if (tid == 1023) s_carry = excl + v;
@@ -332,6 +336,16 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
         tile_offset[ntiles] = s_carry;
         counters->tile_refs = s_carry;
         if (s_carry > ref_capacity) counters->overflow_refs = 1;
+        uint32_t acc = 0;
+        for (int b = 33; b >= 0; b--) {  // heaviest bucket first
+            s_cur[b] = acc;
+            acc += s_hist[b];
+        }
+    }
+    __syncthreads();
+    for (int i = tile_begin + tid; i < tile_end; i += 1024) {
+        uint32_t v = tile_count[i];
+        tile_order[atomicAdd(&s_cur[v ? 32 - __clz(v) : 0], 1u)] = (uint32_t)i;
     }
 }
 
@@ -372,69 +386,157 @@ struct RasterParams {
     const TriRecord *records;
     const uint32_t *refs;
     const uint32_t *tile_offset;
+    const uint32_t *tile_order;
     unsigned long long *keys;  // tile-major: tile * 4096 + y * 64 + x
     const FrameCounters *counters;
     int W, H, tiles_x, tiles_y;
     int row_begin, row_end;
 };
 
-// Per-warp staging of 32 packets (structure of arrays: conflict-free when lanes read different packets).
-struct WarpPackets {
-    int a[3][32], b[3][32], c[3][32];
-    int xs[32], ys[32], nqx[32];
-    uint32_t flags[32];  // bit0 coarse, bit1 exact
-    uint32_t slot[32];
-    float ooa[32], iw0[32], iwda[32], iwdb[32], zw0[32], zwda[32], zwdb[32];
-    uint32_t prefix[33];
+// One batch of up to 256 packets of the tile, structure of arrays in shared memory. Work is then re-distributed
+// over the CTA at the granularity of one quad row inside one 16x16 block ("item"), so a triangle that fills the
+// tile (128 items of 8 quads) is shared by all warps instead of serialising one of them.
+struct TileBatch {
+    int a[3][RASTER_THREADS], b[3][RASTER_THREADS], c[3][RASTER_THREADS];
+    int xs[RASTER_THREADS], ys[RASTER_THREADS];
+    uint32_t geom[RASTER_THREADS];  // nqx | nqy << 8 | coarse << 16 | exact << 17
+    uint32_t slot[RASTER_THREADS];
+    float ooa[RASTER_THREADS], iw0[RASTER_THREADS], iwda[RASTER_THREADS], iwdb[RASTER_THREADS];
+    float zw0[RASTER_THREADS], zwda[RASTER_THREADS], zwdb[RASTER_THREADS];
+    uint32_t prefix[RASTER_THREADS + 1];
+    uint32_t wsum[RASTER_WARPS];
 };
 
-__device__ __forceinline__ void raster_lane(unsigned long long *skeys, const WarpPackets &wp, int pk, int q, int tile_x0, int tile_y0) {
-    const int nqx = wp.nqx[pk];
-    const int qy = q / nqx, qx = q - qy * nqx;
-    PacketSetup p;
+struct FragParams {
+    float ooa, iw0, iwda, iwdb, zw0, zwda, zwdb;
+    uint32_t idlow;
+};
+
+// tilerasterizer.rs:337-342 + depth_test :511-523 folded into one 64-bit atomicMin
+__device__ __forceinline__ void emit_fragment(unsigned long long *skeys, const FragParams &f, float w1, float w2, int pix) {
+    float b1 = fmul(w1, f.ooa), b2 = fmul(w2, f.ooa);
+    float qq = fadd(fadd(f.iw0, fmul(b1, f.iwda)), fmul(b2, f.iwdb));
+    float wpix = fdiv(1.0f, qq);
+    float zz = fadd(fadd(f.zw0, fmul(b1, f.zwda)), fmul(b2, f.zwdb));
+    float z = fmul(zz, wpix);
+    if (z == z) {  // NaN never passes `z <= current` (tilerasterizer.rs:516)
+        unsigned long long key = ((unsigned long long)depth_orderable(z) << 32) | f.idlow;
+        atomicMin(&skeys[pix], key);
+    }
+}
+
+__device__ __forceinline__ void raster_row(unsigned long long *skeys, const TileBatch &tb, int pk, uint32_t local, int tile_x0, int tile_y0) {
+    const uint32_t geom = tb.geom[pk];
+    const int nqx = geom & 0xFF;
+    const bool coarse = (geom >> 16) & 1u, exact = (geom >> 17) & 1u;
+    int qy, bi;
+    if (coarse) {
+        const uint32_t nbx = (uint32_t)(nqx + 7) >> 3;
+        qy = (int)(local / nbx);
+        bi = (int)(local - (uint32_t)qy * nbx);
+    } else {
+        qy = (int)local;
+        bi = 0;
+    }
+    const int qx0 = bi * 8, qx1 = coarse ? min(qx0 + 8, nqx) : nqx;
+    const int xs = tb.xs[pk], ys = tb.ys[pk];
+    int a[3], b[3], c[3];
 #pragma unroll
     for (int e = 0; e < 3; e++) {
-        p.a[e] = wp.a[e][pk];
-        p.b[e] = wp.b[e][pk];
-        p.c[e] = wp.c[e][pk];
+        a[e] = tb.a[e][pk];
+        b[e] = tb.b[e][pk];
+        c[e] = tb.c[e][pk];
     }
-    p.xs = wp.xs[pk];
-    p.ys = wp.ys[pk];
-    const uint32_t fl = wp.flags[pk];
-    p.coarse = fl & 1u;
-    p.exact = fl & 2u;
-    const float ooa = wp.ooa[pk], iw0 = wp.iw0[pk], iwda = wp.iwda[pk], iwdb = wp.iwdb[pk];
-    const float zw0 = wp.zw0[pk], zwda = wp.zwda[pk], zwdb = wp.zwdb[pk];
-    const uint32_t idlow = 0xFFFFFFFFu - wp.slot[pk];
-    const int px0 = (p.xs >> 4) + 2 * qx, py0 = (p.ys >> 4) + 2 * qy;
+    FragParams f;
+    f.ooa = tb.ooa[pk];
+    f.iw0 = tb.iw0[pk];
+    f.iwda = tb.iwda[pk];
+    f.iwdb = tb.iwdb[pk];
+    f.zw0 = tb.zw0[pk];
+    f.zwda = tb.zwda[pk];
+    f.zwdb = tb.zwdb[pk];
+    f.idlow = 0xFFFFFFFFu - tb.slot[pk];
+    const int ysub = ys + qy * 32;                          // sub-pixel y of the quad row
+    int pix = ((ysub >> 4) - tile_y0) * SWR_TILE + ((xs >> 4) + 2 * qx0 - tile_x0);  // lane 0 of the first quad
+    if (exact) {
+        // integer edge functions at the pixel centres, stepped by a*32 per quad (exactly what the f32 chain yields)
+        int e0[3], e1[3], e2[3], e3[3], st[3];
+        const int sx = xs + qx0 * 32 + 8, sy = ysub + 8;
 #pragma unroll
-    for (int l = 0; l < 4; l++) {
-        const int lx = l & 1, ly = l >> 1;
-        float w1, w2;
-        bool cov;
-        if (p.exact) {
-            int e[3];
-            eval_exact(p, (px0 + lx) * 16 + 8, (py0 + ly) * 16 + 8, e);
-            cov = (e[0] | e[1] | e[2]) >= 0;
-            w1 = i2f(e[1]);
-            w2 = i2f(e[2]);
-        } else {
-            float r[3];
-            cov = eval_chain(p, qx, qy, lx, ly, r);
-            cov = cov && (r[0] >= 0.0f && r[1] >= 0.0f && r[2] >= 0.0f);
-            w1 = r[1];
-            w2 = r[2];
+        for (int k = 0; k < 3; k++) {
+            e0[k] = a[k] * sx + b[k] * sy + c[k];
+            e1[k] = e0[k] + a[k] * 16;
+            e2[k] = e0[k] + b[k] * 16;
+            e3[k] = e2[k] + a[k] * 16;
+            st[k] = a[k] * 32;
         }
-        if (cov) {
-            float b1 = fmul(w1, ooa), b2 = fmul(w2, ooa);
-            float qq = fadd(fadd(iw0, fmul(b1, iwda)), fmul(b2, iwdb));
-            float wpix = fdiv(1.0f, qq);
-            float zz = fadd(fadd(zw0, fmul(b1, zwda)), fmul(b2, zwdb));
-            float z = fmul(zz, wpix);
-            if (z == z) {  // NaN never passes `z <= current` (tilerasterizer.rs:516)
-                unsigned long long key = ((unsigned long long)depth_orderable(z) << 32) | idlow;
-                atomicMin(&skeys[(py0 + ly - tile_y0) * SWR_TILE + (px0 + lx - tile_x0)], key);
+        for (int q = qx0; q < qx1; q++, pix += 2) {
+            if ((e0[0] | e0[1] | e0[2]) >= 0) emit_fragment(skeys, f, i2f(e0[1]), i2f(e0[2]), pix);
+            if ((e1[0] | e1[1] | e1[2]) >= 0) emit_fragment(skeys, f, i2f(e1[1]), i2f(e1[2]), pix + 1);
+            if ((e2[0] | e2[1] | e2[2]) >= 0) emit_fragment(skeys, f, i2f(e2[1]), i2f(e2[2]), pix + SWR_TILE);
+            if ((e3[0] | e3[1] | e3[2]) >= 0) emit_fragment(skeys, f, i2f(e3[1]), i2f(e3[2]), pix + SWR_TILE + 1);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                e0[k] += st[k];
+                e1[k] += st[k];
+                e2[k] += st[k];
+                e3[k] += st[k];
             }
+        }
+        return;
+    }
+    // f32 chain replay (tilerasterizer.rs:239-269, 307-329, 371-381)
+    const int bx = coarse ? xs + bi * 256 : xs;
+    const int by = coarse ? ys + (qy >> 3) * 256 : ys;
+    const int j = coarse ? (qy & 7) : qy;
+    float A[3], B[3], C[3];
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+        A[e] = i2f(a[e]);
+        B[e] = i2f(b[e]);
+        C[e] = i2f(c[e]);
+    }
+    if (coarse) {
+        const float cx0 = i2f(bx + 8), cx1 = i2f(bx + 248), cy0 = i2f(by + 8), cy1 = i2f(by + 248);
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            const float ax0 = fmul(A[e], cx0), ax1 = fmul(A[e], cx1), by0 = fmul(B[e], cy0), by1 = fmul(B[e], cy1);
+            const float e00 = fadd(fadd(ax0, by0), C[e]), e10 = fadd(fadd(ax1, by0), C[e]);
+            const float e01 = fadd(fadd(ax0, by1), C[e]), e11 = fadd(fadd(ax1, by1), C[e]);
+            if (fmaxf(fmaxf(e00, e10), fmaxf(e01, e11)) < 0.0f) return;  // block fully outside this edge
+        }
+    }
+    float v0[3], v1[3], v2[3], v3[3], sxf[3];
+    {
+        const float x0 = i2f(bx + 8), x1 = i2f(bx + 24), y0 = i2f(by + 8), y1 = i2f(by + 24);
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            const float ax0 = fmul(A[e], x0), ax1 = fmul(A[e], x1), by0 = fmul(B[e], y0), by1 = fmul(B[e], y1);
+            v0[e] = fadd(fadd(ax0, by0), C[e]);
+            v1[e] = fadd(fadd(ax1, by0), C[e]);
+            v2[e] = fadd(fadd(ax0, by1), C[e]);
+            v3[e] = fadd(fadd(ax1, by1), C[e]);
+            const float syf = i2f(wmul(b[e], 32));
+            sxf[e] = i2f(wmul(a[e], 32));
+            for (int k = 0; k < j; k++) {
+                v0[e] = fadd(v0[e], syf);
+                v1[e] = fadd(v1[e], syf);
+                v2[e] = fadd(v2[e], syf);
+                v3[e] = fadd(v3[e], syf);
+            }
+        }
+    }
+    for (int q = qx0; q < qx1; q++, pix += 2) {
+        if (v0[0] >= 0.0f && v0[1] >= 0.0f && v0[2] >= 0.0f) emit_fragment(skeys, f, v0[1], v0[2], pix);
+        if (v1[0] >= 0.0f && v1[1] >= 0.0f && v1[2] >= 0.0f) emit_fragment(skeys, f, v1[1], v1[2], pix + 1);
+        if (v2[0] >= 0.0f && v2[1] >= 0.0f && v2[2] >= 0.0f) emit_fragment(skeys, f, v2[1], v2[2], pix + SWR_TILE);
+        if (v3[0] >= 0.0f && v3[1] >= 0.0f && v3[2] >= 0.0f) emit_fragment(skeys, f, v3[1], v3[2], pix + SWR_TILE + 1);
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            v0[e] = fadd(v0[e], sxf[e]);
+            v1[e] = fadd(v1[e], sxf[e]);
+            v2[e] = fadd(v2[e], sxf[e]);
+            v3[e] = fadd(v3[e], sxf[e]);
         }
     }
 }
@@ -442,22 +544,21 @@ __device__ __forceinline__ void raster_lane(unsigned long long *skeys, const War
 __global__ void __launch_bounds__(RASTER_THREADS) k_raster_tiles(RasterParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *skeys = reinterpret_cast<unsigned long long *>(smem_raw);
-    WarpPackets *wps = reinterpret_cast<WarpPackets *>(smem_raw + SWR_TILE_PIXELS * 8);
+    TileBatch &tb = *reinterpret_cast<TileBatch *>(smem_raw + SWR_TILE_PIXELS * 8);
 
     if (P.counters->overflow_refs) return;  // tile lists were not written; the host replays the frame
-    const int tile = blockIdx.x + P.row_begin * P.tiles_x;
+    const int tile = (int)P.tile_order[blockIdx.x];
     const int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
     const int tile_x0 = tx * SWR_TILE, tile_y0 = ty * SWR_TILE;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     for (int i = tid; i < SWR_TILE_PIXELS; i += RASTER_THREADS) skeys[i] = SWR_KEY_EMPTY;
-    __syncthreads();
 
     const uint32_t beg = P.tile_offset[tile], end = P.tile_offset[tile + 1];
-    WarpPackets &wp = wps[wid];
-    for (uint32_t base = beg + wid * 32; base < end; base += RASTER_WARPS * 32) {
-        const uint32_t ri = base + lane;
-        uint32_t nq = 0;
+    for (uint32_t base = beg; base < end; base += RASTER_THREADS) {
+        __syncthreads();  // previous batch fully consumed (and key init done)
+        const uint32_t ri = base + tid;
+        uint32_t nitems = 0;
         if (ri < end) {
             const uint32_t slot = __ldg(P.refs + ri);
             TriRecord r;
@@ -470,52 +571,54 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_tiles(RasterParams P)
             PacketSetup ps;
             packet_setup(r, P.W, P.H, tile_x0, tile_y0, ps);
             if (!ps.empty) {
-                nq = (uint32_t)(ps.nqx * ps.nqy);
+                nitems = (uint32_t)((ps.coarse ? ((ps.nqx + 7) >> 3) : 1) * ps.nqy);
 #pragma unroll
                 for (int e = 0; e < 3; e++) {
-                    wp.a[e][lane] = ps.a[e];
-                    wp.b[e][lane] = ps.b[e];
-                    wp.c[e][lane] = ps.c[e];
+                    tb.a[e][tid] = ps.a[e];
+                    tb.b[e][tid] = ps.b[e];
+                    tb.c[e][tid] = ps.c[e];
                 }
-                wp.xs[lane] = ps.xs;
-                wp.ys[lane] = ps.ys;
-                wp.nqx[lane] = ps.nqx;
-                wp.flags[lane] = (ps.coarse ? 1u : 0u) | (ps.exact ? 2u : 0u);
-                wp.slot[lane] = slot;
-                wp.ooa[lane] = r.ooa;
-                wp.iw0[lane] = r.iw0;
-                wp.iwda[lane] = fsub(r.iw1, r.iw0);
-                wp.iwdb[lane] = fsub(r.iw2, r.iw0);
-                wp.zw0[lane] = r.zw0;
-                wp.zwda[lane] = fsub(r.zw1, r.zw0);
-                wp.zwdb[lane] = fsub(r.zw2, r.zw0);
+                tb.xs[tid] = ps.xs;
+                tb.ys[tid] = ps.ys;
+                tb.geom[tid] = (uint32_t)ps.nqx | ((uint32_t)ps.nqy << 8) | (ps.coarse ? 1u << 16 : 0u) | (ps.exact ? 1u << 17 : 0u);
+                tb.slot[tid] = slot;
+                tb.ooa[tid] = r.ooa;
+                tb.iw0[tid] = r.iw0;
+                tb.iwda[tid] = fsub(r.iw1, r.iw0);
+                tb.iwdb[tid] = fsub(r.iw2, r.iw0);
+                tb.zw0[tid] = r.zw0;
+                tb.zwda[tid] = fsub(r.zw1, r.zw0);
+                tb.zwdb[tid] = fsub(r.zw2, r.zw0);
             }
         }
-        // exclusive prefix of quad counts across the warp
-        uint32_t incl = nq;
+        // CTA-wide exclusive prefix of item counts
+        uint32_t incl = nitems;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
             if (lane >= o) incl += t;
         }
-        wp.prefix[lane + 1] = incl;
-        if (lane == 0) wp.prefix[0] = 0;
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        __syncwarp();
-        // load-balanced expansion: lane handles quad item `it`; find its packet by binary search
-        for (uint32_t it = lane; it < total; it += 32) {
-            int lo = 0, hi = 32;
+        if (lane == 31) tb.wsum[wid] = incl;
+        __syncthreads();
+        uint32_t wbase = 0;
 #pragma unroll
-            for (int s = 0; s < 5; s++) {
-                int mid = (lo + hi) >> 1;
-                if (wp.prefix[mid] <= it)
+        for (int w = 0; w < RASTER_WARPS; w++) wbase += (w < wid) ? tb.wsum[w] : 0u;
+        tb.prefix[tid + 1] = wbase + incl;
+        if (tid == 0) tb.prefix[0] = 0;
+        __syncthreads();
+        const uint32_t total = tb.prefix[RASTER_THREADS];
+        for (uint32_t it = tid; it < total; it += RASTER_THREADS) {
+            int lo = 0, hi = RASTER_THREADS;
+#pragma unroll
+            for (int s = 0; s < 8; s++) {
+                const int mid = (lo + hi) >> 1;
+                if (tb.prefix[mid] <= it)
                     lo = mid;
                 else
                     hi = mid;
             }
-            raster_lane(skeys, wp, lo, (int)(it - wp.prefix[lo]), tile_x0, tile_y0);
+            raster_row(skeys, tb, lo, it - tb.prefix[lo], tile_x0, tile_y0);
         }
-        __syncwarp();
     }
     __syncthreads();
     unsigned long long *out = P.keys + (size_t)tile * SWR_TILE_PIXELS;
