@@ -279,9 +279,17 @@ def run_gpu(args):
                                     "sample": "2 full frames (+1 warm-up) of the same workload on the host CPU: C++ restatement of swraster-viewer's rayon+glam path (Rust toolchain unavailable)",
                                     "ms_per_frame": 1e3 / cfps, "ms_clipbin": ost["ms_clipbin"], "ms_raster_shade": ost["ms_raster"], "ms_resolve": ost["ms_resolve"]}
         print(json.dumps(line), flush=True)
-    r.close()
+    # orderly teardown: torch tensors that were used on the library's stream must die before the stream does
+    torch.cuda.synchronize()
+    del ev, flush, pix, stream
+    buf = None
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    r.close()
 
 
 def main():

@@ -70,7 +70,8 @@ struct swr_ctx {
     DevBuf<uint32_t> rects;
     DevBuf<ClipVertex> clip_verts;
     DevBuf<uint32_t> tile_count, tile_offset, tile_cursor, tile_order;
-    DevBuf<uint32_t> clip_queue;
+    DevBuf<uint32_t> clip_queue, clip_ext, clip_list;
+    size_t ext_cap = 0;
     DevBuf<uint32_t> refs;
     DevBuf<unsigned long long> keys;
     DevBuf<float4> color;
@@ -211,6 +212,8 @@ void swr_destroy(swr_ctx *ctx) {
     ctx->tile_cursor.release();
     ctx->tile_order.release();
     ctx->clip_queue.release();
+    ctx->clip_ext.release();
+    ctx->clip_list.release();
     ctx->refs.release();
     ctx->keys.release();
     ctx->color.release();
@@ -442,12 +445,11 @@ static int launch_frame(swr_ctx *ctx) {
         hd[i].prim = d.primitive;
         hd[i].flags = d.flags;
         hd[i].first_tri = d.first_triangle;
-        hd[i].slot_base = (uint32_t)slots;
+        hd[i].reserved = 0;
         hp[i] = (uint32_t)tris;
         uint32_t nt = ctx->prim_ntris[d.primitive];
         tris += nt;
         verts += ctx->prim_nverts[d.primitive];
-        slots += (uint64_t)nt * ((d.flags & SWR_DRAW_CLIP) ? 7 : 1);
         if (d.flags & SWR_DRAW_CLIP) clip_tris += nt;
         if ((uint64_t)d.first_triangle + nt > 0x1FFFFFFFull) {
             ctx->err = "more than 2^29 triangles in one frame: the seq id (tri*8+fan) would overflow";
@@ -455,10 +457,15 @@ static int launch_frame(swr_ctx *ctx) {
         }
     }
     hp[nd] = (uint32_t)tris;
-    if (slots >= 0xFFFFFFFFull || tris >= 0xFFFFFFFFull) {
-        ctx->err = "frame too large for 32-bit record ids";
+    if (tris >= 0x1FFFFFFFull) {
+        ctx->err = "frame too large for 32-bit ids (triangle * 8 + fan)";
         return SWR_ERR_INVALID;
     }
+    // records: [0, tris) = fan 0 of every triangle (dense), then the extension area for fans >= 1 of clipped polygons
+    size_t want_ext = (size_t)clip_tris / 16 + 4096;
+    if (ctx->ext_cap < want_ext && !ctx->rendered_once) ctx->ext_cap = want_ext;
+    if (ctx->ext_cap < 4096) ctx->ext_cap = 4096;
+    slots = tris + ctx->ext_cap;
     ctx->ndraws = nd;
     ctx->total_tris = (uint32_t)tris;
     ctx->nslots = (uint32_t)slots;
@@ -481,7 +488,9 @@ static int launch_frame(swr_ctx *ctx) {
         if (ctx->clip_verts.reserve(want_clip) != cudaSuccess) return SWR_ERR_OOM;
     }
     if (ctx->clip_verts.cap == 0 && ctx->clip_verts.reserve(4096) != cudaSuccess) return SWR_ERR_OOM;
-    if (ctx->clip_queue.reserve(clip_tris + 1) != cudaSuccess) return SWR_ERR_OOM;
+    if (ctx->clip_queue.reserve(clip_tris + 1) != cudaSuccess || ctx->clip_ext.reserve(tris + 1) != cudaSuccess ||
+        ctx->clip_list.reserve(ctx->ext_cap + 1) != cudaSuccess)
+        return SWR_ERR_OOM;
 
     cudaStream_t s = ctx->stream;
     CK(cudaEventRecord(ctx->ev[0], s));
@@ -504,6 +513,9 @@ static int launch_frame(swr_ctx *ctx) {
         sp.clip_verts = ctx->clip_verts.p;
         sp.clip_capacity = (uint32_t)ctx->clip_verts.cap;
         sp.clip_queue = ctx->clip_queue.p;
+        sp.clip_ext = ctx->clip_ext.p;
+        sp.clip_list = ctx->clip_list.p;
+        sp.ext_capacity = (uint32_t)ctx->ext_cap;
         sp.tile_count = ctx->tile_count.p;
         sp.counters = ctx->counters.p;
         sp.W = ctx->W;
@@ -520,9 +532,11 @@ static int launch_frame(swr_ctx *ctx) {
     }
     k_scan_tiles<<<1, 1024, 0, s>>>(ctx->tile_count.p, ctx->tile_offset.p, ctx->tile_cursor.p, ctx->ntiles, ctx->counters.p, (uint32_t)ctx->refs.cap,
                                     ctx->tile_order.p, rb * ctx->tiles_x, re * ctx->tiles_x);
-    if (slots > 0)
-        k_scatter<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(ctx->rects.p, (uint32_t)slots, ctx->tile_cursor.p, ctx->refs.p, (uint32_t)ctx->refs.cap,
-                                                                  ctx->counters.p, ctx->tiles_x);
+    if (tris > 0) {
+        k_scatter<<<(unsigned)((tris + 255) / 256), 256, 0, s>>>(ctx->rects.p, (uint32_t)tris, ctx->tile_cursor.p, ctx->refs.p, ctx->counters.p, ctx->tiles_x);
+        if (clip_tris > 0)
+            k_scatter_list<<<148, 256, 0, s>>>(ctx->rects.p, ctx->clip_list.p, ctx->clip_ext.p, ctx->tile_cursor.p, ctx->refs.p, ctx->counters.p, ctx->tiles_x);
+    }
     CK(cudaEventRecord(ctx->ev[1], s));
     if (re > rb) {
         RasterParams rp{};
@@ -530,6 +544,7 @@ static int launch_frame(swr_ctx *ctx) {
         rp.refs = ctx->refs.p;
         rp.tile_offset = ctx->tile_offset.p;
         rp.tile_order = ctx->tile_order.p;
+        rp.clip_ext = ctx->clip_ext.p;
         rp.keys = ctx->keys.p;
         rp.counters = ctx->counters.p;
         rp.W = ctx->W;
@@ -553,6 +568,7 @@ static int launch_shade(swr_ctx *ctx) {
         ShadeParams sp{};
         sp.keys = ctx->keys.p;
         sp.records = ctx->records.p;
+        sp.clip_ext = ctx->clip_ext.p;
         sp.draws = ctx->draws.p;
         sp.clip_verts = ctx->clip_verts.p;
         sp.scene = ctx->scene;
@@ -592,7 +608,7 @@ static int finish_frame(swr_ctx *ctx) {
         CK(cudaStreamSynchronize(ctx->stream));
         if (!ctx->frame_pending) return SWR_OK;
         const FrameCounters c = *ctx->h_counters;
-        if (!c.overflow_refs && !c.overflow_clip) {
+        if (!c.overflow_refs && !c.overflow_clip && !c.overflow_ext) {
             ctx->frame_pending = false;
             ctx->frame_valid = true;
             ctx->rendered_once = true;
@@ -616,6 +632,7 @@ static int finish_frame(swr_ctx *ctx) {
                 return SWR_ERR_OOM;
             }
         }
+        if (c.overflow_ext) ctx->ext_cap = (size_t)c.ext_records + (size_t)c.ext_records / 4 + 4096;
         if (c.overflow_clip) {
             size_t want = (size_t)c.clip_verts + (size_t)c.clip_verts / 4 + 4096;
             if (ctx->clip_verts.reserve(want) != cudaSuccess) {
@@ -714,6 +731,7 @@ int swr_read_visbuffer(swr_ctx *ctx, uint32_t *depth_bits, uint32_t *seq, float 
     VisParams vp{};
     vp.keys = ctx->keys.p;
     vp.records = ctx->records.p;
+    vp.clip_ext = ctx->clip_ext.p;
     vp.draws = ctx->draws.p;
     vp.ndraws = ctx->ndraws;
     vp.W = ctx->W;

@@ -46,7 +46,7 @@ struct DevDraw {
     uint32_t prim;
     uint32_t flags;
     uint32_t first_tri;  // global triangle base (seq)
-    uint32_t slot_base;  // first record slot of this draw
+    uint32_t reserved;
 };
 
 struct DevPrim {
@@ -98,6 +98,10 @@ struct FrameCounters {
     uint32_t overflow_refs;   // tile_refs exceeded the ref buffer
     uint32_t overflow_clip;   // clip vertex buffer exhausted
     uint32_t clip_queue_n;    // triangles queued for k_clip
+    uint32_t ext_records;     // bump allocator for the records of fans >= 1
+    uint32_t overflow_ext;    // extension records exhausted
+    uint32_t clip_list_n;     // surviving fans >= 1
+    uint32_t pad;
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -22,7 +22,10 @@ struct SetupParams {
     uint32_t *rects;
     ClipVertex *clip_verts;
     uint32_t clip_capacity;
-    uint32_t *clip_queue;  // global triangle ids that need the clipper
+    uint32_t *clip_queue;  // dense triangle ids that need the clipper
+    uint32_t *clip_ext;    // per dense triangle: first extension record of its fans 1..n-3 (written by k_clip)
+    uint32_t *clip_list;   // ids (tri*8+fan, fan >= 1) of clipped fan triangles that survived, for k_scatter_list
+    uint32_t ext_capacity; // extension records available after the total_tris dense ones
     uint32_t *tile_count;
     FrameCounters *counters;
     int W, H, tiles_x, tiles_y;
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams P) {
         const DevDraw &dr = P.draws[d];
         const DevPrim &pr = P.prims[dr.prim];
         const bool clip = (dr.flags & 1u) != 0;
-        const uint32_t slot = dr.slot_base + tri * (clip ? 7u : 1u);
+        const uint32_t slot = g;  // record of fan 0 = dense triangle index; id = g * 8 + fan
         uint32_t i0 = __ldg(pr.idx + 3 * tri), i1 = __ldg(pr.idx + 3 * tri + 1), i2 = __ldg(pr.idx + 3 * tri + 2);
         float4 c0 = mul_vec4(dr.mvp, __ldg(pr.pos + i0));
         float4 c1 = mul_vec4(dr.mvp, __ldg(pr.pos + i1));
@@ -150,10 +153,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams P) {
             }
             if (state == 0) rect = emit_triangle(P, c0, c1, c2, slot, d, seq, SWR_NO_CLIP);
             queued = state == 2;
-            uint32_t *rr = P.rects + slot;
-            rr[0] = rect;
-#pragma unroll
-            for (int k = 1; k < 7; k++) rr[k] = 0;
+            P.rects[slot] = rect;  // k_clip overwrites it when fan 0 of a clipped polygon survives
         } else {
             rect = emit_triangle(P, c0, c1, c2, slot, d, seq, SWR_NO_CLIP);
             P.rects[slot] = rect;
@@ -271,13 +271,23 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip(SetupParams P) {
                     cv.u = v[14]; cv.v = v[15];
                     P.clip_verts[vbase + lane] = cv;
                 }
-                if (room && lane >= 1 && (int)lane <= n - 2 && lane <= 7) {
+                const int nfan = min(n - 2, 8);  // seq carries 3 fan bits; a triangle cut by 6 planes has at most 7 fans
+                uint32_t ext = 0;
+                if (lane == 0 && nfan > 1) {
+                    ext = atomicAdd(&P.counters->ext_records, (uint32_t)(nfan - 1));
+                    if (ext + (uint32_t)(nfan - 1) > P.ext_capacity) P.counters->overflow_ext = 1;
+                    P.clip_ext[gg] = P.total_tris + ext;
+                }
+                ext = __shfl_sync(gmask, ext, 0, 16);
+                const bool room2 = room && (nfan <= 1 || ext + (uint32_t)(nfan - 1) <= P.ext_capacity);
+                if (room2 && lane >= 1 && (int)lane <= nfan) {
                     const float *v0 = poly[cur][0], *v1 = poly[cur][lane], *v2 = poly[cur][lane + 1];
                     const uint32_t fan = lane - 1;
-                    const uint32_t sl = dr.slot_base + ttri * 7u + fan;
+                    const uint32_t sl = fan == 0 ? gg : P.total_tris + ext + fan - 1;
                     rect_out = emit_triangle(P, make_float4(v0[0], v0[1], v0[2], v0[3]), make_float4(v1[0], v1[1], v1[2], v1[3]),
                                              make_float4(v2[0], v2[1], v2[2], v2[3]), sl, dd, (dr.first_tri + ttri) * 8u + fan, vbase);
                     P.rects[sl] = rect_out;
+                    if (fan > 0 && rect_out != 0) P.clip_list[atomicAdd(&P.counters->clip_list_n, 1u)] = gg * 8u + fan;
                 }
             }
         }
@@ -350,13 +360,15 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3 pass 2: scatter refs. One thread per record slot.
+// K3 pass 2: scatter refs (ids = dense triangle * 8 + fan). k_scatter: one thread per dense triangle (fan 0);
+// k_scatter_list: the surviving fans >= 1 of clipped polygons.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_scatter(const uint32_t *rects, uint32_t nslots, uint32_t *tile_cursor, uint32_t *refs,
-                                                 uint32_t ref_capacity, const FrameCounters *counters, int tiles_x) {
-    if (counters->overflow_refs) return;  // lists would not fit: the host grows the buffer and replays the frame
-    uint32_t slot = blockIdx.x * 256 + threadIdx.x;
-    uint32_t rect = slot < nslots ? __ldg(rects + slot) : 0u;
+__device__ __forceinline__ uint32_t record_of_id(uint32_t id, const uint32_t *clip_ext) {
+    const uint32_t fan = id & 7u, t = id >> 3;
+    return fan == 0 ? t : __ldg(clip_ext + t) + fan - 1u;
+}
+
+__device__ __forceinline__ void scatter_rect(uint32_t rect, uint32_t id, uint32_t *tile_cursor, uint32_t *refs, int tiles_x) {
     int tx0 = rect & 0xFF, ty0 = (rect >> 8) & 0xFF, tx1 = (rect >> 16) & 0xFF, ty1 = rect >> 24;
     bool valid = rect != 0;
     bool single = valid && (tx1 - tx0 == 1) && (ty1 - ty0 == 1);
@@ -369,10 +381,33 @@ __global__ void __launch_bounds__(256) k_scatter(const uint32_t *rects, uint32_t
         if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&tile_cursor[tile], (uint32_t)__popc(peers));
         base = __shfl_sync(peers, base, leader);
         uint32_t rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
-        refs[base + rank] = slot;
+        refs[base + rank] = id;
     } else if (valid) {
         for (int ty = ty0; ty < ty1; ty++)
-            for (int tx = tx0; tx < tx1; tx++) refs[atomicAdd(&tile_cursor[ty * tiles_x + tx], 1u)] = slot;
+            for (int tx = tx0; tx < tx1; tx++) refs[atomicAdd(&tile_cursor[ty * tiles_x + tx], 1u)] = id;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scatter(const uint32_t *rects, uint32_t ntris, uint32_t *tile_cursor, uint32_t *refs,
+                                                 const FrameCounters *counters, int tiles_x) {
+    if (counters->overflow_refs) return;  // lists would not fit: the host grows the buffer and replays the frame
+    uint32_t t = blockIdx.x * 256 + threadIdx.x;
+    uint32_t rect = t < ntris ? __ldg(rects + t) : 0u;
+    scatter_rect(rect, t * 8u, tile_cursor, refs, tiles_x);
+}
+
+__global__ void __launch_bounds__(256) k_scatter_list(const uint32_t *rects, const uint32_t *clip_list, const uint32_t *clip_ext,
+                                                      uint32_t *tile_cursor, uint32_t *refs, const FrameCounters *counters, int tiles_x) {
+    if (counters->overflow_refs || counters->overflow_ext) return;
+    const uint32_t n = counters->clip_list_n;
+    for (uint32_t base = blockIdx.x * 256; base < n; base += gridDim.x * 256) {  // uniform trip count per block
+        uint32_t i = base + threadIdx.x;
+        uint32_t id = 0, rect = 0;
+        if (i < n) {
+            id = clip_list[i];
+            rect = __ldg(rects + record_of_id(id, clip_ext));
+        }
+        scatter_rect(rect, id, tile_cursor, refs, tiles_x);
     }
 }
 
@@ -387,7 +422,8 @@ struct RasterParams {
     const uint32_t *refs;
     const uint32_t *tile_offset;
     const uint32_t *tile_order;
-    unsigned long long *keys;  // tile-major: tile * 4096 + y * 64 + x
+    const uint32_t *clip_ext;
+    unsigned long long *keys;  // tile-major: tile * 4096 + y * 64 + x; low word = ~id
     const FrameCounters *counters;
     int W, H, tiles_x, tiles_y;
     int row_begin, row_end;
@@ -546,7 +582,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_tiles(RasterParams P)
     unsigned long long *skeys = reinterpret_cast<unsigned long long *>(smem_raw);
     TileBatch &tb = *reinterpret_cast<TileBatch *>(smem_raw + SWR_TILE_PIXELS * 8);
 
-    if (P.counters->overflow_refs) return;  // tile lists were not written; the host replays the frame
+    if (P.counters->overflow_refs || P.counters->overflow_ext) return;  // lists incomplete; the host replays the frame
     const int tile = (int)P.tile_order[blockIdx.x];
     const int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
     const int tile_x0 = tx * SWR_TILE, tile_y0 = ty * SWR_TILE;
@@ -560,9 +596,9 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_tiles(RasterParams P)
         const uint32_t ri = base + tid;
         uint32_t nitems = 0;
         if (ri < end) {
-            const uint32_t slot = __ldg(P.refs + ri);
+            const uint32_t slot = __ldg(P.refs + ri);  // id = dense triangle * 8 + fan
             TriRecord r;
-            const uint4 *src = reinterpret_cast<const uint4 *>(P.records + slot);
+            const uint4 *src = reinterpret_cast<const uint4 *>(P.records + record_of_id(slot, P.clip_ext));
             uint4 *dst = reinterpret_cast<uint4 *>(&r);
             dst[0] = __ldg(src);
             dst[1] = __ldg(src + 1);
@@ -631,6 +667,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_tiles(RasterParams P)
 struct VisParams {
     const unsigned long long *keys;
     const TriRecord *records;
+    const uint32_t *clip_ext;
     const DevDraw *draws;
     uint32_t ndraws;
     int W, H, tiles_x;
@@ -649,7 +686,7 @@ __global__ void k_read_vis(VisParams P, uint32_t *depth_bits, uint32_t *seq, flo
     float b1 = 0.0f, b2 = 0.0f;
     if (key != SWR_KEY_EMPTY) {
         uint32_t slot = 0xFFFFFFFFu - (uint32_t)key;
-        TriRecord r = P.records[slot];
+        TriRecord r = P.records[record_of_id(slot, P.clip_ext)];
         float z;
         if (resolve_pixel(r, P.W, P.H, px, py, b1, b2, z)) {
             db = __float_as_uint(z);

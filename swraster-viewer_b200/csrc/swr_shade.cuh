@@ -14,6 +14,7 @@
 struct ShadeParams {
     const unsigned long long *keys;
     const TriRecord *records;
+    const uint32_t *clip_ext;
     const DevDraw *draws;
     const ClipVertex *clip_verts;
     DevScene scene;
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 4) k_shade(ShadeParams P) {
     TriRecord rec;
     if (key != SWR_KEY_EMPTY) {
         slot = 0xFFFFFFFFu - (uint32_t)key;
-        rec = P.records[slot];
+        rec = P.records[record_of_id(slot, P.clip_ext)];
         float z;
         if (resolve_pixel(rec, P.W, P.H, px, py, b1, b2, z)) covered = __float_as_uint(z) != SWR_INF_BITS;  // depth.cmpne(INF)
     }
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 4) k_shade(ShadeParams P) {
         if (slot == ps) {
             iw0 = rec.iw0; iw1 = rec.iw1; iw2 = rec.iw2;
         } else {
-            const TriRecord *r = P.records + ps;
+            const TriRecord *r = P.records + record_of_id(ps, P.clip_ext);
             iw0 = __ldg(&r->iw0); iw1 = __ldg(&r->iw1); iw2 = __ldg(&r->iw2);
         }
         // shader.rs:123: w of THIS packet at every lane's stored barycentrics (0,0 for never-written lanes)
