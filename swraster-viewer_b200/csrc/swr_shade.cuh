@@ -401,39 +401,26 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 4) k_shade(ShadeParams P) {
         if (resolve_pixel(rec, P.W, P.H, px, py, b1, b2, z)) covered = __float_as_uint(z) != SWR_INF_BITS;  // depth.cmpne(INF)
     }
     V3 out = v3(0.0f, 0.0f, 0.0f);
-    // tilerasterizer.rs:419-463: consume the distinct packets of the quad; each evaluation sees all four lanes' barycentrics
-    uint32_t qslot[4];
-    bool qcov[4];
+    // tilerasterizer.rs:419-463 evaluates pbr_shader once per distinct packet of the quad, on all four lanes, and keeps
+    // the lanes that own the packet. The only cross-lane term is du_dv * w (shader.rs:130: component k is scaled by
+    // lane k's w, where w = 1 / one_over_w(P) at lane k's STORED barycentrics, 0,0 for never-written lanes). So each
+    // lane shades its own pixel once, with its own packet P evaluated at the four lanes' barycentrics.
+    float qb1[4], qb2[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        qslot[k] = __shfl_sync(qmask, slot, (lane & ~3) + k);
-        qcov[k] = __shfl_sync(qmask, (int)covered, (lane & ~3) + k) != 0;
+    for (int j = 0; j < 4; j++) {
+        qb1[j] = __shfl_sync(qmask, b1, (lane & ~3) + j);
+        qb2[j] = __shfl_sync(qmask, b2, (lane & ~3) + j);
     }
-#pragma unroll 1
-    for (int k = 0; k < 4; k++) {
-        bool first = qcov[k];
-        for (int j = 0; j < k; j++) first = first && !(qcov[j] && qslot[j] == qslot[k]);
-        if (!first) continue;  // uniform across the quad
-        const uint32_t ps = qslot[k];
-        const bool mine = covered && slot == ps;
-        float iw0, iw1, iw2;
-        if (slot == ps) {
-            iw0 = rec.iw0; iw1 = rec.iw1; iw2 = rec.iw2;
-        } else {
-            const TriRecord *r = P.records + record_of_id(ps, P.clip_ext);
-            iw0 = __ldg(&r->iw0); iw1 = __ldg(&r->iw1); iw2 = __ldg(&r->iw2);
-        }
-        // shader.rs:123: w of THIS packet at every lane's stored barycentrics (0,0 for never-written lanes)
-        float w = 1.0f / interp1(iw0, iw1 - iw0, iw2 - iw0, b1, b2);
+    if (covered) {
+        const float iwda = rec.iw1 - rec.iw0, iwdb = rec.iw2 - rec.iw0;
         float wq[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) wq[j] = __shfl_sync(qmask, w, (lane & ~3) + j);
-        if (mine) {
-            ShadePacket sp;
-            build_shade_packet(P, rec, sp);
-            float dd[4] = {sp.du_dv[0] * wq[0], sp.du_dv[1] * wq[1], sp.du_dv[2] * wq[2], sp.du_dv[3] * wq[3]};  // shader.rs:130
-            out = pbr_shader(P, sp, b1, b2, w, dd);
-        }
+        for (int j = 0; j < 4; j++) wq[j] = 1.0f / interp1(rec.iw0, iwda, iwdb, qb1[j], qb2[j]);  // shader.rs:123
+        ShadePacket sp;
+        build_shade_packet(P, rec, sp);
+        float dd[4] = {sp.du_dv[0] * wq[0], sp.du_dv[1] * wq[1], sp.du_dv[2] * wq[2], sp.du_dv[3] * wq[3]};
+        const float w = sub == 0 ? wq[0] : (sub == 1 ? wq[1] : (sub == 2 ? wq[2] : wq[3]));
+        out = pbr_shader(P, sp, b1, b2, w, dd);
     }
     if (!covered && inside) out = compute_skybox(P, px, py);
     if (inside) P.color[(size_t)py * P.Wp + px] = make_float4(out.x, out.y, out.z, 1.0f);
