@@ -110,7 +110,7 @@ static int upload(swr_ctx *ctx, const T *src, size_t n, T **out) {
     return SWR_OK;
 }
 
-static size_t raster_smem_bytes() { return SWR_TILE_PIXELS * 8 + sizeof(TileBatch); }
+static size_t raster_smem_bytes() { return SWR_TILE_PIXELS * 8 + sizeof(TileBatch) + RASTER_WARPS * sizeof(FragQueue); }
 
 extern "C" {
 

@@ -111,6 +111,7 @@ __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b)
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float frcp(float a) { return __frcp_rn(a); }  // correctly rounded 1/a == IEEE 1.0f / a
 __device__ __forceinline__ float i2f(int a) { return __int2float_rn(a); }
 __device__ __forceinline__ int wmul(int a, int b) { return (int)((unsigned)a * (unsigned)b); }
 __device__ __forceinline__ int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
@@ -267,7 +268,7 @@ __device__ __forceinline__ float frag_depth(const TriRecord &r, float w1, float 
     float iwda = fsub(r.iw1, r.iw0), iwdb = fsub(r.iw2, r.iw0);
     float zwda = fsub(r.zw1, r.zw0), zwdb = fsub(r.zw2, r.zw0);
     float q = fadd(fadd(r.iw0, fmul(b1, iwda)), fmul(b2, iwdb));
-    float wp = fdiv(1.0f, q);
+    float wp = frcp(q);
     float zz = fadd(fadd(r.zw0, fmul(b1, zwda)), fmul(b2, zwdb));
     return fmul(zz, wp);
 }

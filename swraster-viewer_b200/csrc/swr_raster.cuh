@@ -434,8 +434,8 @@ struct RasterParams {
 // tile (128 items of 8 quads) is shared by all warps instead of serialising one of them.
 struct TileBatch {
     int a[3][RASTER_THREADS], b[3][RASTER_THREADS], c[3][RASTER_THREADS];
-    int xs[RASTER_THREADS], ys[RASTER_THREADS];
-    uint32_t geom[RASTER_THREADS];  // nqx | nqy << 8 | coarse << 16 | exact << 17
+    // region origin in quads relative to the tile (5 + 5 bits) | nqx << 10 | nqy << 16 | coarse << 22 | exact << 23
+    uint32_t geom[RASTER_THREADS];
     uint32_t slot[RASTER_THREADS];
     float ooa[RASTER_THREADS], iw0[RASTER_THREADS], iwda[RASTER_THREADS], iwdb[RASTER_THREADS];
     float zw0[RASTER_THREADS], zwda[RASTER_THREADS], zwdb[RASTER_THREADS];
@@ -443,28 +443,56 @@ struct TileBatch {
     uint32_t wsum[RASTER_WARPS];
 };
 
-struct FragParams {
-    float ooa, iw0, iwda, iwdb, zw0, zwda, zwdb;
-    uint32_t idlow;
+// Per-warp queue of covered pixels waiting for the depth computation: coverage is found by lanes walking different
+// quad rows (divergent by nature); the expensive part — perspective depth, 64-bit min — then runs up to 32 wide.
+#define FRAGQ_CAP 48
+#define FRAGQ_DRAIN 16
+struct FragQueue {
+    uint32_t pkpix[FRAGQ_CAP];  // packet index in the batch << 16 | pixel index in the tile
+    float w1[FRAGQ_CAP], w2[FRAGQ_CAP];
 };
 
 // tilerasterizer.rs:337-342 + depth_test :511-523 folded into one 64-bit atomicMin
-__device__ __forceinline__ void emit_fragment(unsigned long long *skeys, const FragParams &f, float w1, float w2, int pix) {
-    float b1 = fmul(w1, f.ooa), b2 = fmul(w2, f.ooa);
-    float qq = fadd(fadd(f.iw0, fmul(b1, f.iwda)), fmul(b2, f.iwdb));
-    float wpix = fdiv(1.0f, qq);
-    float zz = fadd(fadd(f.zw0, fmul(b1, f.zwda)), fmul(b2, f.zwdb));
+__device__ __forceinline__ void shade_fragment(unsigned long long *skeys, const TileBatch &tb, uint32_t pkpix, float w1, float w2) {
+    const int pk = pkpix >> 16, pix = pkpix & 0xFFFF;
+    const float ooa = tb.ooa[pk];
+    float b1 = fmul(w1, ooa), b2 = fmul(w2, ooa);
+    float qq = fadd(fadd(tb.iw0[pk], fmul(b1, tb.iwda[pk])), fmul(b2, tb.iwdb[pk]));
+    float wpix = frcp(qq);
+    float zz = fadd(fadd(tb.zw0[pk], fmul(b1, tb.zwda[pk])), fmul(b2, tb.zwdb[pk]));
     float z = fmul(zz, wpix);
     if (z == z) {  // NaN never passes `z <= current` (tilerasterizer.rs:516)
-        unsigned long long key = ((unsigned long long)depth_orderable(z) << 32) | f.idlow;
-        atomicMin(&skeys[pix], key);
+        unsigned long long key = ((unsigned long long)depth_orderable(z) << 32) | (0xFFFFFFFFu - tb.slot[pk]);
+        // keys only ever decrease, so a (possibly stale) read that is already <= key proves the atomic would be a no-op;
+        // the shared-memory 64-bit min is a CAS loop (ATOMS.CAST.SPIN.64), worth skipping for occluded fragments
+        if (key < *reinterpret_cast<volatile unsigned long long *>(&skeys[pix])) atomicMin(&skeys[pix], key);
     }
 }
 
-__device__ __forceinline__ void raster_row(unsigned long long *skeys, const TileBatch &tb, int pk, uint32_t local, int tile_x0, int tile_y0) {
+// Drain up to 32 fragments from the tail of the warp's queue; returns the new count.
+__device__ __forceinline__ int drain_queue(unsigned long long *skeys, const TileBatch &tb, const FragQueue &fq, int qn, int lane) {
+    const int n = min(qn, 32);
+    __syncwarp();
+    if (lane < n) shade_fragment(skeys, tb, fq.pkpix[qn - n + lane], fq.w1[qn - n + lane], fq.w2[qn - n + lane]);
+    __syncwarp();
+    return qn - n;
+}
+
+// One lane's quad row: the four pixels of the current quad as three f32 edge values each. Exact packets use the same
+// f32 stepping (their chain is exact by construction), only their origin is computed with integers.
+struct RowState {
+    float v[4][3];
+    float step[3];
+    int len;  // quads in the row
+    int pix;  // tile pixel index of lane 0 of the current quad
+    int pk;
+};
+
+__device__ __forceinline__ void row_setup(const TileBatch &tb, int pk, uint32_t local, int tile_x0, int tile_y0, RowState &st) {
     const uint32_t geom = tb.geom[pk];
-    const int nqx = geom & 0xFF;
-    const bool coarse = (geom >> 16) & 1u, exact = (geom >> 17) & 1u;
+    const int nqx = (geom >> 10) & 0x3F;
+    const bool coarse = (geom >> 22) & 1u, exact = (geom >> 23) & 1u;
+    st.pk = pk;
     int qy, bi;
     if (coarse) {
         const uint32_t nbx = (uint32_t)(nqx + 7) >> 3;
@@ -475,49 +503,28 @@ __device__ __forceinline__ void raster_row(unsigned long long *skeys, const Tile
         bi = 0;
     }
     const int qx0 = bi * 8, qx1 = coarse ? min(qx0 + 8, nqx) : nqx;
-    const int xs = tb.xs[pk], ys = tb.ys[pk];
+    st.len = qx1 - qx0;
+    const int xq = geom & 31, yq = (geom >> 5) & 31;
+    const int xs = tile_x0 * 16 + xq * 32, ys = tile_y0 * 16 + yq * 32;
     int a[3], b[3], c[3];
 #pragma unroll
     for (int e = 0; e < 3; e++) {
         a[e] = tb.a[e][pk];
         b[e] = tb.b[e][pk];
         c[e] = tb.c[e][pk];
+        st.step[e] = i2f(wmul(a[e], 32));
     }
-    FragParams f;
-    f.ooa = tb.ooa[pk];
-    f.iw0 = tb.iw0[pk];
-    f.iwda = tb.iwda[pk];
-    f.iwdb = tb.iwdb[pk];
-    f.zw0 = tb.zw0[pk];
-    f.zwda = tb.zwda[pk];
-    f.zwdb = tb.zwdb[pk];
-    f.idlow = 0xFFFFFFFFu - tb.slot[pk];
-    const int ysub = ys + qy * 32;                          // sub-pixel y of the quad row
-    int pix = ((ysub >> 4) - tile_y0) * SWR_TILE + ((xs >> 4) + 2 * qx0 - tile_x0);  // lane 0 of the first quad
+    st.pix = (yq + qy) * 2 * SWR_TILE + (xq + qx0) * 2;
     if (exact) {
-        // integer edge functions at the pixel centres, stepped by a*32 per quad (exactly what the f32 chain yields)
-        int e0[3], e1[3], e2[3], e3[3], st[3];
-        const int sx = xs + qx0 * 32 + 8, sy = ysub + 8;
+        // integer edge functions at the pixel centres of the first quad (== the f32 chain values, all exact)
+        const int sx = xs + qx0 * 32 + 8, sy = ys + qy * 32 + 8;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            e0[k] = a[k] * sx + b[k] * sy + c[k];
-            e1[k] = e0[k] + a[k] * 16;
-            e2[k] = e0[k] + b[k] * 16;
-            e3[k] = e2[k] + a[k] * 16;
-            st[k] = a[k] * 32;
-        }
-        for (int q = qx0; q < qx1; q++, pix += 2) {
-            if ((e0[0] | e0[1] | e0[2]) >= 0) emit_fragment(skeys, f, i2f(e0[1]), i2f(e0[2]), pix);
-            if ((e1[0] | e1[1] | e1[2]) >= 0) emit_fragment(skeys, f, i2f(e1[1]), i2f(e1[2]), pix + 1);
-            if ((e2[0] | e2[1] | e2[2]) >= 0) emit_fragment(skeys, f, i2f(e2[1]), i2f(e2[2]), pix + SWR_TILE);
-            if ((e3[0] | e3[1] | e3[2]) >= 0) emit_fragment(skeys, f, i2f(e3[1]), i2f(e3[2]), pix + SWR_TILE + 1);
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                e0[k] += st[k];
-                e1[k] += st[k];
-                e2[k] += st[k];
-                e3[k] += st[k];
-            }
+            const int e0 = a[k] * sx + b[k] * sy + c[k];
+            st.v[0][k] = i2f(e0);
+            st.v[1][k] = i2f(e0 + a[k] * 16);
+            st.v[2][k] = i2f(e0 + b[k] * 16);
+            st.v[3][k] = i2f(e0 + b[k] * 16 + a[k] * 16);
         }
         return;
     }
@@ -534,76 +541,91 @@ __device__ __forceinline__ void raster_row(unsigned long long *skeys, const Tile
     }
     if (coarse) {
         const float cx0 = i2f(bx + 8), cx1 = i2f(bx + 248), cy0 = i2f(by + 8), cy1 = i2f(by + 248);
+        bool reject = false;
 #pragma unroll
         for (int e = 0; e < 3; e++) {
             const float ax0 = fmul(A[e], cx0), ax1 = fmul(A[e], cx1), by0 = fmul(B[e], cy0), by1 = fmul(B[e], cy1);
             const float e00 = fadd(fadd(ax0, by0), C[e]), e10 = fadd(fadd(ax1, by0), C[e]);
             const float e01 = fadd(fadd(ax0, by1), C[e]), e11 = fadd(fadd(ax1, by1), C[e]);
-            if (fmaxf(fmaxf(e00, e10), fmaxf(e01, e11)) < 0.0f) return;  // block fully outside this edge
+            reject = reject || (fmaxf(fmaxf(e00, e10), fmaxf(e01, e11)) < 0.0f);  // block fully outside this edge
+        }
+        if (reject) {
+            st.len = 0;
+            return;
         }
     }
-    float v0[3], v1[3], v2[3], v3[3], sxf[3];
-    {
-        const float x0 = i2f(bx + 8), x1 = i2f(bx + 24), y0 = i2f(by + 8), y1 = i2f(by + 24);
+    const float x0 = i2f(bx + 8), x1 = i2f(bx + 24), y0 = i2f(by + 8), y1 = i2f(by + 24);
 #pragma unroll
-        for (int e = 0; e < 3; e++) {
-            const float ax0 = fmul(A[e], x0), ax1 = fmul(A[e], x1), by0 = fmul(B[e], y0), by1 = fmul(B[e], y1);
-            v0[e] = fadd(fadd(ax0, by0), C[e]);
-            v1[e] = fadd(fadd(ax1, by0), C[e]);
-            v2[e] = fadd(fadd(ax0, by1), C[e]);
-            v3[e] = fadd(fadd(ax1, by1), C[e]);
-            const float syf = i2f(wmul(b[e], 32));
-            sxf[e] = i2f(wmul(a[e], 32));
-            for (int k = 0; k < j; k++) {
-                v0[e] = fadd(v0[e], syf);
-                v1[e] = fadd(v1[e], syf);
-                v2[e] = fadd(v2[e], syf);
-                v3[e] = fadd(v3[e], syf);
-            }
+    for (int e = 0; e < 3; e++) {
+        const float ax0 = fmul(A[e], x0), ax1 = fmul(A[e], x1), by0 = fmul(B[e], y0), by1 = fmul(B[e], y1);
+        float v0 = fadd(fadd(ax0, by0), C[e]), v1 = fadd(fadd(ax1, by0), C[e]);
+        float v2 = fadd(fadd(ax0, by1), C[e]), v3 = fadd(fadd(ax1, by1), C[e]);
+        const float syf = i2f(wmul(b[e], 32));
+        for (int k = 0; k < j; k++) {
+            v0 = fadd(v0, syf);
+            v1 = fadd(v1, syf);
+            v2 = fadd(v2, syf);
+            v3 = fadd(v3, syf);
         }
-    }
-    for (int q = qx0; q < qx1; q++, pix += 2) {
-        if (v0[0] >= 0.0f && v0[1] >= 0.0f && v0[2] >= 0.0f) emit_fragment(skeys, f, v0[1], v0[2], pix);
-        if (v1[0] >= 0.0f && v1[1] >= 0.0f && v1[2] >= 0.0f) emit_fragment(skeys, f, v1[1], v1[2], pix + 1);
-        if (v2[0] >= 0.0f && v2[1] >= 0.0f && v2[2] >= 0.0f) emit_fragment(skeys, f, v2[1], v2[2], pix + SWR_TILE);
-        if (v3[0] >= 0.0f && v3[1] >= 0.0f && v3[2] >= 0.0f) emit_fragment(skeys, f, v3[1], v3[2], pix + SWR_TILE + 1);
-#pragma unroll
-        for (int e = 0; e < 3; e++) {
-            v0[e] = fadd(v0[e], sxf[e]);
-            v1[e] = fadd(v1[e], sxf[e]);
-            v2[e] = fadd(v2[e], sxf[e]);
-            v3[e] = fadd(v3[e], sxf[e]);
-        }
+        st.v[0][e] = v0;
+        st.v[1][e] = v1;
+        st.v[2][e] = v2;
+        st.v[3][e] = v3;
     }
 }
 
-__global__ void __launch_bounds__(RASTER_THREADS) k_raster_tiles(RasterParams P) {
+__global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *skeys = reinterpret_cast<unsigned long long *>(smem_raw);
     TileBatch &tb = *reinterpret_cast<TileBatch *>(smem_raw + SWR_TILE_PIXELS * 8);
+    FragQueue *fqs = reinterpret_cast<FragQueue *>(smem_raw + SWR_TILE_PIXELS * 8 + sizeof(TileBatch));
 
     if (P.counters->overflow_refs || P.counters->overflow_ext) return;  // lists incomplete; the host replays the frame
     const int tile = (int)P.tile_order[blockIdx.x];
     const int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
     const int tile_x0 = tx * SWR_TILE, tile_y0 = ty * SWR_TILE;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    FragQueue &fq = fqs[wid];
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     for (int i = tid; i < SWR_TILE_PIXELS; i += RASTER_THREADS) skeys[i] = SWR_KEY_EMPTY;
 
     const uint32_t beg = P.tile_offset[tile], end = P.tile_offset[tile + 1];
+    // software pipeline over batches: the record of batch n+1 and the ref of batch n+2 are in flight while batch n is rasterised
+    uint32_t slot_next = 0, slot_next2 = 0;
+    uint4 rq0 = make_uint4(0, 0, 0, 0), rq1 = rq0, rq2 = rq0, rq3 = rq0;
+    if (beg + tid < end) {
+        slot_next = __ldg(P.refs + beg + tid);
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.records + record_of_id(slot_next, P.clip_ext));
+        rq0 = __ldg(src);
+        rq1 = __ldg(src + 1);
+        rq2 = __ldg(src + 2);
+        rq3 = __ldg(src + 3);
+    }
+    if (beg + RASTER_THREADS + tid < end) slot_next2 = __ldg(P.refs + beg + RASTER_THREADS + tid);
     for (uint32_t base = beg; base < end; base += RASTER_THREADS) {
         __syncthreads();  // previous batch fully consumed (and key init done)
         const uint32_t ri = base + tid;
         uint32_t nitems = 0;
-        if (ri < end) {
-            const uint32_t slot = __ldg(P.refs + ri);  // id = dense triangle * 8 + fan
-            TriRecord r;
-            const uint4 *src = reinterpret_cast<const uint4 *>(P.records + record_of_id(slot, P.clip_ext));
+        const uint32_t slot = slot_next;
+        TriRecord r;
+        {
             uint4 *dst = reinterpret_cast<uint4 *>(&r);
-            dst[0] = __ldg(src);
-            dst[1] = __ldg(src + 1);
-            dst[2] = __ldg(src + 2);
-            dst[3] = __ldg(src + 3);
+            dst[0] = rq0;
+            dst[1] = rq1;
+            dst[2] = rq2;
+            dst[3] = rq3;
+        }
+        slot_next = slot_next2;
+        if (ri + RASTER_THREADS < end) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(P.records + record_of_id(slot_next, P.clip_ext));
+            rq0 = __ldg(src);
+            rq1 = __ldg(src + 1);
+            rq2 = __ldg(src + 2);
+            rq3 = __ldg(src + 3);
+        }
+        if (ri + 2 * RASTER_THREADS < end) slot_next2 = __ldg(P.refs + ri + 2 * RASTER_THREADS);
+        if (ri < end) {
             PacketSetup ps;
             packet_setup(r, P.W, P.H, tile_x0, tile_y0, ps);
             if (!ps.empty) {
@@ -614,9 +636,8 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_tiles(RasterParams P)
                     tb.b[e][tid] = ps.b[e];
                     tb.c[e][tid] = ps.c[e];
                 }
-                tb.xs[tid] = ps.xs;
-                tb.ys[tid] = ps.ys;
-                tb.geom[tid] = (uint32_t)ps.nqx | ((uint32_t)ps.nqy << 8) | (ps.coarse ? 1u << 16 : 0u) | (ps.exact ? 1u << 17 : 0u);
+                tb.geom[tid] = (uint32_t)((ps.xs >> 5) - tile_x0 / 2) | ((uint32_t)((ps.ys >> 5) - tile_y0 / 2) << 5) | ((uint32_t)ps.nqx << 10) |
+                               ((uint32_t)ps.nqy << 16) | (ps.coarse ? 1u << 22 : 0u) | (ps.exact ? 1u << 23 : 0u);
                 tb.slot[tid] = slot;
                 tb.ooa[tid] = r.ooa;
                 tb.iw0[tid] = r.iw0;
@@ -643,18 +664,51 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_tiles(RasterParams P)
         if (tid == 0) tb.prefix[0] = 0;
         __syncthreads();
         const uint32_t total = tb.prefix[RASTER_THREADS];
-        for (uint32_t it = tid; it < total; it += RASTER_THREADS) {
-            int lo = 0, hi = RASTER_THREADS;
+        int qn = 0;  // fragments queued by this warp (warp-uniform)
+        for (uint32_t it0 = (uint32_t)wid * 32u; it0 < total; it0 += RASTER_THREADS) {  // warp-uniform trip count
+            const uint32_t it = it0 + lane;
+            RowState st;
+            st.len = 0;
+            st.pix = 0;
+            st.pk = 0;
+            if (it < total) {
+                int lo = 0, hi = RASTER_THREADS;
 #pragma unroll
-            for (int s = 0; s < 8; s++) {
-                const int mid = (lo + hi) >> 1;
-                if (tb.prefix[mid] <= it)
-                    lo = mid;
-                else
-                    hi = mid;
+                for (int s = 0; s < 8; s++) {
+                    const int mid = (lo + hi) >> 1;
+                    if (tb.prefix[mid] <= it)
+                        lo = mid;
+                    else
+                        hi = mid;
+                }
+                row_setup(tb, lo, it - tb.prefix[lo], tile_x0, tile_y0, st);
             }
-            raster_row(skeys, tb, lo, it - tb.prefix[lo], tile_x0, tile_y0);
+            const int maxlen = __reduce_max_sync(0xFFFFFFFFu, st.len);
+            for (int s = 0; s < maxlen; s++) {
+                const bool act = s < st.len;
+#pragma unroll
+                for (int l = 0; l < 4; l++) {
+                    const bool cov = act && st.v[l][0] >= 0.0f && st.v[l][1] >= 0.0f && st.v[l][2] >= 0.0f;
+                    const unsigned m = __ballot_sync(0xFFFFFFFFu, cov);
+                    if (m) {
+                        if (cov) {
+                            const int pos = qn + __popc(m & lt_mask);
+                            fq.pkpix[pos] = ((uint32_t)st.pk << 16) | (uint32_t)(st.pix + (l & 1) + (l >> 1) * SWR_TILE);
+                            fq.w1[pos] = st.v[l][1];
+                            fq.w2[pos] = st.v[l][2];
+                        }
+                        qn += __popc(m);
+                        if (qn >= FRAGQ_DRAIN) qn = drain_queue(skeys, tb, fq, qn, lane);
+                    }
+                }
+#pragma unroll
+                for (int l = 0; l < 4; l++)
+#pragma unroll
+                    for (int e = 0; e < 3; e++) st.v[l][e] = fadd(st.v[l][e], st.step[e]);  // one quad to the right
+                st.pix += 2;
+            }
         }
+        while (qn > 0) qn = drain_queue(skeys, tb, fq, qn, lane);  // fragments reference this batch's packets
     }
     __syncthreads();
     unsigned long long *out = P.keys + (size_t)tile * SWR_TILE_PIXELS;
