@@ -225,8 +225,23 @@ int swr_upload_scene(swr_ctx *ctx, const swr_scene_desc *scene);
  * visibility buffer is produced (used by the sort-last composite). */
 int swr_render(swr_ctx *ctx, const swr_camera *camera, const swr_draw *draws, int ndraws, int shade);
 
-/* Shade the current visibility-key buffer (after an external depth composite). */
+/* Shade the current visibility-key buffer again (same frame, e.g. a different camera block is NOT supported:
+ * the records belong to the last swr_render). */
 int swr_shade(swr_ctx *ctx, const swr_camera *camera);
+
+/* Sort-last composite (one context per rank, each rendered with shade = 0 from its own subset of the global
+ * draw list; first_triangle stays global):
+ *   1. swr_keys_to_global    low word of every key becomes ~seq, so keys are comparable across ranks;
+ *   2. (caller) unsigned 64-bit MIN all-reduce over swr_device_keys();
+ *   3. swr_keys_localize     winners owned by this rank get their local id back, others are marked foreign;
+ *                            the winner's barycentrics are written to swr_device_bary() (0 where not owned);
+ *   4. (caller) float SUM all-reduce over swr_device_bary()  — the quad-coupled mip needs every lane's barycentrics;
+ *   5. swr_shade_composited  shades the pixels this rank owns, sky only in tile rows [sky_row_begin, sky_row_end);
+ *   6. swr_resolve + (caller) integer SUM over swr_device_pixels(): unowned pixels resolve to 0. */
+int swr_keys_to_global(swr_ctx *ctx);
+int swr_keys_localize(swr_ctx *ctx);
+int swr_shade_composited(swr_ctx *ctx, const swr_camera *camera, int sky_row_begin, int sky_row_end);
+void *swr_device_bary(swr_ctx *ctx); /* W*H float2, row-major */
 
 /* blit_to_buffer (renderer.rs:293-355): exposure, tonemap, RGBA8 pack into a
  * row-major W*H u32 image on the device; if out_pixels != NULL it is copied to

@@ -77,6 +77,9 @@ struct swr_ctx {
     DevBuf<float4> color;
     DevBuf<uint32_t> pixels;
     DevBuf<float> lum;
+    DevBuf<float2> bary;
+    bool composited = false;
+    int sky_r0 = 0, sky_r1 = 0;
     DevBuf<FrameCounters> counters;
     DevBuf<uint32_t> rsqrt_tab;
     int rsqrt_bits = 0;
@@ -219,6 +222,7 @@ void swr_destroy(swr_ctx *ctx) {
     ctx->color.release();
     ctx->pixels.release();
     ctx->lum.release();
+    ctx->bary.release();
     ctx->counters.release();
     ctx->rsqrt_tab.release();
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -583,6 +587,9 @@ static int launch_shade(swr_ctx *ctx) {
         sp.row_end = re;
         sp.rsqrt_tab = ctx->rsqrt_on ? ctx->rsqrt_tab.p : nullptr;
         sp.rsqrt_bits = ctx->rsqrt_bits;
+        sp.ext_bary = ctx->composited ? ctx->bary.p : nullptr;
+        sp.sky_row_begin = ctx->sky_r0;
+        sp.sky_row_end = ctx->sky_r1;
         dim3 grid(sp.Wp / 16, (re - rb) * SWR_TILE / SHADE_ROWS);
         k_shade<<<grid, SHADE_BLOCK, 0, s>>>(sp);
         const int t0 = rb * ctx->tiles_x, t1 = re * ctx->tiles_x;
@@ -676,6 +683,48 @@ int swr_shade(swr_ctx *ctx, const swr_camera *camera) {
     ctx->last_shade = 1;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     return launch_shade(ctx);
+}
+
+int swr_keys_to_global(swr_ctx *ctx) {
+    if (!ctx) return SWR_ERR_INVALID;
+    int rc;
+    if ((rc = finish_frame(ctx))) return rc;
+    const size_t n = (size_t)ctx->ntiles * SWR_TILE_PIXELS;
+    k_keys_to_global<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->keys.p, n, ctx->records.p, ctx->clip_ext.p);
+    CK(cudaGetLastError());
+    return SWR_OK;
+}
+
+int swr_keys_localize(swr_ctx *ctx) {
+    if (!ctx) return SWR_ERR_INVALID;
+    int rc;
+    if ((rc = finish_frame(ctx))) return rc;
+    if (ctx->bary.reserve((size_t)ctx->W * ctx->H) != cudaSuccess) return SWR_ERR_OOM;
+    dim3 blk(32, 8), grid((ctx->W + 31) / 32, (ctx->H + 7) / 8);
+    k_keys_localize<<<grid, blk, 0, ctx->stream>>>(ctx->keys.p, ctx->tiles_x, ctx->W, ctx->H, ctx->records.p, ctx->clip_ext.p, ctx->draws.p,
+                                                   ctx->tri_prefix.p, ctx->ndraws, ctx->scene.prims, ctx->bary.p);
+    CK(cudaGetLastError());
+    return SWR_OK;
+}
+
+int swr_shade_composited(swr_ctx *ctx, const swr_camera *camera, int sky_row_begin, int sky_row_end) {
+    if (!ctx || !camera) return SWR_ERR_INVALID;
+    if (!ctx->bary.p) {
+        ctx->err = "swr_shade_composited needs swr_keys_localize first";
+        return SWR_ERR_INVALID;
+    }
+    ctx->composited = true;
+    ctx->sky_r0 = sky_row_begin;
+    ctx->sky_r1 = sky_row_end;
+    int rc = swr_shade(ctx, camera);
+    ctx->composited = false;
+    return rc;
+}
+
+void *swr_device_bary(swr_ctx *ctx) {
+    if (!ctx) return nullptr;
+    if (ctx->bary.reserve((size_t)ctx->W * ctx->H) != cudaSuccess) return nullptr;
+    return ctx->bary.p;
 }
 
 int swr_resolve(swr_ctx *ctx, float exposure, uint32_t *out_pixels) {

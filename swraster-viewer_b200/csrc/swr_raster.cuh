@@ -738,7 +738,12 @@ __global__ void k_read_vis(VisParams P, uint32_t *depth_bits, uint32_t *seq, flo
     unsigned long long key = load_key(P.keys, P.tiles_x, px, py);
     uint32_t db = SWR_INF_BITS, sq = 0xFFFFFFFFu;
     float b1 = 0.0f, b2 = 0.0f;
-    if (key != SWR_KEY_EMPTY) {
+    if (key != SWR_KEY_EMPTY && 0xFFFFFFFFu - (uint32_t)key == SWR_ID_FOREIGN) {
+        // sort-last: the winner lives on another rank; only its depth is known here (inverse of depth_orderable)
+        const uint32_t u = (uint32_t)(key >> 32);
+        db = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+        sq = SWR_ID_FOREIGN;
+    } else if (key != SWR_KEY_EMPTY) {
         uint32_t slot = 0xFFFFFFFFu - (uint32_t)key;
         TriRecord r = P.records[record_of_id(slot, P.clip_ext)];
         float z;

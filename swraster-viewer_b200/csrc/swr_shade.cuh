@@ -25,6 +25,10 @@ struct ShadeParams {
     int row_begin, row_end;
     const uint32_t *rsqrt_tab;  // host _mm_rsqrt_ps table (swr_set_rsqrt_table) or NULL
     int rsqrt_bits;
+    // sort-last (after the cross-rank key composite): barycentrics of every pixel's winner, whoever owns it; pixels whose
+    // winner belongs to another rank carry SWR_ID_FOREIGN and are left unshaded (colour.w = 0); sky only in sky rows.
+    const float2 *ext_bary;
+    int sky_row_begin, sky_row_end;
 };
 
 struct V3 {
@@ -394,11 +398,21 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 4) k_shade(ShadeParams P) {
     float b1 = 0.0f, b2 = 0.0f;
     bool covered = false;
     TriRecord rec;
+    bool foreign = false;
     if (key != SWR_KEY_EMPTY) {
         slot = 0xFFFFFFFFu - (uint32_t)key;
-        rec = P.records[record_of_id(slot, P.clip_ext)];
-        float z;
-        if (resolve_pixel(rec, P.W, P.H, px, py, b1, b2, z)) covered = __float_as_uint(z) != SWR_INF_BITS;  // depth.cmpne(INF)
+        if (slot == SWR_ID_FOREIGN) {
+            foreign = true;
+        } else {
+            rec = P.records[record_of_id(slot, P.clip_ext)];
+            float z;
+            if (resolve_pixel(rec, P.W, P.H, px, py, b1, b2, z)) covered = __float_as_uint(z) != SWR_INF_BITS;  // depth.cmpne(INF)
+        }
+    }
+    if (P.ext_bary != nullptr && inside && px < P.W && py < P.H) {
+        const float2 eb = P.ext_bary[(size_t)py * P.W + px];
+        b1 = eb.x;
+        b2 = eb.y;
     }
     V3 out = v3(0.0f, 0.0f, 0.0f);
     // tilerasterizer.rs:419-463 evaluates pbr_shader once per distinct packet of the quad, on all four lanes, and keeps
@@ -422,8 +436,15 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 4) k_shade(ShadeParams P) {
         const float w = sub == 0 ? wq[0] : (sub == 1 ? wq[1] : (sub == 2 ? wq[2] : wq[3]));
         out = pbr_shader(P, sp, b1, b2, w, dd);
     }
-    if (!covered && inside) out = compute_skybox(P, px, py);
-    if (inside) P.color[(size_t)py * P.Wp + px] = make_float4(out.x, out.y, out.z, 1.0f);
+    bool wrote = covered;
+    if (!covered && inside && !(foreign && (uint32_t)(key >> 32) != 0xFF800000u)) {  // foreign winners with finite depth are shaded by their owner
+        const int trow = py >> 6;
+        if (P.ext_bary == nullptr || (trow >= P.sky_row_begin && trow < P.sky_row_end)) {
+            out = compute_skybox(P, px, py);
+            wrote = true;
+        }
+    }
+    if (inside) P.color[(size_t)py * P.Wp + px] = make_float4(out.x, out.y, out.z, wrote ? 1.0f : 0.0f);
 }
 
 // tilerasterizer.rs:103-106: quad #512 of the tile = pixels (0..1, 32..33)
@@ -444,6 +465,7 @@ __global__ void k_luminance(const float4 *color, float *lum, int W, int H, int t
 // renderer.rs:293-355. One thread = 4 horizontally adjacent pixels -> one 128-bit store.
 __device__ __forceinline__ uint32_t f2u8(float f) { return min(__float2uint_rz(f), 255u); }  // Rust `as u8`
 __device__ __forceinline__ uint32_t resolve_pixel_rgba(float4 c, float exposure) {
+    if (c.w == 0.0f) return 0u;  // not shaded by this rank (sort-last): contributes nothing to the sum-combine
     float r = c.x * exposure, g = c.y * exposure, b = c.z * exposure;
     const float k = 0.2f, opk = 1.0f + 0.2f;  // util.rs:37-41
     r = r / (r + k) * opk;
@@ -467,4 +489,53 @@ __global__ void __launch_bounds__(256) k_resolve(const float4 *color, int Wp, ui
     } else {
         for (int k = 0; k < 4 && x + k < W; k++) o[k] = resolve_pixel_rgba(c[k], exposure);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sort-last helpers: local ids <-> global seq in the key's low word
+// ---------------------------------------------------------------------------------------------
+// Before the cross-rank min: replace ~local_id by ~seq (seq is global and ordered like the serial schedule).
+__global__ void k_keys_to_global(unsigned long long *keys, size_t n, const TriRecord *records, const uint32_t *clip_ext) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long k = keys[i];
+    if (k == SWR_KEY_EMPTY) return;
+    const uint32_t id = 0xFFFFFFFFu - (uint32_t)k;
+    const uint32_t seq = records[record_of_id(id, clip_ext)].seq;
+    keys[i] = (k & 0xFFFFFFFF00000000ull) | (unsigned long long)(0xFFFFFFFFu - seq);
+}
+
+// After the min: map seq back to a local id when the winner is one of this rank's draws (binary search over the
+// draws' first_tri), else mark it foreign; write the winner's barycentrics (0 when not mine) for the bary exchange.
+__global__ void k_keys_localize(unsigned long long *keys, int tiles_x, int W, int H, const TriRecord *records, const uint32_t *clip_ext,
+                                const DevDraw *draws, const uint32_t *tri_prefix, uint32_t ndraws, const DevPrim *prims, float2 *bary) {
+    int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+    if (px >= W || py >= H) return;
+    const size_t ki = (size_t)((py >> 6) * tiles_x + (px >> 6)) * SWR_TILE_PIXELS + (py & 63) * SWR_TILE + (px & 63);
+    unsigned long long k = keys[ki];
+    float2 b = make_float2(0.0f, 0.0f);
+    if (k != SWR_KEY_EMPTY) {
+        const uint32_t seq = 0xFFFFFFFFu - (uint32_t)k;
+        const uint32_t G = seq >> 3, fan = seq & 7u;
+        uint32_t id = SWR_ID_FOREIGN;
+        if (ndraws > 0 && G >= draws[0].first_tri) {
+            uint32_t lo = 0, hi = ndraws;  // draws[lo].first_tri <= G
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (draws[mid].first_tri <= G)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            const uint32_t t = G - draws[lo].first_tri;
+            if (t < prims[draws[lo].prim].ntris) id = (tri_prefix[lo] + t) * 8u + fan;
+        }
+        if (id != SWR_ID_FOREIGN) {
+            TriRecord r = records[record_of_id(id, clip_ext)];
+            float z;
+            if (r.seq == seq) resolve_pixel(r, W, H, px, py, b.x, b.y, z);
+        }
+        keys[ki] = (k & 0xFFFFFFFF00000000ull) | (unsigned long long)(0xFFFFFFFFu - id);
+    }
+    bary[(size_t)py * W + px] = b;
 }

@@ -71,3 +71,29 @@ def device_tensor(ptr, nbytes, dtype, device):
     typestr = {torch.int32: "<i4", torch.int64: "<i8", torch.uint8: "|u1"}[dtype]
     a.__cuda_array_interface__ = {"shape": (nbytes // itemsize,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
     return torch.as_tensor(a, device=device)
+
+
+def sort_last_frame(r, scene, camera, rank, world, stream, exposure=2.0):
+    """One sort-last frame on this rank: draws are dealt round-robin (draw index % world), keys are
+    min-reduced, barycentrics sum-reduced, every rank shades the pixels whose winner it owns, RGBA8 is sum-reduced.
+    Every rank ends up with the full image in its device pixel buffer. `stream`: torch ExternalStream of r."""
+    import torch
+    import torch.distributed as dist
+    dev = f"cuda:{torch.cuda.current_device()}"
+    r.render_scene(scene, camera, shade=False, shard=rank, nshards=world)
+    r.keys_to_global()
+    kptr, kbytes = r.device_keys_ptr()
+    keys = device_tensor(kptr, kbytes, torch.int64, dev)
+    with torch.cuda.stream(stream):
+        composite_keys_min(keys)
+    r.keys_localize()
+    bary = device_tensor(r.device_bary_ptr(), r.width * r.height * 8, torch.int32, dev).view(torch.float32)
+    with torch.cuda.stream(stream):
+        dist.all_reduce(bary, op=dist.ReduceOp.SUM)
+    rows = tile_row_ranges(r.tiles_y, world)[rank]
+    r.shade_composited(camera, rows[0], rows[1])
+    r.resolve_device_only(exposure)
+    pix = device_tensor(r.device_pixels_ptr(), r.width * r.height * 4, torch.int32, dev)
+    with torch.cuda.stream(stream):
+        dist.all_reduce(pix, op=dist.ReduceOp.SUM)
+    return pix

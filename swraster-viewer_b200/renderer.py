@@ -48,6 +48,11 @@ def load_libraries():
     core.swr_upload_scene.argtypes = [vp, C.POINTER(abi.SceneDesc)]
     core.swr_render.argtypes = [vp, C.POINTER(abi.Camera), C.POINTER(abi.Draw), i32, i32]
     core.swr_shade.argtypes = [vp, C.POINTER(abi.Camera)]
+    core.swr_keys_to_global.argtypes = [vp]
+    core.swr_keys_localize.argtypes = [vp]
+    core.swr_shade_composited.argtypes = [vp, C.POINTER(abi.Camera), i32, i32]
+    core.swr_device_bary.restype = vp
+    core.swr_device_bary.argtypes = [vp]
     core.swr_resolve.argtypes = [vp, f32, vp]
     core.swr_read_tile_luminance.argtypes = [vp, vp]
     core.swr_read_visbuffer.argtypes = [vp, vp, vp, vp, vp]
@@ -205,6 +210,19 @@ class Renderer:
 
     def shade(self, camera):
         self._check_core(self.core.swr_shade(self.ctx, C.byref(camera.abi)))
+
+    # ---- sort-last steps (see include/swr.h) ----------------------------------------------------
+    def keys_to_global(self):
+        self._check_core(self.core.swr_keys_to_global(self.ctx))
+
+    def keys_localize(self):
+        self._check_core(self.core.swr_keys_localize(self.ctx))
+
+    def shade_composited(self, camera, sky_row_begin, sky_row_end):
+        self._check_core(self.core.swr_shade_composited(self.ctx, C.byref(camera.abi), sky_row_begin, sky_row_end))
+
+    def device_bary_ptr(self):
+        return self.core.swr_device_bary(self.ctx)
 
     def synchronize(self):
         self._check_core(self.core.swr_synchronize(self.ctx))
