@@ -99,6 +99,7 @@ struct swr_ctx {
     DevCamera dcam{};
     swr_frame_stats stats{};
     bool rendered_once = false;
+    uint64_t refs_emitted = 0;
 };
 
 template <typename T>
@@ -622,10 +623,19 @@ static int finish_frame(swr_ctx *ctx) {
             swr_frame_stats &st = ctx->stats;
             st.triangles_submitted = ctx->total_tris;
             st.vertices_submitted = ctx->total_verts;
-            st.triangles_binned = c.tris_binned;
+            uint64_t binned = 0, uncovered = 0;
+            for (int k = 0; k < 32; k++) {
+                binned += c.tris_binned[k];
+                uncovered += c.refs_uncovered[k];
+            }
+            st.triangles_binned = binned;
             st.triangles_clipped = c.tris_clipped;
-            st.tile_refs = c.tile_refs;
+            st.tile_refs = c.tile_refs + uncovered;  // the reference's R: every (triangle, tile) packet it would push
+            ctx->refs_emitted = c.tile_refs;
             st.tiles = (uint32_t)ctx->ntiles;
+#ifdef SWR_PROFILE_COUNTERS
+            fprintf(stderr, "[swr dbg] items %llu batches %llu quad-steps %llu fragments %llu warp-iters %llu\n", c.dbg[0], c.dbg[1], c.dbg[2], c.dbg[3], c.dbg[4]);
+#endif
             cudaEventElapsedTime(&st.ms_setup_bin, ctx->ev[0], ctx->ev[1]);
             cudaEventElapsedTime(&st.ms_raster, ctx->ev[1], ctx->ev[2]);
             st.ms_shade = 0.0f;

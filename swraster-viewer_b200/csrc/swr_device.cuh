@@ -94,7 +94,10 @@ struct DevCamera {
 };
 
 struct FrameCounters {
-    unsigned long long tris_binned, tris_clipped, tile_refs;
+    unsigned long long tris_clipped, tile_refs;
+    // statistics spread over 32 slots (block index & 31) so that the per-block atomics do not serialise on one address
+    unsigned long long tris_binned[32];
+    unsigned long long refs_uncovered[32];  // refs of triangles that provably cover no pixel: counted, not emitted
     uint32_t clip_verts;      // bump allocator for ClipVertex
     uint32_t overflow_refs;   // tile_refs exceeded the ref buffer
     uint32_t overflow_clip;   // clip vertex buffer exhausted
@@ -103,6 +106,7 @@ struct FrameCounters {
     uint32_t overflow_ext;    // extension records exhausted
     uint32_t clip_list_n;     // surviving fans >= 1
     uint32_t pad;
+    unsigned long long dbg[8];  // SWR_PROFILE_COUNTERS builds only
 };
 
 // ---------------------------------------------------------------------------------------------

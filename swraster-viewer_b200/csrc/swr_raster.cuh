@@ -67,7 +67,8 @@ __device__ __forceinline__ void count_tiles(uint32_t rect, uint32_t *tile_count,
 // renderer.rs:668-760 minus attribute set-up (deferred to shading). Returns the packed tile rectangle
 // (0 = culled / off-screen / not owned) and writes the record when it survives.
 __device__ __forceinline__ uint32_t emit_triangle(const SetupParams &P, float4 c0, float4 c1, float4 c2, uint32_t slot,
-                                                  uint32_t draw, uint32_t seq, uint32_t clipref) {
+                                                  uint32_t draw, uint32_t seq, uint32_t clipref, bool &nocover) {
+    nocover = false;
     float Wf = (float)P.W, Hf = (float)P.H;
     TriRecord r;
     snap_vertex(c0, Wf, Hf, r.X0, r.Y0);
@@ -85,6 +86,30 @@ __device__ __forceinline__ uint32_t emit_triangle(const SetupParams &P, float4 c
     ty0 = max(ty0, P.row_begin);
     ty1 = min(ty1, P.row_end);
     if (tx1 <= tx0 || ty1 <= ty0) return 0;
+    const uint32_t rect = (uint32_t)tx0 | ((uint32_t)ty0 << 8) | ((uint32_t)tx1 << 16) | ((uint32_t)ty1 << 24);
+    {
+        // The reference bins every surviving triangle, including sub-pixel ones that touch no pixel centre
+        // (SURVEY 8a R6). When the edge arithmetic is provably exact everywhere on screen (|a|*x+|b|*y+|c| < 2^24), coverage
+        // implies a pixel centre inside the triangle's bounding box; if there is none the packet cannot produce a
+        // fragment, so it is only COUNTED (stats equal the reference's) and neither record nor refs are written.
+        const int mnX = min(min(r.X0, r.X1), r.X2), mxX = max(max(r.X0, r.X1), r.X2);
+        const int mnY = min(min(r.Y0, r.Y1), r.Y2), mxY = max(max(r.Y0, r.Y1), r.Y2);
+        const bool no_centre = (((mxX - 8) >> 4) < ((mnX - 8 + 15) >> 4)) || (((mxY - 8) >> 4) < ((mnY - 8 + 15) >> 4));
+        if (no_centre) {
+            const long long xhi = (long long)P.W * 16 + 64, yhi = (long long)P.H * 16 + 64;
+            const int ax[3] = {wsub(r.Y2, r.Y1), wsub(r.Y0, r.Y2), wsub(r.Y1, r.Y0)};
+            const int bx[3] = {wsub(r.X1, r.X2), wsub(r.X2, r.X0), wsub(r.X0, r.X1)};
+            const int cx[3] = {wsub(wmul(r.X2, r.Y1), wmul(r.X1, r.Y2)), wsub(wmul(r.X0, r.Y2), wmul(r.X2, r.Y0)), wsub(wmul(r.X1, r.Y0), wmul(r.X0, r.Y1))};
+            bool ex = true;
+#pragma unroll
+            for (int e = 0; e < 3; e++)
+                ex = ex && ((long long)abs((long long)ax[e]) * xhi + (long long)abs((long long)bx[e]) * yhi + abs((long long)cx[e]) + 1 < (1ll << 24));
+            if (ex) {
+                nocover = true;
+                return rect;
+            }
+        }
+    }
     int aabs = area < 0 ? (int)(0u - (unsigned)area) : area;
     r.ooa = fdiv(1.0f, i2f(aabs));
     r.iw0 = fdiv(1.0f, c0.w);
@@ -102,7 +127,25 @@ __device__ __forceinline__ uint32_t emit_triangle(const SetupParams &P, float4 c
     dst[1] = src[1];
     dst[2] = src[2];
     dst[3] = src[3];
-    return (uint32_t)tx0 | ((uint32_t)ty0 << 8) | ((uint32_t)tx1 << 16) | ((uint32_t)ty1 << 24);
+    return rect;
+}
+
+// Book-keeping for triangles emit_triangle classified as "cannot cover": they count as binned and their tile
+// references count towards R, exactly like the reference's packets, but nothing is written. Block-collective:
+// one pair of atomics per block, spread over 32 counter slots. Returns the rectangle to bin (0 if uncovered).
+__device__ __forceinline__ uint32_t account_block(uint32_t rect, bool nocover, FrameCounters *counters, uint32_t *s_unc) {
+    uint32_t n = 0;
+    if (nocover && rect) n = (((rect >> 16) & 0xFF) - (rect & 0xFF)) * ((rect >> 24) - ((rect >> 8) & 0xFF));
+    if (threadIdx.x == 0) *s_unc = 0;
+    const int binned = __syncthreads_count(rect != 0);
+    const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, n);
+    if ((threadIdx.x & 31) == 0 && tot) atomicAdd(s_unc, tot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (binned) atomicAdd(&counters->tris_binned[blockIdx.x & 31], (unsigned long long)binned);
+        if (*s_unc) atomicAdd(&counters->refs_uncovered[blockIdx.x & 31], (unsigned long long)*s_unc);
+    }
+    return nocover ? 0u : rect;
 }
 
 // glam dot4 with the clip-plane constants of renderer.rs:581-588: (px*x + pz*z) + (py*y + pw*w)
@@ -114,14 +157,14 @@ __device__ __forceinline__ float plane_dist(int pl, float4 v) {
 }
 
 __global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams P) {
-    __shared__ uint32_t s_draw0;
+    __shared__ uint32_t s_draw0, s_unc;
     const uint32_t tid = threadIdx.x;
     const uint32_t g0 = blockIdx.x * SETUP_THREADS;
     if (tid == 0) s_draw0 = find_draw(P.tri_prefix, P.ndraws, g0);
     __syncthreads();
     const uint32_t g = g0 + tid;
     uint32_t rect = 0;
-    bool queued = false;
+    bool queued = false, nocover = false;
     if (g < P.total_tris) {
         uint32_t d = s_draw0;
         while (g >= P.tri_prefix[d + 1]) d++;
@@ -151,18 +194,16 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams P) {
                         state = 2;
                 }
             }
-            if (state == 0) rect = emit_triangle(P, c0, c1, c2, slot, d, seq, SWR_NO_CLIP);
+            if (state == 0) rect = emit_triangle(P, c0, c1, c2, slot, d, seq, SWR_NO_CLIP, nocover);
             queued = state == 2;
-            P.rects[slot] = rect;  // k_clip overwrites it when fan 0 of a clipped polygon survives
         } else {
-            rect = emit_triangle(P, c0, c1, c2, slot, d, seq, SWR_NO_CLIP);
-            P.rects[slot] = rect;
+            rect = emit_triangle(P, c0, c1, c2, slot, d, seq, SWR_NO_CLIP, nocover);
         }
+        P.rects[slot] = nocover ? 0u : rect;  // k_clip overwrites it when fan 0 of a clipped polygon survives
     }
-    count_tiles(rect, P.tile_count, P.tiles_x);
     const unsigned lane = tid & 31;
-    unsigned surv = __ballot_sync(0xFFFFFFFFu, rect != 0);
-    if (lane == 0 && surv) atomicAdd(&P.counters->tris_binned, (unsigned long long)__popc(surv));
+    rect = account_block(rect, nocover, P.counters, &s_unc);
+    count_tiles(rect, P.tile_count, P.tiles_x);
     // warp-aggregated append to the clip queue
     unsigned qm = __ballot_sync(0xFFFFFFFFu, queued);
     if (qm) {
@@ -181,6 +222,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams P) {
 
 __global__ void __launch_bounds__(CLIP_THREADS) k_clip(SetupParams P) {
     __shared__ float s_poly[CLIP_GROUPS][2][16][17];  // renderer.rs:31-37 as 16 floats per vertex (+1 pad)
+    __shared__ uint32_t s_unc;
     const uint32_t qn = P.counters->clip_queue_n;
     const uint32_t tid = threadIdx.x;
     const uint32_t grp = tid >> 4, lane = tid & 15;
@@ -188,6 +230,7 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip(SetupParams P) {
     for (uint32_t base = blockIdx.x * CLIP_GROUPS; base < qn; base += gridDim.x * CLIP_GROUPS) {
         const uint32_t e = base + grp;
         uint32_t rect_out = 0;
+        bool nocover_out = false;
         if (e < qn) {
             const uint32_t gg = P.clip_queue[e];
             const uint32_t dd = find_draw(P.tri_prefix, P.ndraws, gg);
@@ -285,16 +328,14 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip(SetupParams P) {
                     const uint32_t fan = lane - 1;
                     const uint32_t sl = fan == 0 ? gg : P.total_tris + ext + fan - 1;
                     rect_out = emit_triangle(P, make_float4(v0[0], v0[1], v0[2], v0[3]), make_float4(v1[0], v1[1], v1[2], v1[3]),
-                                             make_float4(v2[0], v2[1], v2[2], v2[3]), sl, dd, (dr.first_tri + ttri) * 8u + fan, vbase);
-                    P.rects[sl] = rect_out;
-                    if (fan > 0 && rect_out != 0) P.clip_list[atomicAdd(&P.counters->clip_list_n, 1u)] = gg * 8u + fan;
+                                             make_float4(v2[0], v2[1], v2[2], v2[3]), sl, dd, (dr.first_tri + ttri) * 8u + fan, vbase, nocover_out);
+                    P.rects[sl] = nocover_out ? 0u : rect_out;
+                    if (fan > 0 && rect_out != 0 && !nocover_out) P.clip_list[atomicAdd(&P.counters->clip_list_n, 1u)] = gg * 8u + fan;
                 }
             }
         }
-        __syncwarp();  // both half-warps reconverge for the warp-aggregated counting
+        rect_out = account_block(rect_out, nocover_out, P.counters, &s_unc);  // block-uniform loop: safe to use block barriers
         count_tiles(rect_out, P.tile_count, P.tiles_x);
-        unsigned sv = __ballot_sync(0xFFFFFFFFu, rect_out != 0);
-        if ((tid & 31) == 0 && sv) atomicAdd(&P.counters->tris_binned, (unsigned long long)__popc(sv));
     }
 }
 
@@ -424,7 +465,7 @@ struct RasterParams {
     const uint32_t *tile_order;
     const uint32_t *clip_ext;
     unsigned long long *keys;  // tile-major: tile * 4096 + y * 64 + x; low word = ~id
-    const FrameCounters *counters;
+    FrameCounters *counters;
     int W, H, tiles_x, tiles_y;
     int row_begin, row_end;
 };
@@ -664,6 +705,13 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
         if (tid == 0) tb.prefix[0] = 0;
         __syncthreads();
         const uint32_t total = tb.prefix[RASTER_THREADS];
+#ifdef SWR_PROFILE_COUNTERS
+        if (tid == 0) {
+            atomicAdd((unsigned long long *)&P.counters->dbg[0], (unsigned long long)total);  // items (quad rows)
+            atomicAdd((unsigned long long *)&P.counters->dbg[1], 1ull);                       // batches
+        }
+        unsigned long long dbg_steps = 0, dbg_frags = 0, dbg_maxsteps = 0;
+#endif
         int qn = 0;  // fragments queued by this warp (warp-uniform)
         for (uint32_t it0 = (uint32_t)wid * 32u; it0 < total; it0 += RASTER_THREADS) {  // warp-uniform trip count
             const uint32_t it = it0 + lane;
@@ -684,6 +732,10 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
                 row_setup(tb, lo, it - tb.prefix[lo], tile_x0, tile_y0, st);
             }
             const int maxlen = __reduce_max_sync(0xFFFFFFFFu, st.len);
+#ifdef SWR_PROFILE_COUNTERS
+            dbg_steps += st.len;
+            if (lane == 0) dbg_maxsteps += maxlen;
+#endif
             for (int s = 0; s < maxlen; s++) {
                 const bool act = s < st.len;
 #pragma unroll
@@ -698,6 +750,9 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
                             fq.w2[pos] = st.v[l][2];
                         }
                         qn += __popc(m);
+#ifdef SWR_PROFILE_COUNTERS
+                        if (lane == 0) dbg_frags += __popc(m);
+#endif
                         if (qn >= FRAGQ_DRAIN) qn = drain_queue(skeys, tb, fq, qn, lane);
                     }
                 }
@@ -709,6 +764,13 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
             }
         }
         while (qn > 0) qn = drain_queue(skeys, tb, fq, qn, lane);  // fragments reference this batch's packets
+#ifdef SWR_PROFILE_COUNTERS
+        atomicAdd((unsigned long long *)&P.counters->dbg[2], dbg_steps);      // quads stepped (useful lanes)
+        if (lane == 0) {
+            atomicAdd((unsigned long long *)&P.counters->dbg[3], dbg_frags);     // covered pixels
+            atomicAdd((unsigned long long *)&P.counters->dbg[4], dbg_maxsteps);  // warp row-loop iterations
+        }
+#endif
     }
     __syncthreads();
     unsigned long long *out = P.keys + (size_t)tile * SWR_TILE_PIXELS;
