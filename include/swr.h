@@ -248,6 +248,10 @@ void *swr_device_bary(swr_ctx *ctx); /* W*H float2, row-major */
  * that HOST buffer and the call synchronises. */
 int swr_resolve(swr_ctx *ctx, float exposure, uint32_t *out_pixels);
 
+/* Per-tile triangle-reference counts of the last frame (row-major tiles; 0 for tiles this context does not own):
+ * the cost signal for balancing sort-first row bands. */
+int swr_read_tile_counts(swr_ctx *ctx, uint32_t *out_per_tile);
+
 /* Per-tile metering luminance (tilerasterizer.rs:103-106), row-major tiles. */
 int swr_read_tile_luminance(swr_ctx *ctx, float *out_per_tile);
 

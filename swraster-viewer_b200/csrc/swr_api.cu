@@ -7,6 +7,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include "../../include/swr.h"
 #include "swr_shade.cuh"
 
@@ -81,6 +82,7 @@ struct swr_ctx {
     bool composited = false;
     int sky_r0 = 0, sky_r1 = 0;
     DevBuf<FrameCounters> counters;
+    DevBuf<unsigned long long> dbg_tiles;
     DevBuf<uint32_t> rsqrt_tab;
     int rsqrt_bits = 0;
     bool rsqrt_on = false;
@@ -535,8 +537,10 @@ static int launch_frame(swr_ctx *ctx) {
             k_clip<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), CLIP_THREADS, 0, s>>>(sp);
         }
     }
+    const size_t unit_cap = (size_t)ctx->ntiles + ctx->refs.cap / RASTER_UNIT_REFS + 1;
+    if (ctx->tile_order.reserve(unit_cap) != cudaSuccess) return SWR_ERR_OOM;
     k_scan_tiles<<<1, 1024, 0, s>>>(ctx->tile_count.p, ctx->tile_offset.p, ctx->tile_cursor.p, ctx->ntiles, ctx->counters.p, (uint32_t)ctx->refs.cap,
-                                    ctx->tile_order.p, rb * ctx->tiles_x, re * ctx->tiles_x);
+                                    ctx->tile_order.p, (uint32_t)unit_cap, rb * ctx->tiles_x, re * ctx->tiles_x);
     if (tris > 0) {
         k_scatter<<<(unsigned)((tris + 255) / 256), 256, 0, s>>>(ctx->rects.p, (uint32_t)tris, ctx->tile_cursor.p, ctx->refs.p, ctx->counters.p, ctx->tiles_x);
         if (clip_tris > 0)
@@ -548,17 +552,23 @@ static int launch_frame(swr_ctx *ctx) {
         rp.records = ctx->records.p;
         rp.refs = ctx->refs.p;
         rp.tile_offset = ctx->tile_offset.p;
-        rp.tile_order = ctx->tile_order.p;
+        rp.unit_list = ctx->tile_order.p;
         rp.clip_ext = ctx->clip_ext.p;
         rp.keys = ctx->keys.p;
         rp.counters = ctx->counters.p;
+#ifdef SWR_PROFILE_COUNTERS
+        if (ctx->dbg_tiles.reserve((size_t)ctx->ntiles * 4) == cudaSuccess) rp.dbg_tiles = ctx->dbg_tiles.p;
+#endif
         rp.W = ctx->W;
         rp.H = ctx->H;
         rp.tiles_x = ctx->tiles_x;
         rp.tiles_y = ctx->tiles_y;
         rp.row_begin = rb;
         rp.row_end = re;
-        k_raster_tiles<<<(unsigned)((re - rb) * ctx->tiles_x), RASTER_THREADS, raster_smem_bytes(), s>>>(rp);
+        // keys of the owned rows start EMPTY: tiles split over several CTAs merge into them with atomicMin
+        CK(cudaMemsetAsync(ctx->keys.p + (size_t)rb * ctx->tiles_x * SWR_TILE_PIXELS, 0xFF, (size_t)(re - rb) * ctx->tiles_x * SWR_TILE_PIXELS * 8, s));
+        const size_t owned = (size_t)(re - rb) * ctx->tiles_x;
+        k_raster_tiles<<<(unsigned)(owned + ctx->refs.cap / RASTER_UNIT_REFS + 1), RASTER_THREADS, raster_smem_bytes(), s>>>(rp);
     }
     CK(cudaEventRecord(ctx->ev[2], s));
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
@@ -634,6 +644,22 @@ static int finish_frame(swr_ctx *ctx) {
             ctx->refs_emitted = c.tile_refs;
             st.tiles = (uint32_t)ctx->ntiles;
 #ifdef SWR_PROFILE_COUNTERS
+            if (ctx->dbg_tiles.p) {
+                std::vector<unsigned long long> h((size_t)ctx->ntiles * 4);
+                cudaMemcpy(h.data(), ctx->dbg_tiles.p, h.size() * 8, cudaMemcpyDeviceToHost);
+                unsigned long long mx = 0, sum = 0, mxi = 0;
+                for (int t = 0; t < ctx->ntiles; t++) {
+                    sum += h[t * 4];
+                    if (h[t * 4] > mx) { mx = h[t * 4]; mxi = t; }
+                }
+                fprintf(stderr, "[swr dbg] tile cycles: max %llu (tile %llu refs %llu items %llu slot %llu) mean %llu sum/592 %llu\n", mx, mxi, h[mxi * 4 + 1],
+                        h[mxi * 4 + 2], h[mxi * 4 + 3], sum / ctx->ntiles, sum / 592);
+                // 10 slowest tiles
+                std::vector<int> idx(ctx->ntiles);
+                for (int t = 0; t < ctx->ntiles; t++) idx[t] = t;
+                std::partial_sort(idx.begin(), idx.begin() + 10, idx.end(), [&](int a, int b) { return h[a * 4] > h[b * 4]; });
+                for (int k = 0; k < 10; k++) fprintf(stderr, "   tile %d cycles %llu refs %llu items %llu slot %llu\n", idx[k], h[idx[k] * 4], h[idx[k] * 4 + 1], h[idx[k] * 4 + 2], h[idx[k] * 4 + 3]);
+            }
             fprintf(stderr, "[swr dbg] items %llu batches %llu quad-steps %llu fragments %llu warp-iters %llu\n", c.dbg[0], c.dbg[1], c.dbg[2], c.dbg[3], c.dbg[4]);
 #endif
             cudaEventElapsedTime(&st.ms_setup_bin, ctx->ev[0], ctx->ev[1]);
@@ -766,6 +792,14 @@ int swr_resolve(swr_ctx *ctx, float exposure, uint32_t *out_pixels) {
 int swr_synchronize(swr_ctx *ctx) {
     if (!ctx) return SWR_ERR_INVALID;
     return finish_frame(ctx);
+}
+
+int swr_read_tile_counts(swr_ctx *ctx, uint32_t *out) {
+    if (!ctx || !out) return SWR_ERR_INVALID;
+    int rc;
+    if ((rc = finish_frame(ctx))) return rc;
+    CK(cudaMemcpy(out, ctx->tile_count.p, ctx->ntiles * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return SWR_OK;
 }
 
 int swr_read_tile_luminance(swr_ctx *ctx, float *out) {

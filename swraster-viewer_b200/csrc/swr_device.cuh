@@ -105,7 +105,7 @@ struct FrameCounters {
     uint32_t ext_records;     // bump allocator for the records of fans >= 1
     uint32_t overflow_ext;    // extension records exhausted
     uint32_t clip_list_n;     // surviving fans >= 1
-    uint32_t pad;
+    uint32_t raster_units;    // entries of the raster work list
     unsigned long long dbg[8];  // SWR_PROFILE_COUNTERS builds only
 };
 

@@ -340,11 +340,16 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip(SetupParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// exclusive scan over tiles (<= 65,025) + heaviest-first order of the owned tiles: one CTA
+// exclusive scan over tiles (<= 65,025) + the raster work list: one CTA.
+// A raster unit is (tile, chunk of <= RASTER_UNIT_REFS refs); tiles with more refs are split over several CTAs (their
+// keys are merged with a global 64-bit atomicMin), so one hot tile cannot become the long pole of the frame.
+// Units are ordered heaviest-first (bit-length buckets of their ref count).
 // ---------------------------------------------------------------------------------------------
+#define RASTER_UNIT_REFS 2048u
+
 __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count, uint32_t *tile_offset, uint32_t *tile_cursor, int ntiles,
-                                                     FrameCounters *counters, uint32_t ref_capacity, uint32_t *tile_order, int tile_begin,
-                                                     int tile_end) {
+                                                     FrameCounters *counters, uint32_t ref_capacity, uint32_t *unit_list, uint32_t unit_capacity,
+                                                     int tile_begin, int tile_end) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
     __shared__ uint32_t s_hist[34], s_cur[34];
@@ -377,7 +382,11 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
         if (i < ntiles) {
             tile_offset[i] = excl;
             tile_cursor[i] = excl;
-            if (i >= tile_begin && i < tile_end) atomicAdd(&s_hist[v ? 32 - __clz(v) : 0], 1u);  // bucket = bit length
+            if (i >= tile_begin && i < tile_end) {
+                const uint32_t nfull = v / RASTER_UNIT_REFS, rem = v % RASTER_UNIT_REFS;
+                if (nfull) atomicAdd(&s_hist[32 - __clz(RASTER_UNIT_REFS)], nfull);
+                if (rem || !nfull) atomicAdd(&s_hist[rem ? 32 - __clz(rem) : 0], 1u);  // an empty tile still needs its keys written
+            }
         }
         __syncthreads();
         if (tid == 1023) s_carry = excl + v;
@@ -392,11 +401,16 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
             s_cur[b] = acc;
             acc += s_hist[b];
         }
+        counters->raster_units = acc <= unit_capacity ? acc : 0;
+        if (acc > unit_capacity) counters->overflow_refs = 1;  // cannot happen: capacity covers ntiles + ref_capacity / unit
     }
     __syncthreads();
+    if (counters->overflow_refs) return;
     for (int i = tile_begin + tid; i < tile_end; i += 1024) {
-        uint32_t v = tile_count[i];
-        tile_order[atomicAdd(&s_cur[v ? 32 - __clz(v) : 0], 1u)] = (uint32_t)i;
+        const uint32_t v = tile_count[i];
+        const uint32_t nfull = v / RASTER_UNIT_REFS, rem = v % RASTER_UNIT_REFS;
+        for (uint32_t k = 0; k < nfull; k++) unit_list[atomicAdd(&s_cur[32 - __clz(RASTER_UNIT_REFS)], 1u)] = ((uint32_t)i << 12) | k;
+        if (rem || !nfull) unit_list[atomicAdd(&s_cur[rem ? 32 - __clz(rem) : 0], 1u)] = ((uint32_t)i << 12) | nfull;
     }
 }
 
@@ -462,10 +476,11 @@ struct RasterParams {
     const TriRecord *records;
     const uint32_t *refs;
     const uint32_t *tile_offset;
-    const uint32_t *tile_order;
+    const uint32_t *unit_list;  // tile << 12 | chunk, heaviest first; counters->raster_units entries
     const uint32_t *clip_ext;
     unsigned long long *keys;  // tile-major: tile * 4096 + y * 64 + x; low word = ~id
     FrameCounters *counters;
+    unsigned long long *dbg_tiles;  // SWR_PROFILE_COUNTERS: per tile {cycles, refs, items, launch slot}
     int W, H, tiles_x, tiles_y;
     int row_begin, row_end;
 };
@@ -622,7 +637,10 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
     FragQueue *fqs = reinterpret_cast<FragQueue *>(smem_raw + SWR_TILE_PIXELS * 8 + sizeof(TileBatch));
 
     if (P.counters->overflow_refs || P.counters->overflow_ext) return;  // lists incomplete; the host replays the frame
-    const int tile = (int)P.tile_order[blockIdx.x];
+    if (blockIdx.x >= P.counters->raster_units) return;
+    const uint32_t unit = P.unit_list[blockIdx.x];
+    const int tile = (int)(unit >> 12);
+    const uint32_t chunk = unit & 0xFFFu;
     const int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
     const int tile_x0 = tx * SWR_TILE, tile_y0 = ty * SWR_TILE;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -630,8 +648,14 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
     const unsigned lt_mask = (1u << lane) - 1u;
 
     for (int i = tid; i < SWR_TILE_PIXELS; i += RASTER_THREADS) skeys[i] = SWR_KEY_EMPTY;
+#ifdef SWR_PROFILE_COUNTERS
+    const long long dbg_t0 = clock64();
+    unsigned long long dbg_items = 0;
+#endif
 
-    const uint32_t beg = P.tile_offset[tile], end = P.tile_offset[tile + 1];
+    const uint32_t tile_beg = P.tile_offset[tile], tile_end = P.tile_offset[tile + 1];
+    const bool split = tile_end - tile_beg > RASTER_UNIT_REFS;  // several CTAs share this tile: merge with atomics at the end
+    const uint32_t beg = tile_beg + chunk * RASTER_UNIT_REFS, end = min(beg + RASTER_UNIT_REFS, tile_end);
     // software pipeline over batches: the record of batch n+1 and the ref of batch n+2 are in flight while batch n is rasterised
     uint32_t slot_next = 0, slot_next2 = 0;
     uint4 rq0 = make_uint4(0, 0, 0, 0), rq1 = rq0, rq2 = rq0, rq3 = rq0;
@@ -706,6 +730,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
         __syncthreads();
         const uint32_t total = tb.prefix[RASTER_THREADS];
 #ifdef SWR_PROFILE_COUNTERS
+        dbg_items += total;
         if (tid == 0) {
             atomicAdd((unsigned long long *)&P.counters->dbg[0], (unsigned long long)total);  // items (quad rows)
             atomicAdd((unsigned long long *)&P.counters->dbg[1], 1ull);                       // batches
@@ -774,7 +799,22 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
     }
     __syncthreads();
     unsigned long long *out = P.keys + (size_t)tile * SWR_TILE_PIXELS;
-    for (int i = tid; i < SWR_TILE_PIXELS; i += RASTER_THREADS) out[i] = skeys[i];
+    if (!split) {
+        for (int i = tid; i < SWR_TILE_PIXELS; i += RASTER_THREADS) out[i] = skeys[i];
+    } else {  // the key buffer was reset to EMPTY before the launch
+        for (int i = tid; i < SWR_TILE_PIXELS; i += RASTER_THREADS) {
+            const unsigned long long k = skeys[i];
+            if (k != SWR_KEY_EMPTY) atomicMin(&out[i], k);
+        }
+    }
+#ifdef SWR_PROFILE_COUNTERS
+    if (tid == 0 && P.dbg_tiles && chunk == 0) {
+        P.dbg_tiles[tile * 4 + 0] = (unsigned long long)(clock64() - dbg_t0);
+        P.dbg_tiles[tile * 4 + 1] = end - beg;
+        P.dbg_tiles[tile * 4 + 2] = dbg_items;
+        P.dbg_tiles[tile * 4 + 3] = blockIdx.x;
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------

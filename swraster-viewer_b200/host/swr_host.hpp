@@ -243,8 +243,31 @@ inline FrustumTestResult test_sphere_frustum(const float *model, const float *sp
 
 // Host half of render_scene: renderer.rs:357-367 (node order) and :369-468 (classification, mvp).
 // `shard`/`nshards` select every draw whose index % nshards == shard (sort-last); ids stay global.
+// Sort-first helper (not in the reference): true when the world-space sphere cannot touch the pixel rows [y0, y1) of a
+// `height`-row image. Conservative: the band is widened by 2 pixels (snapping, exclusive bbox) and the radius uses the
+// LARGEST axis scale of the model matrix. A draw culled here has no triangle whose bounding box reaches the band, so
+// dropping it from this rank's draw list changes nothing in the band (ids stay global through first_triangle).
+inline bool sphere_outside_row_band(const float *model, const float *sphere, const swr_camera &cam, int y0, int y1, int height) {
+    float lx = std::sqrt(dot4(model + 0, model + 0)), ly = std::sqrt(dot4(model + 4, model + 4)), lz = std::sqrt(dot4(model + 8, model + 8));
+    float radius = sphere[3] * std::fmax(lx, std::fmax(ly, lz)) * 1.0001f;
+    float c[4], cv[4];
+    for (int r = 0; r < 3; r++) c[r] = ((model[r] * sphere[0] + model[4 + r] * sphere[1]) + model[8 + r] * sphere[2]) + model[12 + r];
+    c[3] = 1.0f;
+    mul_vec4(cam.view_matrix, c, cv);
+    const float *top = cam.view_clip_planes[4];  // normalize(0, 1, -tan_y): rendercamera.rs:146
+    if (!(top[1] > 0.0f)) return false;
+    float h = -top[1] / top[2];                  // 1 / tan(fov/2) == projection[1][1]
+    if (!(h > 0.0f) || !std::isfinite(h)) return false;
+    float nhi = 1.0f - 2.0f * (float)(y0 - 2) / (float)height;  // ndc y of the band's upper edge
+    float nlo = 1.0f - 2.0f * (float)(y1 + 2) / (float)height;
+    // inside the band (in front of the camera, z < 0):  nlo <= h*y / (-z) <= nhi
+    float du = (h * cv[1] + nhi * cv[2]) / std::sqrt(h * h + nhi * nhi);  // > 0: above the upper plane
+    float dl = (h * cv[1] + nlo * cv[2]) / std::sqrt(h * h + nlo * nlo);  // < 0: below the lower plane
+    return du > radius || dl < -radius;
+}
+
 inline void build_draw_list(const swr_scene_desc &sc, const swr_camera &cam, std::vector<swr_draw> &draws, int shard = 0,
-                            int nshards = 1) {
+                            int nshards = 1, int band_y0 = 0, int band_y1 = 0, int band_height = 0) {
     std::vector<uint32_t> nodes_by_distance(sc.nnodes);
     std::vector<float> key(sc.nnodes);
     for (uint32_t i = 0; i < sc.nnodes; i++) {
@@ -276,7 +299,8 @@ inline void build_draw_list(const swr_scene_desc &sc, const swr_camera &cam, std
             FrustumTestResult t = test_sphere_frustum(node.transform, prim.bounding_sphere, cam);
             if (t == FrustumTestResult::Outside) continue;
             uint32_t ntris = prim.nindices / 3;
-            if ((int)(di % (uint32_t)nshards) == shard) {
+            const bool band_culled = band_y1 > band_y0 && sphere_outside_row_band(node.transform, prim.bounding_sphere, cam, band_y0, band_y1, band_height);
+            if ((int)(di % (uint32_t)nshards) == shard && !band_culled) {
                 swr_draw d{};
                 std::memcpy(d.model, model.m, 64);
                 std::memcpy(d.mvp, mvp.m, 64);
@@ -359,7 +383,11 @@ class Renderer {
     swr_ctx *ctx() const { return ctx_; }
     float auto_exposure() const { return auto_exposure_; }
     const std::vector<swr_draw> &draws() const { return draws_; }
-    void set_tile_rows(int r0, int r1) { check(swr_set_tile_rows(ctx_, r0, r1), "swr_set_tile_rows"); }
+    void set_tile_rows(int r0, int r1) {
+        check(swr_set_tile_rows(ctx_, r0, r1), "swr_set_tile_rows");
+        row0_ = r0;
+        row1_ = r1;
+    }
 
     // render_scene(&mut self, scene, camera) — renderer.rs:201
     void render_scene(const Scene &scene, const RenderCamera &camera) { render_scene(scene, camera.to_abi()); }
@@ -368,7 +396,9 @@ class Renderer {
             check(swr_upload_scene(ctx_, scene.desc), "swr_upload_scene");
             uploaded_ = scene.desc;
         }
-        build_draw_list(*scene.desc, cam, draws_, shard, nshards);
+        const int tiles_y = (height_ + SWR_TILE_SIZE - 1) / SWR_TILE_SIZE;
+        const bool band = row1_ > row0_ && (row0_ > 0 || row1_ < tiles_y);  // sort-first: drop draws that cannot reach my rows
+        build_draw_list(*scene.desc, cam, draws_, shard, nshards, band ? row0_ * SWR_TILE_SIZE : 0, band ? row1_ * SWR_TILE_SIZE : 0, height_);
         check(swr_render(ctx_, &cam, draws_.data(), (int)draws_.size(), shade ? 1 : 0), "swr_render");
     }
 
@@ -411,6 +441,7 @@ class Renderer {
     }
     int width_, height_;
     int rsqrt_bits_ = 0;
+    int row0_ = 0, row1_ = 0;
     swr_ctx *ctx_ = nullptr;
     const swr_scene_desc *uploaded_ = nullptr;
     std::vector<swr_draw> draws_;

@@ -49,6 +49,18 @@ int swrh_render_scene(void *r, const swr_scene_desc *scene, const swr_camera *ca
     SWRH_TRY(((swr::Renderer *)r)->render_scene(swr::Scene(scene), *cam, shade != 0, shard, nshards));
 }
 
+int swrh_build_draws_band(const swr_scene_desc *scene, const swr_camera *cam, swr_draw *out, int max_draws, int y0, int y1, int height) {
+    try {
+        std::vector<swr_draw> draws;
+        swr::build_draw_list(*scene, *cam, draws, 0, 1, y0, y1, height);
+        for (size_t i = 0; i < draws.size() && (int)i < max_draws; i++) out[i] = draws[i];
+        return (int)draws.size();
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+int swrh_num_draws(void *r) { return (int)((swr::Renderer *)r)->draws().size(); }
 int swrh_update_auto_exposure(void *r, float dt) { SWRH_TRY(((swr::Renderer *)r)->update_auto_exposure(dt)); }
 float swrh_auto_exposure(void *r) { return ((swr::Renderer *)r)->auto_exposure(); }
 

@@ -22,6 +22,23 @@ def tile_row_ranges(tiles_y, world):
     return out
 
 
+def balanced_row_ranges(tile_counts, world, pixel_cost=2000.0):
+    """Contiguous tile-row bands with (nearly) equal cost. tile_counts: (tiles_y, tiles_x) refs per tile from a full
+    probe frame (Renderer.read_tile_counts) — identical on every rank, so all ranks derive the same split without
+    communicating. Row cost = refs + pixel_cost per tile (raster work + shading work)."""
+    tiles_y, tiles_x = tile_counts.shape
+    cost = tile_counts.astype(np.float64).sum(axis=1) + pixel_cost * tiles_x
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    cuts = [0]
+    for k in range(1, world):
+        target = cum[-1] * k / world
+        r = int(np.searchsorted(cum, target))
+        r = r if abs(cum[min(r, tiles_y)] - target) <= abs(cum[max(r - 1, 0)] - target) else r - 1
+        cuts.append(min(max(r, cuts[-1] + (1 if tiles_y - cuts[-1] > world - k else 0)), tiles_y - (world - k)))
+    cuts.append(tiles_y)
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
 def gather_strips(image, ranges, height, dst=0):
     """image: (H, W) int32 torch tensor whose rows [64*r0, 64*r1) are valid on this rank.
     Returns the assembled image on `dst` (in place in `image`), None elsewhere. Uses send/recv so strips of

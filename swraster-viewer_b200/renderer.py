@@ -55,6 +55,7 @@ def load_libraries():
     core.swr_device_bary.argtypes = [vp]
     core.swr_resolve.argtypes = [vp, f32, vp]
     core.swr_read_tile_luminance.argtypes = [vp, vp]
+    core.swr_read_tile_counts.argtypes = [vp, vp]
     core.swr_read_visbuffer.argtypes = [vp, vp, vp, vp, vp]
     core.swr_read_color.argtypes = [vp, vp]
     core.swr_synchronize.argtypes = [vp]
@@ -80,6 +81,7 @@ def load_libraries():
     host.swrh_reference_rsqrt_bits.argtypes = [vp]
     host.swrh_render_scene.argtypes = [vp, C.POINTER(abi.SceneDesc), C.POINTER(abi.Camera), i32, i32, i32]
     host.swrh_update_auto_exposure.argtypes = [vp, f32]
+    host.swrh_num_draws.argtypes = [vp]
     host.swrh_auto_exposure.restype = f32
     host.swrh_auto_exposure.argtypes = [vp]
     host.swrh_blit_to_buffer.argtypes = [vp, vp, C.c_size_t, C.c_size_t]
@@ -194,6 +196,11 @@ class Renderer:
         self._scene = scene  # keep the arrays alive while the context references the descriptor
         self._check(self.host.swrh_render_scene(self._h, C.byref(scene.desc()), C.byref(camera.abi), int(shade), shard, nshards))
 
+    @property
+    def num_draws(self):
+        """Draws submitted by the last render_scene (after frustum / band culling)."""
+        return self.host.swrh_num_draws(self._h)
+
     def update_auto_exposure(self, delta_time):
         self._check(self.host.swrh_update_auto_exposure(self._h, delta_time))
 
@@ -243,6 +250,11 @@ class Renderer:
         out = np.empty(self.tiles_x * self.tiles_y, np.float32)
         self._check_core(self.core.swr_read_tile_luminance(self.ctx, out.ctypes.data))
         return out
+
+    def read_tile_counts(self):
+        out = np.empty(self.tiles_x * self.tiles_y, np.uint32)
+        self._check_core(self.core.swr_read_tile_counts(self.ctx, out.ctypes.data))
+        return out.reshape(self.tiles_y, self.tiles_x)
 
     def stats(self):
         st = abi.FrameStats()

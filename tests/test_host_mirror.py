@@ -11,7 +11,7 @@ import pytest
 import swraster_viewer_b200 as swr
 from swraster_viewer_b200 import abi, scenes
 from swraster_viewer_b200.renderer import build_draws
-from swraster_viewer_b200.multigpu import tile_row_ranges
+from swraster_viewer_b200.multigpu import tile_row_ranges, balanced_row_ranges
 from helpers import small_configs, SMALL
 
 
@@ -70,6 +70,43 @@ def test_tile_row_ranges_partition():
             assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
             sizes = [b - a for a, b in r]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_balanced_row_ranges_partition_and_balance():
+    rng = np.random.default_rng(3)
+    for tiles_y in (17, 34, 68):
+        counts = (rng.random((tiles_y, 60)) ** 4 * 30000).astype(np.uint32)
+        counts[tiles_y // 3] *= 6  # one very heavy row
+        cost = counts.sum(1) + 2000.0 * 60
+        for world in (1, 2, 4, 8):
+            r = balanced_row_ranges(counts, world)
+            assert len(r) == world and r[0][0] == 0 and r[-1][1] == tiles_y
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:])) and all(b > a for a, b in r)
+            band = [cost[a:b].sum() for a, b in r]
+            even = [cost[a:b].sum() for a, b in tile_row_ranges(tiles_y, world)]
+            assert max(band) <= max(even) * 1.001  # never worse than the even split
+
+
+def test_band_culling_is_conservative():
+    """Draws dropped for a row band must have no triangle bbox inside the band: the union of the per-band lists is the
+    full list and every draw kept by the oracle-equivalent full list appears in each band it can touch."""
+    import ctypes as C
+    _, host = swr.load_libraries()
+    host.swrh_build_draws_band = getattr(host, "swrh_build_draws_band")
+    name, scene, spec, W, H = small_configs()[2]
+    cam = swr.RenderCamera.from_spec(spec, W, H)
+    full, n = build_draws(scene, cam)
+    keys_full = {(full[i].first_triangle, full[i].primitive) for i in range(n)}
+    tiles_y = (H + 63) // 64
+    seen = set()
+    for r0, r1 in tile_row_ranges(tiles_y, 3):
+        arr = (abi.Draw * n)()
+        m = host.swrh_build_draws_band(C.byref(scene.desc()), C.byref(cam.abi), arr, n, r0 * 64, r1 * 64, H)
+        assert 0 < m <= n
+        band = {(arr[i].first_triangle, arr[i].primitive) for i in range(m)}
+        assert band <= keys_full
+        seen |= band
+    assert len(seen) > 0.5 * len(keys_full)
 
 
 def _free_port():
