@@ -50,6 +50,7 @@ struct Staging {  // pinned host mirror of the per-frame draw table, rotated so 
 
 struct swr_ctx {
     int device = 0;
+    int num_sms = 148;
     int W = 0, H = 0, tiles_x = 0, tiles_y = 0, ntiles = 0;
     int row_begin = 0, row_end = 0;
     cudaStream_t stream = nullptr;
@@ -158,6 +159,7 @@ swr_ctx *swr_create(int width, int height, int device) {
     }
     swr_ctx *ctx = new swr_ctx();
     ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
     ctx->W = width;
     ctx->H = height;
     ctx->tiles_x = (width + SWR_TILE - 1) / SWR_TILE;
@@ -537,10 +539,11 @@ static int launch_frame(swr_ctx *ctx) {
             k_clip<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), CLIP_THREADS, 0, s>>>(sp);
         }
     }
-    const size_t unit_cap = (size_t)ctx->ntiles + ctx->refs.cap / RASTER_UNIT_REFS + 1;
+    const size_t unit_cap = (size_t)ctx->ntiles + ctx->refs.cap / RASTER_UNIT_MIN + 1;
+    const uint32_t cta_slots = (uint32_t)ctx->num_sms * 4u;  // k_raster_tiles: 4 CTAs per SM
     if (ctx->tile_order.reserve(unit_cap) != cudaSuccess) return SWR_ERR_OOM;
     k_scan_tiles<<<1, 1024, 0, s>>>(ctx->tile_count.p, ctx->tile_offset.p, ctx->tile_cursor.p, ctx->ntiles, ctx->counters.p, (uint32_t)ctx->refs.cap,
-                                    ctx->tile_order.p, (uint32_t)unit_cap, rb * ctx->tiles_x, re * ctx->tiles_x);
+                                    ctx->tile_order.p, (uint32_t)unit_cap, rb * ctx->tiles_x, re * ctx->tiles_x, cta_slots);
     if (tris > 0) {
         k_scatter<<<(unsigned)((tris + 255) / 256), 256, 0, s>>>(ctx->rects.p, (uint32_t)tris, ctx->tile_cursor.p, ctx->refs.p, ctx->counters.p, ctx->tiles_x);
         if (clip_tris > 0)
@@ -567,8 +570,7 @@ static int launch_frame(swr_ctx *ctx) {
         rp.row_end = re;
         // keys of the owned rows start EMPTY: tiles split over several CTAs merge into them with atomicMin
         CK(cudaMemsetAsync(ctx->keys.p + (size_t)rb * ctx->tiles_x * SWR_TILE_PIXELS, 0xFF, (size_t)(re - rb) * ctx->tiles_x * SWR_TILE_PIXELS * 8, s));
-        const size_t owned = (size_t)(re - rb) * ctx->tiles_x;
-        k_raster_tiles<<<(unsigned)(owned + ctx->refs.cap / RASTER_UNIT_REFS + 1), RASTER_THREADS, raster_smem_bytes(), s>>>(rp);
+        k_raster_tiles<<<cta_slots, RASTER_THREADS, raster_smem_bytes(), s>>>(rp);  // persistent: one CTA per resident slot
     }
     CK(cudaEventRecord(ctx->ev[2], s));
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));

@@ -106,6 +106,9 @@ struct FrameCounters {
     uint32_t overflow_ext;    // extension records exhausted
     uint32_t clip_list_n;     // surviving fans >= 1
     uint32_t raster_units;    // entries of the raster work list
+    uint32_t raster_unit_refs; // refs per unit chosen for this frame
+    uint32_t raster_next;     // work-list cursor of the persistent raster CTAs
+    uint32_t pad;
     unsigned long long dbg[8];  // SWR_PROFILE_COUNTERS builds only
 };
 

@@ -345,13 +345,14 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip(SetupParams P) {
 // keys are merged with a global 64-bit atomicMin), so one hot tile cannot become the long pole of the frame.
 // Units are ordered heaviest-first (bit-length buckets of their ref count).
 // ---------------------------------------------------------------------------------------------
-#define RASTER_UNIT_REFS 2048u
+#define RASTER_UNIT_MAX 2048u
+#define RASTER_UNIT_MIN 256u
 
 __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count, uint32_t *tile_offset, uint32_t *tile_cursor, int ntiles,
                                                      FrameCounters *counters, uint32_t ref_capacity, uint32_t *unit_list, uint32_t unit_capacity,
-                                                     int tile_begin, int tile_end) {
+                                                     int tile_begin, int tile_end, uint32_t cta_slots) {
     __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
+    __shared__ uint32_t s_carry, s_unit;
     __shared__ uint32_t s_hist[34], s_cur[34];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_carry = 0;
@@ -382,11 +383,6 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
         if (i < ntiles) {
             tile_offset[i] = excl;
             tile_cursor[i] = excl;
-            if (i >= tile_begin && i < tile_end) {
-                const uint32_t nfull = v / RASTER_UNIT_REFS, rem = v % RASTER_UNIT_REFS;
-                if (nfull) atomicAdd(&s_hist[32 - __clz(RASTER_UNIT_REFS)], nfull);
-                if (rem || !nfull) atomicAdd(&s_hist[rem ? 32 - __clz(rem) : 0], 1u);  // an empty tile still needs its keys written
-            }
         }
         __syncthreads();
         if (tid == 1023) s_carry = excl + v;
@@ -396,21 +392,41 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
         tile_offset[ntiles] = s_carry;
         counters->tile_refs = s_carry;
         if (s_carry > ref_capacity) counters->overflow_refs = 1;
+        // unit size: aim at ~3 units per resident CTA slot so that the tail is short even when this context owns only a
+        // band of the screen (sort-first), but never below one batch or above RASTER_UNIT_MAX
+        uint32_t u = s_carry / (3u * cta_slots);
+        u = ((u + 255u) / 256u) * 256u;
+        s_unit = min(max(u, RASTER_UNIT_MIN), RASTER_UNIT_MAX);
+    }
+    __syncthreads();
+    if (counters->overflow_refs) return;
+    const uint32_t U = s_unit;
+    const int ub = 32 - __clz(U);
+    for (int i = tile_begin + tid; i < tile_end; i += 1024) {
+        const uint32_t v = tile_count[i];
+        const uint32_t nfull = v / U, rem = v % U;
+        if (nfull) atomicAdd(&s_hist[ub], nfull);
+        if (rem || !nfull) atomicAdd(&s_hist[rem ? 32 - __clz(rem) : 0], 1u);  // an empty tile still needs its keys written
+    }
+    __syncthreads();
+    if (tid == 0) {
         uint32_t acc = 0;
         for (int b = 33; b >= 0; b--) {  // heaviest bucket first
             s_cur[b] = acc;
             acc += s_hist[b];
         }
         counters->raster_units = acc <= unit_capacity ? acc : 0;
-        if (acc > unit_capacity) counters->overflow_refs = 1;  // cannot happen: capacity covers ntiles + ref_capacity / unit
+        counters->raster_unit_refs = U;
+        counters->raster_next = 0;
+        if (acc > unit_capacity) counters->overflow_refs = 1;  // cannot happen: capacity covers ntiles + ref_capacity / RASTER_UNIT_MIN
     }
     __syncthreads();
     if (counters->overflow_refs) return;
     for (int i = tile_begin + tid; i < tile_end; i += 1024) {
         const uint32_t v = tile_count[i];
-        const uint32_t nfull = v / RASTER_UNIT_REFS, rem = v % RASTER_UNIT_REFS;
-        for (uint32_t k = 0; k < nfull; k++) unit_list[atomicAdd(&s_cur[32 - __clz(RASTER_UNIT_REFS)], 1u)] = ((uint32_t)i << 12) | k;
-        if (rem || !nfull) unit_list[atomicAdd(&s_cur[rem ? 32 - __clz(rem) : 0], 1u)] = ((uint32_t)i << 12) | nfull;
+        const uint32_t nfull = v / U, rem = v % U;
+        for (uint32_t k = 0; k < nfull; k++) unit_list[atomicAdd(&s_cur[ub], 1u)] = ((uint32_t)i << 14) | k;
+        if (rem || !nfull) unit_list[atomicAdd(&s_cur[rem ? 32 - __clz(rem) : 0], 1u)] = ((uint32_t)i << 14) | nfull;
     }
 }
 
@@ -476,7 +492,7 @@ struct RasterParams {
     const TriRecord *records;
     const uint32_t *refs;
     const uint32_t *tile_offset;
-    const uint32_t *unit_list;  // tile << 12 | chunk, heaviest first; counters->raster_units entries
+    const uint32_t *unit_list;  // tile << 14 | chunk, heaviest first; counters->raster_units entries
     const uint32_t *clip_ext;
     unsigned long long *keys;  // tile-major: tile * 4096 + y * 64 + x; low word = ~id
     FrameCounters *counters;
@@ -637,10 +653,17 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
     FragQueue *fqs = reinterpret_cast<FragQueue *>(smem_raw + SWR_TILE_PIXELS * 8 + sizeof(TileBatch));
 
     if (P.counters->overflow_refs || P.counters->overflow_ext) return;  // lists incomplete; the host replays the frame
-    if (blockIdx.x >= P.counters->raster_units) return;
-    const uint32_t unit = P.unit_list[blockIdx.x];
-    const int tile = (int)(unit >> 12);
-    const uint32_t chunk = unit & 0xFFFu;
+    __shared__ uint32_t s_unit_index;
+    const uint32_t nunits = P.counters->raster_units, unit_refs = P.counters->raster_unit_refs;
+  // persistent CTA: fetch work units (heaviest first) until the list is drained
+  for (;;) {
+    __syncthreads();  // everybody is done with the previous unit's shared memory
+    if (threadIdx.x == 0) s_unit_index = atomicAdd(&P.counters->raster_next, 1u);
+    __syncthreads();
+    if (s_unit_index >= nunits) break;
+    const uint32_t unit = P.unit_list[s_unit_index];
+    const int tile = (int)(unit >> 14);
+    const uint32_t chunk = unit & 0x3FFFu;
     const int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
     const int tile_x0 = tx * SWR_TILE, tile_y0 = ty * SWR_TILE;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -654,8 +677,8 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
 #endif
 
     const uint32_t tile_beg = P.tile_offset[tile], tile_end = P.tile_offset[tile + 1];
-    const bool split = tile_end - tile_beg > RASTER_UNIT_REFS;  // several CTAs share this tile: merge with atomics at the end
-    const uint32_t beg = tile_beg + chunk * RASTER_UNIT_REFS, end = min(beg + RASTER_UNIT_REFS, tile_end);
+    const bool split = tile_end - tile_beg > unit_refs;  // several CTAs share this tile: merge with atomics at the end
+    const uint32_t beg = tile_beg + chunk * unit_refs, end = min(beg + unit_refs, tile_end);
     // software pipeline over batches: the record of batch n+1 and the ref of batch n+2 are in flight while batch n is rasterised
     uint32_t slot_next = 0, slot_next2 = 0;
     uint4 rq0 = make_uint4(0, 0, 0, 0), rq1 = rq0, rq2 = rq0, rq3 = rq0;
@@ -815,6 +838,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
         P.dbg_tiles[tile * 4 + 3] = blockIdx.x;
     }
 #endif
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
