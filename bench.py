@@ -18,6 +18,8 @@ vis-buffer shading, resolve).
 """
 import argparse
 import json
+
+import numpy as np
 import os
 import subprocess
 import sys
@@ -163,8 +165,11 @@ def run_gpu(args):
     ranges = tile_row_ranges(tiles_y, world)
     if world > 1:
         # probe frame on every rank (full screen, identical everywhere) -> cost-balanced contiguous row bands
-        r.render_scene(scene, cam, shade=False)
-        ranges = balanced_row_ranges(r.read_tile_counts(), world)
+        for _ in range(3):
+            r.render_scene(scene, cam, shade=False)
+        cyc = torch.from_numpy(r.read_tile_costs()[1].astype(np.int64)).to(f"cuda:{local}")
+        dist.broadcast(cyc, src=0)  # measured cycles differ slightly per rank: everybody uses rank 0's
+        ranges = balanced_row_ranges(cyc.cpu().numpy(), world)
         r.set_tile_rows(*ranges[rank])
     buf = swr.RenderBuffer(W, H, pinned=True)
     stream = torch.cuda.ExternalStream(r.cuda_stream(), device=local)

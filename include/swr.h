@@ -248,9 +248,9 @@ void *swr_device_bary(swr_ctx *ctx); /* W*H float2, row-major */
  * that HOST buffer and the call synchronises. */
 int swr_resolve(swr_ctx *ctx, float exposure, uint32_t *out_pixels);
 
-/* Per-tile triangle-reference counts of the last frame (row-major tiles; 0 for tiles this context does not own):
- * the cost signal for balancing sort-first row bands. */
-int swr_read_tile_counts(swr_ctx *ctx, uint32_t *out_per_tile);
+/* Per-tile cost signals of the last frame (row-major tiles; 0 for tiles this context does not own), for balancing
+ * sort-first row bands: triangle references binned into the tile and SM cycles its rasterisation took. Either may be NULL. */
+int swr_read_tile_costs(swr_ctx *ctx, uint32_t *refs_per_tile, uint32_t *raster_cycles_per_tile);
 
 /* Per-tile metering luminance (tilerasterizer.rs:103-106), row-major tiles. */
 int swr_read_tile_luminance(swr_ctx *ctx, float *out_per_tile);

@@ -71,7 +71,8 @@ struct swr_ctx {
     DevBuf<TriRecord> records;
     DevBuf<uint32_t> rects;
     DevBuf<ClipVertex> clip_verts;
-    DevBuf<uint32_t> tile_count, tile_offset, tile_cursor, tile_order;
+    DevBuf<uint32_t> tile_count, tile_offset, tile_cursor, tile_order, tile_cycles, tile_cycles_prev, tile_count_prev, tile_unit;
+    bool have_history = false;
     DevBuf<uint32_t> clip_queue, clip_ext, clip_list;
     size_t ext_cap = 0;
     DevBuf<uint32_t> refs;
@@ -178,7 +179,8 @@ swr_ctx *swr_create(int width, int height, int device) {
     for (int i = 0; ok && i < 4; i++) ok = cudaEventCreateWithFlags(&ctx->staging[i].done, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMallocHost(&ctx->h_counters, sizeof(FrameCounters)) == cudaSuccess;
     ok = ok && ctx->tile_count.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_offset.reserve(ctx->ntiles + 1) == cudaSuccess &&
-         ctx->tile_cursor.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_order.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->keys.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess &&
+         ctx->tile_cursor.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_cycles.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_cycles_prev.reserve(ctx->ntiles + 1) == cudaSuccess &&
+         ctx->tile_count_prev.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_unit.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_order.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->keys.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess &&
          ctx->color.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess && ctx->pixels.reserve((size_t)width * height) == cudaSuccess &&
          ctx->lum.reserve(ctx->ntiles) == cudaSuccess && ctx->counters.reserve(1) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_raster_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes()) == cudaSuccess;
@@ -219,6 +221,10 @@ void swr_destroy(swr_ctx *ctx) {
     ctx->tile_offset.release();
     ctx->tile_cursor.release();
     ctx->tile_order.release();
+    ctx->tile_cycles.release();
+    ctx->tile_cycles_prev.release();
+    ctx->tile_count_prev.release();
+    ctx->tile_unit.release();
     ctx->clip_queue.release();
     ctx->clip_ext.release();
     ctx->clip_list.release();
@@ -272,6 +278,7 @@ int swr_set_tile_rows(swr_ctx *ctx, int row_begin, int row_end) {
     }
     ctx->row_begin = row_begin;
     ctx->row_end = row_end;
+    ctx->have_history = false;
     return SWR_OK;
 }
 
@@ -281,6 +288,7 @@ int swr_upload_scene(swr_ctx *ctx, const swr_scene_desc *s) {
     CK(cudaStreamSynchronize(ctx->stream));
     free_scene(ctx);
     ctx->frame_valid = false;
+    ctx->have_history = false;
     if (s->nmaterials == 0 || s->cubemap < 0 || s->cubemap_specular < 0 || s->brdf_lut < 0 || (uint32_t)s->cubemap >= s->ntextures ||
         (uint32_t)s->cubemap_specular >= s->ntextures || (uint32_t)s->brdf_lut >= s->ntextures) {
         ctx->err = "scene needs at least one material (scene.rs:493) and cubemap / cubemap_specular / brdf_lut textures";
@@ -507,6 +515,9 @@ static int launch_frame(swr_ctx *ctx) {
     CK(cudaMemcpyAsync(ctx->tri_prefix.p, hp, (size_t)(nd + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(st.done, s));
     CK(cudaMemsetAsync(ctx->tile_count.p, 0, (ctx->ntiles + 1) * sizeof(uint32_t), s));
+    // raster cycles of the previous frame become the history that sizes this frame's work units
+    std::swap(ctx->tile_cycles.p, ctx->tile_cycles_prev.p);
+    CK(cudaMemsetAsync(ctx->tile_cycles.p, 0, (ctx->ntiles + 1) * sizeof(uint32_t), s));
     CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(FrameCounters), s));
 
     const int rb = ctx->row_begin, re = ctx->row_end;
@@ -543,7 +554,9 @@ static int launch_frame(swr_ctx *ctx) {
     const uint32_t cta_slots = (uint32_t)ctx->num_sms * 4u;  // k_raster_tiles: 4 CTAs per SM
     if (ctx->tile_order.reserve(unit_cap) != cudaSuccess) return SWR_ERR_OOM;
     k_scan_tiles<<<1, 1024, 0, s>>>(ctx->tile_count.p, ctx->tile_offset.p, ctx->tile_cursor.p, ctx->ntiles, ctx->counters.p, (uint32_t)ctx->refs.cap,
-                                    ctx->tile_order.p, (uint32_t)unit_cap, rb * ctx->tiles_x, re * ctx->tiles_x, cta_slots);
+                                    ctx->tile_order.p, (uint32_t)unit_cap, rb * ctx->tiles_x, re * ctx->tiles_x, cta_slots, ctx->tile_unit.p,
+                                    ctx->tile_count_prev.p, ctx->tile_cycles_prev.p, ctx->have_history ? 1 : 0);
+    ctx->have_history = true;
     if (tris > 0) {
         k_scatter<<<(unsigned)((tris + 255) / 256), 256, 0, s>>>(ctx->rects.p, (uint32_t)tris, ctx->tile_cursor.p, ctx->refs.p, ctx->counters.p, ctx->tiles_x);
         if (clip_tris > 0)
@@ -559,8 +572,10 @@ static int launch_frame(swr_ctx *ctx) {
         rp.clip_ext = ctx->clip_ext.p;
         rp.keys = ctx->keys.p;
         rp.counters = ctx->counters.p;
+        rp.tile_cycles = ctx->tile_cycles.p;
+        rp.tile_unit = ctx->tile_unit.p;
 #ifdef SWR_PROFILE_COUNTERS
-        if (ctx->dbg_tiles.reserve((size_t)ctx->ntiles * 4) == cudaSuccess) rp.dbg_tiles = ctx->dbg_tiles.p;
+        if (ctx->dbg_tiles.reserve((size_t)8192 * 4) == cudaSuccess) rp.dbg_tiles = ctx->dbg_tiles.p;
 #endif
         rp.W = ctx->W;
         rp.H = ctx->H;
@@ -647,20 +662,24 @@ static int finish_frame(swr_ctx *ctx) {
             st.tiles = (uint32_t)ctx->ntiles;
 #ifdef SWR_PROFILE_COUNTERS
             if (ctx->dbg_tiles.p) {
-                std::vector<unsigned long long> h((size_t)ctx->ntiles * 4);
+                const int nu = c.raster_units < 8192 ? (int)c.raster_units : 8192;
+                std::vector<unsigned long long> h((size_t)8192 * 4);
                 cudaMemcpy(h.data(), ctx->dbg_tiles.p, h.size() * 8, cudaMemcpyDeviceToHost);
-                unsigned long long mx = 0, sum = 0, mxi = 0;
-                for (int t = 0; t < ctx->ntiles; t++) {
+                unsigned long long sum = 0, tmin = ~0ull, tmax = 0;
+                std::vector<int> idx(nu);
+                for (int t = 0; t < nu; t++) {
+                    idx[t] = t;
                     sum += h[t * 4];
-                    if (h[t * 4] > mx) { mx = h[t * 4]; mxi = t; }
+                    unsigned long long te = h[t * 4 + 3] >> 20, ts = te - h[t * 4];
+                    if (ts < tmin) tmin = ts;
+                    if (te > tmax) tmax = te;
                 }
-                fprintf(stderr, "[swr dbg] tile cycles: max %llu (tile %llu refs %llu items %llu slot %llu) mean %llu sum/592 %llu\n", mx, mxi, h[mxi * 4 + 1],
-                        h[mxi * 4 + 2], h[mxi * 4 + 3], sum / ctx->ntiles, sum / 592);
-                // 10 slowest tiles
-                std::vector<int> idx(ctx->ntiles);
-                for (int t = 0; t < ctx->ntiles; t++) idx[t] = t;
-                std::partial_sort(idx.begin(), idx.begin() + 10, idx.end(), [&](int a, int b) { return h[a * 4] > h[b * 4]; });
-                for (int k = 0; k < 10; k++) fprintf(stderr, "   tile %d cycles %llu refs %llu items %llu slot %llu\n", idx[k], h[idx[k] * 4], h[idx[k] * 4 + 1], h[idx[k] * 4 + 2], h[idx[k] * 4 + 3]);
+                std::sort(idx.begin(), idx.end(), [&](int a, int b) { return h[a * 4] > h[b * 4]; });
+                fprintf(stderr, "[swr dbg] units %u (unit refs default %u): sum cycles %llu, /592 = %llu, span %llu; slowest:\n", c.raster_units, c.raster_unit_refs, sum, sum / 592, tmax - tmin);
+                for (int k = 0; k < 6 && k < nu; k++)
+                    fprintf(stderr, "   unit %d tile %llu cycles %llu refs %llu items %llu\n", idx[k], h[idx[k] * 4 + 3] & 0xFFFFF, h[idx[k] * 4], h[idx[k] * 4 + 1], h[idx[k] * 4 + 2]);
+                int med = idx[nu / 2];
+                fprintf(stderr, "   median unit cycles %llu refs %llu items %llu\n", h[med * 4], h[med * 4 + 1], h[med * 4 + 2]);
             }
             fprintf(stderr, "[swr dbg] items %llu batches %llu quad-steps %llu fragments %llu warp-iters %llu\n", c.dbg[0], c.dbg[1], c.dbg[2], c.dbg[3], c.dbg[4]);
 #endif
@@ -796,11 +815,12 @@ int swr_synchronize(swr_ctx *ctx) {
     return finish_frame(ctx);
 }
 
-int swr_read_tile_counts(swr_ctx *ctx, uint32_t *out) {
-    if (!ctx || !out) return SWR_ERR_INVALID;
+int swr_read_tile_costs(swr_ctx *ctx, uint32_t *refs, uint32_t *cycles) {
+    if (!ctx) return SWR_ERR_INVALID;
     int rc;
     if ((rc = finish_frame(ctx))) return rc;
-    CK(cudaMemcpy(out, ctx->tile_count.p, ctx->ntiles * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (refs) CK(cudaMemcpy(refs, ctx->tile_count.p, ctx->ntiles * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (cycles) CK(cudaMemcpy(cycles, ctx->tile_cycles.p, ctx->ntiles * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return SWR_OK;
 }
 

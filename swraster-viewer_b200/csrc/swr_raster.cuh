@@ -346,16 +346,35 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip(SetupParams P) {
 // Units are ordered heaviest-first (bit-length buckets of their ref count).
 // ---------------------------------------------------------------------------------------------
 #define RASTER_UNIT_MAX 2048u
-#define RASTER_UNIT_MIN 256u
+#define RASTER_UNIT_MIN 32u
+
+// Unit size of one tile. With history (previous frame's measured raster cycles and ref count of this tile) the chunk is
+// sized so that one unit costs about `target_cycles`; without history a ref-count based default is used.
+__device__ __forceinline__ uint32_t tile_unit_refs(uint32_t refs, uint32_t prev_refs, uint32_t prev_cycles, float target_cycles, uint32_t default_unit) {
+    uint32_t u = default_unit;
+    if (prev_refs >= 16u && prev_cycles > 0u && target_cycles > 0.0f) {
+        const float cycles_per_ref = (float)prev_cycles / (float)prev_refs;
+        const float want = target_cycles / cycles_per_ref;
+        u = want >= (float)RASTER_UNIT_MAX ? RASTER_UNIT_MAX : (uint32_t)want;
+    }
+    u = ((u + 31u) / 32u) * 32u;
+    return min(max(u, RASTER_UNIT_MIN), RASTER_UNIT_MAX);
+}
 
 __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count, uint32_t *tile_offset, uint32_t *tile_cursor, int ntiles,
                                                      FrameCounters *counters, uint32_t ref_capacity, uint32_t *unit_list, uint32_t unit_capacity,
-                                                     int tile_begin, int tile_end, uint32_t cta_slots) {
+                                                     int tile_begin, int tile_end, uint32_t cta_slots, uint32_t *tile_unit,
+                                                     uint32_t *prev_count, const uint32_t *prev_cycles, int have_history) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry, s_unit;
+    __shared__ float s_target;
+    __shared__ unsigned long long s_cyc;
     __shared__ uint32_t s_hist[34], s_cur[34];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_carry = 0;
+    if (tid == 0) {
+        s_carry = 0;
+        s_cyc = 0;
+    }
     if (tid < 34) s_hist[tid] = 0;
     __syncthreads();
     for (int base = 0; base < ntiles; base += 1024) {
@@ -383,6 +402,10 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
         if (i < ntiles) {
             tile_offset[i] = excl;
             tile_cursor[i] = excl;
+            if (have_history && i >= tile_begin && i < tile_end && prev_count[i] >= 16u) {
+                // expected cycles of this tile now = cycles per ref last frame x refs now
+                atomicAdd(&s_cyc, (unsigned long long)((float)prev_cycles[i] / (float)prev_count[i] * (float)v));
+            }
         }
         __syncthreads();
         if (tid == 1023) s_carry = excl + v;
@@ -392,26 +415,28 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
         tile_offset[ntiles] = s_carry;
         counters->tile_refs = s_carry;
         if (s_carry > ref_capacity) counters->overflow_refs = 1;
-        // unit size: aim at ~3 units per resident CTA slot so that the tail is short even when this context owns only a
-        // band of the screen (sort-first), but never below one batch or above RASTER_UNIT_MAX
+        // default unit: ~3 units per resident CTA slot, so the tail stays short even when this context owns only a band
         uint32_t u = s_carry / (3u * cta_slots);
         u = ((u + 255u) / 256u) * 256u;
-        s_unit = min(max(u, RASTER_UNIT_MIN), RASTER_UNIT_MAX);
+        s_unit = min(max(u, 256u), RASTER_UNIT_MAX);
+        s_target = have_history ? (float)s_cyc / (float)(4u * cta_slots) : 0.0f;
     }
     __syncthreads();
     if (counters->overflow_refs) return;
     const uint32_t U = s_unit;
-    const int ub = 32 - __clz(U);
+    const float target = s_target;
     for (int i = tile_begin + tid; i < tile_end; i += 1024) {
         const uint32_t v = tile_count[i];
-        const uint32_t nfull = v / U, rem = v % U;
-        if (nfull) atomicAdd(&s_hist[ub], nfull);
+        const uint32_t ut = tile_unit_refs(v, have_history ? prev_count[i] : 0u, have_history ? prev_cycles[i] : 0u, target, U);
+        tile_unit[i] = ut;
+        const uint32_t nfull = v / ut, rem = v % ut;
+        if (nfull) atomicAdd(&s_hist[32 - __clz(ut)], nfull);
         if (rem || !nfull) atomicAdd(&s_hist[rem ? 32 - __clz(rem) : 0], 1u);  // an empty tile still needs its keys written
     }
     __syncthreads();
     if (tid == 0) {
         uint32_t acc = 0;
-        for (int b = 33; b >= 0; b--) {  // heaviest bucket first
+        for (int b = 33; b >= 0; b--) {  // biggest units first (with history all full units cost about the same)
             s_cur[b] = acc;
             acc += s_hist[b];
         }
@@ -424,9 +449,11 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
     if (counters->overflow_refs) return;
     for (int i = tile_begin + tid; i < tile_end; i += 1024) {
         const uint32_t v = tile_count[i];
-        const uint32_t nfull = v / U, rem = v % U;
-        for (uint32_t k = 0; k < nfull; k++) unit_list[atomicAdd(&s_cur[ub], 1u)] = ((uint32_t)i << 14) | k;
+        const uint32_t ut = tile_unit[i];
+        const uint32_t nfull = v / ut, rem = v % ut;
+        for (uint32_t k = 0; k < nfull; k++) unit_list[atomicAdd(&s_cur[32 - __clz(ut)], 1u)] = ((uint32_t)i << 14) | k;
         if (rem || !nfull) unit_list[atomicAdd(&s_cur[rem ? 32 - __clz(rem) : 0], 1u)] = ((uint32_t)i << 14) | nfull;
+        prev_count[i] = v;  // history for the next frame
     }
 }
 
@@ -497,6 +524,8 @@ struct RasterParams {
     unsigned long long *keys;  // tile-major: tile * 4096 + y * 64 + x; low word = ~id
     FrameCounters *counters;
     unsigned long long *dbg_tiles;  // SWR_PROFILE_COUNTERS: per tile {cycles, refs, items, launch slot}
+    const uint32_t *tile_unit;      // refs per unit of each tile (k_scan_tiles)
+    uint32_t *tile_cycles;          // per tile: SM cycles spent rasterising it (summed over its units): load-balancing signal
     int W, H, tiles_x, tiles_y;
     int row_begin, row_end;
 };
@@ -654,7 +683,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
 
     if (P.counters->overflow_refs || P.counters->overflow_ext) return;  // lists incomplete; the host replays the frame
     __shared__ uint32_t s_unit_index;
-    const uint32_t nunits = P.counters->raster_units, unit_refs = P.counters->raster_unit_refs;
+    const uint32_t nunits = P.counters->raster_units;
   // persistent CTA: fetch work units (heaviest first) until the list is drained
   for (;;) {
     __syncthreads();  // everybody is done with the previous unit's shared memory
@@ -667,6 +696,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
     const int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
     const int tile_x0 = tx * SWR_TILE, tile_y0 = ty * SWR_TILE;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long unit_t0 = clock64();
     FragQueue &fq = fqs[wid];
     const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -677,6 +707,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
 #endif
 
     const uint32_t tile_beg = P.tile_offset[tile], tile_end = P.tile_offset[tile + 1];
+    const uint32_t unit_refs = P.tile_unit[tile];
     const bool split = tile_end - tile_beg > unit_refs;  // several CTAs share this tile: merge with atomics at the end
     const uint32_t beg = tile_beg + chunk * unit_refs, end = min(beg + unit_refs, tile_end);
     // software pipeline over batches: the record of batch n+1 and the ref of batch n+2 are in flight while batch n is rasterised
@@ -830,12 +861,13 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
             if (k != SWR_KEY_EMPTY) atomicMin(&out[i], k);
         }
     }
+    if (tid == 0) atomicAdd(&P.tile_cycles[tile], (uint32_t)(clock64() - unit_t0));
 #ifdef SWR_PROFILE_COUNTERS
-    if (tid == 0 && P.dbg_tiles && chunk == 0) {
-        P.dbg_tiles[tile * 4 + 0] = (unsigned long long)(clock64() - dbg_t0);
-        P.dbg_tiles[tile * 4 + 1] = end - beg;
-        P.dbg_tiles[tile * 4 + 2] = dbg_items;
-        P.dbg_tiles[tile * 4 + 3] = blockIdx.x;
+    if (tid == 0 && P.dbg_tiles && s_unit_index < 8192) {
+        P.dbg_tiles[s_unit_index * 4 + 0] = (unsigned long long)(clock64() - dbg_t0);
+        P.dbg_tiles[s_unit_index * 4 + 1] = end - beg;
+        P.dbg_tiles[s_unit_index * 4 + 2] = dbg_items;
+        P.dbg_tiles[s_unit_index * 4 + 3] = (unsigned long long)tile | ((unsigned long long)(clock64() & 0xFFFFFFFFFFull) << 20);
     }
 #endif
   }

@@ -22,12 +22,16 @@ def tile_row_ranges(tiles_y, world):
     return out
 
 
-def balanced_row_ranges(tile_counts, world, pixel_cost=2000.0):
-    """Contiguous tile-row bands with (nearly) equal cost. tile_counts: (tiles_y, tiles_x) refs per tile from a full
-    probe frame (Renderer.read_tile_counts) — identical on every rank, so all ranks derive the same split without
-    communicating. Row cost = refs + pixel_cost per tile (raster work + shading work)."""
-    tiles_y, tiles_x = tile_counts.shape
-    cost = tile_counts.astype(np.float64).sum(axis=1) + pixel_cost * tiles_x
+def balanced_row_ranges(tile_cost, world, pixel_cost=None):
+    """Contiguous tile-row bands with (nearly) equal cost. tile_cost: (tiles_y, tiles_x) per-tile raster cost from a
+    full probe frame (Renderer.read_tile_costs: measured raster cycles, or ref counts) — identical on every rank up to
+    timing noise, so rank 0's split is broadcast by the caller when cycles are used. Row cost = raster cost + a
+    per-tile shading share (`pixel_cost`, default: 0.9 x mean raster cost, the measured shade:raster ratio on C3)."""
+    tiles_y, tiles_x = tile_cost.shape
+    tc = tile_cost.astype(np.float64)
+    if pixel_cost is None:
+        pixel_cost = 0.9 * tc.mean() + 1.0
+    cost = tc.sum(axis=1) + pixel_cost * tiles_x
     cum = np.concatenate([[0.0], np.cumsum(cost)])
     cuts = [0]
     for k in range(1, world):

@@ -55,7 +55,7 @@ def load_libraries():
     core.swr_device_bary.argtypes = [vp]
     core.swr_resolve.argtypes = [vp, f32, vp]
     core.swr_read_tile_luminance.argtypes = [vp, vp]
-    core.swr_read_tile_counts.argtypes = [vp, vp]
+    core.swr_read_tile_costs.argtypes = [vp, vp, vp]
     core.swr_read_visbuffer.argtypes = [vp, vp, vp, vp, vp]
     core.swr_read_color.argtypes = [vp, vp]
     core.swr_synchronize.argtypes = [vp]
@@ -251,10 +251,15 @@ class Renderer:
         self._check_core(self.core.swr_read_tile_luminance(self.ctx, out.ctypes.data))
         return out
 
+    def read_tile_costs(self):
+        """(refs, raster cycles) per tile of the last frame, each (tiles_y, tiles_x)."""
+        refs = np.empty(self.tiles_x * self.tiles_y, np.uint32)
+        cyc = np.empty(self.tiles_x * self.tiles_y, np.uint32)
+        self._check_core(self.core.swr_read_tile_costs(self.ctx, refs.ctypes.data, cyc.ctypes.data))
+        return refs.reshape(self.tiles_y, self.tiles_x), cyc.reshape(self.tiles_y, self.tiles_x)
+
     def read_tile_counts(self):
-        out = np.empty(self.tiles_x * self.tiles_y, np.uint32)
-        self._check_core(self.core.swr_read_tile_counts(self.ctx, out.ctypes.data))
-        return out.reshape(self.tiles_y, self.tiles_x)
+        return self.read_tile_costs()[0]
 
     def stats(self):
         st = abi.FrameStats()

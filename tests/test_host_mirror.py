@@ -77,7 +77,7 @@ def test_balanced_row_ranges_partition_and_balance():
     for tiles_y in (17, 34, 68):
         counts = (rng.random((tiles_y, 60)) ** 4 * 30000).astype(np.uint32)
         counts[tiles_y // 3] *= 6  # one very heavy row
-        cost = counts.sum(1) + 2000.0 * 60
+        cost = counts.sum(1) + (0.9 * counts.mean() + 1.0) * 60
         for world in (1, 2, 4, 8):
             r = balanced_row_ranges(counts, world)
             assert len(r) == world and r[0][0] == 0 and r[-1][1] == tiles_y
