@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 W, H = 3840, 2160
 WORKLOAD = "C3: procedural 10M-triangle instanced scene (icosphere 20480 / torus 8192 / box-grid 1200 tris, seeded scatter, scales 0.05-4, camera inside the cloud, heavy clipping), 3840x2160"
-KERNELS_PER_FRAME = 7  # k_setup, k_scan_tiles, k_scatter, k_raster_tiles, k_shade, k_luminance, k_resolve
+KERNELS_PER_FRAME = 9  # k_setup, k_clip, k_scan_tiles, k_scatter, k_scatter_list, k_raster_tiles, k_shade, k_luminance, k_resolve
 
 
 def build_scene():
@@ -261,6 +261,11 @@ def run_gpu(args):
                   "ms_raster": 4 * st0["tile_refs"] + 8 * W * H // world,
                   "ms_shade": 4 * W * H // world}[dom]
         achieved = kbytes / (dom_ms * 1e-3) / 1e9
+        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this same command (N=1)
+        traffic = None
+        tj = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if world == 1 and os.path.exists(tj):
+            traffic = json.load(open(tj)).get(kname.split("+")[0])
         ndraws = None
         h2d = r.num_draws * (144 + 4) + 4
         line = {
@@ -273,7 +278,7 @@ def run_gpu(args):
             "e2e": {"value": K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": W * H * 4, "ms_per_step": 1e3 * e2e_s / K},
             "gpu_launches": KERNELS_PER_FRAME * K * 2 + KERNELS_PER_FRAME * (max(3, args.warmup) + 2),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel_ms": dom_ms, "kernel_algorithmic_bytes": kbytes,
                          "frame": {"algorithmic_bytes": B, "achieved": B / (ms * 1e-3) / 1e9, "frac": B / (ms * 1e-3) / 1e9 / peak},
                          "phase_ms": {k: v / K for k, v in phase.items()}},

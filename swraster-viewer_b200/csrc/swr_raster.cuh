@@ -368,12 +368,13 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry, s_unit;
     __shared__ float s_target;
-    __shared__ unsigned long long s_cyc;
+    __shared__ float s_cyc;
     __shared__ uint32_t s_hist[34], s_cur[34];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float my_cyc = 0.0f;
     if (tid == 0) {
         s_carry = 0;
-        s_cyc = 0;
+        s_cyc = 0.0f;
     }
     if (tid < 34) s_hist[tid] = 0;
     __syncthreads();
@@ -404,13 +405,17 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
             tile_cursor[i] = excl;
             if (have_history && i >= tile_begin && i < tile_end && prev_count[i] >= 16u) {
                 // expected cycles of this tile now = cycles per ref last frame x refs now
-                atomicAdd(&s_cyc, (unsigned long long)((float)prev_cycles[i] / (float)prev_count[i] * (float)v));
+                my_cyc += (float)prev_cycles[i] / (float)prev_count[i] * (float)v;
             }
         }
         __syncthreads();
         if (tid == 1023) s_carry = excl + v;
         __syncthreads();
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_cyc += __shfl_xor_sync(0xFFFFFFFFu, my_cyc, o);
+    if (lane == 0 && my_cyc > 0.0f) atomicAdd(&s_cyc, my_cyc);
+    __syncthreads();
     if (tid == 0) {
         tile_offset[ntiles] = s_carry;
         counters->tile_refs = s_carry;
@@ -419,7 +424,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
         uint32_t u = s_carry / (3u * cta_slots);
         u = ((u + 255u) / 256u) * 256u;
         s_unit = min(max(u, 256u), RASTER_UNIT_MAX);
-        s_target = have_history ? (float)s_cyc / (float)(4u * cta_slots) : 0.0f;
+        s_target = have_history ? s_cyc / (float)(4u * cta_slots) : 0.0f;
     }
     __syncthreads();
     if (counters->overflow_refs) return;
