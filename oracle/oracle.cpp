@@ -249,10 +249,11 @@ struct RasterPacket {
 struct BlockArena {
     std::mutex m;
     char *cur = nullptr, *end = nullptr;
+    size_t nallocs = 0;
     void *alloc(size_t bytes) {
         std::lock_guard<std::mutex> g(m);
         bytes = (bytes + 63) & ~size_t(63);
-        if (cur == nullptr || cur + bytes > end) {
+        if (cur == nullptr || cur + bytes + 4096 > end) {
             size_t chunk = std::max<size_t>(bytes, size_t(256) << 20);
             chunk = (chunk + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);
             void *p = aligned_alloc(size_t(2) << 20, chunk);
@@ -264,7 +265,9 @@ struct BlockArena {
             end = cur + chunk;
         }
         void *r = cur;
-        cur += bytes;
+        // skew consecutive blocks by an odd number of cache lines: 256 KiB blocks at a power-of-two stride would put every
+        // tile's write front into the same L2 sets (measured: clip/bin 2x slower), which ordinary heap allocations avoid
+        cur += bytes + 64 * (size_t)(1 + (nallocs++ * 37) % 61);
         return r;
     }
 };
@@ -1165,7 +1168,8 @@ static void render_scene(Oracle &o, bool shade) {  // renderer.rs:201-220
             uint32_t nt = o.scene->primitives[o.draws[di].primitive].nindices / 3;
             for (uint32_t t = 0; t < nt; t += 128) batches.push_back({di, t, std::min(nt, t + 128)});
         }
-#pragma omp parallel for schedule(dynamic, 4) num_threads(o.nthreads)
+// rayon splits a range recursively (large contiguous pieces first, smaller ones when stealing): guided scheduling
+#pragma omp parallel for schedule(guided, 1) num_threads(o.nthreads)
         for (long b = 0; b < (long)batches.size(); b++) {
             const Batch &bt = batches[b];
             for (uint32_t t = bt.t0; t < bt.t1; t++) process_triangle(o, o.draws[bt.draw], t);

@@ -545,14 +545,15 @@ struct TileBatch {
     uint32_t slot[RASTER_THREADS];
     float ooa[RASTER_THREADS], iw0[RASTER_THREADS], iwda[RASTER_THREADS], iwdb[RASTER_THREADS];
     float zw0[RASTER_THREADS], zwda[RASTER_THREADS], zwdb[RASTER_THREADS];
-    uint32_t prefix[RASTER_THREADS + 1];
+    uint32_t zmin_hi[RASTER_THREADS];  // orderable lower bound of every fragment depth of the packet (0 = unknown)
+    uint16_t prefix[RASTER_THREADS + 2];  // item prefix (<= 256 * 165 items per batch)
     uint32_t wsum[RASTER_WARPS];
 };
 
 // Per-warp queue of covered pixels waiting for the depth computation: coverage is found by lanes walking different
 // quad rows (divergent by nature); the expensive part — perspective depth, 64-bit min — then runs up to 32 wide.
-#define FRAGQ_CAP 48
-#define FRAGQ_DRAIN 16
+#define FRAGQ_CAP 44
+#define FRAGQ_DRAIN 12
 struct FragQueue {
     uint32_t pkpix[FRAGQ_CAP];  // packet index in the batch << 16 | pixel index in the tile
     float w1[FRAGQ_CAP], w2[FRAGQ_CAP];
@@ -592,6 +593,7 @@ struct RowState {
     int len;  // quads in the row
     int pix;  // tile pixel index of lane 0 of the current quad
     int pk;
+    uint32_t zmin_hi;
 };
 
 __device__ __forceinline__ void row_setup(const TileBatch &tb, int pk, uint32_t local, int tile_x0, int tile_y0, RowState &st) {
@@ -599,6 +601,7 @@ __device__ __forceinline__ void row_setup(const TileBatch &tb, int pk, uint32_t 
     const int nqx = (geom >> 10) & 0x3F;
     const bool coarse = (geom >> 22) & 1u, exact = (geom >> 23) & 1u;
     st.pk = pk;
+    st.zmin_hi = tb.zmin_hi[pk];
     int qy, bi;
     if (coarse) {
         const uint32_t nbx = (uint32_t)(nqx + 7) >> 3;
@@ -770,6 +773,18 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
                 tb.zw0[tid] = r.zw0;
                 tb.zwda[tid] = fsub(r.zw1, r.zw0);
                 tb.zwdb[tid] = fsub(r.zw2, r.zw0);
+                // Early-Z bound. Fragment depth = interp(z/w) / interp(1/w) is the perspective-correct blend of the vertex
+                // clip-space z_k = zw_k / iw_k, so it lies in [min z_k, max z_k] up to a few ulps (and a hair of
+                // extrapolation when the f32 chain covers a centre just outside the exact triangle). The bound is pushed down
+                // by 1e-3 of the range + 1e-5 relative; when 1/w is not strictly positive and finite no bound is used.
+                uint32_t zhi = 0u;
+                if (r.iw0 > 0.0f && r.iw1 > 0.0f && r.iw2 > 0.0f && r.iw0 < 3.0e38f && r.iw1 < 3.0e38f && r.iw2 < 3.0e38f) {
+                    const float z0 = r.zw0 / r.iw0, z1 = r.zw1 / r.iw1, z2 = r.zw2 / r.iw2;
+                    const float zmn = fminf(z0, fminf(z1, z2)), zmx = fmaxf(z0, fmaxf(z1, z2));
+                    const float lo = zmn - (zmx - zmn) * 1.0e-3f - fabsf(zmn) * 1.0e-5f - 1.0e-30f;
+                    if (lo == lo && fabsf(lo) < 3.0e38f) zhi = depth_orderable(lo);
+                }
+                tb.zmin_hi[tid] = zhi;
             }
         }
         // CTA-wide exclusive prefix of item counts
@@ -784,7 +799,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
         uint32_t wbase = 0;
 #pragma unroll
         for (int w = 0; w < RASTER_WARPS; w++) wbase += (w < wid) ? tb.wsum[w] : 0u;
-        tb.prefix[tid + 1] = wbase + incl;
+        tb.prefix[tid + 1] = (uint16_t)(wbase + incl);
         if (tid == 0) tb.prefix[0] = 0;
         __syncthreads();
         const uint32_t total = tb.prefix[RASTER_THREADS];
@@ -824,7 +839,9 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
                 const bool act = s < st.len;
 #pragma unroll
                 for (int l = 0; l < 4; l++) {
-                    const bool cov = act && st.v[l][0] >= 0.0f && st.v[l][1] >= 0.0f && st.v[l][2] >= 0.0f;
+                    bool cov = act && st.v[l][0] >= 0.0f && st.v[l][1] >= 0.0f && st.v[l][2] >= 0.0f;
+                    // early-Z: the packet's depth lower bound is already behind what the pixel holds -> it cannot win
+                    if (cov) cov = st.zmin_hi <= reinterpret_cast<volatile uint32_t *>(skeys)[2 * (st.pix + (l & 1) + (l >> 1) * SWR_TILE) + 1];
                     const unsigned m = __ballot_sync(0xFFFFFFFFu, cov);
                     if (m) {
                         if (cov) {
