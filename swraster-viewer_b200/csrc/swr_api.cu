@@ -354,10 +354,6 @@ int swr_upload_scene(swr_ctx *ctx, const swr_scene_desc *s) {
         d.tex_emissive = t[3];
         d.tex_occlusion = t[4];
         d.tex_transmission = t[5];
-        if (m.flags & SWR_MAT_ALPHA_TESTED) {
-            ctx->err = "alpha-tested materials are not implemented yet (SURVEY 8f N1)";
-            return SWR_ERR_INVALID;
-        }
         mats[i] = d;
     }
     std::vector<DevTex> texs(s->ntextures);
@@ -528,6 +524,7 @@ static int launch_frame(swr_ctx *ctx) {
         sp.ndraws = nd;
         sp.total_tris = (uint32_t)tris;
         sp.prims = ctx->scene.prims;
+        sp.mats = ctx->scene.mats;
         sp.records = ctx->records.p;
         sp.rects = ctx->rects.p;
         sp.clip_verts = ctx->clip_verts.p;
@@ -570,6 +567,11 @@ static int launch_frame(swr_ctx *ctx) {
         rp.tile_offset = ctx->tile_offset.p;
         rp.unit_list = ctx->tile_order.p;
         rp.clip_ext = ctx->clip_ext.p;
+        rp.draws = ctx->draws.p;
+        rp.prims = ctx->scene.prims;
+        rp.mats = ctx->scene.mats;
+        rp.texs = ctx->scene.texs;
+        rp.clip_verts = ctx->clip_verts.p;
         rp.keys = ctx->keys.p;
         rp.counters = ctx->counters.p;
         rp.tile_cycles = ctx->tile_cycles.p;

@@ -15,6 +15,7 @@
 #define SWR_NO_CLIP 0xFFFFFFFFu
 #define SWR_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define SWR_INF_BITS 0x7F800000u
+#define SWR_REC_ALPHA 0x80000000u  // TriRecord.draw bit 31: the triangle's material is alpha-tested (shader.rs:40-43)
 #define SWR_ID_FOREIGN 0xFFFFFFFEu  // sort-last: the pixel's winner belongs to another rank
 
 // One surviving (post cull/clip) triangle: 64 bytes, 4 x 128-bit.

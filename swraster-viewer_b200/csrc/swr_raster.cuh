@@ -11,6 +11,7 @@
 //   k_read_vis     parity read-back of (depth bits, seq, bary1, bary2)
 #pragma once
 #include "swr_device.cuh"
+#include "swr_texture.cuh"
 
 struct SetupParams {
     const DevDraw *draws;
@@ -18,6 +19,7 @@ struct SetupParams {
     uint32_t ndraws;
     uint32_t total_tris;
     const DevPrim *prims;
+    const DevMat *mats;
     TriRecord *records;
     uint32_t *rects;
     ClipVertex *clip_verts;
@@ -44,6 +46,11 @@ __device__ __forceinline__ uint32_t find_draw(const uint32_t *prefix, uint32_t n
             hi = mid;
     }
     return lo;
+}
+
+__device__ __forceinline__ uint32_t record_of_id(uint32_t id, const uint32_t *clip_ext) {
+    const uint32_t fan = id & 7u, t = id >> 3;
+    return fan == 0 ? t : __ldg(clip_ext + t) + fan - 1u;
 }
 
 // Count one triangle's tile rectangle into tile_count. Single-tile rectangles (the common case) are
@@ -172,6 +179,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams P) {
         const DevDraw &dr = P.draws[d];
         const DevPrim &pr = P.prims[dr.prim];
         const bool clip = (dr.flags & 1u) != 0;
+        const uint32_t dflag = d | ((P.mats[pr.material].flags & 1u) ? SWR_REC_ALPHA : 0u);
         const uint32_t slot = g;  // record of fan 0 = dense triangle index; id = g * 8 + fan
         uint32_t i0 = __ldg(pr.idx + 3 * tri), i1 = __ldg(pr.idx + 3 * tri + 1), i2 = __ldg(pr.idx + 3 * tri + 2);
         float4 c0 = mul_vec4(dr.mvp, __ldg(pr.pos + i0));
@@ -194,10 +202,10 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams P) {
                         state = 2;
                 }
             }
-            if (state == 0) rect = emit_triangle(P, c0, c1, c2, slot, d, seq, SWR_NO_CLIP, nocover);
+            if (state == 0) rect = emit_triangle(P, c0, c1, c2, slot, dflag, seq, SWR_NO_CLIP, nocover);
             queued = state == 2;
         } else {
-            rect = emit_triangle(P, c0, c1, c2, slot, d, seq, SWR_NO_CLIP, nocover);
+            rect = emit_triangle(P, c0, c1, c2, slot, dflag, seq, SWR_NO_CLIP, nocover);
         }
         P.rects[slot] = nocover ? 0u : rect;  // k_clip overwrites it when fan 0 of a clipped polygon survives
     }
@@ -328,7 +336,8 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip(SetupParams P) {
                     const uint32_t fan = lane - 1;
                     const uint32_t sl = fan == 0 ? gg : P.total_tris + ext + fan - 1;
                     rect_out = emit_triangle(P, make_float4(v0[0], v0[1], v0[2], v0[3]), make_float4(v1[0], v1[1], v1[2], v1[3]),
-                                             make_float4(v2[0], v2[1], v2[2], v2[3]), sl, dd, (dr.first_tri + ttri) * 8u + fan, vbase, nocover_out);
+                                             make_float4(v2[0], v2[1], v2[2], v2[3]), sl, dd | ((P.mats[pr.material].flags & 1u) ? SWR_REC_ALPHA : 0u),
+                                             (dr.first_tri + ttri) * 8u + fan, vbase, nocover_out);
                     P.rects[sl] = nocover_out ? 0u : rect_out;
                     if (fan > 0 && rect_out != 0 && !nocover_out) P.clip_list[atomicAdd(&P.counters->clip_list_n, 1u)] = gg * 8u + fan;
                 }
@@ -466,10 +475,6 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
 // K3 pass 2: scatter refs (ids = dense triangle * 8 + fan). k_scatter: one thread per dense triangle (fan 0);
 // k_scatter_list: the surviving fans >= 1 of clipped polygons.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t record_of_id(uint32_t id, const uint32_t *clip_ext) {
-    const uint32_t fan = id & 7u, t = id >> 3;
-    return fan == 0 ? t : __ldg(clip_ext + t) + fan - 1u;
-}
 
 __device__ __forceinline__ void scatter_rect(uint32_t rect, uint32_t id, uint32_t *tile_cursor, uint32_t *refs, int tiles_x) {
     int tx0 = rect & 0xFF, ty0 = (rect >> 8) & 0xFF, tx1 = (rect >> 16) & 0xFF, ty1 = rect >> 24;
@@ -526,6 +531,11 @@ struct RasterParams {
     const uint32_t *tile_offset;
     const uint32_t *unit_list;  // tile << 14 | chunk, heaviest first; counters->raster_units entries
     const uint32_t *clip_ext;
+    const DevDraw *draws;  // the next five are only touched by alpha-tested fragments
+    const DevPrim *prims;
+    const DevMat *mats;
+    const DevTex *texs;
+    const ClipVertex *clip_verts;
     unsigned long long *keys;  // tile-major: tile * 4096 + y * 64 + x; low word = ~id
     FrameCounters *counters;
     unsigned long long *dbg_tiles;  // SWR_PROFILE_COUNTERS: per tile {cycles, refs, items, launch slot}
@@ -540,7 +550,7 @@ struct RasterParams {
 // tile (128 items of 8 quads) is shared by all warps instead of serialising one of them.
 struct TileBatch {
     int a[3][RASTER_THREADS], b[3][RASTER_THREADS], c[3][RASTER_THREADS];
-    // region origin in quads relative to the tile (5 + 5 bits) | nqx << 10 | nqy << 16 | coarse << 22 | exact << 23
+    // region origin in quads relative to the tile (5 + 5 bits) | nqx << 10 | nqy << 16 | coarse << 22 | exact << 23 | alpha-tested << 24
     uint32_t geom[RASTER_THREADS];
     uint32_t slot[RASTER_THREADS];
     float ooa[RASTER_THREADS], iw0[RASTER_THREADS], iwda[RASTER_THREADS], iwdb[RASTER_THREADS];
@@ -559,8 +569,71 @@ struct FragQueue {
     float w1[FRAGQ_CAP], w2[FRAGQ_CAP];
 };
 
-// tilerasterizer.rs:337-342 + depth_test :511-523 folded into one 64-bit atomicMin
-__device__ __forceinline__ void shade_fragment(unsigned long long *skeys, const TileBatch &tb, uint32_t pkpix, float w1, float w2) {
+// Texture coordinates of a record's three vertices: the primitive's uv stream, or the clipped polygon's stored vertices.
+__device__ __forceinline__ void fetch_tri_uv(const DevDraw *draws, const DevPrim *prims, const ClipVertex *clip_verts, const TriRecord &r,
+                                             float uu[3], float vv[3]) {
+    if (r.clip == SWR_NO_CLIP) {
+        const DevDraw &dr = draws[r.draw & ~SWR_REC_ALPHA];
+        const DevPrim &pr = prims[dr.prim];
+        const uint32_t tri = (r.seq >> 3) - dr.first_tri;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float2 uv = __ldg(pr.uv + __ldg(pr.idx + 3 * tri + k));
+            uu[k] = uv.x;
+            vv[k] = uv.y;
+        }
+    } else {
+        const uint32_t fan = r.seq & 7u;
+        const uint32_t vi[3] = {r.clip, r.clip + fan + 1u, r.clip + fan + 2u};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            uu[k] = __ldg(&clip_verts[vi[k]].u);
+            vv[k] = __ldg(&clip_verts[vi[k]].v);
+        }
+    }
+}
+
+// renderer.rs:738-754: packet.du_dv from the snapped positions and uv/w
+__device__ __forceinline__ void packet_du_dv(const TriRecord &r, const float uw[3], const float vw[3], float du_dv[4]) {
+    float dx1 = i2f(wsub(r.X1, r.X0)), dx2 = i2f(wsub(r.X2, r.X0)), dy1 = i2f(wsub(r.Y1, r.Y0)), dy2 = i2f(wsub(r.Y2, r.Y0));
+    float du1 = uw[1] - uw[0], du2 = uw[2] - uw[0], dv1 = vw[1] - vw[0], dv2 = vw[2] - vw[0];
+    float s = r.ooa * 16.0f;
+    du_dv[0] = (du1 * dy2 - du2 * dy1) * s;
+    du_dv[1] = (du2 * dx1 - du1 * dx2) * s;
+    du_dv[2] = (dv1 * dy2 - dv2 * dy1) * s;
+    du_dv[3] = (dv2 * dx1 - dv1 * dx2) * s;
+}
+
+struct RasterParams;
+// shader.rs:311-329 get_alpha_test_mask for one fragment: base-colour alpha at the fragment's uv, mip from the packet's
+// UNSCALED du_dv, compared with the material's cutoff. Slow path (re-reads the record and the uv stream): alpha-tested
+// materials are the exception.
+__device__ __noinline__ bool alpha_test_fragment(const TriRecord *records, const uint32_t *clip_ext, const DevDraw *draws, const DevPrim *prims,
+                                                const DevMat *mats, const DevTex *texs, const ClipVertex *clip_verts, uint32_t id, float b1,
+                                                float b2, float w) {
+    const TriRecord r = records[record_of_id(id, clip_ext)];
+    const DevMat &mat = mats[prims[draws[r.draw & ~SWR_REC_ALPHA].prim].material];
+    if (mat.tex_base < 0) return true;  // out_mask = mask
+    float uu[3], vv[3], uw[3], vw[3], du_dv[4];
+    fetch_tri_uv(draws, prims, clip_verts, r, uu, vv);
+    const float iw[3] = {r.iw0, r.iw1, r.iw2};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        uw[k] = uu[k] * iw[k];
+        vw[k] = vv[k] * iw[k];
+    }
+    packet_du_dv(r, uw, vw, du_dv);
+    const float u = (uw[0] + b1 * (uw[1] - uw[0]) + b2 * (uw[2] - uw[0])) * w;
+    const float v = (vw[0] + b1 * (vw[1] - vw[0]) + b2 * (vw[2] - vw[0])) * w;
+    const float alpha = sample4(texs[mat.tex_base], u, v, du_dv).w;
+    return alpha >= mat.alpha_cutoff;
+}
+
+// tilerasterizer.rs:337-342 + depth_test :511-523 (+ the alpha test of shader.rs:40-43) folded into one 64-bit atomicMin.
+// The alpha test does not depend on the depth state, so dropping alpha-failed fragments before the min is equivalent to
+// the reference's "depth test, then mask, then conditional depth write" for any packet order.
+template <typename RP>
+__device__ __forceinline__ void shade_fragment(const RP &P, unsigned long long *skeys, const TileBatch &tb, uint32_t pkpix, float w1, float w2) {
     const int pk = pkpix >> 16, pix = pkpix & 0xFFFF;
     const float ooa = tb.ooa[pk];
     float b1 = fmul(w1, ooa), b2 = fmul(w2, ooa);
@@ -569,18 +642,25 @@ __device__ __forceinline__ void shade_fragment(unsigned long long *skeys, const 
     float zz = fadd(fadd(tb.zw0[pk], fmul(b1, tb.zwda[pk])), fmul(b2, tb.zwdb[pk]));
     float z = fmul(zz, wpix);
     if (z == z) {  // NaN never passes `z <= current` (tilerasterizer.rs:516)
-        unsigned long long key = ((unsigned long long)depth_orderable(z) << 32) | (0xFFFFFFFFu - tb.slot[pk]);
+        const uint32_t id = tb.slot[pk];
+        unsigned long long key = ((unsigned long long)depth_orderable(z) << 32) | (0xFFFFFFFFu - id);
         // keys only ever decrease, so a (possibly stale) read that is already <= key proves the atomic would be a no-op;
         // the shared-memory 64-bit min is a CAS loop (ATOMS.CAST.SPIN.64), worth skipping for occluded fragments
-        if (key < *reinterpret_cast<volatile unsigned long long *>(&skeys[pix])) atomicMin(&skeys[pix], key);
+        if (key < *reinterpret_cast<volatile unsigned long long *>(&skeys[pix])) {
+            if ((tb.geom[pk] >> 24) & 1u) {
+                if (!alpha_test_fragment(P.records, P.clip_ext, P.draws, P.prims, P.mats, P.texs, P.clip_verts, id, b1, b2, wpix)) return;
+            }
+            atomicMin(&skeys[pix], key);
+        }
     }
 }
 
 // Drain up to 32 fragments from the tail of the warp's queue; returns the new count.
-__device__ __forceinline__ int drain_queue(unsigned long long *skeys, const TileBatch &tb, const FragQueue &fq, int qn, int lane) {
+template <typename RP>
+__device__ __forceinline__ int drain_queue(const RP &P, unsigned long long *skeys, const TileBatch &tb, const FragQueue &fq, int qn, int lane) {
     const int n = min(qn, 32);
     __syncwarp();
-    if (lane < n) shade_fragment(skeys, tb, fq.pkpix[qn - n + lane], fq.w1[qn - n + lane], fq.w2[qn - n + lane]);
+    if (lane < n) shade_fragment(P, skeys, tb, fq.pkpix[qn - n + lane], fq.w1[qn - n + lane], fq.w2[qn - n + lane]);
     __syncwarp();
     return qn - n;
 }
@@ -764,7 +844,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
                     tb.c[e][tid] = ps.c[e];
                 }
                 tb.geom[tid] = (uint32_t)((ps.xs >> 5) - tile_x0 / 2) | ((uint32_t)((ps.ys >> 5) - tile_y0 / 2) << 5) | ((uint32_t)ps.nqx << 10) |
-                               ((uint32_t)ps.nqy << 16) | (ps.coarse ? 1u << 22 : 0u) | (ps.exact ? 1u << 23 : 0u);
+                               ((uint32_t)ps.nqy << 16) | (ps.coarse ? 1u << 22 : 0u) | (ps.exact ? 1u << 23 : 0u) | ((r.draw & SWR_REC_ALPHA) ? 1u << 24 : 0u);
                 tb.slot[tid] = slot;
                 tb.ooa[tid] = r.ooa;
                 tb.iw0[tid] = r.iw0;
@@ -854,7 +934,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
 #ifdef SWR_PROFILE_COUNTERS
                         if (lane == 0) dbg_frags += __popc(m);
 #endif
-                        if (qn >= FRAGQ_DRAIN) qn = drain_queue(skeys, tb, fq, qn, lane);
+                        if (qn >= FRAGQ_DRAIN) qn = drain_queue(P, skeys, tb, fq, qn, lane);
                     }
                 }
 #pragma unroll
@@ -864,7 +944,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
                 st.pix += 2;
             }
         }
-        while (qn > 0) qn = drain_queue(skeys, tb, fq, qn, lane);  // fragments reference this batch's packets
+        while (qn > 0) qn = drain_queue(P, skeys, tb, fq, qn, lane);  // fragments reference this batch's packets
 #ifdef SWR_PROFILE_COUNTERS
         atomicAdd((unsigned long long *)&P.counters->dbg[2], dbg_steps);      // quads stepped (useful lanes)
         if (lane == 0) {

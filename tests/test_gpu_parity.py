@@ -119,3 +119,36 @@ def test_create_rejects_bad_arguments():
     assert core.swr_create(65, 64, 0) is None  # odd width
     assert b"even" in core.swr_last_error(None)
     assert core.swr_create(64, 64, 99) is None
+
+
+def alpha_scene():
+    """Alpha-tested (glTF MASK) terrain with holes over two opaque objects: exercises shader.rs:40-43 / 311-329."""
+    import math
+    from swraster_viewer_b200 import abi, scenes
+    tex = scenes.checker_noise_texture(64, 21, abi.TEX_SRGB, abi.WRAP_REPEAT, alpha_holes=True)
+    mats = [scenes.Material((1, 1, 1, 1), 0.0, 0.7, flags=abi.MAT_ALPHA_TESTED, base_color_texture=0, alpha_cutoff=0.5),
+            scenes.Material((0.9, 0.3, 0.2, 1), 0.0, 0.4)]
+    meshes = [[scenes.height_field(40, 5, extent=4.0, height=0.6, uv_repeat=2.0, material=0)], [scenes.uv_sphere(24, 16, 1.0, 1)]]
+    nodes = [scenes.Node(scenes.IDENT, 0), scenes.Node(scenes.trs((0.3, -0.9, 0.2), 1.2), 1), scenes.Node(scenes.trs((-1.8, 1.2, 0.8), 0.6), 1),
+             scenes.Node(scenes.trs((0.0, 1.5, 5.5), 2.5, (1, 0, 0), 1.2), 0)]  # a second alpha-tested sheet crossing the near plane
+    sc = scenes.SceneData(meshes, nodes, mats, [tex], voxel_dim=8, cube_size=32, seed=9)
+    cam = scenes.CameraSpec((0.4, 3.2, 6.0), (0.0, 0.2, 0.0), math.pi / 4, float(sc.bounds_diagonal) * 2.0)
+    return sc, cam
+
+
+def test_alpha_tested_material():
+    sc, spec = alpha_scene()
+    W, H = 448, 256
+    cam = swr.RenderCamera.from_spec(spec, W, H)
+    g = render_gpu(sc, cam, W, H)
+    o = render_oracle(sc, cam, W, H)
+    assert np.array_equal(g["seq"], o["seq"]), f"{np.count_nonzero(g['seq'] != o['seq'])} pixels differ"
+    assert np.array_equal(g["depth"], o["depth"])
+    assert np.array_equal(g["bary1"].view(np.uint32), o["bary1"].view(np.uint32))
+    # holes must actually show what is behind: some pixels inside the terrain's footprint belong to the sphere draws
+    ids = o["seq"][o["seq"] != 0xFFFFFFFF] >> 3
+    assert len(np.unique(ids)) > 500
+    err = np.abs(rgba_bytes(g["pixels"]) - rgba_bytes(o["pixels"]))
+    assert err.max() <= RGBA_TOL_LSB
+    for k in ("triangles_binned", "triangles_clipped", "tile_refs"):
+        assert g["stats"][k] == o["stats"][k]
