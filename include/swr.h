@@ -163,7 +163,9 @@ typedef struct swr_camera {
     float reserved[2];
 } swr_camera;
 
-#define SWR_DRAW_CLIP 1u /* primitive sphere intersects the frustum: renderer.rs:453-462 */
+#define SWR_DRAW_CLIP 1u        /* primitive sphere intersects the frustum: renderer.rs:453-462 */
+#define SWR_DRAW_TRANSLUCENT 2u /* primitive of mesh.primitives_translucent (renderer.rs:407-419): forward-shaded after the opaque
+                                 * pass, back to front per tile; first_triangle counts within the translucent draws only */
 
 /* One (node, opaque primitive) pair that survived the sphere/frustum test, in the
  * reference's serial submission order (renderer.rs:207 -> :396 -> :490).

@@ -308,6 +308,7 @@ struct PacketQueue {
 struct Tile {  // tilerasterizer.rs:25-38
     int32_t min_x, min_y, max_x, max_y;
     PacketQueue packets_opaque;
+    PacketQueue packets_translucent;
     std::vector<V3x4> color;
     std::vector<V4> depth;
     std::vector<U4> packet_index;
@@ -548,7 +549,9 @@ static void get_filtered_gi_sh4(const swr_voxel_grid_desc &g, V3x4 pos, V3x4 out
 // ---------------------------------------------------------------------------------
 // shader.rs:110-309 pbr_shader::<false>
 // ---------------------------------------------------------------------------------
-static V3x4 pbr_shader(const Oracle &o, const RasterPacket &packet, const swr_material_desc &mat, V4 bary1, V4 bary2) {
+// TRANSLUCENT = true adds the KHR_materials_transmission blend over `current_color` (shader.rs:265-277)
+static V3x4 pbr_shader(const Oracle &o, const RasterPacket &packet, const swr_material_desc &mat, V4 bary1, V4 bary2, bool translucent = false,
+                       V3x4 current_color = V3x4()) {
     const swr_scene_desc &sc = *o.scene;
     const V4 EPS = splat(1e-6f), PI = splat(3.14159265358979323846f), ONE = splat(1.0f), ZERO = splat(0.0f);
     V4 w = 1.0f / packet.one_over_w.interpolate(bary1, bary2);
@@ -648,7 +651,17 @@ static V3x4 pbr_shader(const Oracle &o, const RasterPacket &packet, const swr_ma
     V4 ao_spec = ONE + (ao - ONE) * splat(0.5f);
     color_indirect_specular = color_indirect_specular * (ao_spec * sky_visibility);
 
-    V3x4 color = color_direct_diffuse + color_direct_specular + color_indirect_diffuse + color_indirect_specular;
+    V3x4 color;
+    if (translucent) {
+        V4 transmission = splat(mat.transmission);
+        if (mat.transmission_texture >= 0) transmission = transmission * sample4_rgb(sc.textures[mat.transmission_texture], uv_x, uv_y, du_dv).x;
+        transmission = vclamp(transmission, ZERO, ONE);
+        V4 inv_transmission = ONE - transmission;
+        color = (current_color * base * transmission) + ((color_direct_diffuse + color_indirect_diffuse) * inv_transmission) + color_direct_specular +
+                color_indirect_specular;
+    } else {
+        color = color_direct_diffuse + color_direct_specular + color_indirect_diffuse + color_indirect_specular;
+    }
     V3x4 emissive_mat = v3splat(1.0f);
     if (mat.emissive_texture >= 0)
         emissive_mat = srgb_to_linear_fast(sample4_rgb(sc.textures[mat.emissive_texture], uv_x, uv_y, du_dv));
@@ -665,6 +678,7 @@ static const int SUBPIXEL_SCALE = 16, SUBPIXEL_SHIFT = 4, STEP = 32, HALF_PIXEL 
                  COARSE_PX = 16, COARSE_SUB = 256, TILE = 64;
 
 struct RasterParams {
+    bool translucent = false;  // TranslucentForwardShader instead of VBufferOpaqueShader
     const RasterPacket *packet;
     uint32_t packet_index;
     const swr_material_desc *material;
@@ -715,7 +729,12 @@ static void fine_raster(const Oracle &o, Tile &tile, const RasterParams &rp, int
                 V4 cur = tile.depth[index];
                 M4 fmask = mand(mask, cmple(z, cur));
                 V4 fdepth = select(fmask, z, cur);
-                if (many(fmask)) {
+                if (many(fmask) && rp.translucent) {
+                    // TranslucentForwardShader::shade shader.rs:66-76 (depth is tested but never written)
+                    V3x4 cur_col = tile.color[index];
+                    V3x4 col = pbr_shader(o, *rp.packet, *rp.material, bary1, bary2, true, cur_col);
+                    tile.color[index] = v3select(fmask, col, cur_col);
+                } else if (many(fmask)) {
                     // VBufferOpaqueShader::shade shader.rs:32-63
                     M4 m = fmask;
                     bool alpha_tested = (rp.material->flags & SWR_MAT_ALPHA_TESTED) != 0;
@@ -768,8 +787,9 @@ static inline int32_t wmul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a 
 static inline int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
 static inline int32_t wsub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
 
-static void rasterize_packet(const Oracle &o, Tile &tile, uint32_t packet_index, const RasterPacket &p) {  // :114-218
+static void rasterize_packet(const Oracle &o, Tile &tile, uint32_t packet_index, const RasterPacket &p, bool translucent = false) {  // :114-218
     RasterParams rp;
+    rp.translucent = translucent;
     rp.packet = &p;
     rp.packet_index = packet_index;
     const swr_primitive_desc &prim = o.scene->primitives[p.primitive_index];
@@ -870,6 +890,13 @@ static void shade_vbuffer(const Oracle &o, Tile &tile, bool skybox_only) {  // :
     }
 }
 
+// OrderedFloat total order used by sort_by_key (renderer.rs:361-366): NaN sorts last.
+static inline bool of_less(float a, float b) {
+    bool an = a != a, bn = b != b;
+    if (an || bn) return !an && bn;
+    return a < b;
+}
+
 static void render_tile(Oracle &o, Tile &tile, bool shade) {  // :72-111
     std::fill(tile.depth.begin(), tile.depth.end(), splat(INFINITY));
     uint32_t n = tile.packets_opaque.len();
@@ -879,6 +906,23 @@ static void render_tile(Oracle &o, Tile &tile, bool shade) {  // :72-111
     }
     if (shade) {
         shade_vbuffer(o, tile, n == 0);
+        // :92-101 sort translucent packets back to front and forward-shade them. The reference's quicksort
+        // (bumpqueue.rs:155-202) is unstable; equal avg_z keeps submission order here (documented in DESIGN.md).
+        uint32_t nt = tile.packets_translucent.len();
+        if (nt) {
+            std::vector<uint32_t> order(nt);
+            for (uint32_t i = 0; i < nt; i++) order[i] = i;
+            // OrderedFloat descending; with a parallel bin phase the push order is arbitrary, so ties fall back to seq
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+                const RasterPacket &pa = tile.packets_translucent.ref(a), &pb = tile.packets_translucent.ref(b);
+                if (pa.avg_z != pb.avg_z) return of_less(pb.avg_z, pa.avg_z);
+                return pa.seq < pb.seq;
+            });
+            for (uint32_t i = 0; i < nt; i++) {
+                RasterPacket packet = tile.packets_translucent.get(order[i]);
+                rasterize_packet(o, tile, i, packet, true);
+            }
+        }
         // :103-106
         const V3x4 &cq = tile.color[tile.color.size() / 2];
         V4 lum = cq.x * 0.2126f + cq.y * 0.7152f + cq.z * 0.0722f;
@@ -897,7 +941,7 @@ static inline void clip_to_screen_subpixels(const Oracle &o, F4 v, int32_t &X, i
     Y = f2i(roundf(sy * 16.0f));
 }
 
-static void bin_triangle(Oracle &o, const Vertex tri[3], uint32_t mesh_index, uint32_t primitive_index, uint32_t seq) {  // :668-831
+static void bin_triangle(Oracle &o, const Vertex tri[3], uint32_t mesh_index, uint32_t primitive_index, uint32_t seq, bool opaque) {  // :668-831
     int32_t X[3], Y[3];
     for (int i = 0; i < 3; i++) clip_to_screen_subpixels(o, tri[i].pos_clip, X[i], Y[i]);
     int32_t area = wsub(wmul(wsub(X[1], X[0]), wsub(Y[2], Y[0])), wmul(wsub(X[2], X[0]), wsub(Y[1], Y[0])));
@@ -958,7 +1002,8 @@ static void bin_triangle(Oracle &o, const Vertex tri[3], uint32_t mesh_index, ui
     pk.pos_world_over_w.set(pww[0], pww[1], pww[2]);
     pk.primitive_index = primitive_index;
     pk.mesh_index = mesh_index;
-    pk.avg_z = 0.0f;
+    // renderer.rs:765-775
+    pk.avg_z = opaque ? 0.0f : (tri[0].pos_clip.z + tri[1].pos_clip.z + tri[2].pos_clip.z) / 3.0f;
     pk.seq = seq;
 
     bool any = false;
@@ -975,7 +1020,10 @@ static void bin_triangle(Oracle &o, const Vertex tri[3], uint32_t mesh_index, ui
                 pk.min_y = cminy;
                 pk.max_x = cmaxx;
                 pk.max_y = cmaxy;
-                t.packets_opaque.push(pk);
+                if (opaque)
+                    t.packets_opaque.push(pk);
+                else
+                    t.packets_translucent.push(pk);
                 any = true;
                 if (x >= tile_w)
                     ndup++;  // column overflow wrapped into the next tile row: identical duplicate
@@ -984,9 +1032,11 @@ static void bin_triangle(Oracle &o, const Vertex tri[3], uint32_t mesh_index, ui
             }
         }
     }
-    if (any) o.stats.tris_binned.fetch_add(1, std::memory_order_relaxed);
-    o.stats.packets.fetch_add(npk, std::memory_order_relaxed);
-    o.stats.packets_dup.fetch_add(ndup, std::memory_order_relaxed);
+    if (opaque) {  // the reported counters describe the opaque pass (what the BASELINE configs exercise)
+        if (any) o.stats.tris_binned.fetch_add(1, std::memory_order_relaxed);
+        o.stats.packets.fetch_add(npk, std::memory_order_relaxed);
+        o.stats.packets_dup.fetch_add(ndup, std::memory_order_relaxed);
+    }
 }
 
 static inline Vertex intersect(const Vertex &v0, const Vertex &v1, F4 plane) {  // :598-609
@@ -1014,7 +1064,7 @@ static inline Vertex intersect(const Vertex &v0, const Vertex &v1, F4 plane) {  
     return r;
 }
 
-static void clip_against_frustum(Oracle &o, const Vertex tri[3], uint32_t mesh_index, uint32_t primitive_index, uint32_t seq_base) {  // :579-665
+static void clip_against_frustum(Oracle &o, const Vertex tri[3], uint32_t mesh_index, uint32_t primitive_index, uint32_t seq_base, bool opaque) {  // :579-665
     static const F4 PLANES[6] = {{0, 0, 1, 1}, {0, 0, -1, 1}, {1, 0, 0, 1}, {-1, 0, 0, 1}, {0, 1, 0, 1}, {0, -1, 0, 1}};
     Vertex poly[16], np[16];
     int n = 3;
@@ -1046,10 +1096,10 @@ static void clip_against_frustum(Oracle &o, const Vertex tri[3], uint32_t mesh_i
         n = m;
     }
     if (n < 3) return;
-    if (touched) o.stats.tris_clipped.fetch_add(1, std::memory_order_relaxed);
+    if (touched && opaque) o.stats.tris_clipped.fetch_add(1, std::memory_order_relaxed);
     for (int i = 1; i < n - 1; i++) {
         Vertex t[3] = {poly[0], poly[i], poly[i + 1]};
-        bin_triangle(o, t, mesh_index, primitive_index, seq_base + (uint32_t)(i - 1));
+        bin_triangle(o, t, mesh_index, primitive_index, seq_base + (uint32_t)(i - 1), opaque);
     }
 }
 
@@ -1068,10 +1118,11 @@ static void process_triangle(Oracle &o, const Draw &d, uint32_t tri_idx) {  // r
         tri[k].uv = F2{prim.texcoords[i * 2 + 0], prim.texcoords[i * 2 + 1]};
     }
     uint32_t seq = (d.first_triangle + tri_idx) * 8u;
+    const bool opaque = !(d.flags & SWR_DRAW_TRANSLUCENT);
     if (d.flags & SWR_DRAW_CLIP)
-        clip_against_frustum(o, tri, d.mesh, d.primitive, seq);
+        clip_against_frustum(o, tri, d.mesh, d.primitive, seq, opaque);
     else
-        bin_triangle(o, tri, d.mesh, d.primitive, seq);
+        bin_triangle(o, tri, d.mesh, d.primitive, seq, opaque);
 }
 
 // scene.rs:53-63 Mat4 * &BoundingSphere, renderer.rs:130-142 test_sphere_frustum
@@ -1099,13 +1150,6 @@ static int classify_sphere(const swr_camera &cam, const float *model, const floa
     return result;
 }
 
-// OrderedFloat total order used by sort_by_key (renderer.rs:361-366): NaN sorts last.
-static inline bool of_less(float a, float b) {
-    bool an = a != a, bn = b != b;
-    if (an || bn) return !an && bn;
-    return a < b;
-}
-
 static void build_draws(Oracle &o) {  // renderer.rs:357-468
     const swr_scene_desc &sc = *o.scene;
     std::vector<uint32_t> order(sc.nnodes);
@@ -1117,7 +1161,7 @@ static void build_draws(Oracle &o) {  // renderer.rs:357-468
         key[i] = dot3(d, d);
     }
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return of_less(key[a], key[b]); });
-    uint32_t first_tri = 0;
+    uint32_t first_tri = 0, first_tri_t = 0;
     o.draws.clear();
     o.tris_submitted = 0;
     o.verts_submitted = 0;
@@ -1125,23 +1169,31 @@ static void build_draws(Oracle &o) {  // renderer.rs:357-468
         const swr_node_desc &node = sc.nodes[ni];
         if (node.mesh_index < 0) continue;
         const swr_mesh_desc &mesh = sc.meshes[node.mesh_index];
-        for (uint32_t pi = mesh.first_primitive; pi < mesh.first_primitive + mesh.num_primitives; pi++) {
-            const swr_primitive_desc &prim = sc.primitives[pi];
-            if (sc.materials[prim.material_index].flags & SWR_MAT_TRANSLUCENT) continue;  // translucent pass: SURVEY §8f N1
-            int cls = classify_sphere(*o.cam, node.transform, prim.bounding_sphere);
-            if (cls == 2) continue;
-            Draw d;
-            memcpy(d.model, node.transform, sizeof(d.model));
-            mul_mat4(o.cam->view_project_matrix, node.transform, d.mvp);  // renderer.rs:378
-            d.primitive = pi;
-            d.mesh = (uint32_t)node.mesh_index;
-            d.flags = cls == 1 ? SWR_DRAW_CLIP : 0;
-            d.first_triangle = first_tri;
-            uint32_t nt = prim.nindices / 3;
-            first_tri += nt;
-            o.tris_submitted += nt;
-            o.verts_submitted += prim.nverts;
-            o.draws.push_back(d);
+        for (int pass = 0; pass < 2; pass++) {  // render_mesh: primitives_opaque, then primitives_translucent (renderer.rs:386-420)
+            for (uint32_t pi = mesh.first_primitive; pi < mesh.first_primitive + mesh.num_primitives; pi++) {
+                const swr_primitive_desc &prim = sc.primitives[pi];
+                const bool tr = (sc.materials[prim.material_index].flags & SWR_MAT_TRANSLUCENT) != 0;
+                if (tr != (pass == 1)) continue;
+                int cls = classify_sphere(*o.cam, node.transform, prim.bounding_sphere);
+                if (cls == 2) continue;
+                Draw d;
+                memcpy(d.model, node.transform, sizeof(d.model));
+                mul_mat4(o.cam->view_project_matrix, node.transform, d.mvp);  // renderer.rs:378
+                d.primitive = pi;
+                d.mesh = (uint32_t)node.mesh_index;
+                d.flags = (cls == 1 ? SWR_DRAW_CLIP : 0) | (tr ? SWR_DRAW_TRANSLUCENT : 0);
+                uint32_t nt = prim.nindices / 3;
+                if (tr) {  // translucent packets have their own queue, hence their own submission order ids
+                    d.first_triangle = first_tri_t;
+                    first_tri_t += nt;
+                } else {
+                    d.first_triangle = first_tri;
+                    first_tri += nt;
+                    o.tris_submitted += nt;
+                    o.verts_submitted += prim.nverts;
+                }
+                o.draws.push_back(d);
+            }
         }
     }
 }
@@ -1248,6 +1300,7 @@ int orc_render(void *h, const swr_scene_desc *scene, const swr_camera *cam, int 
     o.stats.packets_dup = 0;
     for (Tile *t : o.tiles) {
         t->packets_opaque.reset();
+        t->packets_translucent.reset();
         std::fill(t->written.begin(), t->written.end(), U4{{0, 0, 0, 0}});
         if (fresh) {
             std::fill(t->packet_index.begin(), t->packet_index.end(), U4{{0, 0, 0, 0}});
@@ -1295,7 +1348,10 @@ int orc_render(void *h, const swr_scene_desc *scene, const swr_camera *cam, int 
         st->ms_clipbin = o.ms_clipbin;
         st->ms_raster = o.ms_raster;
     }
-    for (Tile *t : o.tiles) t->packets_opaque.reset();  // tilerasterizer.rs:109
+    for (Tile *t : o.tiles) {  // tilerasterizer.rs:109-110
+        t->packets_opaque.reset();
+        t->packets_translucent.reset();
+    }
     return 0;
 }
 

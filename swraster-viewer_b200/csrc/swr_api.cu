@@ -48,6 +48,30 @@ struct Staging {  // pinned host mirror of the per-frame draw table, rotated so 
     cudaEvent_t done = nullptr;
 };
 
+// Everything one geometry pass (set-up, clip, bin) owns. Two instances: the opaque primitives (visibility buffer) and the
+// translucent ones (forward-shaded afterwards, tilerasterizer.rs:92-101).
+struct GeomSet {
+    DevBuf<DevDraw> draws;
+    DevBuf<uint32_t> tri_prefix;
+    DevBuf<TriRecord> records;
+    DevBuf<uint32_t> rects;
+    DevBuf<float> avgz;  // translucent set only: packet.avg_z per record (renderer.rs:765-775)
+    DevBuf<ClipVertex> clip_verts;
+    DevBuf<uint32_t> clip_queue, clip_ext, clip_list;
+    size_t ext_cap = 0;
+    DevBuf<uint32_t> tile_count, tile_offset, tile_cursor;
+    DevBuf<uint32_t> refs;
+    DevBuf<FrameCounters> counters;
+    FrameCounters *h_counters = nullptr;  // pinned
+    Staging staging[4];
+    int staging_next = 0;
+    std::vector<swr_draw> last_draws;
+    uint32_t ndraws = 0, total_tris = 0;
+    uint64_t total_verts = 0;
+    uint64_t refs_emitted = 0;
+    bool rendered_once = false;
+};
+
 struct swr_ctx {
     int device = 0;
     int num_sms = 148;
@@ -65,17 +89,10 @@ struct swr_ctx {
     DevScene scene{};
     std::vector<uint32_t> prim_ntris, prim_nverts;
 
-    // frame
-    DevBuf<DevDraw> draws;
-    DevBuf<uint32_t> tri_prefix;
-    DevBuf<TriRecord> records;
-    DevBuf<uint32_t> rects;
-    DevBuf<ClipVertex> clip_verts;
-    DevBuf<uint32_t> tile_count, tile_offset, tile_cursor, tile_order, tile_cycles, tile_cycles_prev, tile_count_prev, tile_unit;
+    // frame: geometry sets (opaque pass, translucent pass) + shared per-frame buffers
+    GeomSet op, tr;
+    DevBuf<uint32_t> tile_order, tile_cycles, tile_cycles_prev, tile_count_prev, tile_unit;
     bool have_history = false;
-    DevBuf<uint32_t> clip_queue, clip_ext, clip_list;
-    size_t ext_cap = 0;
-    DevBuf<uint32_t> refs;
     DevBuf<unsigned long long> keys;
     DevBuf<float4> color;
     DevBuf<uint32_t> pixels;
@@ -83,27 +100,19 @@ struct swr_ctx {
     DevBuf<float2> bary;
     bool composited = false;
     int sky_r0 = 0, sky_r1 = 0;
-    DevBuf<FrameCounters> counters;
     DevBuf<unsigned long long> dbg_tiles;
     DevBuf<uint32_t> rsqrt_tab;
     int rsqrt_bits = 0;
     bool rsqrt_on = false;
-    FrameCounters *h_counters = nullptr;  // pinned
-    Staging staging[4];
-    int staging_next = 0;
-
+    DevBuf<unsigned long long> tsort_keys;  // translucent pass: per-tile sorted (avg_z desc, seq) keys
+    DevBuf<uint32_t> tsort_ids;
     // replay info
-    std::vector<swr_draw> last_draws;
     swr_camera last_cam{};
     int last_shade = 0;
     bool frame_pending = false;
     bool frame_valid = false;
-    uint32_t ndraws = 0, nslots = 0, total_tris = 0;
-    uint64_t total_verts = 0;
     DevCamera dcam{};
     swr_frame_stats stats{};
-    bool rendered_once = false;
-    uint64_t refs_emitted = 0;
 };
 
 template <typename T>
@@ -176,13 +185,13 @@ swr_ctx *swr_create(int width, int height, int device) {
     bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < 5; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     for (int i = 0; ok && i < 2; i++) ok = cudaEventCreate(&ctx->ev_res[i]) == cudaSuccess;
-    for (int i = 0; ok && i < 4; i++) ok = cudaEventCreateWithFlags(&ctx->staging[i].done, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaMallocHost(&ctx->h_counters, sizeof(FrameCounters)) == cudaSuccess;
-    ok = ok && ctx->tile_count.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_offset.reserve(ctx->ntiles + 1) == cudaSuccess &&
-         ctx->tile_cursor.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_cycles.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_cycles_prev.reserve(ctx->ntiles + 1) == cudaSuccess &&
+    for (int i = 0; ok && i < 4; i++) ok = cudaEventCreateWithFlags(&ctx->op.staging[i].done, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMallocHost(&ctx->op.h_counters, sizeof(FrameCounters)) == cudaSuccess;
+    ok = ok && ctx->op.tile_count.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->op.tile_offset.reserve(ctx->ntiles + 1) == cudaSuccess &&
+         ctx->op.tile_cursor.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_cycles.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_cycles_prev.reserve(ctx->ntiles + 1) == cudaSuccess &&
          ctx->tile_count_prev.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_unit.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_order.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->keys.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess &&
          ctx->color.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess && ctx->pixels.reserve((size_t)width * height) == cudaSuccess &&
-         ctx->lum.reserve(ctx->ntiles) == cudaSuccess && ctx->counters.reserve(1) == cudaSuccess;
+         ctx->lum.reserve(ctx->ntiles) == cudaSuccess && ctx->op.counters.reserve(1) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_raster_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes()) == cudaSuccess;
     if (ok) {
         ok = cudaMemsetAsync(ctx->keys.p, 0xFF, (size_t)ctx->ntiles * SWR_TILE_PIXELS * 8, ctx->stream) == cudaSuccess &&
@@ -212,35 +221,39 @@ void swr_destroy(swr_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_scene(ctx);
-    ctx->draws.release();
-    ctx->tri_prefix.release();
-    ctx->records.release();
-    ctx->rects.release();
-    ctx->clip_verts.release();
-    ctx->tile_count.release();
-    ctx->tile_offset.release();
-    ctx->tile_cursor.release();
+    for (GeomSet *g : {&ctx->op, &ctx->tr}) {
+        g->draws.release();
+        g->tri_prefix.release();
+        g->records.release();
+        g->rects.release();
+        g->avgz.release();
+        g->clip_verts.release();
+        g->clip_queue.release();
+        g->clip_ext.release();
+        g->clip_list.release();
+        g->tile_count.release();
+        g->tile_offset.release();
+        g->tile_cursor.release();
+        g->refs.release();
+        g->counters.release();
+        if (g->h_counters) cudaFreeHost(g->h_counters);
+        for (auto &st : g->staging) {
+            if (st.host) cudaFreeHost(st.host);
+            if (st.done) cudaEventDestroy(st.done);
+        }
+    }
     ctx->tile_order.release();
     ctx->tile_cycles.release();
     ctx->tile_cycles_prev.release();
     ctx->tile_count_prev.release();
     ctx->tile_unit.release();
-    ctx->clip_queue.release();
-    ctx->clip_ext.release();
-    ctx->clip_list.release();
-    ctx->refs.release();
     ctx->keys.release();
     ctx->color.release();
     ctx->pixels.release();
     ctx->lum.release();
     ctx->bary.release();
-    ctx->counters.release();
     ctx->rsqrt_tab.release();
-    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
-    for (auto &s : ctx->staging) {
-        if (s.host) cudaFreeHost(s.host);
-        if (s.done) cudaEventDestroy(s.done);
-    }
+    ctx->dbg_tiles.release();
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
     for (auto &e : ctx->ev_res)
@@ -428,14 +441,14 @@ int swr_upload_scene(swr_ctx *ctx, const swr_scene_desc *s) {
     return SWR_OK;
 }
 
-// Enqueue one frame from ctx->last_* (no host synchronisation).
-static int launch_frame(swr_ctx *ctx) {
-    const std::vector<swr_draw> &draws = ctx->last_draws;
+// Geometry half of a pass for one set of draws: host tables -> k_setup -> k_clip -> scan -> scatter. No host synchronisation.
+static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
+    const std::vector<swr_draw> &draws = g.last_draws;
     const uint32_t nd = (uint32_t)draws.size();
-    // host-side tables: DevDraw + local triangle prefix + slot bases
     size_t bytes = (size_t)nd * sizeof(DevDraw) + (size_t)(nd + 1) * sizeof(uint32_t);
-    Staging &st = ctx->staging[ctx->staging_next];
-    ctx->staging_next = (ctx->staging_next + 1) & 3;
+    Staging &st = g.staging[g.staging_next];
+    g.staging_next = (g.staging_next + 1) & 3;
+    if (!st.done) CK(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
     CK(cudaEventSynchronize(st.done));
     if (st.bytes < bytes) {
         if (st.host) cudaFreeHost(st.host);
@@ -446,7 +459,7 @@ static int launch_frame(swr_ctx *ctx) {
     }
     DevDraw *hd = (DevDraw *)st.host;
     uint32_t *hp = (uint32_t *)((char *)st.host + (size_t)nd * sizeof(DevDraw));
-    uint64_t tris = 0, slots = 0, verts = 0, clip_tris = 0;
+    uint64_t tris = 0, verts = 0, clip_tris = 0;
     for (uint32_t i = 0; i < nd; i++) {
         const swr_draw &d = draws[i];
         if (d.primitive >= ctx->prim_ntris.size()) {
@@ -476,65 +489,64 @@ static int launch_frame(swr_ctx *ctx) {
     }
     // records: [0, tris) = fan 0 of every triangle (dense), then the extension area for fans >= 1 of clipped polygons
     size_t want_ext = (size_t)clip_tris / 16 + 4096;
-    if (ctx->ext_cap < want_ext && !ctx->rendered_once) ctx->ext_cap = want_ext;
-    if (ctx->ext_cap < 4096) ctx->ext_cap = 4096;
-    slots = tris + ctx->ext_cap;
-    ctx->ndraws = nd;
-    ctx->total_tris = (uint32_t)tris;
-    ctx->nslots = (uint32_t)slots;
-    ctx->total_verts = verts;
-    if (ctx->draws.reserve(nd + 1) != cudaSuccess || ctx->tri_prefix.reserve(nd + 2) != cudaSuccess || ctx->records.reserve(slots + 1) != cudaSuccess ||
-        ctx->rects.reserve(slots + 1) != cudaSuccess) {
+    if (g.ext_cap < want_ext && !g.rendered_once) g.ext_cap = want_ext;
+    if (g.ext_cap < 4096) g.ext_cap = 4096;
+    const size_t slots = tris + g.ext_cap;
+    g.ndraws = nd;
+    g.total_tris = (uint32_t)tris;
+    g.total_verts = verts;
+    bool ok = g.draws.reserve(nd + 1) == cudaSuccess && g.tri_prefix.reserve(nd + 2) == cudaSuccess && g.records.reserve(slots + 1) == cudaSuccess &&
+              g.rects.reserve(slots + 1) == cudaSuccess && g.tile_count.reserve(ctx->ntiles + 1) == cudaSuccess &&
+              g.tile_offset.reserve(ctx->ntiles + 1) == cudaSuccess && g.tile_cursor.reserve(ctx->ntiles + 1) == cudaSuccess &&
+              g.counters.reserve(1) == cudaSuccess && (!translucent || g.avgz.reserve(slots + 1) == cudaSuccess);
+    if (ok && !g.h_counters) ok = cudaMallocHost(&g.h_counters, sizeof(FrameCounters)) == cudaSuccess;
+    if (!ok) {
         ctx->err = "out of device memory for per-frame triangle records";
         return SWR_ERR_OOM;
     }
     size_t want_refs = (size_t)(tris + tris / 2) + (1u << 16);
-    if (ctx->refs.cap < want_refs && !ctx->rendered_once) {
-        if (ctx->refs.reserve(want_refs) != cudaSuccess) {
+    if (g.refs.cap < want_refs && !g.rendered_once) {
+        if (g.refs.reserve(want_refs) != cudaSuccess) {
             ctx->err = "out of device memory for tile lists";
             return SWR_ERR_OOM;
         }
     }
-    if (ctx->refs.cap == 0 && ctx->refs.reserve(1u << 16) != cudaSuccess) return SWR_ERR_OOM;
+    if (g.refs.cap == 0 && g.refs.reserve(1u << 16) != cudaSuccess) return SWR_ERR_OOM;
     size_t want_clip = (size_t)clip_tris / 4 + 4096;
-    if (ctx->clip_verts.cap < want_clip && !ctx->rendered_once) {
-        if (ctx->clip_verts.reserve(want_clip) != cudaSuccess) return SWR_ERR_OOM;
+    if (g.clip_verts.cap < want_clip && !g.rendered_once) {
+        if (g.clip_verts.reserve(want_clip) != cudaSuccess) return SWR_ERR_OOM;
     }
-    if (ctx->clip_verts.cap == 0 && ctx->clip_verts.reserve(4096) != cudaSuccess) return SWR_ERR_OOM;
-    if (ctx->clip_queue.reserve(clip_tris + 1) != cudaSuccess || ctx->clip_ext.reserve(tris + 1) != cudaSuccess ||
-        ctx->clip_list.reserve(ctx->ext_cap + 1) != cudaSuccess)
+    if (g.clip_verts.cap == 0 && g.clip_verts.reserve(4096) != cudaSuccess) return SWR_ERR_OOM;
+    if (g.clip_queue.reserve(clip_tris + 1) != cudaSuccess || g.clip_ext.reserve(tris + 1) != cudaSuccess || g.clip_list.reserve(g.ext_cap + 1) != cudaSuccess)
         return SWR_ERR_OOM;
 
     cudaStream_t s = ctx->stream;
-    CK(cudaEventRecord(ctx->ev[0], s));
-    if (nd) CK(cudaMemcpyAsync(ctx->draws.p, hd, (size_t)nd * sizeof(DevDraw), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->tri_prefix.p, hp, (size_t)(nd + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    if (nd) CK(cudaMemcpyAsync(g.draws.p, hd, (size_t)nd * sizeof(DevDraw), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(g.tri_prefix.p, hp, (size_t)(nd + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(st.done, s));
-    CK(cudaMemsetAsync(ctx->tile_count.p, 0, (ctx->ntiles + 1) * sizeof(uint32_t), s));
-    // raster cycles of the previous frame become the history that sizes this frame's work units
-    std::swap(ctx->tile_cycles.p, ctx->tile_cycles_prev.p);
-    CK(cudaMemsetAsync(ctx->tile_cycles.p, 0, (ctx->ntiles + 1) * sizeof(uint32_t), s));
-    CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(FrameCounters), s));
+    CK(cudaMemsetAsync(g.tile_count.p, 0, (ctx->ntiles + 1) * sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(g.counters.p, 0, sizeof(FrameCounters), s));
 
     const int rb = ctx->row_begin, re = ctx->row_end;
     if (tris > 0) {
         SetupParams sp{};
-        sp.draws = ctx->draws.p;
-        sp.tri_prefix = ctx->tri_prefix.p;
+        sp.draws = g.draws.p;
+        sp.tri_prefix = g.tri_prefix.p;
         sp.ndraws = nd;
         sp.total_tris = (uint32_t)tris;
         sp.prims = ctx->scene.prims;
         sp.mats = ctx->scene.mats;
-        sp.records = ctx->records.p;
-        sp.rects = ctx->rects.p;
-        sp.clip_verts = ctx->clip_verts.p;
-        sp.clip_capacity = (uint32_t)ctx->clip_verts.cap;
-        sp.clip_queue = ctx->clip_queue.p;
-        sp.clip_ext = ctx->clip_ext.p;
-        sp.clip_list = ctx->clip_list.p;
-        sp.ext_capacity = (uint32_t)ctx->ext_cap;
-        sp.tile_count = ctx->tile_count.p;
-        sp.counters = ctx->counters.p;
+        sp.records = g.records.p;
+        sp.rects = g.rects.p;
+        sp.avgz = translucent ? g.avgz.p : nullptr;
+        sp.clip_verts = g.clip_verts.p;
+        sp.clip_capacity = (uint32_t)g.clip_verts.cap;
+        sp.clip_queue = g.clip_queue.p;
+        sp.clip_ext = g.clip_ext.p;
+        sp.clip_list = g.clip_list.p;
+        sp.ext_capacity = (uint32_t)g.ext_cap;
+        sp.tile_count = g.tile_count.p;
+        sp.counters = g.counters.p;
         sp.W = ctx->W;
         sp.H = ctx->H;
         sp.tiles_x = ctx->tiles_x;
@@ -547,33 +559,52 @@ static int launch_frame(swr_ctx *ctx) {
             k_clip<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), CLIP_THREADS, 0, s>>>(sp);
         }
     }
-    const size_t unit_cap = (size_t)ctx->ntiles + ctx->refs.cap / RASTER_UNIT_MIN + 1;
-    const uint32_t cta_slots = (uint32_t)ctx->num_sms * 4u;  // k_raster_tiles: 4 CTAs per SM
-    if (ctx->tile_order.reserve(unit_cap) != cudaSuccess) return SWR_ERR_OOM;
-    k_scan_tiles<<<1, 1024, 0, s>>>(ctx->tile_count.p, ctx->tile_offset.p, ctx->tile_cursor.p, ctx->ntiles, ctx->counters.p, (uint32_t)ctx->refs.cap,
-                                    ctx->tile_order.p, (uint32_t)unit_cap, rb * ctx->tiles_x, re * ctx->tiles_x, cta_slots, ctx->tile_unit.p,
-                                    ctx->tile_count_prev.p, ctx->tile_cycles_prev.p, ctx->have_history ? 1 : 0);
-    ctx->have_history = true;
-    if (tris > 0) {
-        k_scatter<<<(unsigned)((tris + 255) / 256), 256, 0, s>>>(ctx->rects.p, (uint32_t)tris, ctx->tile_cursor.p, ctx->refs.p, ctx->counters.p, ctx->tiles_x);
-        if (clip_tris > 0)
-            k_scatter_list<<<148, 256, 0, s>>>(ctx->rects.p, ctx->clip_list.p, ctx->clip_ext.p, ctx->tile_cursor.p, ctx->refs.p, ctx->counters.p, ctx->tiles_x);
+    if (translucent) {
+        k_scan_simple<<<1, 1024, 0, s>>>(g.tile_count.p, g.tile_offset.p, g.tile_cursor.p, ctx->ntiles, g.counters.p, (uint32_t)g.refs.cap);
+    } else {
+        const size_t unit_cap = (size_t)ctx->ntiles + g.refs.cap / RASTER_UNIT_MIN + 1;
+        const uint32_t cta_slots = (uint32_t)ctx->num_sms * 4u;  // k_raster_tiles: 4 CTAs per SM
+        if (ctx->tile_order.reserve(unit_cap) != cudaSuccess) return SWR_ERR_OOM;
+        k_scan_tiles<<<1, 1024, 0, s>>>(g.tile_count.p, g.tile_offset.p, g.tile_cursor.p, ctx->ntiles, g.counters.p, (uint32_t)g.refs.cap, ctx->tile_order.p,
+                                        (uint32_t)unit_cap, rb * ctx->tiles_x, re * ctx->tiles_x, cta_slots, ctx->tile_unit.p, ctx->tile_count_prev.p,
+                                        ctx->tile_cycles_prev.p, ctx->have_history ? 1 : 0);
+        ctx->have_history = true;
     }
+    if (tris > 0) {
+        k_scatter<<<(unsigned)((tris + 255) / 256), 256, 0, s>>>(g.rects.p, (uint32_t)tris, g.tile_cursor.p, g.refs.p, g.counters.p, ctx->tiles_x);
+        if (clip_tris > 0) k_scatter_list<<<148, 256, 0, s>>>(g.rects.p, g.clip_list.p, g.clip_ext.p, g.tile_cursor.p, g.refs.p, g.counters.p, ctx->tiles_x);
+    }
+    CK(cudaGetLastError());
+    return SWR_OK;
+}
+
+// Enqueue the opaque pass of one frame from ctx->op.last_draws: geometry + tile rasteriser (no host synchronisation).
+static int launch_frame(swr_ctx *ctx) {
+    cudaStream_t s = ctx->stream;
+    GeomSet &g = ctx->op;
+    CK(cudaEventRecord(ctx->ev[0], s));
+    // raster cycles of the previous frame become the history that sizes this frame's work units
+    std::swap(ctx->tile_cycles.p, ctx->tile_cycles_prev.p);
+    CK(cudaMemsetAsync(ctx->tile_cycles.p, 0, (ctx->ntiles + 1) * sizeof(uint32_t), s));
+    int rc = launch_geometry(ctx, g, false);
+    if (rc) return rc;
+    const int rb = ctx->row_begin, re = ctx->row_end;
+    const uint32_t cta_slots = (uint32_t)ctx->num_sms * 4u;
     CK(cudaEventRecord(ctx->ev[1], s));
     if (re > rb) {
         RasterParams rp{};
-        rp.records = ctx->records.p;
-        rp.refs = ctx->refs.p;
-        rp.tile_offset = ctx->tile_offset.p;
+        rp.records = g.records.p;
+        rp.refs = g.refs.p;
+        rp.tile_offset = g.tile_offset.p;
         rp.unit_list = ctx->tile_order.p;
-        rp.clip_ext = ctx->clip_ext.p;
-        rp.draws = ctx->draws.p;
+        rp.clip_ext = g.clip_ext.p;
+        rp.draws = g.draws.p;
         rp.prims = ctx->scene.prims;
         rp.mats = ctx->scene.mats;
         rp.texs = ctx->scene.texs;
-        rp.clip_verts = ctx->clip_verts.p;
+        rp.clip_verts = g.clip_verts.p;
         rp.keys = ctx->keys.p;
-        rp.counters = ctx->counters.p;
+        rp.counters = g.counters.p;
         rp.tile_cycles = ctx->tile_cycles.p;
         rp.tile_unit = ctx->tile_unit.p;
 #ifdef SWR_PROFILE_COUNTERS
@@ -590,9 +621,32 @@ static int launch_frame(swr_ctx *ctx) {
         k_raster_tiles<<<cta_slots, RASTER_THREADS, raster_smem_bytes(), s>>>(rp);  // persistent: one CTA per resident slot
     }
     CK(cudaEventRecord(ctx->ev[2], s));
-    CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(g.h_counters, g.counters.p, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
     CK(cudaGetLastError());
     return SWR_OK;
+}
+
+static void fill_shade_params(swr_ctx *ctx, const GeomSet &g, ShadeParams &sp) {
+    sp.keys = ctx->keys.p;
+    sp.records = g.records.p;
+    sp.clip_ext = g.clip_ext.p;
+    sp.draws = g.draws.p;
+    sp.clip_verts = g.clip_verts.p;
+    sp.scene = ctx->scene;
+    sp.cam = ctx->dcam;
+    sp.color = ctx->color.p;
+    sp.W = ctx->W;
+    sp.H = ctx->H;
+    sp.tiles_x = ctx->tiles_x;
+    sp.Wp = ctx->tiles_x * SWR_TILE;
+    sp.Hp = ctx->tiles_y * SWR_TILE;
+    sp.row_begin = ctx->row_begin;
+    sp.row_end = ctx->row_end;
+    sp.rsqrt_tab = ctx->rsqrt_on ? ctx->rsqrt_tab.p : nullptr;
+    sp.rsqrt_bits = ctx->rsqrt_bits;
+    sp.ext_bary = ctx->composited ? ctx->bary.p : nullptr;
+    sp.sky_row_begin = ctx->sky_r0;
+    sp.sky_row_end = ctx->sky_r1;
 }
 
 static int launch_shade(swr_ctx *ctx) {
@@ -600,28 +654,23 @@ static int launch_shade(swr_ctx *ctx) {
     const int rb = ctx->row_begin, re = ctx->row_end;
     if (re > rb) {
         ShadeParams sp{};
-        sp.keys = ctx->keys.p;
-        sp.records = ctx->records.p;
-        sp.clip_ext = ctx->clip_ext.p;
-        sp.draws = ctx->draws.p;
-        sp.clip_verts = ctx->clip_verts.p;
-        sp.scene = ctx->scene;
-        sp.cam = ctx->dcam;
-        sp.color = ctx->color.p;
-        sp.W = ctx->W;
-        sp.H = ctx->H;
-        sp.tiles_x = ctx->tiles_x;
-        sp.Wp = ctx->tiles_x * SWR_TILE;
-        sp.Hp = ctx->tiles_y * SWR_TILE;
-        sp.row_begin = rb;
-        sp.row_end = re;
-        sp.rsqrt_tab = ctx->rsqrt_on ? ctx->rsqrt_tab.p : nullptr;
-        sp.rsqrt_bits = ctx->rsqrt_bits;
-        sp.ext_bary = ctx->composited ? ctx->bary.p : nullptr;
-        sp.sky_row_begin = ctx->sky_r0;
-        sp.sky_row_end = ctx->sky_r1;
+        fill_shade_params(ctx, ctx->op, sp);
         dim3 grid(sp.Wp / 16, (re - rb) * SWR_TILE / SHADE_ROWS);
         k_shade<<<grid, SHADE_BLOCK, 0, s>>>(sp);
+        if (!ctx->tr.last_draws.empty() && !ctx->composited) {
+            // translucent pass (tilerasterizer.rs:92-101): own geometry set, per-tile back-to-front sort, forward shading
+            int rc = launch_geometry(ctx, ctx->tr, true);
+            if (rc) return rc;
+            GeomSet &t = ctx->tr;
+            k_sort_translucent<<<ctx->ntiles, 256, 0, s>>>(t.refs.p, t.tile_offset.p, t.avgz.p, t.clip_ext.p, t.counters.p);
+            ForwardParams fp{};
+            fill_shade_params(ctx, t, fp.sh);
+            fp.refs = t.refs.p;
+            fp.offset = t.tile_offset.p;
+            fp.counters = t.counters.p;
+            k_forward_translucent<<<grid, SHADE_BLOCK, 0, s>>>(fp);
+            CK(cudaMemcpyAsync(t.h_counters, t.counters.p, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
+        }
         const int t0 = rb * ctx->tiles_x, t1 = re * ctx->tiles_x;
         k_luminance<<<(t1 - t0 + 127) / 128, 128, 0, s>>>(ctx->color.p, ctx->lum.p, sp.Wp, sp.Hp, ctx->tiles_x, ctx->ntiles, t0, t1);
     }
@@ -644,14 +693,23 @@ static int finish_frame(swr_ctx *ctx) {
     for (int attempt = 0; attempt < 4; attempt++) {
         CK(cudaStreamSynchronize(ctx->stream));
         if (!ctx->frame_pending) return SWR_OK;
-        const FrameCounters c = *ctx->h_counters;
-        if (!c.overflow_refs && !c.overflow_clip && !c.overflow_ext) {
+        const FrameCounters c = *ctx->op.h_counters;
+        FrameCounters ct{};
+        const bool tr_ran = ctx->last_shade && !ctx->tr.last_draws.empty() && ctx->tr.h_counters;
+        if (tr_ran) ct = *ctx->tr.h_counters;
+        if (ct.overflow_sort) {
+            ctx->err = "a tile holds more than 4096 translucent triangles: the in-kernel back-to-front sort does not support that";
+            ctx->frame_pending = false;
+            return SWR_ERR_INVALID;
+        }
+        if (!c.overflow_refs && !c.overflow_clip && !c.overflow_ext && !ct.overflow_refs && !ct.overflow_clip && !ct.overflow_ext) {
+            ctx->tr.rendered_once = ctx->tr.rendered_once || tr_ran;
             ctx->frame_pending = false;
             ctx->frame_valid = true;
-            ctx->rendered_once = true;
+            ctx->op.rendered_once = true;
             swr_frame_stats &st = ctx->stats;
-            st.triangles_submitted = ctx->total_tris;
-            st.vertices_submitted = ctx->total_verts;
+            st.triangles_submitted = ctx->op.total_tris;
+            st.vertices_submitted = ctx->op.total_verts;
             uint64_t binned = 0, uncovered = 0;
             for (int k = 0; k < 32; k++) {
                 binned += c.tris_binned[k];
@@ -660,7 +718,7 @@ static int finish_frame(swr_ctx *ctx) {
             st.triangles_binned = binned;
             st.triangles_clipped = c.tris_clipped;
             st.tile_refs = c.tile_refs + uncovered;  // the reference's R: every (triangle, tile) packet it would push
-            ctx->refs_emitted = c.tile_refs;
+            ctx->op.refs_emitted = c.tile_refs;
             st.tiles = (uint32_t)ctx->ntiles;
 #ifdef SWR_PROFILE_COUNTERS
             if (ctx->dbg_tiles.p) {
@@ -691,19 +749,25 @@ static int finish_frame(swr_ctx *ctx) {
             if (ctx->last_shade) cudaEventElapsedTime(&st.ms_shade, ctx->ev[2], ctx->ev[3]);
             return SWR_OK;
         }
-        if (c.overflow_refs) {
-            size_t want = (size_t)c.tile_refs + (size_t)c.tile_refs / 4 + 4096;
-            if (ctx->refs.reserve(want) != cudaSuccess) {
-                ctx->err = "out of device memory growing tile lists";
-                return SWR_ERR_OOM;
+        struct Grow {
+            GeomSet *g;
+            const FrameCounters *c;
+        } grow[2] = {{&ctx->op, &c}, {&ctx->tr, &ct}};
+        for (const Grow &gw : grow) {
+            if (gw.c->overflow_refs) {
+                size_t want = (size_t)gw.c->tile_refs + (size_t)gw.c->tile_refs / 4 + 4096;
+                if (gw.g->refs.reserve(want) != cudaSuccess) {
+                    ctx->err = "out of device memory growing tile lists";
+                    return SWR_ERR_OOM;
+                }
             }
-        }
-        if (c.overflow_ext) ctx->ext_cap = (size_t)c.ext_records + (size_t)c.ext_records / 4 + 4096;
-        if (c.overflow_clip) {
-            size_t want = (size_t)c.clip_verts + (size_t)c.clip_verts / 4 + 4096;
-            if (ctx->clip_verts.reserve(want) != cudaSuccess) {
-                ctx->err = "out of device memory growing clip vertex buffer";
-                return SWR_ERR_OOM;
+            if (gw.c->overflow_ext) gw.g->ext_cap = (size_t)gw.c->ext_records + (size_t)gw.c->ext_records / 4 + 4096;
+            if (gw.c->overflow_clip) {
+                size_t want = (size_t)gw.c->clip_verts + (size_t)gw.c->clip_verts / 4 + 4096;
+                if (gw.g->clip_verts.reserve(want) != cudaSuccess) {
+                    ctx->err = "out of device memory growing clip vertex buffer";
+                    return SWR_ERR_OOM;
+                }
             }
         }
         int rc = launch_frame(ctx);
@@ -723,7 +787,9 @@ int swr_render(swr_ctx *ctx, const swr_camera *camera, const swr_draw *draws, in
     CK(cudaSetDevice(ctx->device));
     int rc;
     if (ctx->frame_pending && (rc = finish_frame(ctx))) return rc;  // settle a previous frame's growth before reusing buffers
-    ctx->last_draws.assign(draws, draws + ndraws);
+    ctx->op.last_draws.clear();
+    ctx->tr.last_draws.clear();
+    for (int i = 0; i < ndraws; i++) ((draws[i].flags & SWR_DRAW_TRANSLUCENT) ? ctx->tr : ctx->op).last_draws.push_back(draws[i]);
     set_camera(ctx, camera);
     ctx->last_shade = shade;
     if ((rc = launch_frame(ctx))) return rc;
@@ -749,7 +815,7 @@ int swr_keys_to_global(swr_ctx *ctx) {
     int rc;
     if ((rc = finish_frame(ctx))) return rc;
     const size_t n = (size_t)ctx->ntiles * SWR_TILE_PIXELS;
-    k_keys_to_global<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->keys.p, n, ctx->records.p, ctx->clip_ext.p);
+    k_keys_to_global<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->keys.p, n, ctx->op.records.p, ctx->op.clip_ext.p);
     CK(cudaGetLastError());
     return SWR_OK;
 }
@@ -760,8 +826,8 @@ int swr_keys_localize(swr_ctx *ctx) {
     if ((rc = finish_frame(ctx))) return rc;
     if (ctx->bary.reserve((size_t)ctx->W * ctx->H) != cudaSuccess) return SWR_ERR_OOM;
     dim3 blk(32, 8), grid((ctx->W + 31) / 32, (ctx->H + 7) / 8);
-    k_keys_localize<<<grid, blk, 0, ctx->stream>>>(ctx->keys.p, ctx->tiles_x, ctx->W, ctx->H, ctx->records.p, ctx->clip_ext.p, ctx->draws.p,
-                                                   ctx->tri_prefix.p, ctx->ndraws, ctx->scene.prims, ctx->bary.p);
+    k_keys_localize<<<grid, blk, 0, ctx->stream>>>(ctx->keys.p, ctx->tiles_x, ctx->W, ctx->H, ctx->op.records.p, ctx->op.clip_ext.p, ctx->op.draws.p,
+                                                   ctx->op.tri_prefix.p, ctx->op.ndraws, ctx->scene.prims, ctx->bary.p);
     CK(cudaGetLastError());
     return SWR_OK;
 }
@@ -821,7 +887,7 @@ int swr_read_tile_costs(swr_ctx *ctx, uint32_t *refs, uint32_t *cycles) {
     if (!ctx) return SWR_ERR_INVALID;
     int rc;
     if ((rc = finish_frame(ctx))) return rc;
-    if (refs) CK(cudaMemcpy(refs, ctx->tile_count.p, ctx->ntiles * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (refs) CK(cudaMemcpy(refs, ctx->op.tile_count.p, ctx->ntiles * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (cycles) CK(cudaMemcpy(cycles, ctx->tile_cycles.p, ctx->ntiles * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return SWR_OK;
 }
@@ -847,10 +913,10 @@ int swr_read_visbuffer(swr_ctx *ctx, uint32_t *depth_bits, uint32_t *seq, float 
     CK(cudaMalloc(&d, n * 16));
     VisParams vp{};
     vp.keys = ctx->keys.p;
-    vp.records = ctx->records.p;
-    vp.clip_ext = ctx->clip_ext.p;
-    vp.draws = ctx->draws.p;
-    vp.ndraws = ctx->ndraws;
+    vp.records = ctx->op.records.p;
+    vp.clip_ext = ctx->op.clip_ext.p;
+    vp.draws = ctx->op.draws.p;
+    vp.ndraws = ctx->op.ndraws;
     vp.W = ctx->W;
     vp.H = ctx->H;
     vp.tiles_x = ctx->tiles_x;

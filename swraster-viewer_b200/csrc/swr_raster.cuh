@@ -22,6 +22,7 @@ struct SetupParams {
     const DevMat *mats;
     TriRecord *records;
     uint32_t *rects;
+    float *avgz;  // translucent set: packet.avg_z per record (renderer.rs:765-775), else NULL
     ClipVertex *clip_verts;
     uint32_t clip_capacity;
     uint32_t *clip_queue;  // dense triangle ids that need the clipper
@@ -128,6 +129,7 @@ __device__ __forceinline__ uint32_t emit_triangle(const SetupParams &P, float4 c
     r.draw = draw;
     r.seq = seq;
     r.clip = clipref;
+    if (P.avgz) P.avgz[slot] = fdiv(fadd(fadd(c0.z, c1.z), c2.z), 3.0f);
     uint4 *dst = reinterpret_cast<uint4 *>(&P.records[slot]);
     const uint4 *src = reinterpret_cast<const uint4 *>(&r);
     dst[0] = src[0];

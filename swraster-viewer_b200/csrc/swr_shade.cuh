@@ -221,7 +221,9 @@ __device__ __forceinline__ V3 interp3(V3 a, V3 da, V3 db, float b1, float b2) {
 }
 
 // shader.rs:110-309, TRANSLUCENT = false. `du_dv` is already scaled lane-wise by the quad's w values.
-__device__ __forceinline__ V3 pbr_shader(const ShadeParams &P, const ShadePacket &sp, float b1, float b2, float w, const float du_dv[4]) {
+// shader.rs:110-309; `translucent` adds the KHR_materials_transmission blend over `current` (shader.rs:265-277).
+__device__ __forceinline__ V3 pbr_shader(const ShadeParams &P, const ShadePacket &sp, float b1, float b2, float w, const float du_dv[4],
+                                         bool translucent = false, V3 current = V3{0.0f, 0.0f, 0.0f}) {
     const DevScene &sc = P.scene;
     const DevMat &mat = sc.mats[sp.material];
     const float EPS = 1e-6f, PI = 3.14159265358979323846f;
@@ -319,7 +321,17 @@ __device__ __forceinline__ V3 pbr_shader(const ShadeParams &P, const ShadePacket
     float ao_spec = 1.0f + (ao - 1.0f) * 0.5f;
     color_indirect_specular = color_indirect_specular * (ao_spec * sky_visibility);
 
-    V3 color = color_direct_diffuse + color_direct_specular + color_indirect_diffuse + color_indirect_specular;
+    V3 color;
+    if (translucent) {
+        float transmission = mat.transmission;
+        if (mat.tex_transmission >= 0) transmission = transmission * sample4(sc.texs[mat.tex_transmission], uv_x, uv_y, du_dv).x;
+        transmission = sse_clamp(transmission, 0.0f, 1.0f);
+        const float inv_transmission = 1.0f - transmission;
+        color = (current * base * transmission) + ((color_direct_diffuse + color_indirect_diffuse) * inv_transmission) + color_direct_specular +
+                color_indirect_specular;
+    } else {
+        color = color_direct_diffuse + color_direct_specular + color_indirect_diffuse + color_indirect_specular;
+    }
     V3 emissive_mat = one3;
     if (mat.tex_emissive >= 0) {
         float4 s = sample4(sc.texs[mat.tex_emissive], uv_x, uv_y, du_dv);
@@ -449,6 +461,180 @@ __global__ void __launch_bounds__(256) k_resolve(const float4 *color, int Wp, ui
     } else {
         for (int k = 0; k < 4 && x + k < W; k++) o[k] = resolve_pixel_rgba(c[k], exposure);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Translucent pass (tilerasterizer.rs:92-101, shader.rs:66-76): per tile, packets sorted back to front, forward-shaded
+// over the opaque colour, depth-tested against (never written to) the opaque depth.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_scan_simple(const uint32_t *count, uint32_t *offset, uint32_t *cursor, int ntiles, FrameCounters *counters,
+                                                     uint32_t ref_capacity) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += 1024) {
+        int i = base + tid;
+        uint32_t v = i < ntiles ? count[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        uint32_t excl = s_carry + s_warp[wid] + incl - v;
+        if (i < ntiles) {
+            offset[i] = excl;
+            cursor[i] = excl;
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        offset[ntiles] = s_carry;
+        counters->tile_refs = s_carry;
+        if (s_carry > ref_capacity) counters->overflow_refs = 1;
+    }
+}
+
+// Sort one tile's translucent refs by (avg_z descending, submission order ascending) — the reference's sort key is avg_z
+// only and its quicksort is unstable (bumpqueue.rs:155-202); ties keep submission order here. Bitonic sort in shared memory.
+#define TSORT_MAX 4096
+__global__ void __launch_bounds__(256) k_sort_translucent(uint32_t *refs, const uint32_t *offset, const float *avgz, const uint32_t *clip_ext,
+                                                          FrameCounters *counters) {
+    __shared__ unsigned long long s_key[TSORT_MAX];
+    if (counters->overflow_refs || counters->overflow_ext) return;
+    const uint32_t beg = offset[blockIdx.x], n = offset[blockIdx.x + 1] - beg;
+    if (n <= 1) return;
+    if (n > TSORT_MAX) {
+        if (threadIdx.x == 0) counters->overflow_sort = 1;
+        return;
+    }
+    uint32_t m = 1;
+    while (m < n) m <<= 1;
+    for (uint32_t i = threadIdx.x; i < m; i += 256) {
+        unsigned long long k = ~0ull;
+        if (i < n) {
+            const uint32_t id = refs[beg + i];
+            const float az = avgz[record_of_id(id, clip_ext)];
+            uint32_t b = __float_as_uint(az);
+            uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // OrderedFloat order (NaN above +inf)
+            k = ((unsigned long long)(0xFFFFFFFFu - ord) << 32) | id;
+        }
+        s_key[i] = k;
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= m; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < m; i += 256) {
+                const uint32_t l = i ^ j;
+                if (l > i) {
+                    const unsigned long long a = s_key[i], b = s_key[l];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) {
+                        s_key[i] = b;
+                        s_key[l] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (uint32_t i = threadIdx.x; i < n; i += 256) refs[beg + i] = (uint32_t)s_key[i];
+}
+
+struct ForwardParams {
+    ShadeParams sh;            // records / clip_ext / draws / clip_verts of the TRANSLUCENT set; keys = opaque visibility keys
+    const uint32_t *refs;      // translucent refs, sorted per tile
+    const uint32_t *offset;
+    const FrameCounters *counters;
+};
+
+__global__ void __launch_bounds__(SHADE_BLOCK, SWR_SHADE_MINB) k_forward_translucent(ForwardParams F) {
+    const ShadeParams &P = F.sh;
+    if (F.counters->overflow_refs || F.counters->overflow_ext || F.counters->overflow_sort) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int quad = lane >> 2, sub = lane & 3;
+    const int bx0 = blockIdx.x * 16, by0 = P.row_begin * SWR_TILE + blockIdx.y * SHADE_ROWS;
+    const int px = bx0 + quad * 2 + (sub & 1);
+    const int py = by0 + warp * 2 + (sub >> 1);
+    const unsigned qmask = 0xFu << (lane & ~3);
+    const int tile = (by0 >> 6) * P.tiles_x + (bx0 >> 6);
+    const uint32_t beg = F.offset[tile], end = F.offset[tile + 1];
+    if (beg == end) return;
+    // opaque depth of my pixel (never modified by this pass): inverse of depth_orderable; empty -> +inf
+    const unsigned long long key = load_key(P.keys, P.tiles_x, px, py);
+    float zopaque = __uint_as_float(SWR_INF_BITS);
+    if (key != SWR_KEY_EMPTY) {
+        const uint32_t u = (uint32_t)(key >> 32);
+        zopaque = __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+    }
+    const size_t ci = (size_t)py * P.Wp + px;
+    float4 c4 = P.color[ci];
+    V3 colour = v3(c4.x, c4.y, c4.z);
+    const int tile_x0 = bx0 & ~(SWR_TILE - 1), tile_y0 = by0 & ~(SWR_TILE - 1);
+    for (uint32_t i = beg; i < end; i++) {
+        const uint32_t id = __ldg(F.refs + i);
+        const TriRecord rec = P.records[record_of_id(id, P.clip_ext)];
+        PacketSetup ps;
+        packet_setup(rec, P.W, P.H, tile_x0, tile_y0, ps);
+        if (ps.empty) continue;
+        // block-uniform reject: does the packet's quad region touch this 16 x SHADE_ROWS block?
+        const int rx0 = ps.xs >> 4, ry0 = ps.ys >> 4, rx1 = rx0 + ps.nqx * 2, ry1 = ry0 + ps.nqy * 2;
+        if (rx1 <= bx0 || rx0 >= bx0 + 16 || ry1 <= by0 || ry0 >= by0 + SHADE_ROWS) continue;
+        // my quad inside the region?  (quads are aligned to even pixels, so all four lanes agree)
+        const bool inreg = px >= rx0 && px < rx1 && py >= ry0 && py < ry1;
+        float w0 = -1.0f, w1 = -1.0f, w2 = -1.0f;
+        bool evaluated = false;
+        if (inreg) {
+            if (ps.exact) {
+                int e[3];
+                eval_exact(ps, px * 16 + 8, py * 16 + 8, e);
+                w0 = i2f(e[0]);
+                w1 = i2f(e[1]);
+                w2 = i2f(e[2]);
+                evaluated = true;
+            } else {
+                float rr[3];
+                evaluated = eval_chain(ps, ((px & ~1) * 16 - ps.xs) >> 5, ((py & ~1) * 16 - ps.ys) >> 5, px & 1, py & 1, rr);
+                w0 = rr[0];
+                w1 = rr[1];
+                w2 = rr[2];
+            }
+        }
+        const bool cov = evaluated && w0 >= 0.0f && w1 >= 0.0f && w2 >= 0.0f;
+        if (!(__ballot_sync(qmask, cov) & qmask)) continue;  // tilerasterizer.rs:334-335 mask.any() per quad
+        // tilerasterizer.rs:337-342 for all four lanes of the quad
+        float b1, b2;
+        const float z = frag_depth(rec, w1, w2, b1, b2);
+        const bool pass = cov && z <= zopaque;  // depth_test :511-523
+        if (!(__ballot_sync(qmask, pass) & qmask)) continue;
+        const float iwda = rec.iw1 - rec.iw0, iwdb = rec.iw2 - rec.iw0;
+        const float w = 1.0f / interp1(rec.iw0, iwda, iwdb, b1, b2);  // shader.rs:123
+        float wq[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) wq[j] = __shfl_sync(qmask, w, (lane & ~3) + j);
+        if (pass) {
+            ShadePacket sp;
+            build_shade_packet(P, rec, sp);
+            float dd[4] = {sp.du_dv[0] * wq[0], sp.du_dv[1] * wq[1], sp.du_dv[2] * wq[2], sp.du_dv[3] * wq[3]};
+            colour = pbr_shader(P, sp, b1, b2, w, dd, true, colour);
+        }
+    }
+    P.color[ci] = make_float4(colour.x, colour.y, colour.z, c4.w);
 }
 
 // ---------------------------------------------------------------------------------------------

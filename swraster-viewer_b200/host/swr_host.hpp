@@ -283,7 +283,7 @@ inline void build_draw_list(const swr_scene_desc &sc, const swr_camera &cam, std
         return x < y;
     });
     draws.clear();
-    uint32_t first_tri = 0, di = 0;
+    uint32_t first_tri = 0, first_tri_t = 0, di = 0;
     for (uint32_t ni : nodes_by_distance) {
         const swr_node_desc &node = sc.nodes[ni];
         if (node.mesh_index < 0) continue;
@@ -292,25 +292,33 @@ inline void build_draw_list(const swr_scene_desc &sc, const swr_camera &cam, std
         std::memcpy(model.m, node.transform, 64);
         std::memcpy(vp.m, cam.view_project_matrix, 64);
         mvp = mul(vp, model);  // renderer.rs:378
-        for (uint32_t pi = mesh.first_primitive; pi < mesh.first_primitive + mesh.num_primitives; pi++) {
-            const swr_primitive_desc &prim = sc.primitives[pi];
-            // Opaque list only; the translucent pass is SURVEY §8(f) N1.
-            if (sc.materials[prim.material_index].flags & SWR_MAT_TRANSLUCENT) continue;
-            FrustumTestResult t = test_sphere_frustum(node.transform, prim.bounding_sphere, cam);
-            if (t == FrustumTestResult::Outside) continue;
-            uint32_t ntris = prim.nindices / 3;
-            const bool band_culled = band_y1 > band_y0 && sphere_outside_row_band(node.transform, prim.bounding_sphere, cam, band_y0, band_y1, band_height);
-            if ((int)(di % (uint32_t)nshards) == shard && !band_culled) {
-                swr_draw d{};
-                std::memcpy(d.model, model.m, 64);
-                std::memcpy(d.mvp, mvp.m, 64);
-                d.primitive = pi;
-                d.flags = t == FrustumTestResult::Intersecting ? SWR_DRAW_CLIP : 0u;
-                d.first_triangle = first_tri;
-                draws.push_back(d);
+        for (int pass = 0; pass < 2; pass++) {  // render_mesh: primitives_opaque, then primitives_translucent (renderer.rs:386-420)
+            for (uint32_t pi = mesh.first_primitive; pi < mesh.first_primitive + mesh.num_primitives; pi++) {
+                const swr_primitive_desc &prim = sc.primitives[pi];
+                const bool translucent = (sc.materials[prim.material_index].flags & SWR_MAT_TRANSLUCENT) != 0;
+                if (translucent != (pass == 1)) continue;
+                FrustumTestResult t = test_sphere_frustum(node.transform, prim.bounding_sphere, cam);
+                if (t == FrustumTestResult::Outside) continue;
+                uint32_t ntris = prim.nindices / 3;
+                const bool band_culled = band_y1 > band_y0 && sphere_outside_row_band(node.transform, prim.bounding_sphere, cam, band_y0, band_y1, band_height);
+                // translucent primitives are never sharded (sort-last composites the opaque visibility buffer only)
+                const bool mine = translucent ? shard == 0 || nshards == 1 : (int)(di % (uint32_t)nshards) == shard;
+                if (mine && !band_culled) {
+                    swr_draw d{};
+                    std::memcpy(d.model, model.m, 64);
+                    std::memcpy(d.mvp, mvp.m, 64);
+                    d.primitive = pi;
+                    d.flags = (t == FrustumTestResult::Intersecting ? SWR_DRAW_CLIP : 0u) | (translucent ? SWR_DRAW_TRANSLUCENT : 0u);
+                    d.first_triangle = translucent ? first_tri_t : first_tri;
+                    draws.push_back(d);
+                }
+                if (translucent) {
+                    first_tri_t += ntris;  // translucent packets have their own queue, hence their own submission ids
+                } else {
+                    first_tri += ntris;
+                    di++;
+                }
             }
-            first_tri += ntris;
-            di++;
         }
     }
 }

@@ -764,3 +764,23 @@ def scene_materials_test(seed=11, tex_size=64, **kw):
     sc = SceneData(meshes, nodes, mats, texs, seed=seed, gi_variation=0.5, **kw)
     cam = CameraSpec((0.5, 3.0, 6.5), (0.0, 0.8, 0.0), math.pi / 4, float(sc.bounds_diagonal) * 2.0)
     return sc, cam
+
+
+def scene_translucent_test(seed=31, **kw):
+    """Opaque terrain + objects with KHR_materials_transmission objects in front of, between and intersecting them:
+    exercises the per-tile back-to-front forward pass (tilerasterizer.rs:92-101, shader.rs:66-76, 265-277)."""
+    texs = [checker_noise_texture(64, seed, abi.TEX_SRGB, abi.WRAP_REPEAT), checker_noise_texture(32, seed + 1, abi.TEX_LINEAR, abi.WRAP_REPEAT)]
+    mats = [
+        Material((1, 1, 1, 1), 0.0, 0.8, base_color_texture=0),
+        Material((0.9, 0.3, 0.2, 1), 0.2, 0.4),
+        Material((0.6, 0.9, 1.0, 1), 0.0, 0.15, transmission=0.8, flags=abi.MAT_TRANSLUCENT),
+        Material((1.0, 0.8, 0.5, 1), 0.0, 0.3, transmission=0.6, flags=abi.MAT_TRANSLUCENT, transmission_texture=1, base_color_texture=0),
+    ]
+    meshes = [[height_field(24, seed, extent=4.0, height=0.7, uv_repeat=2.0, material=0)], [uv_sphere(20, 14, 1.0, 1)],
+              [uv_sphere(24, 16, 1.0, 2)], [torus(28, 14, material=3), box_grid(3, 1)]]
+    nodes = [Node(IDENT, 0), Node(trs((-0.4, 1.0, -0.5), 0.8), 1), Node(trs((0.4, 1.2, 1.4), 1.0), 2),
+             Node(trs((-1.3, 1.3, 1.8), 0.9, (1, 0.2, 0.1), 0.9), 3), Node(trs((1.4, 1.0, 0.2), 0.7, (0, 1, 0), 0.5), 2),
+             Node(trs((0.2, 1.6, 5.2), 1.6), 2)]  # a glass sphere crossing the near plane
+    sc = SceneData(meshes, nodes, mats, texs, seed=seed, gi_variation=0.3, **kw)
+    cam = CameraSpec((0.3, 2.6, 6.2), (0.0, 0.9, 0.0), math.pi / 4, float(sc.bounds_diagonal) * 2.0)
+    return sc, cam

@@ -12,7 +12,7 @@ SMALL = dict(voxel_dim=8, cube_size=32)
 
 
 def small_configs():
-    """(name, scene, camera spec, W, H): scaled-down C1..C5 plus the all-materials scene."""
+    """(name, scene, camera spec, W, H): scaled-down C1..C5, the all-materials scene and the translucent scene."""
     return [
         ("c1_sphere", *scenes.scene_c1_sphere(48, 48, **SMALL), 448, 256),
         ("c2_terrain", *scenes.scene_c2_terrain(96, 128, **SMALL), 448, 256),
@@ -20,6 +20,7 @@ def small_configs():
         ("c4_micro", *scenes.scene_c4_micro(161, **SMALL), 256, 144),
         ("c5_shards", *scenes.scene_c5_shards(4, 65, **SMALL), 384, 216),
         ("materials", *scenes.scene_materials_test(**SMALL), 448, 256),
+        ("translucent", *scenes.scene_translucent_test(**SMALL), 448, 256),
     ]
 
 

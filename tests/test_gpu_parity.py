@@ -16,7 +16,7 @@ def configs():
     return small_configs()
 
 
-@pytest.mark.parametrize("idx", range(6))
+@pytest.mark.parametrize("idx", range(7))
 def test_visbuffer_bit_exact_and_colour(configs, idx):
     name, scene, spec, W, H = configs[idx]
     cam = swr.RenderCamera.from_spec(spec, W, H)
