@@ -250,6 +250,13 @@ void *swr_device_bary(swr_ctx *ctx); /* W*H float2, row-major */
  * that HOST buffer and the call synchronises. */
 int swr_resolve(swr_ctx *ctx, float exposure, uint32_t *out_pixels);
 
+/* Pipelined form of swr_resolve for callers that overlap the read-back of frame N with the rendering of frame N+1 (what
+ * the reference's App does with present(N-1) || render(N), main.rs:526-597): resolves into one of two device pixel
+ * buffers and copies it to `out_pixels` (pinned host memory) on a separate stream, without blocking. *ticket identifies
+ * the copy; swr_wait_pixels(ticket) blocks until `out_pixels` is complete. At most two copies may be outstanding. */
+int swr_resolve_async(swr_ctx *ctx, float exposure, uint32_t *out_pixels, int *ticket);
+int swr_wait_pixels(swr_ctx *ctx, int ticket);
+
 /* Per-tile cost signals of the last frame (row-major tiles; 0 for tiles this context does not own), for balancing
  * sort-first row bands: triangle references binned into the tile and SM cycles its rasterisation took. Either may be NULL. */
 int swr_read_tile_costs(swr_ctx *ctx, uint32_t *refs_per_tile, uint32_t *raster_cycles_per_tile);

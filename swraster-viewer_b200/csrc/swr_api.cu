@@ -96,6 +96,18 @@ struct swr_ctx {
     DevBuf<unsigned long long> keys;
     DevBuf<float4> color;
     DevBuf<uint32_t> pixels;
+    // asynchronous read-back (swr_resolve_async): second pixel buffer, copy stream, per-buffer events
+    DevBuf<uint32_t> pixels_alt;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_resolved[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    bool copy_pending[2] = {false, false};
+    int pix_cur = 0;
+    struct {
+        bool valid = false;
+        int idx = 0;
+        float exposure = 0.0f;
+        uint32_t *host = nullptr;
+    } last_async;
     DevBuf<float> lum;
     DevBuf<float2> bary;
     bool composited = false;
@@ -250,6 +262,12 @@ void swr_destroy(swr_ctx *ctx) {
     ctx->keys.release();
     ctx->color.release();
     ctx->pixels.release();
+    ctx->pixels_alt.release();
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_resolved[i]) cudaEventDestroy(ctx->ev_resolved[i]);
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     ctx->lum.release();
     ctx->bary.release();
     ctx->rsqrt_tab.release();
@@ -687,6 +705,8 @@ static void set_camera(swr_ctx *ctx, const swr_camera *cam) {
     ctx->dcam.one_over_height = cam->one_over_height;
 }
 
+static int issue_resolve_copy(swr_ctx *ctx, int idx, float exposure, uint32_t *host);
+
 // Synchronise, and if a device-side buffer overflowed grow it and replay the frame.
 static int finish_frame(swr_ctx *ctx) {
     CK(cudaSetDevice(ctx->device));
@@ -773,6 +793,8 @@ static int finish_frame(swr_ctx *ctx) {
         int rc = launch_frame(ctx);
         if (rc) return rc;
         if (ctx->last_shade && (rc = launch_shade(ctx))) return rc;
+        // an asynchronous resolve + read-back was already queued behind the frame that just got replayed: redo it
+        if (ctx->last_async.valid && (rc = issue_resolve_copy(ctx, ctx->last_async.idx, ctx->last_async.exposure, ctx->last_async.host))) return rc;
     }
     ctx->err = "frame did not fit after growing buffers";
     return SWR_ERR_OOM;
@@ -787,6 +809,7 @@ int swr_render(swr_ctx *ctx, const swr_camera *camera, const swr_draw *draws, in
     CK(cudaSetDevice(ctx->device));
     int rc;
     if (ctx->frame_pending && (rc = finish_frame(ctx))) return rc;  // settle a previous frame's growth before reusing buffers
+    ctx->last_async.valid = false;
     ctx->op.last_draws.clear();
     ctx->tr.last_draws.clear();
     for (int i = 0; i < ndraws; i++) ((draws[i].flags & SWR_DRAW_TRANSLUCENT) ? ctx->tr : ctx->op).last_draws.push_back(draws[i]);
@@ -866,15 +889,70 @@ int swr_resolve(swr_ctx *ctx, float exposure, uint32_t *out_pixels) {
     CK(cudaEventRecord(ctx->ev_res[0], s));
     if (y1 > y0) {
         dim3 grid((unsigned)((W + 255) / 256), (unsigned)((y1 - y0 + 3) / 4));
-        k_resolve<<<grid, 256, 0, s>>>(ctx->color.p, ctx->tiles_x * SWR_TILE, ctx->pixels.p, ctx->W, (int)y0, (int)y1, exposure);
+        if (ctx->copy_pending[ctx->pix_cur]) CK(cudaStreamWaitEvent(s, ctx->ev_copied[ctx->pix_cur], 0));
+        k_resolve<<<grid, 256, 0, s>>>(ctx->color.p, ctx->tiles_x * SWR_TILE, (uint32_t *)swr_device_pixels(ctx), ctx->W, (int)y0, (int)y1, exposure);
     }
     CK(cudaEventRecord(ctx->ev_res[1], s));
     CK(cudaGetLastError());
     if (out_pixels) {
-        if (y1 > y0) CK(cudaMemcpyAsync(out_pixels + y0 * W, ctx->pixels.p + y0 * W, (y1 - y0) * W * 4, cudaMemcpyDeviceToHost, s));
+        if (y1 > y0) CK(cudaMemcpyAsync(out_pixels + y0 * W, (uint32_t *)swr_device_pixels(ctx) + y0 * W, (y1 - y0) * W * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         cudaEventElapsedTime(&ctx->stats.ms_resolve, ctx->ev_res[0], ctx->ev_res[1]);
     }
+    return SWR_OK;
+}
+
+// resolve into pixel buffer `idx` on the main stream, then copy it to `host` on the copy stream
+static int issue_resolve_copy(swr_ctx *ctx, int idx, float exposure, uint32_t *host) {
+    cudaStream_t s = ctx->stream;
+    const size_t W = ctx->W;
+    size_t y0 = (size_t)ctx->row_begin * SWR_TILE, y1 = (size_t)ctx->row_end * SWR_TILE;
+    if (y1 > (size_t)ctx->H) y1 = ctx->H;
+    uint32_t *dst = idx ? ctx->pixels_alt.p : ctx->pixels.p;
+    if (ctx->copy_pending[idx]) CK(cudaStreamWaitEvent(s, ctx->ev_copied[idx], 0));  // the previous copy out of this buffer
+    if (y1 > y0) {
+        dim3 grid((unsigned)((W + 255) / 256), (unsigned)((y1 - y0 + 3) / 4));
+        k_resolve<<<grid, 256, 0, s>>>(ctx->color.p, ctx->tiles_x * SWR_TILE, dst, ctx->W, (int)y0, (int)y1, exposure);
+    }
+    CK(cudaEventRecord(ctx->ev_resolved[idx], s));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_resolved[idx], 0));
+    if (y1 > y0) CK(cudaMemcpyAsync(host + y0 * W, dst + y0 * W, (y1 - y0) * W * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_copied[idx], ctx->copy_stream));
+    ctx->copy_pending[idx] = true;
+    CK(cudaGetLastError());
+    return SWR_OK;
+}
+
+int swr_resolve_async(swr_ctx *ctx, float exposure, uint32_t *out_pixels, int *ticket) {
+    if (!ctx || !out_pixels || !ticket) return SWR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CK(cudaEventCreateWithFlags(&ctx->ev_resolved[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+        }
+        if (ctx->pixels_alt.reserve((size_t)ctx->W * ctx->H) != cudaSuccess) return SWR_ERR_OOM;
+    }
+    const int idx = ctx->pix_cur ^ 1;
+    int rc = issue_resolve_copy(ctx, idx, exposure, out_pixels);
+    if (rc) return rc;
+    ctx->pix_cur = idx;
+    ctx->last_async.valid = true;
+    ctx->last_async.idx = idx;
+    ctx->last_async.exposure = exposure;
+    ctx->last_async.host = out_pixels;
+    *ticket = idx;
+    return SWR_OK;
+}
+
+int swr_wait_pixels(swr_ctx *ctx, int ticket) {
+    if (!ctx || ticket < 0 || ticket > 1) return SWR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    // the frame behind the newest ticket may still need a buffer-growth replay (which re-issues its resolve + copy)
+    if (ctx->frame_pending && ctx->last_async.valid && ctx->last_async.idx == ticket && (rc = finish_frame(ctx))) return rc;
+    if (ctx->copy_pending[ticket]) CK(cudaEventSynchronize(ctx->ev_copied[ticket]));
     return SWR_OK;
 }
 
@@ -959,7 +1037,7 @@ int swr_get_stats(swr_ctx *ctx, swr_frame_stats *out) {
     return SWR_OK;
 }
 
-void *swr_device_pixels(swr_ctx *ctx) { return ctx ? ctx->pixels.p : nullptr; }
+void *swr_device_pixels(swr_ctx *ctx) { return ctx ? (ctx->pix_cur ? ctx->pixels_alt.p : ctx->pixels.p) : nullptr; }
 void *swr_device_keys(swr_ctx *ctx) { return ctx ? ctx->keys.p : nullptr; }
 size_t swr_device_keys_bytes(swr_ctx *ctx) { return ctx ? (size_t)ctx->ntiles * SWR_TILE_PIXELS * 8 : 0; }
 void *swr_cuda_stream(swr_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }

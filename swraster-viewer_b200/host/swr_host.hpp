@@ -443,6 +443,16 @@ class Renderer {
         check(swr_resolve(ctx_, auto_exposure_, buffer.pixels), "swr_resolve");
     }
 
+    // Pipelined blit (the reference's App overlaps present(N-1) with render(N), main.rs:526-597): starts resolve + read-back
+    // of the frame just rendered into `buffer` (pinned memory) and returns a ticket; wait_blit(ticket) completes it.
+    int blit_to_buffer_async(RenderBuffer &buffer) {
+        if ((int)buffer.width != width_ || (int)buffer.height < height_) throw std::runtime_error("RenderBuffer size mismatch");
+        int ticket = -1;
+        check(swr_resolve_async(ctx_, auto_exposure_, buffer.pixels, &ticket), "swr_resolve_async");
+        return ticket;
+    }
+    void wait_blit(int ticket) { check(swr_wait_pixels(ctx_, ticket), "swr_wait_pixels"); }
+
    private:
     void check(int rc, const char *what) {
         if (rc != 0) throw std::runtime_error(std::string(what) + ": " + swr_last_error(ctx_));

@@ -68,6 +68,11 @@ int swrh_blit_to_buffer(void *r, uint32_t *pixels, size_t width, size_t height) 
     SWRH_TRY(swr::RenderBuffer buf(width, height, pixels); ((swr::Renderer *)r)->blit_to_buffer(buf));
 }
 
+int swrh_blit_to_buffer_async(void *r, uint32_t *pixels, size_t width, size_t height, int *ticket) {
+    SWRH_TRY(swr::RenderBuffer buf(width, height, pixels); *ticket = ((swr::Renderer *)r)->blit_to_buffer_async(buf));
+}
+int swrh_wait_blit(void *r, int ticket) { SWRH_TRY(((swr::Renderer *)r)->wait_blit(ticket)); }
+
 // Host draw list only (no device work): for cross-checks against the oracle's own R1/R2.
 int swrh_build_draws(const swr_scene_desc *scene, const swr_camera *cam, swr_draw *out, int max_draws, int shard, int nshards) {
     try {

@@ -85,6 +85,8 @@ def load_libraries():
     host.swrh_auto_exposure.restype = f32
     host.swrh_auto_exposure.argtypes = [vp]
     host.swrh_blit_to_buffer.argtypes = [vp, vp, C.c_size_t, C.c_size_t]
+    host.swrh_blit_to_buffer_async.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.POINTER(i32)]
+    host.swrh_wait_blit.argtypes = [vp, i32]
     host.swrh_build_draws.argtypes = [C.POINTER(abi.SceneDesc), C.POINTER(abi.Camera), C.POINTER(abi.Draw), i32, i32, i32]
     _libs = (core, host)
     return _libs
@@ -210,6 +212,15 @@ class Renderer:
 
     def blit_to_buffer(self, buffer):
         self._check(self.host.swrh_blit_to_buffer(self._h, buffer.pixels.ctypes.data, buffer.width, buffer.height))
+
+    def blit_to_buffer_async(self, buffer):
+        """Start resolve + read-back into `buffer` (pinned) without blocking; returns a ticket for wait_blit."""
+        t = C.c_int(-1)
+        self._check(self.host.swrh_blit_to_buffer_async(self._h, buffer.pixels.ctypes.data, buffer.width, buffer.height, C.byref(t)))
+        return t.value
+
+    def wait_blit(self, ticket):
+        self._check(self.host.swrh_wait_blit(self._h, ticket))
 
     # ---- C-ABI extras used by tests / bench -----------------------------------------------
     def resolve_device_only(self, exposure=abi.DEFAULT_EXPOSURE):

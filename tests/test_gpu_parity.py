@@ -152,3 +152,26 @@ def test_alpha_tested_material():
     assert err.max() <= RGBA_TOL_LSB
     for k in ("triangles_binned", "triangles_clipped", "tile_refs"):
         assert g["stats"][k] == o["stats"][k]
+
+
+def test_async_blit_matches_sync(configs):
+    """swr_resolve_async / swr_wait_pixels (pipelined read-back into pinned memory) delivers the same pixels as blit_to_buffer."""
+    name, scene, spec, W, H = configs[5]
+    cam = swr.RenderCamera.from_spec(spec, W, H)
+    r = swr.Renderer(W, H)
+    ref = swr.RenderBuffer(W, H)
+    r.render_scene(scene, cam)
+    r.blit_to_buffer(ref)
+    bufs = [swr.RenderBuffer(W, H, pinned=True), swr.RenderBuffer(W, H, pinned=True)]
+    prev = None
+    for i in range(5):
+        r.render_scene(scene, cam)
+        tk = r.blit_to_buffer_async(bufs[i & 1])
+        if prev is not None:
+            r.wait_blit(prev[0])
+            assert np.array_equal(prev[1].pixels, ref.pixels)
+            prev[1].pixels[:] = 0
+        prev = (tk, bufs[i & 1])
+    r.wait_blit(prev[0])
+    assert np.array_equal(prev[1].pixels, ref.pixels)
+    r.close()
