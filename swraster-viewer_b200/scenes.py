@@ -784,3 +784,95 @@ def scene_translucent_test(seed=31, **kw):
     sc = SceneData(meshes, nodes, mats, texs, seed=seed, gi_variation=0.3, **kw)
     cam = CameraSpec((0.3, 2.6, 6.2), (0.0, 0.9, 0.0), math.pi / 4, float(sc.bounds_diagonal) * 2.0)
     return sc, cam
+
+
+# ----------------------------------------------------------------------------------
+# glTF 2.0 export: lets anyone with a Rust toolchain load these procedural scenes into the real swraster-viewer
+# (scene.rs:145-354 reads POSITION / NORMAL / TANGENT / TEXCOORD_0, u32 indices, pbrMetallicRoughness factors, node
+# matrices). Textures are referenced by URI and written as PNG when Pillow is available.
+# ----------------------------------------------------------------------------------
+def export_gltf(scene, path):
+    """Write `scene` as <path>.gltf + <path>.bin (+ PNGs). Returns the glTF dict."""
+    import json
+    import os
+    blobs, views, accessors = [], [], []
+    offset = 0
+
+    def add(arr, target, comp, typ, minmax=False):
+        nonlocal offset
+        raw = np.ascontiguousarray(arr).tobytes()
+        pad = (-len(raw)) % 4
+        views.append({"buffer": 0, "byteOffset": offset, "byteLength": len(raw), "target": target})
+        acc = {"bufferView": len(views) - 1, "componentType": comp, "count": int(arr.shape[0]), "type": typ}
+        if minmax:
+            acc["min"] = [float(x) for x in arr.min(0)]
+            acc["max"] = [float(x) for x in arr.max(0)]
+        accessors.append(acc)
+        blobs.append(raw + b"\0" * pad)
+        offset += len(raw) + pad
+        return len(accessors) - 1
+
+    FLOAT, UINT, ARRAY, ELEMENT = 5126, 5125, 34962, 34963
+    base = os.path.splitext(path)[0]
+    images, textures, samplers = [], [], []
+    wrap_code = {abi.WRAP_REPEAT: 10497, abi.WRAP_MIRRORED_REPEAT: 33648, abi.WRAP_CLAMP_TO_EDGE: 33071}
+    user_textures = scene.textures[:scene.cubemap_index]  # cubemap / prefiltered / LUT are built-ins of the viewer
+    for i, t in enumerate(user_textures):
+        uri = f"{os.path.basename(base)}_tex{i}.png"
+        try:
+            from PIL import Image
+            px = t.data[: t.width * t.height].reshape(t.height, t.width)
+            rgba = np.stack([(px >> 24) & 255, (px >> 16) & 255, (px >> 8) & 255, px & 255], -1).astype(np.uint8)
+            Image.fromarray(rgba, "RGBA").save(os.path.join(os.path.dirname(path) or ".", uri))
+        except ImportError:
+            pass
+        images.append({"uri": uri})
+        samplers.append({"wrapS": wrap_code[t.wrap_s], "wrapT": wrap_code[t.wrap_t]})
+        textures.append({"source": i, "sampler": i})
+    materials = []
+    for m in scene.materials:
+        pbr = {"baseColorFactor": [float(x) for x in m.base_color_factor], "metallicFactor": float(m.metallic_factor),
+               "roughnessFactor": float(m.roughness_factor)}
+        g = {"pbrMetallicRoughness": pbr, "emissiveFactor": [float(x) for x in m.emissive_factor]}
+        if m.base_color_texture >= 0:
+            pbr["baseColorTexture"] = {"index": m.base_color_texture}
+        if m.metallic_roughness_texture >= 0:
+            pbr["metallicRoughnessTexture"] = {"index": m.metallic_roughness_texture}
+        if m.normal_texture >= 0:
+            g["normalTexture"] = {"index": m.normal_texture}
+        if m.emissive_texture >= 0:
+            g["emissiveTexture"] = {"index": m.emissive_texture}
+        if m.occlusion_texture >= 0:
+            g["occlusionTexture"] = {"index": m.occlusion_texture, "strength": float(m.occlusion_strength)}
+        if m.flags & abi.MAT_ALPHA_TESTED:
+            g["alphaMode"], g["alphaCutoff"] = "MASK", float(m.alpha_cutoff)
+        if m.flags & abi.MAT_TRANSLUCENT:
+            ext = {"transmissionFactor": float(m.transmission)}
+            if m.transmission_texture >= 0:
+                ext["transmissionTexture"] = {"index": m.transmission_texture}
+            g["extensions"] = {"KHR_materials_transmission": ext}
+        materials.append(g)
+    meshes = []
+    for prims in scene.meshes:
+        gp = []
+        for p in prims:
+            attrs = {"POSITION": add(p.positions[:, :3].astype(F32), ARRAY, FLOAT, "VEC3", True),
+                     "NORMAL": add(p.normals[:, :3].astype(F32), ARRAY, FLOAT, "VEC3"),
+                     "TANGENT": add(p.tangents.astype(F32), ARRAY, FLOAT, "VEC4"),
+                     "TEXCOORD_0": add(p.texcoords.astype(F32), ARRAY, FLOAT, "VEC2")}
+            gp.append({"attributes": attrs, "indices": add(p.indices.astype(np.uint32), ELEMENT, UINT, "SCALAR"),
+                       "material": int(p.material_index), "mode": 4})
+        meshes.append({"primitives": gp})
+    nodes = [{"mesh": int(n.mesh_index), "matrix": [float(x) for x in n.transform]} for n in scene.nodes]
+    gltf = {"asset": {"version": "2.0", "generator": "swraster-viewer_b200 scenes.py"}, "scene": 0,
+            "scenes": [{"nodes": list(range(len(nodes)))}], "nodes": nodes, "meshes": meshes, "materials": materials,
+            "accessors": accessors, "bufferViews": views, "buffers": [{"uri": os.path.basename(base) + ".bin", "byteLength": offset}]}
+    if textures:
+        gltf.update(textures=textures, images=images, samplers=samplers)
+    if any(m.flags & abi.MAT_TRANSLUCENT for m in scene.materials):
+        gltf["extensionsUsed"] = ["KHR_materials_transmission"]
+    with open(base + ".bin", "wb") as f:
+        f.write(b"".join(blobs))
+    with open(base + ".gltf", "w") as f:
+        json.dump(gltf, f)
+    return gltf
