@@ -91,7 +91,7 @@ struct swr_ctx {
 
     // frame: geometry sets (opaque pass, translucent pass) + shared per-frame buffers
     GeomSet op, tr;
-    DevBuf<uint32_t> tile_order, tile_cycles, tile_cycles_prev, tile_count_prev, tile_unit;
+    DevBuf<uint32_t> unit_list, tile_cycles, tile_cycles_prev, tile_count_prev, tile_unit;
     bool have_history = false;
     DevBuf<unsigned long long> keys;
     DevBuf<float4> color;
@@ -201,7 +201,7 @@ swr_ctx *swr_create(int width, int height, int device) {
     ok = ok && cudaMallocHost(&ctx->op.h_counters, sizeof(FrameCounters)) == cudaSuccess;
     ok = ok && ctx->op.tile_count.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->op.tile_offset.reserve(ctx->ntiles + 1) == cudaSuccess &&
          ctx->op.tile_cursor.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_cycles.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_cycles_prev.reserve(ctx->ntiles + 1) == cudaSuccess &&
-         ctx->tile_count_prev.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_unit.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_order.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->keys.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess &&
+         ctx->tile_count_prev.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_unit.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->unit_list.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->keys.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess &&
          ctx->color.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess && ctx->pixels.reserve((size_t)width * height) == cudaSuccess &&
          ctx->lum.reserve(ctx->ntiles) == cudaSuccess && ctx->op.counters.reserve(1) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_raster_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes()) == cudaSuccess;
@@ -254,7 +254,7 @@ void swr_destroy(swr_ctx *ctx) {
             if (st.done) cudaEventDestroy(st.done);
         }
     }
-    ctx->tile_order.release();
+    ctx->unit_list.release();
     ctx->tile_cycles.release();
     ctx->tile_cycles_prev.release();
     ctx->tile_count_prev.release();
@@ -582,8 +582,8 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
     } else {
         const size_t unit_cap = (size_t)ctx->ntiles + g.refs.cap / RASTER_UNIT_MIN + 1;
         const uint32_t cta_slots = (uint32_t)ctx->num_sms * 4u;  // k_raster_tiles: 4 CTAs per SM
-        if (ctx->tile_order.reserve(unit_cap) != cudaSuccess) return SWR_ERR_OOM;
-        k_scan_tiles<<<1, 1024, 0, s>>>(g.tile_count.p, g.tile_offset.p, g.tile_cursor.p, ctx->ntiles, g.counters.p, (uint32_t)g.refs.cap, ctx->tile_order.p,
+        if (ctx->unit_list.reserve(unit_cap) != cudaSuccess) return SWR_ERR_OOM;
+        k_scan_tiles<<<1, 1024, 0, s>>>(g.tile_count.p, g.tile_offset.p, g.tile_cursor.p, ctx->ntiles, g.counters.p, (uint32_t)g.refs.cap, ctx->unit_list.p,
                                         (uint32_t)unit_cap, rb * ctx->tiles_x, re * ctx->tiles_x, cta_slots, ctx->tile_unit.p, ctx->tile_count_prev.p,
                                         ctx->tile_cycles_prev.p, ctx->have_history ? 1 : 0);
         ctx->have_history = true;
@@ -614,7 +614,7 @@ static int launch_frame(swr_ctx *ctx) {
         rp.records = g.records.p;
         rp.refs = g.refs.p;
         rp.tile_offset = g.tile_offset.p;
-        rp.unit_list = ctx->tile_order.p;
+        rp.unit_list = ctx->unit_list.p;
         rp.clip_ext = g.clip_ext.p;
         rp.draws = g.draws.p;
         rp.prims = ctx->scene.prims;
