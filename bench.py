@@ -328,6 +328,10 @@ def run_gpu(args):
 
 
 def main():
+    if "--impl" in sys.argv and "reference" in sys.argv:
+        # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host core, and libgomp reads this at load time
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+        os.environ.pop("OMP_PROC_BIND", None)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
