@@ -187,7 +187,7 @@ typedef struct swr_frame_stats {
     uint64_t triangles_clipped;   /* polygons that went through the clipper  */
     uint64_t tile_refs;           /* R: (triangle, tile) references          */
     uint32_t tiles;
-    uint32_t reserved;
+    uint32_t clusters_culled;     /* 128-triangle clusters rejected before set-up (frustum / row band) */
     float ms_setup_bin;           /* CUDA-event ms: set-up + count + scan + scatter */
     float ms_raster;              /* tile rasteriser */
     float ms_shade;               /* vis-buffer shading */

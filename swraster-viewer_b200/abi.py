@@ -89,7 +89,7 @@ class FrameStats(C.Structure):
     _fields_ = [
         ("triangles_submitted", C.c_uint64), ("vertices_submitted", C.c_uint64),
         ("triangles_binned", C.c_uint64), ("triangles_clipped", C.c_uint64), ("tile_refs", C.c_uint64),
-        ("tiles", C.c_uint32), ("reserved", C.c_uint32),
+        ("tiles", C.c_uint32), ("clusters_culled", C.c_uint32),
         ("ms_setup_bin", C.c_float), ("ms_raster", C.c_float), ("ms_shade", C.c_float), ("ms_resolve", C.c_float),
     ]
 

@@ -52,7 +52,8 @@ struct Staging {  // pinned host mirror of the per-frame draw table, rotated so 
 // translucent ones (forward-shaded afterwards, tilerasterizer.rs:92-101).
 struct GeomSet {
     DevBuf<DevDraw> draws;
-    DevBuf<uint32_t> tri_prefix;
+    DevBuf<uint32_t> tri_prefix, cl_prefix;
+    DevBuf<uint2> work;  // surviving (draw, cluster) pairs of the frame
     DevBuf<TriRecord> records;
     DevBuf<uint32_t> rects;
     DevBuf<float> avgz;  // translucent set only: packet.avg_z per record (renderer.rs:765-775)
@@ -66,7 +67,7 @@ struct GeomSet {
     Staging staging[4];
     int staging_next = 0;
     std::vector<swr_draw> last_draws;
-    uint32_t ndraws = 0, total_tris = 0;
+    uint32_t ndraws = 0, total_tris = 0, clusters = 0, clusters_kept = 0;
     uint64_t total_verts = 0;
     uint64_t refs_emitted = 0;
     bool rendered_once = false;
@@ -236,6 +237,7 @@ void swr_destroy(swr_ctx *ctx) {
     for (GeomSet *g : {&ctx->op, &ctx->tr}) {
         g->draws.release();
         g->tri_prefix.release();
+        g->work.release();
         g->records.release();
         g->rects.release();
         g->avgz.release();
@@ -357,6 +359,14 @@ int swr_upload_scene(swr_ctx *ctx, const swr_scene_desc *s) {
         d.nverts = p.nverts;
         d.ntris = p.nindices / 3;
         d.material = p.material_index;
+        d.ncl = (d.ntris + SWR_CLUSTER_TRIS - 1) / SWR_CLUSTER_TRIS;
+        if (d.ncl) {
+            float4 *sph = nullptr;
+            CK(cudaMalloc(&sph, (size_t)d.ncl * sizeof(float4)));
+            ctx->scene_allocs.push_back(sph);
+            k_cluster_bounds<<<(d.ncl + 7) / 8, 256, 0, ctx->stream>>>(pos, idx, d.ntris, sph, d.ncl);
+            d.cl_sphere = sph;
+        }
         prims[i] = d;
         ctx->prim_ntris[i] = d.ntris;
         ctx->prim_nverts[i] = p.nverts;
@@ -463,7 +473,7 @@ int swr_upload_scene(swr_ctx *ctx, const swr_scene_desc *s) {
 static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
     const std::vector<swr_draw> &draws = g.last_draws;
     const uint32_t nd = (uint32_t)draws.size();
-    size_t bytes = (size_t)nd * sizeof(DevDraw) + (size_t)(nd + 1) * sizeof(uint32_t);
+    size_t bytes = (size_t)nd * sizeof(DevDraw) + 2 * (size_t)(nd + 1) * sizeof(uint32_t);
     Staging &st = g.staging[g.staging_next];
     g.staging_next = (g.staging_next + 1) & 3;
     if (!st.done) CK(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
@@ -477,7 +487,8 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
     }
     DevDraw *hd = (DevDraw *)st.host;
     uint32_t *hp = (uint32_t *)((char *)st.host + (size_t)nd * sizeof(DevDraw));
-    uint64_t tris = 0, verts = 0, clip_tris = 0;
+    uint32_t *hc = hp + (nd + 1);
+    uint64_t tris = 0, verts = 0, clip_tris = 0, clusters = 0;
     for (uint32_t i = 0; i < nd; i++) {
         const swr_draw &d = draws[i];
         if (d.primitive >= ctx->prim_ntris.size()) {
@@ -491,8 +502,10 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
         hd[i].first_tri = d.first_triangle;
         hd[i].reserved = 0;
         hp[i] = (uint32_t)tris;
+        hc[i] = (uint32_t)clusters;
         uint32_t nt = ctx->prim_ntris[d.primitive];
         tris += nt;
+        clusters += (nt + SWR_CLUSTER_TRIS - 1) / SWR_CLUSTER_TRIS;
         verts += ctx->prim_nverts[d.primitive];
         if (d.flags & SWR_DRAW_CLIP) clip_tris += nt;
         if ((uint64_t)d.first_triangle + nt > 0x1FFFFFFFull) {
@@ -501,6 +514,7 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
         }
     }
     hp[nd] = (uint32_t)tris;
+    hc[nd] = (uint32_t)clusters;
     if (tris >= 0x1FFFFFFFull) {
         ctx->err = "frame too large for 32-bit ids (triangle * 8 + fan)";
         return SWR_ERR_INVALID;
@@ -512,8 +526,9 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
     const size_t slots = tris + g.ext_cap;
     g.ndraws = nd;
     g.total_tris = (uint32_t)tris;
+    g.clusters = (uint32_t)clusters;
     g.total_verts = verts;
-    bool ok = g.draws.reserve(nd + 1) == cudaSuccess && g.tri_prefix.reserve(nd + 2) == cudaSuccess && g.records.reserve(slots + 1) == cudaSuccess &&
+    bool ok = g.draws.reserve(nd + 1) == cudaSuccess && g.tri_prefix.reserve(2 * (size_t)nd + 4) == cudaSuccess && g.work.reserve(clusters + 1) == cudaSuccess && g.records.reserve(slots + 1) == cudaSuccess &&
               g.rects.reserve(slots + 1) == cudaSuccess && g.tile_count.reserve(ctx->ntiles + 1) == cudaSuccess &&
               g.tile_offset.reserve(ctx->ntiles + 1) == cudaSuccess && g.tile_cursor.reserve(ctx->ntiles + 1) == cudaSuccess &&
               g.counters.reserve(1) == cudaSuccess && (!translucent || g.avgz.reserve(slots + 1) == cudaSuccess);
@@ -540,7 +555,7 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
 
     cudaStream_t s = ctx->stream;
     if (nd) CK(cudaMemcpyAsync(g.draws.p, hd, (size_t)nd * sizeof(DevDraw), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(g.tri_prefix.p, hp, (size_t)(nd + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(g.tri_prefix.p, hp, 2 * (size_t)(nd + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(st.done, s));
     CK(cudaMemsetAsync(g.tile_count.p, 0, (ctx->ntiles + 1) * sizeof(uint32_t), s));
     CK(cudaMemsetAsync(g.counters.p, 0, sizeof(FrameCounters), s));
@@ -552,6 +567,13 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
         sp.tri_prefix = g.tri_prefix.p;
         sp.ndraws = nd;
         sp.total_tris = (uint32_t)tris;
+        sp.cl_prefix = g.tri_prefix.p + (nd + 1);
+        sp.total_clusters = (uint32_t)clusters;
+        sp.work = g.work.p;
+        // sort-first: NDC y range of the rows this rank owns, widened by 2 px against the snapping of renderer.rs:834-846
+        sp.use_band = (rb > 0 || re < ctx->tiles_y) ? 1 : 0;
+        sp.band_hi = 1.0f - 2.0f * ((float)(rb * 64) - 2.0f) / (float)ctx->H;
+        sp.band_lo = 1.0f - 2.0f * ((float)(re * 64) + 2.0f) / (float)ctx->H;
         sp.prims = ctx->scene.prims;
         sp.mats = ctx->scene.mats;
         sp.records = g.records.p;
@@ -571,7 +593,9 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
         sp.tiles_y = ctx->tiles_y;
         sp.row_begin = rb;
         sp.row_end = re;
-        k_setup<<<(unsigned)((tris + SETUP_THREADS - 1) / SETUP_THREADS), SETUP_THREADS, 0, s>>>(sp);
+        const unsigned geom_grid = (unsigned)std::min<uint64_t>(clusters, (uint64_t)ctx->num_sms * 16u);
+        k_cull<<<(unsigned)((clusters + 255) / 256), 256, 0, s>>>(sp);
+        k_setup<<<geom_grid, SETUP_THREADS, 0, s>>>(sp);
         if (clip_tris > 0) {
             uint64_t want = (clip_tris + CLIP_GROUPS - 1) / CLIP_GROUPS;
             k_clip<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), CLIP_THREADS, 0, s>>>(sp);
@@ -589,7 +613,9 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
         ctx->have_history = true;
     }
     if (tris > 0) {
-        k_scatter<<<(unsigned)((tris + 255) / 256), 256, 0, s>>>(g.rects.p, (uint32_t)tris, g.tile_cursor.p, g.refs.p, g.counters.p, ctx->tiles_x);
+        const unsigned geom_grid = (unsigned)std::min<uint64_t>(clusters, (uint64_t)ctx->num_sms * 16u);
+        k_scatter<<<geom_grid, SWR_CLUSTER_TRIS, 0, s>>>(g.rects.p, g.work.p, g.tri_prefix.p, g.draws.p, ctx->scene.prims, g.tile_cursor.p, g.refs.p, g.counters.p,
+                                                           ctx->tiles_x);
         if (clip_tris > 0) k_scatter_list<<<148, 256, 0, s>>>(g.rects.p, g.clip_list.p, g.clip_ext.p, g.tile_cursor.p, g.refs.p, g.counters.p, ctx->tiles_x);
     }
     CK(cudaGetLastError());
@@ -740,6 +766,7 @@ static int finish_frame(swr_ctx *ctx) {
             st.tile_refs = c.tile_refs + uncovered;  // the reference's R: every (triangle, tile) packet it would push
             ctx->op.refs_emitted = c.tile_refs;
             st.tiles = (uint32_t)ctx->ntiles;
+            st.clusters_culled = ctx->op.clusters - c.work_n;
 #ifdef SWR_PROFILE_COUNTERS
             if (ctx->dbg_tiles.p) {
                 const int nu = c.raster_units < 8192 ? (int)c.raster_units : 8192;

@@ -12,6 +12,7 @@
 #define SWR_TILE 64
 #define SWR_TILE_PIXELS 4096
 #define SWR_MAX_MIPS 16
+#define SWR_CLUSTER_TRIS 128  // culling granularity: consecutive triangles of a primitive
 #define SWR_NO_CLIP 0xFFFFFFFFu
 #define SWR_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define SWR_INF_BITS 0x7F800000u
@@ -57,7 +58,8 @@ struct DevPrim {
     const float4 *tan;
     const float2 *uv;
     const uint32_t *idx;
-    uint32_t nverts, ntris, material, pad;
+    const float4 *cl_sphere;  // object-space bounding sphere per cluster (k_cluster_bounds at upload)
+    uint32_t nverts, ntris, material, ncl;
 };
 
 struct DevTex {
@@ -109,6 +111,7 @@ struct FrameCounters {
     uint32_t raster_units;    // entries of the raster work list
     uint32_t raster_unit_refs; // refs per unit chosen for this frame
     uint32_t raster_next;     // work-list cursor of the persistent raster CTAs
+    uint32_t work_n;          // surviving (draw, cluster) pairs (k_cull)
     uint32_t overflow_sort;   // a tile holds more translucent packets than the in-kernel sort supports
     unsigned long long dbg[8];  // SWR_PROFILE_COUNTERS builds only
 };

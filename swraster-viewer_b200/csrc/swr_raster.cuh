@@ -16,6 +16,11 @@
 struct SetupParams {
     const DevDraw *draws;
     const uint32_t *tri_prefix;  // ndraws + 1, local triangle prefix
+    const uint32_t *cl_prefix;   // ndraws + 1, cluster prefix (clusters of SWR_CLUSTER_TRIS consecutive triangles)
+    uint32_t total_clusters;
+    uint2 *work;                 // surviving (draw, cluster) pairs of this frame (k_cull); counters->work_n entries
+    float band_lo, band_hi;      // NDC y range of this rank's rows (widened by 2 px); used when use_band != 0 (sort-first)
+    int use_band;
     uint32_t ndraws;
     uint32_t total_tris;
     const DevPrim *prims;
@@ -35,7 +40,7 @@ struct SetupParams {
     int row_begin, row_end;  // owned tile rows (sort-first)
 };
 
-#define SETUP_THREADS 256
+#define SETUP_THREADS SWR_CLUSTER_TRIS  // one block iteration = one cluster
 
 __device__ __forceinline__ uint32_t find_draw(const uint32_t *prefix, uint32_t n, uint32_t g) {
     uint32_t lo = 0, hi = n;  // prefix[lo] <= g < prefix[hi]
@@ -165,62 +170,161 @@ __device__ __forceinline__ float plane_dist(int pl, float4 v) {
     return fadd(fadd(fmul(px, v.x), fmul(pz, v.z)), fadd(fmul(py, v.y), fmul(1.0f, v.w)));
 }
 
+// Upload-time: bounding sphere (object space) of every cluster of SWR_CLUSTER_TRIS consecutive triangles. One warp per cluster.
+__global__ void k_cluster_bounds(const float4 *pos, const uint32_t *idx, uint32_t ntris, float4 *spheres, uint32_t ncl) {
+    const uint32_t cl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (cl >= ncl) return;
+    const uint32_t i0 = cl * SWR_CLUSTER_TRIS * 3, i1 = min(i0 + SWR_CLUSTER_TRIS * 3, ntris * 3);
+    float3 mn = make_float3(3.0e38f, 3.0e38f, 3.0e38f), mx = make_float3(-3.0e38f, -3.0e38f, -3.0e38f);
+    for (uint32_t i = i0 + lane; i < i1; i += 32) {
+        const float4 p = pos[idx[i]];
+        mn = make_float3(fminf(mn.x, p.x), fminf(mn.y, p.y), fminf(mn.z, p.z));
+        mx = make_float3(fmaxf(mx.x, p.x), fmaxf(mx.y, p.y), fmaxf(mx.z, p.z));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn.x = fminf(mn.x, __shfl_xor_sync(0xFFFFFFFFu, mn.x, o));
+        mn.y = fminf(mn.y, __shfl_xor_sync(0xFFFFFFFFu, mn.y, o));
+        mn.z = fminf(mn.z, __shfl_xor_sync(0xFFFFFFFFu, mn.z, o));
+        mx.x = fmaxf(mx.x, __shfl_xor_sync(0xFFFFFFFFu, mx.x, o));
+        mx.y = fmaxf(mx.y, __shfl_xor_sync(0xFFFFFFFFu, mx.y, o));
+        mx.z = fmaxf(mx.z, __shfl_xor_sync(0xFFFFFFFFu, mx.z, o));
+    }
+    const float3 c = make_float3(0.5f * (mn.x + mx.x), 0.5f * (mn.y + mx.y), 0.5f * (mn.z + mx.z));
+    float r2 = 0.0f;
+    for (uint32_t i = i0 + lane; i < i1; i += 32) {
+        const float4 p = pos[idx[i]];
+        const float dx = p.x - c.x, dy = p.y - c.y, dz = p.z - c.z;
+        r2 = fmaxf(r2, dx * dx + dy * dy + dz * dz);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xFFFFFFFFu, r2, o));
+    if (lane == 0) spheres[cl] = make_float4(c.x, c.y, c.z, sqrtf(r2) * 1.0001f + 1.0e-30f);
+}
+
+// Per frame: keep the (draw, cluster) pairs whose bounding sphere can reach the clip-space frustum (and, for sort-first,
+// this rank's row band). The planes are the clipper's own (renderer.rs:581-588) pulled back to object space through the
+// draw's mvp, so the test needs no scale extraction; every comparison is pushed out by a margin two orders of magnitude
+// above the f32 rounding of k_setup's own mvp product. A dropped cluster therefore only holds triangles the reference's
+// clipper reduces to nothing, or triangles whose pixels all lie in rows this rank does not own.
+// Draws the reference classified Inside are never clipped, whatever their real position (the node sphere quirk), so
+// they are kept unless they are provably in front of the eye (inside both z planes => w > 0) and outside the band.
+// One thread per (draw, cluster).
+__device__ __forceinline__ float cull_plane(const float *m, float kx, float ky, float kz, float kw, float4 sp, float &reach) {
+    // plane = kx*row0 + ky*row1 + kz*row2 + kw*row3 of the column-major mvp
+    const float a = kx * m[0] + ky * m[1] + kz * m[2] + kw * m[3], b = kx * m[4] + ky * m[5] + kz * m[6] + kw * m[7];
+    const float c = kx * m[8] + ky * m[9] + kz * m[10] + kw * m[11], d = kx * m[12] + ky * m[13] + kz * m[14] + kw * m[15];
+    const float mag = fabsf(kx) + fabsf(ky) + fabsf(kz) + fabsf(kw);
+    const float terms = fabsf(m[0] * sp.x) + fabsf(m[1] * sp.x) + fabsf(m[2] * sp.x) + fabsf(m[3] * sp.x) + fabsf(m[4] * sp.y) + fabsf(m[5] * sp.y) +
+                        fabsf(m[6] * sp.y) + fabsf(m[7] * sp.y) + fabsf(m[8] * sp.z) + fabsf(m[9] * sp.z) + fabsf(m[10] * sp.z) + fabsf(m[11] * sp.z) +
+                        fabsf(m[12]) + fabsf(m[13]) + fabsf(m[14]) + fabsf(m[15]);
+    const float rn = sp.w * sqrtf(a * a + b * b + c * c);
+    reach = rn * 1.001f + 1.0e-4f * mag * (terms + rn) + 1.0e-30f;
+    return a * sp.x + b * sp.y + c * sp.z + d;
+}
+
+__global__ void __launch_bounds__(256) k_cull(SetupParams P) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    bool keep = false;
+    uint32_t d = 0, cl = 0;
+    if (i < P.total_clusters) {
+        d = find_draw(P.cl_prefix, P.ndraws, i);
+        cl = i - P.cl_prefix[d];
+        const DevDraw &dr = P.draws[d];
+        const float4 sp = __ldg(P.prims[dr.prim].cl_sphere + cl);
+        const float *m = dr.mvp;
+        const bool clip = (dr.flags & 1u) != 0;
+        float reach;
+        bool out = false;      // provably outside one plane
+        bool front = true;     // provably inside both z planes (every point has w > 0)
+        float dist = cull_plane(m, 0.0f, 0.0f, 1.0f, 1.0f, sp, reach);
+        out |= dist < -reach, front &= dist > reach;
+        dist = cull_plane(m, 0.0f, 0.0f, -1.0f, 1.0f, sp, reach);
+        out |= dist < -reach, front &= dist > reach;
+        dist = cull_plane(m, 1.0f, 0.0f, 0.0f, 1.0f, sp, reach);
+        out |= dist < -reach;
+        dist = cull_plane(m, -1.0f, 0.0f, 0.0f, 1.0f, sp, reach);
+        out |= dist < -reach;
+        dist = cull_plane(m, 0.0f, 1.0f, 0.0f, 1.0f, sp, reach);
+        out |= dist < -reach;
+        dist = cull_plane(m, 0.0f, -1.0f, 0.0f, 1.0f, sp, reach);
+        out |= dist < -reach;
+        if (!clip) out = false;
+        if (P.use_band && (clip || front)) {
+            dist = cull_plane(m, 0.0f, 1.0f, 0.0f, -P.band_lo, sp, reach);  // y >= lo * w
+            out |= dist < -reach;
+            dist = cull_plane(m, 0.0f, -1.0f, 0.0f, P.band_hi, sp, reach);  // y <= hi * w
+            out |= dist < -reach;
+        }
+        keep = !out;  // NaNs compare false everywhere: never culled
+    }
+    const unsigned bm = __ballot_sync(0xFFFFFFFFu, keep);
+    if (bm) {
+        const unsigned lane = threadIdx.x & 31;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&P.counters->work_n, (uint32_t)__popc(bm));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (keep) P.work[base + __popc(bm & ((1u << lane) - 1u))] = make_uint2(d, cl);
+    }
+}
+
+// K1: persistent over the surviving clusters; one block iteration = one cluster, one thread = one triangle.
 __global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams P) {
-    __shared__ uint32_t s_draw0, s_unc;
+    __shared__ uint32_t s_unc;
     const uint32_t tid = threadIdx.x;
-    const uint32_t g0 = blockIdx.x * SETUP_THREADS;
-    if (tid == 0) s_draw0 = find_draw(P.tri_prefix, P.ndraws, g0);
-    __syncthreads();
-    const uint32_t g = g0 + tid;
-    uint32_t rect = 0;
-    bool queued = false, nocover = false;
-    if (g < P.total_tris) {
-        uint32_t d = s_draw0;
-        while (g >= P.tri_prefix[d + 1]) d++;
-        const uint32_t tri = g - P.tri_prefix[d];
+    const unsigned lane = tid & 31;
+    const uint32_t nwork = P.counters->work_n;
+    for (uint32_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+        const uint2 w = P.work[wi];
+        const uint32_t d = w.x;
         const DevDraw &dr = P.draws[d];
         const DevPrim &pr = P.prims[dr.prim];
-        const bool clip = (dr.flags & 1u) != 0;
-        const uint32_t dflag = d | ((P.mats[pr.material].flags & 1u) ? SWR_REC_ALPHA : 0u);
-        const uint32_t slot = g;  // record of fan 0 = dense triangle index; id = g * 8 + fan
-        uint32_t i0 = __ldg(pr.idx + 3 * tri), i1 = __ldg(pr.idx + 3 * tri + 1), i2 = __ldg(pr.idx + 3 * tri + 2);
-        float4 c0 = mul_vec4(dr.mvp, __ldg(pr.pos + i0));
-        float4 c1 = mul_vec4(dr.mvp, __ldg(pr.pos + i1));
-        float4 c2 = mul_vec4(dr.mvp, __ldg(pr.pos + i2));
-        const uint32_t seq = (dr.first_tri + tri) * 8u;
-        if (clip) {
-            // Exact classification against renderer.rs:621-648: planes are visited in order; while all three
-            // vertices are inside the polygon is passed through unchanged, so the first plane with any vertex
-            // outside decides: all three outside -> the polygon becomes empty (nothing is emitted);
-            // mixed -> the real clipper is needed; no such plane -> the triangle goes through untouched.
-            int state = 0;  // 0 all-in, 1 empty, 2 needs clipping
+        const uint32_t tri = w.y * SWR_CLUSTER_TRIS + tid;
+        const uint32_t g = P.tri_prefix[d] + tri;
+        uint32_t rect = 0;
+        bool queued = false, nocover = false;
+        if (tri < pr.ntris) {
+            const bool clip = (dr.flags & 1u) != 0;
+            const uint32_t dflag = d | ((P.mats[pr.material].flags & 1u) ? SWR_REC_ALPHA : 0u);
+            const uint32_t slot = g;  // record of fan 0 = dense triangle index; id = g * 8 + fan
+            uint32_t i0 = __ldg(pr.idx + 3 * tri), i1 = __ldg(pr.idx + 3 * tri + 1), i2 = __ldg(pr.idx + 3 * tri + 2);
+            float4 c0 = mul_vec4(dr.mvp, __ldg(pr.pos + i0));
+            float4 c1 = mul_vec4(dr.mvp, __ldg(pr.pos + i1));
+            float4 c2 = mul_vec4(dr.mvp, __ldg(pr.pos + i2));
+            const uint32_t seq = (dr.first_tri + tri) * 8u;
+            if (clip) {
+                // Exact classification against renderer.rs:621-648: planes are visited in order; while all three
+                // vertices are inside the polygon is passed through unchanged, so the first plane with any vertex
+                // outside decides: all three outside -> the polygon becomes empty (nothing is emitted);
+                // mixed -> the real clipper is needed; no such plane -> the triangle goes through untouched.
+                int state = 0;  // 0 all-in, 1 empty, 2 needs clipping
 #pragma unroll
-            for (int pl = 0; pl < 6; pl++) {
-                if (state == 0) {
-                    int in = (plane_dist(pl, c0) >= 0.0f ? 1 : 0) + (plane_dist(pl, c1) >= 0.0f ? 1 : 0) + (plane_dist(pl, c2) >= 0.0f ? 1 : 0);
-                    if (in == 0)
-                        state = 1;
-                    else if (in != 3)
-                        state = 2;
+                for (int pl = 0; pl < 6; pl++) {
+                    if (state == 0) {
+                        int in = (plane_dist(pl, c0) >= 0.0f ? 1 : 0) + (plane_dist(pl, c1) >= 0.0f ? 1 : 0) + (plane_dist(pl, c2) >= 0.0f ? 1 : 0);
+                        if (in == 0)
+                            state = 1;
+                        else if (in != 3)
+                            state = 2;
+                    }
                 }
+                if (state == 0) rect = emit_triangle(P, c0, c1, c2, slot, dflag, seq, SWR_NO_CLIP, nocover);
+                queued = state == 2;
+            } else {
+                rect = emit_triangle(P, c0, c1, c2, slot, dflag, seq, SWR_NO_CLIP, nocover);
             }
-            if (state == 0) rect = emit_triangle(P, c0, c1, c2, slot, dflag, seq, SWR_NO_CLIP, nocover);
-            queued = state == 2;
-        } else {
-            rect = emit_triangle(P, c0, c1, c2, slot, dflag, seq, SWR_NO_CLIP, nocover);
+            P.rects[slot] = nocover ? 0u : rect;  // k_clip overwrites it when fan 0 of a clipped polygon survives
         }
-        P.rects[slot] = nocover ? 0u : rect;  // k_clip overwrites it when fan 0 of a clipped polygon survives
-    }
-    const unsigned lane = tid & 31;
-    rect = account_block(rect, nocover, P.counters, &s_unc);
-    count_tiles(rect, P.tile_count, P.tiles_x);
-    // warp-aggregated append to the clip queue
-    unsigned qm = __ballot_sync(0xFFFFFFFFu, queued);
-    if (qm) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&P.counters->clip_queue_n, (uint32_t)__popc(qm));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (queued) P.clip_queue[base + __popc(qm & ((1u << lane) - 1u))] = g;
+        rect = account_block(rect, nocover, P.counters, &s_unc);
+        count_tiles(rect, P.tile_count, P.tiles_x);
+        // warp-aggregated append to the clip queue
+        unsigned qm = __ballot_sync(0xFFFFFFFFu, queued);
+        if (qm) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&P.counters->clip_queue_n, (uint32_t)__popc(qm));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (queued) P.clip_queue[base + __popc(qm & ((1u << lane) - 1u))] = g;
+        }
     }
 }
 
@@ -498,12 +602,19 @@ __device__ __forceinline__ void scatter_rect(uint32_t rect, uint32_t id, uint32_
     }
 }
 
-__global__ void __launch_bounds__(256) k_scatter(const uint32_t *rects, uint32_t ntris, uint32_t *tile_cursor, uint32_t *refs,
-                                                 const FrameCounters *counters, int tiles_x) {
+// fan-0 records of the surviving clusters (same work list as k_setup): persistent, one cluster per block iteration
+__global__ void __launch_bounds__(SWR_CLUSTER_TRIS) k_scatter(const uint32_t *rects, const uint2 *work, const uint32_t *tri_prefix, const DevDraw *draws,
+                                                              const DevPrim *prims, uint32_t *tile_cursor, uint32_t *refs, const FrameCounters *counters,
+                                                              int tiles_x) {
     if (counters->overflow_refs) return;  // lists would not fit: the host grows the buffer and replays the frame
-    uint32_t t = blockIdx.x * 256 + threadIdx.x;
-    uint32_t rect = t < ntris ? __ldg(rects + t) : 0u;
-    scatter_rect(rect, t * 8u, tile_cursor, refs, tiles_x);
+    const uint32_t nwork = counters->work_n;
+    for (uint32_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+        const uint2 w = work[wi];
+        const uint32_t tri = w.y * SWR_CLUSTER_TRIS + threadIdx.x;
+        const uint32_t t = tri_prefix[w.x] + tri;
+        const uint32_t rect = tri < prims[draws[w.x].prim].ntris ? __ldg(rects + t) : 0u;
+        scatter_rect(rect, t * 8u, tile_cursor, refs, tiles_x);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_scatter_list(const uint32_t *rects, const uint32_t *clip_list, const uint32_t *clip_ext,
