@@ -11,8 +11,9 @@ vis-buffer shading, resolve).
   e2e       the same frames through the public host API (Renderer.render_scene + blit_to_buffer into a pinned
             host buffer): draw-list build + H2D of camera/draw table + all kernels + D2H of the RGBA8 frame,
             wall clock, max over ranks.
-  N > 1     sort-first: every rank holds the scene and owns a contiguous range of tile rows; RGBA8 strips are
-            gathered to rank 0 over NCCL inside the timed region ("scaling": "strong" — total work fixed).
+  N > 1     sort-first: every rank holds the scene and owns a contiguous range of tile rows; each rank's resolve kernel
+            stores its RGBA8 rows straight into rank 0's frame over NVLink peer memory (swr_peer_*), inside the timed
+            region ("scaling": "strong" — total work fixed).
   --impl reference   the reference's CPU path (oracle port: C++ restatement with the reference's parallel
             structure, all host threads) on the same config, rank 0 only.
 """
@@ -146,7 +147,7 @@ def run_gpu(args):
     import torch.distributed as dist
     import swraster_viewer_b200 as swr
     from swraster_viewer_b200 import abi
-    from swraster_viewer_b200.multigpu import tile_row_ranges, balanced_row_ranges, gather_strips, device_tensor
+    from swraster_viewer_b200.multigpu import tile_row_ranges, balanced_row_ranges, PeerAssembly, device_tensor
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -181,23 +182,27 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # N > 1: the frame is assembled in rank 0's pixel buffer by the other ranks' resolve kernels (peer stores over NVLink
+    # + a device-side handshake, include/swr.h swr_peer_*): no collective on the data path
+    pa = PeerAssembly(r, dst=0) if world > 1 else None
+
     def step_device():
         r.render_scene(scene, cam)
-        r.resolve_device_only(2.0)
         if world > 1:
-            with torch.cuda.stream(stream):
-                gather_strips(pix, ranges, H, dst=0)
+            pa.frame(2.0)
+            pa.release()
+        else:
+            r.resolve_device_only(2.0)
 
     def step_e2e():
         r.render_scene(scene, cam)
         if world > 1:
-            r.resolve_device_only(2.0)
-            with torch.cuda.stream(stream):
-                gather_strips(pix, ranges, H, dst=0)
+            pa.frame(2.0)
             if rank == 0:
-                # D2H of the assembled frame on rank 0 (the caller's RenderBuffer)
+                # D2H of the assembled frame on rank 0 (the caller's RenderBuffer), then hand the buffer back
                 with torch.cuda.stream(stream):
                     buf._t.view(H, W).copy_(pix, non_blocking=True)
+            pa.release()
             stream.synchronize()
         else:
             r.blit_to_buffer(buf)
@@ -295,9 +300,9 @@ def run_gpu(args):
             "mtriangles_per_sec": fps * T / 1e6,
             "config": {"workload": WORKLOAD, "width": W, "height": H, "triangles_submitted": T, "scene_triangles": scene.total_triangles,
                        "vertices_submitted": st0["vertices_submitted"], "tile_refs": int(cnt[0]), "triangles_binned": int(cnt[1]),
-                       "l2": "256 MiB device write between timed frames (L2 flush)", "parallelism": (f"sort-first x{world}: cost-balanced contiguous tile-row bands {ranges}, per-band draw culling, NCCL strip gather" if world > 1 else "single GPU")},
+                       "l2": "256 MiB device write between timed frames (L2 flush)", "parallelism": (f"sort-first x{world}: cost-balanced contiguous tile-row bands {ranges}, per-band draw culling, peer-store frame assembly on rank 0 (NVLink P2P, no collective)" if world > 1 else "single GPU")},
             "e2e": {"value": K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": W * H * 4, "ms_per_step": 1e3 * e2e_s / K,
-                    "mode": "pipelined: read-back of frame N overlaps frame N+1 (swr_resolve_async)" if world == 1 else "synchronous + NCCL strip gather",
+                    "mode": "pipelined: read-back of frame N overlaps frame N+1 (swr_resolve_async)" if world == 1 else "synchronous + peer-store frame assembly on rank 0 (NVLink P2P, no collective)",
                     "synchronous_value": K / e2e_sync_s},
             "gpu_launches": KERNELS_PER_FRAME * K * 2 + KERNELS_PER_FRAME * (max(3, args.warmup) + 2),
             "clocks": clocks,

@@ -274,6 +274,27 @@ int swr_read_color(swr_ctx *ctx, float *rgb);
 int swr_synchronize(swr_ctx *ctx);
 int swr_get_stats(swr_ctx *ctx, swr_frame_stats *out);
 
+/* Sort-first frame assembly over NVLink peer memory: instead of resolving locally and gathering strips with a
+ * collective, every contributing rank's resolve kernel stores its rows straight into the assembling rank's pixel buffer
+ * and signals completion there (one kernel: tonemap + pack + peer stores + release). Replaces the strip gather a host
+ * would otherwise issue after Renderer::blit_to_buffer (renderer.rs:293-355) per rank.
+ *   assembling rank:   swr_peer_export -> 64-byte handle (send it to the others with any transport);
+ *                      per frame f = 1,2,...: swr_render, swr_resolve(NULL) (its own rows), swr_peer_collect(f, n_contributors),
+ *                      consume swr_device_pixels() on the context's stream, swr_peer_release(f);
+ *   contributing rank: swr_peer_open(handle) once (or swr_peer_attach with a device pointer that is already mapped
+ *                      in this process: several contexts driven by one process), per frame swr_render,
+ *                      swr_resolve_peer(exposure, f).
+ * Everything is enqueued on the contexts' streams; the waits are device-side and give up after ~2 s
+ * (SWR_ERR_CUDA at the next synchronising call) so a protocol error cannot wedge the GPU. Frame numbers must
+ * increase by one per frame on every rank. Do not mix with swr_resolve_async on the assembling rank. */
+#define SWR_PEER_HANDLE_BYTES 64
+int swr_peer_export(swr_ctx *ctx, void *handle_out);
+int swr_peer_open(swr_ctx *ctx, const void *handle);
+int swr_peer_attach(swr_ctx *ctx, void *assembler_device_pixels);
+int swr_resolve_peer(swr_ctx *ctx, float exposure, uint32_t frame);
+int swr_peer_collect(swr_ctx *ctx, uint32_t frame, int contributors);
+int swr_peer_release(swr_ctx *ctx, uint32_t frame);
+
 /* Device pointers for zero-copy interop (NCCL gather / composite from the host
  * language): RGBA8 image (W*H u32, row-major) and the 64-bit visibility keys
  * (tile-major: tile (ty*tiles_x+tx) owns 4096 consecutive keys, y*64+x inside the

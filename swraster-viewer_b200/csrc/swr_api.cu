@@ -123,6 +123,11 @@ struct swr_ctx {
     swr_camera last_cam{};
     int last_shade = 0;
     bool frame_pending = false;
+    // peer frame assembly (swr_peer_*): mapping of the assembling rank's pixel buffer + local bookkeeping
+    uint32_t *peer_pixels = nullptr;   // assembler's pixels as seen from this context (own buffer on the assembler)
+    void *peer_ipc_base = nullptr;     // non-null when opened through an IPC handle (closed on destroy)
+    DevBuf<uint32_t> peer_local;       // [0] CTAs done (k_resolve_peer), [1] timeout flag
+    bool peer_exported = false;
     bool frame_valid = false;
     DevCamera dcam{};
     swr_frame_stats stats{};
@@ -203,13 +208,14 @@ swr_ctx *swr_create(int width, int height, int device) {
     ok = ok && ctx->op.tile_count.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->op.tile_offset.reserve(ctx->ntiles + 1) == cudaSuccess &&
          ctx->op.tile_cursor.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_cycles.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_cycles_prev.reserve(ctx->ntiles + 1) == cudaSuccess &&
          ctx->tile_count_prev.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_unit.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->unit_list.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->keys.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess &&
-         ctx->color.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess && ctx->pixels.reserve((size_t)width * height) == cudaSuccess &&
+         ctx->color.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess && ctx->pixels.reserve((size_t)width * height + SWR_PEER_WORDS) == cudaSuccess && ctx->peer_local.reserve(16) == cudaSuccess &&
          ctx->lum.reserve(ctx->ntiles) == cudaSuccess && ctx->op.counters.reserve(1) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_raster_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes()) == cudaSuccess;
     if (ok) {
         ok = cudaMemsetAsync(ctx->keys.p, 0xFF, (size_t)ctx->ntiles * SWR_TILE_PIXELS * 8, ctx->stream) == cudaSuccess &&
              cudaMemsetAsync(ctx->color.p, 0, (size_t)ctx->ntiles * SWR_TILE_PIXELS * sizeof(float4), ctx->stream) == cudaSuccess &&
-             cudaMemsetAsync(ctx->pixels.p, 0, (size_t)width * height * 4, ctx->stream) == cudaSuccess &&
+             cudaMemsetAsync(ctx->pixels.p, 0, ((size_t)width * height + SWR_PEER_WORDS) * 4, ctx->stream) == cudaSuccess &&
+             cudaMemsetAsync(ctx->peer_local.p, 0, 16 * 4, ctx->stream) == cudaSuccess &&
              cudaMemsetAsync(ctx->lum.p, 0, ctx->ntiles * sizeof(float), ctx->stream) == cudaSuccess &&
              cudaStreamSynchronize(ctx->stream) == cudaSuccess;
     }
@@ -256,6 +262,8 @@ void swr_destroy(swr_ctx *ctx) {
             if (st.done) cudaEventDestroy(st.done);
         }
     }
+    if (ctx->peer_ipc_base) cudaIpcCloseMemHandle(ctx->peer_ipc_base);
+    ctx->peer_local.release();
     ctx->unit_list.release();
     ctx->tile_cycles.release();
     ctx->tile_cycles_prev.release();
@@ -598,7 +606,9 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
         k_setup<<<geom_grid, SETUP_THREADS, 0, s>>>(sp);
         if (clip_tris > 0) {
             uint64_t want = (clip_tris + CLIP_GROUPS - 1) / CLIP_GROUPS;
-            k_clip<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), CLIP_THREADS, 0, s>>>(sp);
+            // many short CTAs: an iteration lasts as long as its slowest polygon (block barriers in the accounting), so fine grains win
+            const uint64_t cap = (uint64_t)ctx->num_sms * 8u;
+            k_clip<<<(unsigned)(want < cap ? want : cap), CLIP_THREADS, 0, s>>>(sp);
         }
     }
     if (translucent) {
@@ -929,6 +939,106 @@ int swr_resolve(swr_ctx *ctx, float exposure, uint32_t *out_pixels) {
     return SWR_OK;
 }
 
+// ---- peer frame assembly (include/swr.h) ---------------------------------------------------------------------------
+static int peer_check_timeout(swr_ctx *ctx) {  // called from synchronising entry points
+    uint32_t flag = 0;
+    CK(cudaMemcpy(&flag, ctx->peer_local.p + 1, 4, cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaMemset(ctx->peer_local.p + 1, 0, 4);
+        ctx->err = "peer frame assembly: a device-side wait timed out (frame numbers out of step, or a rank stopped)";
+        return SWR_ERR_CUDA;
+    }
+    return SWR_OK;
+}
+
+int swr_peer_export(swr_ctx *ctx, void *handle_out) {
+    if (!ctx || !handle_out) return SWR_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) <= SWR_PEER_HANDLE_BYTES, "handle size");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint32_t init[2] = {0u, 1u};  // nothing received; frame 1 may be written
+    CK(cudaMemset(ctx->pixels.p + (size_t)ctx->W * ctx->H, 0, SWR_PEER_WORDS * 4));
+    CK(cudaMemcpy(ctx->pixels.p + (size_t)ctx->W * ctx->H + SWR_PEER_FREE, &init[1], 4, cudaMemcpyHostToDevice));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->pixels.p));
+    memset(handle_out, 0, SWR_PEER_HANDLE_BYTES);
+    memcpy(handle_out, &h, sizeof(h));
+    ctx->peer_pixels = ctx->pixels.p;
+    ctx->peer_exported = true;
+    ctx->pix_cur = 0;
+    return SWR_OK;
+}
+
+int swr_peer_attach(swr_ctx *ctx, void *assembler_device_pixels) {
+    if (!ctx || !assembler_device_pixels) return SWR_ERR_INVALID;
+    ctx->peer_pixels = (uint32_t *)assembler_device_pixels;
+    return SWR_OK;
+}
+
+int swr_peer_open(swr_ctx *ctx, const void *handle) {
+    if (!ctx || !handle) return SWR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->peer_ipc_base) {
+        cudaIpcCloseMemHandle(ctx->peer_ipc_base);
+        ctx->peer_ipc_base = nullptr;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_ipc_base = p;
+    ctx->peer_pixels = (uint32_t *)p;
+    return SWR_OK;
+}
+
+int swr_resolve_peer(swr_ctx *ctx, float exposure, uint32_t frame) {
+    if (!ctx) return SWR_ERR_INVALID;
+    if (!ctx->peer_pixels || ctx->peer_exported) {
+        ctx->err = "swr_resolve_peer needs swr_peer_open / swr_peer_attach first (and is for contributing ranks)";
+        return SWR_ERR_INVALID;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t W = ctx->W;
+    size_t y0 = (size_t)ctx->row_begin * SWR_TILE, y1 = (size_t)ctx->row_end * SWR_TILE;
+    if (y1 > (size_t)ctx->H) y1 = ctx->H;
+    uint32_t *ctrl = ctx->peer_pixels + (size_t)ctx->W * ctx->H;
+    CK(cudaEventRecord(ctx->ev_res[0], s));
+    k_peer_wait<<<1, 1, 0, s>>>(ctrl + SWR_PEER_FREE, frame, ctx->peer_local.p + 1);
+    // an empty band still contributes (one CTA that only signals) so the assembler's count stays in step
+    dim3 grid((unsigned)((W + 255) / 256), (unsigned)(y1 > y0 ? (y1 - y0 + 3) / 4 : 1));
+    k_resolve_peer<<<grid, 256, 0, s>>>(ctx->color.p, ctx->tiles_x * SWR_TILE, ctx->peer_pixels, ctrl, ctx->W, (int)y0, (int)(y1 > y0 ? y1 : y0), exposure,
+                                        ctx->peer_local.p, ctx->peer_local.p + 1);
+    CK(cudaEventRecord(ctx->ev_res[1], s));
+    CK(cudaGetLastError());
+    return SWR_OK;
+}
+
+int swr_peer_collect(swr_ctx *ctx, uint32_t frame, int contributors) {
+    if (!ctx || contributors < 0) return SWR_ERR_INVALID;
+    if (!ctx->peer_exported) {
+        ctx->err = "swr_peer_collect is for the rank that called swr_peer_export";
+        return SWR_ERR_INVALID;
+    }
+    CK(cudaSetDevice(ctx->device));
+    uint32_t *ctrl = ctx->pixels.p + (size_t)ctx->W * ctx->H;
+    if (contributors > 0) k_peer_wait<<<1, 1, 0, ctx->stream>>>(ctrl + SWR_PEER_DONE, frame * (uint32_t)contributors, ctx->peer_local.p + 1);
+    CK(cudaGetLastError());
+    return SWR_OK;
+}
+
+int swr_peer_release(swr_ctx *ctx, uint32_t frame) {
+    if (!ctx) return SWR_ERR_INVALID;
+    if (!ctx->peer_exported) {
+        ctx->err = "swr_peer_release is for the rank that called swr_peer_export";
+        return SWR_ERR_INVALID;
+    }
+    CK(cudaSetDevice(ctx->device));
+    k_peer_release<<<1, 1, 0, ctx->stream>>>(ctx->pixels.p + (size_t)ctx->W * ctx->H, frame + 1u);
+    CK(cudaGetLastError());
+    return SWR_OK;
+}
+
 // resolve into pixel buffer `idx` on the main stream, then copy it to `host` on the copy stream
 static int issue_resolve_copy(swr_ctx *ctx, int idx, float exposure, uint32_t *host) {
     cudaStream_t s = ctx->stream;
@@ -985,7 +1095,9 @@ int swr_wait_pixels(swr_ctx *ctx, int ticket) {
 
 int swr_synchronize(swr_ctx *ctx) {
     if (!ctx) return SWR_ERR_INVALID;
-    return finish_frame(ctx);
+    int rc = finish_frame(ctx);
+    if (rc == SWR_OK && ctx->peer_pixels) rc = peer_check_timeout(ctx);
+    return rc;
 }
 
 int swr_read_tile_costs(swr_ctx *ctx, uint32_t *refs, uint32_t *cycles) {

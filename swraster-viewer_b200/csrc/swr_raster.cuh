@@ -567,13 +567,20 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
     }
     __syncthreads();
     if (counters->overflow_refs) return;
-    for (int i = tile_begin + tid; i < tile_end; i += 1024) {
+    // one warp per tile: a hot tile has hundreds of units, emitted 32 at a time instead of one by one
+    for (int i = tile_begin + wid; i < tile_end; i += 32) {
         const uint32_t v = tile_count[i];
         const uint32_t ut = tile_unit[i];
         const uint32_t nfull = v / ut, rem = v % ut;
-        for (uint32_t k = 0; k < nfull; k++) unit_list[atomicAdd(&s_cur[32 - __clz(ut)], 1u)] = ((uint32_t)i << 14) | k;
-        if (rem || !nfull) unit_list[atomicAdd(&s_cur[rem ? 32 - __clz(rem) : 0], 1u)] = ((uint32_t)i << 14) | nfull;
-        prev_count[i] = v;  // history for the next frame
+        uint32_t base = 0, tail = 0;
+        if (lane == 0) {
+            if (nfull) base = atomicAdd(&s_cur[32 - __clz(ut)], nfull);
+            if (rem || !nfull) tail = atomicAdd(&s_cur[rem ? 32 - __clz(rem) : 0], 1u);
+            prev_count[i] = v;  // history for the next frame
+        }
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        for (uint32_t k = lane; k < nfull; k += 32) unit_list[base + k] = ((uint32_t)i << 14) | k;
+        if (lane == 0 && (rem || !nfull)) unit_list[tail] = ((uint32_t)i << 14) | nfull;
     }
 }
 
@@ -901,15 +908,15 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
     FragQueue &fq = fqs[wid];
     const unsigned lt_mask = (1u << lane) - 1u;
 
+    const uint32_t tile_beg = P.tile_offset[tile], tile_end = P.tile_offset[tile + 1];
+    const uint32_t unit_refs = P.tile_unit[tile];
+    const bool split = tile_end - tile_beg > unit_refs;  // several CTAs share this tile: merge with atomics at the end
     for (int i = tid; i < SWR_TILE_PIXELS; i += RASTER_THREADS) skeys[i] = SWR_KEY_EMPTY;
 #ifdef SWR_PROFILE_COUNTERS
     const long long dbg_t0 = clock64();
     unsigned long long dbg_items = 0;
 #endif
 
-    const uint32_t tile_beg = P.tile_offset[tile], tile_end = P.tile_offset[tile + 1];
-    const uint32_t unit_refs = P.tile_unit[tile];
-    const bool split = tile_end - tile_beg > unit_refs;  // several CTAs share this tile: merge with atomics at the end
     const uint32_t beg = tile_beg + chunk * unit_refs, end = min(beg + unit_refs, tile_end);
     // software pipeline over batches: the record of batch n+1 and the ref of batch n+2 are in flight while batch n is rasterised
     uint32_t slot_next = 0, slot_next2 = 0;

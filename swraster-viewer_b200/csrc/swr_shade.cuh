@@ -463,6 +463,78 @@ __global__ void __launch_bounds__(256) k_resolve(const float4 *color, int Wp, ui
     }
 }
 
+// Peer frame assembly (sort-first): the pixel buffer of the assembling rank carries SWR_PEER_WORDS control words behind
+// its W*H pixels: [0] = contributions received (monotonic count), [16] = frame number contributors may write.
+#define SWR_PEER_WORDS 64
+#define SWR_PEER_DONE 0
+#define SWR_PEER_FREE 16
+#define SWR_PEER_TIMEOUT_NS 2000000000ull
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *ctr >= target (system scope); false after SWR_PEER_TIMEOUT_NS
+__device__ __forceinline__ bool peer_wait(const uint32_t *ctr, uint32_t target) {
+    const unsigned long long t0 = global_timer_ns();
+    while ((int32_t)(ld_acquire_sys(ctr) - target) < 0) {
+        if (global_timer_ns() - t0 > SWR_PEER_TIMEOUT_NS) return false;
+        __nanosleep(200);
+    }
+    return true;
+}
+
+// k_resolve into the assembling rank's buffer: store this rank's rows over NVLink and let the last CTA publish the
+// contribution (fence + system-scope atomic on the assembler's counter). The buffer-reuse guard (k_peer_wait) runs
+// as a one-thread kernel in front so that only one remote poll is in flight instead of one per CTA.
+__global__ void __launch_bounds__(256) k_resolve_peer(const float4 *color, int Wp, uint32_t *pixels, uint32_t *ctrl, int W, int y0, int y1, float exposure,
+                                                      uint32_t *local_done, const uint32_t *timeout_flag) {
+    if (*timeout_flag == 0u) {  // after a timeout the buffer may still be in use: contribute nothing but still signal
+        const int x = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
+        const int y = y0 + blockIdx.y * 4 + (threadIdx.x >> 6);
+        if (y < y1 && x < W) {
+            const float4 *c = color + (size_t)y * Wp + x;
+            uint32_t *o = pixels + (size_t)y * W + x;
+            if (x + 3 < W && (W & 3) == 0) {
+                uint4 v;
+                v.x = resolve_pixel_rgba(c[0], exposure);
+                v.y = resolve_pixel_rgba(c[1], exposure);
+                v.z = resolve_pixel_rgba(c[2], exposure);
+                v.w = resolve_pixel_rgba(c[3], exposure);
+                *reinterpret_cast<uint4 *>(o) = v;
+            } else {
+                for (int k = 0; k < 4 && x + k < W; k++) o[k] = resolve_pixel_rgba(c[k], exposure);
+            }
+        }
+    }
+    __threadfence_system();  // this thread's peer stores are performed before the CTA is counted
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t n = gridDim.x * gridDim.y;
+        if (atomicAdd(local_done, 1u) == n - 1u) {
+            *local_done = 0u;  // next frame
+            __threadfence_system();
+            atomicAdd_system(ctrl + SWR_PEER_DONE, 1u);
+        }
+    }
+}
+
+__global__ void k_peer_wait(const uint32_t *ctr, uint32_t target, uint32_t *timeout_flag) {
+    if (!peer_wait(ctr, target)) *timeout_flag = 1u;
+    __threadfence_system();
+}
+
+__global__ void k_peer_release(uint32_t *ctrl, uint32_t next_frame) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ctrl + SWR_PEER_FREE), "r"(next_frame) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // Translucent pass (tilerasterizer.rs:92-101, shader.rs:66-76): per tile, packets sorted back to front, forward-shaded
 // over the opaque colour, depth-tested against (never written to) the opaque depth.

@@ -69,6 +69,40 @@ def gather_strips(image, ranges, height, dst=0):
     return image if rank == dst else None
 
 
+class PeerAssembly:
+    """Sort-first frame assembly without a collective on the data path: contributing ranks' resolve kernels store their
+    rows straight into the assembling rank's pixel buffer over NVLink peer memory and signal it (include/swr.h,
+    swr_peer_*). torch.distributed only carries the 64-byte handle once. Per frame:
+        pa.frame(exposure)            # every rank, after render_scene; returns once the work is enqueued
+        ... rank dst consumes renderer.device_pixels_ptr() on the renderer's stream ...
+        pa.release()                  # rank dst: the buffer may be overwritten by the next frame
+    """
+
+    def __init__(self, renderer, dst=0):
+        import torch
+        import torch.distributed as dist
+        self.r, self.dst = renderer, dst
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.f = 0
+        obj = [renderer.peer_export() if self.rank == dst else None]
+        dist.broadcast_object_list(obj, src=dst)
+        if self.rank != dst:
+            renderer.peer_open(obj[0])
+        dist.barrier()
+
+    def frame(self, exposure):
+        self.f += 1
+        if self.rank == self.dst:
+            self.r.resolve_device_only(exposure)
+            self.r.peer_collect(self.f, self.world - 1)
+        else:
+            self.r.resolve_peer(exposure, self.f)
+
+    def release(self):
+        if self.rank == self.dst:
+            self.r.peer_release(self.f)
+
+
 def composite_keys_min(keys):
     """keys: int64 torch tensor holding the UNSIGNED 64-bit visibility keys of this rank (empty = all ones).
     All-reduce with unsigned MIN: flip the sign bit so signed order == unsigned order, reduce, flip back."""

@@ -65,6 +65,12 @@ def load_libraries():
         getattr(core, n).argtypes = [vp]
     core.swr_device_keys_bytes.restype = C.c_size_t
     core.swr_device_keys_bytes.argtypes = [vp]
+    core.swr_peer_export.argtypes = [vp, vp]
+    core.swr_peer_open.argtypes = [vp, vp]
+    core.swr_peer_attach.argtypes = [vp, vp]
+    core.swr_resolve_peer.argtypes = [vp, f32, C.c_uint32]
+    core.swr_peer_collect.argtypes = [vp, C.c_uint32, i32]
+    core.swr_peer_release.argtypes = [vp, C.c_uint32]
     core.swr_sizeof.restype = C.c_size_t
     core.swr_sizeof.argtypes = [i32]
 
@@ -238,6 +244,29 @@ class Renderer:
 
     def shade_composited(self, camera, sky_row_begin, sky_row_end):
         self._check_core(self.core.swr_shade_composited(self.ctx, C.byref(camera.abi), sky_row_begin, sky_row_end))
+
+    # ---- sort-first frame assembly over peer memory (see include/swr.h) ---------------------------
+    def peer_export(self):
+        """Assembling rank: bytes of the handle the contributing ranks open."""
+        h = (C.c_ubyte * abi.PEER_HANDLE_BYTES)()
+        self._check_core(self.core.swr_peer_export(self.ctx, h))
+        return bytes(h)
+
+    def peer_open(self, handle):
+        h = (C.c_ubyte * abi.PEER_HANDLE_BYTES).from_buffer_copy(handle)
+        self._check_core(self.core.swr_peer_open(self.ctx, h))
+
+    def peer_attach(self, device_ptr):
+        self._check_core(self.core.swr_peer_attach(self.ctx, device_ptr))
+
+    def resolve_peer(self, exposure, frame):
+        self._check_core(self.core.swr_resolve_peer(self.ctx, exposure, frame))
+
+    def peer_collect(self, frame, contributors):
+        self._check_core(self.core.swr_peer_collect(self.ctx, frame, contributors))
+
+    def peer_release(self, frame):
+        self._check_core(self.core.swr_peer_release(self.ctx, frame))
 
     def device_bary_ptr(self):
         return self.core.swr_device_bary(self.ctx)

@@ -175,3 +175,61 @@ def test_async_blit_matches_sync(configs):
     r.wait_blit(prev[0])
     assert np.array_equal(prev[1].pixels, ref.pixels)
     r.close()
+
+
+def _device_pixels_host(r, W, H):
+    """Copy the renderer's device pixel buffer to the host on the renderer's own stream."""
+    import torch
+    from swraster_viewer_b200.multigpu import device_tensor
+    stream = torch.cuda.ExternalStream(r.cuda_stream(), device=0)
+    with torch.cuda.stream(stream):
+        out = device_tensor(r.device_pixels_ptr(), W * H * 4, torch.int32, "cuda:0").cpu()
+    stream.synchronize()
+    return out.numpy().view(np.uint32)
+
+
+def test_peer_assembly_equals_full_frame(configs):
+    """Sort-first assembly through peer stores (swr_peer_*): a contributing context resolves its rows straight into the
+    assembling context's pixel buffer; the assembled image equals the single-context frame, frame after frame (the
+    free/done handshake is exercised three times). Two contexts on one device stand in for two ranks."""
+    name, scene, spec, W, H = configs[2]
+    cam = swr.RenderCamera.from_spec(spec, W, H)
+    full = render_gpu(scene, cam, W, H)["pixels"]
+    tiles_y = (H + 63) // 64
+    cut = tiles_y // 2
+    a, b = swr.Renderer(W, H), swr.Renderer(W, H)
+    a.set_tile_rows(0, cut)
+    b.set_tile_rows(cut, tiles_y)
+    assert len(a.peer_export()) == 64
+    b.peer_attach(a.device_pixels_ptr())
+    for f in (1, 2, 3):
+        b.render_scene(scene, cam)
+        b.resolve_peer(2.0, f)
+        a.render_scene(scene, cam)
+        a.resolve_device_only(2.0)
+        a.peer_collect(f, 1)
+        got = _device_pixels_host(a, W, H)
+        a.peer_release(f)
+        a.synchronize()
+        b.synchronize()
+        assert np.array_equal(got, full.reshape(-1)), f"frame {f}"
+    b.close()
+    a.close()
+
+
+def test_peer_wait_times_out_instead_of_hanging(configs):
+    """A contributor that runs ahead of the assembler (frame number never released) gives up after ~2 s and reports it."""
+    name, scene, spec, W, H = configs[0]
+    cam = swr.RenderCamera.from_spec(spec, W, H)
+    a, b = swr.Renderer(W, H), swr.Renderer(W, H)
+    a.peer_export()
+    b.peer_attach(a.device_pixels_ptr())
+    b.render_scene(scene, cam)
+    b.resolve_peer(2.0, 7)  # only frame 1 has been released
+    with pytest.raises(Exception, match="timed out"):
+        b.synchronize()
+    b.synchronize()  # the flag is cleared: the context stays usable
+    with pytest.raises(Exception, match="swr_peer_open"):
+        a.resolve_peer(2.0, 1)  # the assembler does not contribute to itself
+    b.close()
+    a.close()

@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch, torch.distributed as dist
 import swraster_viewer_b200 as swr
 from swraster_viewer_b200 import scenes
-from swraster_viewer_b200.multigpu import balanced_row_ranges, gather_strips, device_tensor, sort_last_frame
+from swraster_viewer_b200.multigpu import balanced_row_ranges, PeerAssembly, device_tensor, sort_last_frame
 
 cfg = sys.argv[1]
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
@@ -46,15 +46,17 @@ if cfg == "c4":
         ranges = balanced_row_ranges(cyc.cpu().numpy(), world)
         r.set_tile_rows(*ranges[rank])
     pix = None
+    pa = PeerAssembly(r, dst=0) if world > 1 else None
 
     def frame():
         global pix
         r.render_scene(sc, cam)
-        r.resolve_device_only(2.0)
         pix = device_tensor(r.device_pixels_ptr(), W * H * 4, torch.int32, dev).view(H, W)
         if world > 1:
-            with torch.cuda.stream(stream):
-                gather_strips(pix, ranges, H, dst=0)
+            pa.frame(2.0)  # the other ranks' resolve kernels store their rows into rank 0's buffer (NVLink peer memory)
+            pa.release()
+        else:
+            r.resolve_device_only(2.0)
 else:
     def frame():
         global pix
@@ -91,7 +93,7 @@ if rank == 0:
     same = bool(np.array_equal(buf.pixels, result))
     T = sc.total_triangles
     line = {"config": cfg, "n_gpus": world, "width": W, "height": H, "scene_triangles": T, "ms_per_frame": float(ms[0]), "frames_per_sec": 1e3 / float(ms[0]),
-            "mtriangles_per_sec": T / float(ms[0]) / 1e3, "mode": "sort-first (balanced tile-row bands, NCCL strip gather)" if cfg == "c4" else "sort-last (u64-min key composite, bary/pixel sum over NCCL)",
+            "mtriangles_per_sec": T / float(ms[0]) / 1e3, "mode": "sort-first (balanced tile-row bands, peer-store frame assembly)" if cfg == "c4" else "sort-last (u64-min key composite, bary/pixel sum over NCCL)",
             "equals_single_gpu_render": same, "scene_build_s": round(gen_s, 1), "rank0_stats": {k: (float(v) if isinstance(v, float) else int(v)) for k, v in st.items()}}
     print(json.dumps(line), flush=True)
     assert same, "multi-GPU image differs from the single-GPU render"

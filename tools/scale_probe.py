@@ -65,7 +65,7 @@ for i in range(steps + 3):
         for k in ("ms_setup_bin", "ms_raster", "ms_shade"):
             acc[k] += s[k]
 s = r.stats()
-out = {"rank": rank, "rows": ranges[rank] if world > 1 else ranges[0], "draws": r.num_draws(), "T": s["triangles_submitted"], "binned": s["triangles_binned"],
+out = {"rank": rank, "rows": ranges[rank] if world > 1 else ranges[0], "draws": r.num_draws, "T": s["triangles_submitted"], "binned": s["triangles_binned"],
        "R": s["tile_refs"], "culled": s["clusters_culled"]}
 out.update({k: round(v / steps, 3) for k, v in acc.items()})
 for k in range(world):
