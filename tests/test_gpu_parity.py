@@ -233,3 +233,69 @@ def test_peer_wait_times_out_instead_of_hanging(configs):
         a.resolve_peer(2.0, 1)  # the assembler does not contribute to itself
     b.close()
     a.close()
+
+
+def cluster_scene():
+    """Large meshes around and behind the camera under rotated, non-uniformly scaled and sheared transforms: most
+    128-triangle clusters are outside the frustum, some straddle it, and the band split cuts through the rest."""
+    import math
+    from swraster_viewer_b200 import scenes
+    mats = [scenes.Material((0.8, 0.7, 0.3, 1), 0.1, 0.6), scenes.Material((0.2, 0.5, 0.9, 1), 0.0, 0.4)]
+    meshes = [[scenes.height_field(160, 11, extent=30.0, height=1.5, uv_repeat=4.0, material=0)], [scenes.uv_sphere(96, 64, 1.0, 1)]]
+
+    def stretched(translate, sx, sy, sz, axis, angle, shear=0.0):
+        m = scenes.trs(translate, 1.0, axis, angle).reshape(4, 4).T.astype(np.float64)  # row-major 4x4
+        s = np.diag([sx, sy, sz, 1.0])
+        s[0, 1] = shear
+        return np.ascontiguousarray((m @ s).T.reshape(-1).astype(np.float32))
+
+    def needle(eye, target, dist, thin, long):
+        """Unit sphere stretched to `long` along the camera's up axis (and `thin` across), centred `dist` in front of the eye."""
+        f = np.array(target, np.float64) - np.array(eye, np.float64)
+        f /= np.linalg.norm(f)
+        r = np.cross(f, [0.0, 1.0, 0.0])
+        r /= np.linalg.norm(r)
+        u = np.cross(r, f)
+        m = np.eye(4)
+        m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = r * thin, u * long, f * thin, np.array(eye) + f * dist
+        return np.ascontiguousarray(m.T.reshape(-1).astype(np.float32))
+
+    eye, target = (0.0, 1.0, 4.0), (0.5, 0.2, -4.0)
+    nodes = [scenes.Node(stretched((0, -1.0, 0), 1.0, 1.0, 1.0, (0, 1, 0), 0.3), 0),               # terrain all around (and behind) the eye
+             scenes.Node(stretched((2.0, 1.0, -6.0), 3.0, 0.4, 1.5, (1, 1, 0), 0.8, 0.5), 1),      # sheared ellipsoid across the frustum edge
+             scenes.Node(stretched((-14.0, 2.0, -3.0), 6.0, 6.0, 0.3, (0, 0, 1), 1.1), 1),         # flat disc mostly outside to the left
+             scenes.Node(stretched((0.0, 0.5, 9.0), 2.0, 2.0, 2.0, (0, 1, 0), 0.0), 1),            # behind the camera
+             scenes.Node(stretched((0.3, 0.4, 0.5), 0.3, 0.3, 0.3, (0, 1, 0), 0.0), 1),            # small, really inside: drawn unclipped
+             # a vertical needle: the reference sizes the node sphere with the MEAN axis scale (scene.rs:53-63), so this is
+             # classified Inside and rasterised UNCLIPPED although it sticks out of the top and bottom of the frustum;
+             # cluster culling may only band-cull such draws (and only in front of the eye), never frustum-cull them
+             scenes.Node(needle(eye, target, 12.0, 0.2, 6.6), 1)]
+    sc = scenes.SceneData(meshes, nodes, mats, [], voxel_dim=8, cube_size=32, seed=13)
+    cam = scenes.CameraSpec(eye, target, math.pi / 4, float(sc.bounds_diagonal) * 2.0)
+    return sc, cam
+
+
+def test_cluster_culling_keeps_the_image(configs):
+    """k_cull may only drop clusters that contribute nothing: full frame and every row band equal the oracle, while a
+    large share of the clusters is actually rejected (frustum planes on the full frame, plus the band planes)."""
+    sc, spec = cluster_scene()
+    W, H = 512, 320
+    cam = swr.RenderCamera.from_spec(spec, W, H)
+    o = render_oracle(sc, cam, W, H)
+    g = render_gpu(sc, cam, W, H)
+    assert g["stats"]["clusters_culled"] > 50, g["stats"]
+    for k in ("seq", "depth"):
+        assert np.array_equal(g[k], o[k]), k
+    assert np.array_equal(g["bary1"].view(np.uint32), o["bary1"].view(np.uint32))
+    for k in ("triangles_binned", "triangles_clipped", "tile_refs"):
+        assert g["stats"][k] == o["stats"][k], k
+    assert np.abs(rgba_bytes(g["pixels"]) - rgba_bytes(o["pixels"])).max() <= RGBA_TOL_LSB
+    tiles_y = (H + 63) // 64
+    culled = []
+    for row in range(tiles_y):
+        b = render_gpu(sc, cam, W, H, rows=(row, row + 1))
+        y0, y1 = row * 64, min(row * 64 + 64, H)
+        for k in ("seq", "depth", "pixels"):
+            assert np.array_equal(b[k].reshape(H, W)[y0:y1], g[k].reshape(H, W)[y0:y1]), (row, k)
+        culled.append(b["stats"]["clusters_culled"])
+    assert min(culled) > g["stats"]["clusters_culled"], (culled, g["stats"]["clusters_culled"])
