@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 
 W, H = 3840, 2160
 WORKLOAD = "C3: procedural 10M-triangle instanced scene (icosphere 20480 / torus 8192 / box-grid 1200 tris, seeded scatter, scales 0.05-4, camera inside the cloud, heavy clipping), 3840x2160"
-KERNELS_PER_FRAME = 9  # k_setup, k_clip, k_scan_tiles, k_scatter, k_scatter_list, k_raster_tiles, k_shade, k_luminance, k_resolve
+KERNELS_PER_FRAME = 10  # k_cull, k_setup, k_clip, k_scan_tiles, k_scatter, k_scatter_list, k_raster_tiles, k_shade, k_luminance, k_resolve
 
 
 def build_scene():
@@ -292,7 +292,16 @@ def run_gpu(args):
         tj = os.path.join(ROOT, "profiles", "r01_traffic.json")
         if world == 1 and os.path.exists(tj):
             traffic = json.load(open(tj)).get(kname.split("+")[0])
-        ndraws = None
+        # What really bounds these kernels is instruction issue, not HBM: warp instructions per launch from the
+        # same committed ncu capture against the SM issue rate (4 schedulers x 1 warp instruction / clock / SM).
+        issue = None
+        ij = os.path.join(ROOT, "profiles", "r01_warp_inst.json")
+        if world == 1 and os.path.exists(ij) and clocks and clocks.get("sm_mhz"):
+            winst = json.load(open(ij)).get(kname.split("+")[0])
+            if winst:
+                ipeak = torch.cuda.get_device_properties(local).multi_processor_count * 4 * clocks["sm_mhz"] * 1e6 / 1e9
+                issue = {"warp_inst_per_launch": winst, "achieved": winst / (dom_ms * 1e-3) / 1e9, "peak": ipeak, "unit": "G warp-inst/s",
+                         "frac": winst / (dom_ms * 1e-3) / 1e9 / ipeak, "source": "smsp__inst_executed.sum (profiles/r01_warp_inst.json) / live kernel time"}
         h2d = r.num_draws * (144 + 4) + 4
         line = {
             "metric": "frames_per_sec_3840x2160", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
@@ -304,12 +313,14 @@ def run_gpu(args):
             "e2e": {"value": K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": W * H * 4, "ms_per_step": 1e3 * e2e_s / K,
                     "mode": "pipelined: read-back of frame N overlaps frame N+1 (swr_resolve_async)" if world == 1 else "synchronous + peer-store frame assembly on rank 0 (NVLink P2P, no collective)",
                     "synchronous_value": K / e2e_sync_s},
-            "gpu_launches": KERNELS_PER_FRAME * K * 2 + KERNELS_PER_FRAME * (max(3, args.warmup) + 2),
+            # our kernels launched inside the timed regions on this rank: K device-timed frames + K e2e frames (+ K synchronous e2e frames at N=1;
+            # + k_peer_wait / k_peer_release per frame on the assembling rank at N>1)
+            "gpu_launches": (KERNELS_PER_FRAME * 3 * K) if world == 1 else ((KERNELS_PER_FRAME + 2) * 2 * K),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel_ms": dom_ms, "kernel_algorithmic_bytes": kbytes,
                          "frame": {"algorithmic_bytes": B, "achieved": B / (ms * 1e-3) / 1e9, "frac": B / (ms * 1e-3) / 1e9 / peak},
-                         "phase_ms": {k: v / K for k, v in phase.items()}},
+                         "phase_ms": {k: v / K for k, v in phase.items()}, "issue": issue},
         }
         if world == 1 and not args.no_cpu:
             ncores = os.cpu_count() or 1

@@ -69,4 +69,10 @@ extern "C" {
     pub fn swr_resolve(ctx: *mut swr_ctx, exposure: f32, out_pixels: *mut u32) -> c_int;
     pub fn swr_read_tile_luminance(ctx: *mut swr_ctx, out_per_tile: *mut f32) -> c_int;
     pub fn swr_device_pixels(ctx: *mut swr_ctx) -> *mut c_void;
+    // sort-first frame assembly over NVLink peer memory (one process per GPU): see include/swr.h
+    pub fn swr_peer_export(ctx: *mut swr_ctx, handle_out: *mut u8) -> c_int; // SWR_PEER_HANDLE_BYTES = 64
+    pub fn swr_peer_open(ctx: *mut swr_ctx, handle: *const u8) -> c_int;
+    pub fn swr_resolve_peer(ctx: *mut swr_ctx, exposure: f32, frame: u32) -> c_int;
+    pub fn swr_peer_collect(ctx: *mut swr_ctx, frame: u32, contributors: c_int) -> c_int;
+    pub fn swr_peer_release(ctx: *mut swr_ctx, frame: u32) -> c_int;
 }

@@ -71,16 +71,9 @@ __device__ __forceinline__ void count_tiles(uint32_t rect, uint32_t *tile_count,
         int tile = ty0 * tiles_x + tx0;
         unsigned peers = __match_any_sync(sm, tile);
         if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&tile_count[tile], (uint32_t)__popc(peers));
-    }
-    // multi-tile rectangles are rare but can be large (a near triangle covers hundreds of tiles): the warp expands
-    // them together, 32 tiles at a time, instead of leaving one lane with a long serial loop
-    unsigned mm = __ballot_sync(0xFFFFFFFFu, valid && !single);
-    while (mm) {
-        const int src = __ffs(mm) - 1;
-        mm &= mm - 1;
-        const uint32_t r = __shfl_sync(0xFFFFFFFFu, rect, src);
-        const int x0 = r & 0xFF, y0 = (r >> 8) & 0xFF, w = (int)((r >> 16) & 0xFF) - x0, n = w * ((int)(r >> 24) - y0);
-        for (int k = threadIdx.x & 31; k < n; k += 32) atomicAdd(&tile_count[(y0 + k / w) * tiles_x + x0 + k % w], 1u);
+    } else if (valid) {
+        for (int ty = ty0; ty < ty1; ty++)
+            for (int tx = tx0; tx < tx1; tx++) atomicAdd(&tile_count[ty * tiles_x + tx], 1u);
     }
 }
 
@@ -610,16 +603,9 @@ __device__ __forceinline__ void scatter_rect(uint32_t rect, uint32_t id, uint32_
         base = __shfl_sync(peers, base, leader);
         uint32_t rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
         refs[base + rank] = id;
-    }
-    // multi-tile rectangles: expanded by the whole warp (see count_tiles); 32 independent atomics in flight instead of
-    // one lane's chain of dependent ones
-    unsigned mm = __ballot_sync(0xFFFFFFFFu, valid && !single);
-    while (mm) {
-        const int src = __ffs(mm) - 1;
-        mm &= mm - 1;
-        const uint32_t r = __shfl_sync(0xFFFFFFFFu, rect, src), rid = __shfl_sync(0xFFFFFFFFu, id, src);
-        const int x0 = r & 0xFF, y0 = (r >> 8) & 0xFF, w = (int)((r >> 16) & 0xFF) - x0, n = w * ((int)(r >> 24) - y0);
-        for (int k = threadIdx.x & 31; k < n; k += 32) refs[atomicAdd(&tile_cursor[(y0 + k / w) * tiles_x + x0 + k % w], 1u)] = rid;
+    } else if (valid) {
+        for (int ty = ty0; ty < ty1; ty++)
+            for (int tx = tx0; tx < tx1; tx++) refs[atomicAdd(&tile_cursor[ty * tiles_x + tx], 1u)] = id;
     }
 }
 

@@ -32,4 +32,15 @@ for r in rr[2:]:
             lines.append(f"  {w:66s} {r[h.index(w)]:>18s} {rr[1][h.index(w)]}")
     lines.append("")
 open(out, "w").write("\n".join(lines) + "\n")
+if len(sys.argv) > 4:  # also: per-kernel DRAM traffic and warp-instruction counts per launch, as bench.py reads them
+    import json, os
+    traffic, winst = {}, {}
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rr[2:]:
+        k = r[h.index("Kernel Name")].split("(")[0]
+        rd, wr = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+        traffic[k] = int(float(r[rd].replace(",", "")) * scale[rr[1][rd]] + float(r[wr].replace(",", "")) * scale[rr[1][wr]])
+        winst[k] = int(float(r[h.index("smsp__inst_executed.sum")].replace(",", "")))
+    json.dump(traffic, open(os.path.join(sys.argv[4], "r01_traffic.json"), "w"), indent=1)
+    json.dump(winst, open(os.path.join(sys.argv[4], "r01_warp_inst.json"), "w"), indent=1)
 print("\n".join(lines))
