@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 
 W, H = 3840, 2160
 WORKLOAD = "C3: procedural 10M-triangle instanced scene (icosphere 20480 / torus 8192 / box-grid 1200 tris, seeded scatter, scales 0.05-4, camera inside the cloud, heavy clipping), 3840x2160"
-KERNELS_PER_FRAME = 10  # k_cull, k_setup, k_clip, k_scan_tiles, k_scatter, k_scatter_list, k_raster_tiles, k_shade, k_luminance, k_resolve
+KERNELS_PER_FRAME = 11  # k_cull, k_compact, k_setup, k_clip, k_scan_tiles, k_scatter, k_scatter_list, k_raster_tiles, k_shade, k_luminance, k_resolve
 
 
 def build_scene():

@@ -53,7 +53,8 @@ struct Staging {  // pinned host mirror of the per-frame draw table, rotated so 
 struct GeomSet {
     DevBuf<DevDraw> draws;
     DevBuf<uint32_t> tri_prefix, cl_prefix;
-    DevBuf<uint2> work;  // surviving (draw, cluster) pairs of the frame
+    DevBuf<uint32_t> cull;  // k_cull output: keep mask, per-block counts and offsets, draw of every cluster
+    DevBuf<uint2> work;     // k_compact output: surviving (draw, cluster) pairs in submission order
     DevBuf<TriRecord> records;
     DevBuf<uint32_t> rects;
     DevBuf<float> avgz;  // translucent set only: packet.avg_z per record (renderer.rs:765-775)
@@ -67,7 +68,9 @@ struct GeomSet {
     Staging staging[4];
     int staging_next = 0;
     std::vector<swr_draw> last_draws;
-    uint32_t ndraws = 0, total_tris = 0, clusters = 0, clusters_kept = 0;
+    uint32_t ndraws = 0, total_tris = 0, clusters = 0;
+    unsigned geom_grid = 1;
+    uint32_t work_hint = 0;  // clusters that survived k_cull in the last finished frame: sizes the next set-up / scatter grids
     uint64_t total_verts = 0;
     uint64_t refs_emitted = 0;
     bool rendered_once = false;
@@ -243,6 +246,7 @@ void swr_destroy(swr_ctx *ctx) {
     for (GeomSet *g : {&ctx->op, &ctx->tr}) {
         g->draws.release();
         g->tri_prefix.release();
+        g->cull.release();
         g->work.release();
         g->records.release();
         g->rects.release();
@@ -536,7 +540,7 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
     g.total_tris = (uint32_t)tris;
     g.clusters = (uint32_t)clusters;
     g.total_verts = verts;
-    bool ok = g.draws.reserve(nd + 1) == cudaSuccess && g.tri_prefix.reserve(2 * (size_t)nd + 4) == cudaSuccess && g.work.reserve(clusters + 1) == cudaSuccess && g.records.reserve(slots + 1) == cudaSuccess &&
+    bool ok = g.draws.reserve(nd + 1) == cudaSuccess && g.tri_prefix.reserve(2 * (size_t)nd + 4) == cudaSuccess && g.cull.reserve(((clusters + 255) / 256) * 10 + clusters + 16) == cudaSuccess && g.work.reserve(clusters + 1) == cudaSuccess && g.records.reserve(slots + 1) == cudaSuccess &&
               g.rects.reserve(slots + 1) == cudaSuccess && g.tile_count.reserve(ctx->ntiles + 1) == cudaSuccess &&
               g.tile_offset.reserve(ctx->ntiles + 1) == cudaSuccess && g.tile_cursor.reserve(ctx->ntiles + 1) == cudaSuccess &&
               g.counters.reserve(1) == cudaSuccess && (!translucent || g.avgz.reserve(slots + 1) == cudaSuccess);
@@ -569,14 +573,19 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
     CK(cudaMemsetAsync(g.counters.p, 0, sizeof(FrameCounters), s));
 
     const int rb = ctx->row_begin, re = ctx->row_end;
+    SetupParams sp{};
     if (tris > 0) {
-        SetupParams sp{};
         sp.draws = g.draws.p;
         sp.tri_prefix = g.tri_prefix.p;
         sp.ndraws = nd;
         sp.total_tris = (uint32_t)tris;
         sp.cl_prefix = g.tri_prefix.p + (nd + 1);
         sp.total_clusters = (uint32_t)clusters;
+        sp.ncull_blocks = (uint32_t)((clusters + 255) / 256);
+        sp.cl_mask = g.cull.p;
+        sp.cl_blk = sp.cl_mask + (size_t)sp.ncull_blocks * 8;
+        sp.cl_blk_off = sp.cl_blk + sp.ncull_blocks;
+        sp.cl_draw = sp.cl_blk_off + sp.ncull_blocks + 1;
         sp.work = g.work.p;
         // sort-first: NDC y range of the rows this rank owns, widened by 2 px against the snapping of renderer.rs:834-846
         sp.use_band = (rb > 0 || re < ctx->tiles_y) ? 1 : 0;
@@ -601,8 +610,15 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
         sp.tiles_y = ctx->tiles_y;
         sp.row_begin = rb;
         sp.row_end = re;
-        const unsigned geom_grid = (unsigned)std::min<uint64_t>(clusters, (uint64_t)ctx->num_sms * 16u);
-        k_cull<<<(unsigned)((clusters + 255) / 256), 256, 0, s>>>(sp);
+        // One block per surviving cluster, dispatched in list order (the hardware retires blocks roughly in order, which keeps
+        // the tile lists close to submission order: front to back, as the reference sorts its nodes — early-Z lives on that).
+        // The survivor count is only known on the device, so the grid is sized from the previous frame's count; blocks
+        // stride over whatever is left when the guess is short and exit at once when it is long.
+        const uint64_t guess = g.work_hint ? (uint64_t)g.work_hint + g.work_hint / 8 + 64 : clusters;
+        const unsigned geom_grid = (unsigned)std::min<uint64_t>(clusters, std::max<uint64_t>(guess, (uint64_t)ctx->num_sms * 16u));
+        g.geom_grid = geom_grid;
+        k_cull<<<sp.ncull_blocks, 256, 0, s>>>(sp);
+        k_compact<<<sp.ncull_blocks, 256, 0, s>>>(sp);
         k_setup<<<geom_grid, SETUP_THREADS, 0, s>>>(sp);
         if (clip_tris > 0) {
             uint64_t want = (clip_tris + CLIP_GROUPS - 1) / CLIP_GROUPS;
@@ -623,9 +639,7 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
         ctx->have_history = true;
     }
     if (tris > 0) {
-        const unsigned geom_grid = (unsigned)std::min<uint64_t>(clusters, (uint64_t)ctx->num_sms * 16u);
-        k_scatter<<<geom_grid, SWR_CLUSTER_TRIS, 0, s>>>(g.rects.p, g.work.p, g.tri_prefix.p, g.draws.p, ctx->scene.prims, g.tile_cursor.p, g.refs.p, g.counters.p,
-                                                           ctx->tiles_x);
+        k_scatter<<<g.geom_grid, SWR_CLUSTER_TRIS, 0, s>>>(sp, g.tile_cursor.p, g.refs.p);
         if (clip_tris > 0) k_scatter_list<<<148, 256, 0, s>>>(g.rects.p, g.clip_list.p, g.clip_ext.p, g.tile_cursor.p, g.refs.p, g.counters.p, ctx->tiles_x);
     }
     CK(cudaGetLastError());
@@ -777,6 +791,8 @@ static int finish_frame(swr_ctx *ctx) {
             ctx->op.refs_emitted = c.tile_refs;
             st.tiles = (uint32_t)ctx->ntiles;
             st.clusters_culled = ctx->op.clusters - c.work_n;
+            ctx->op.work_hint = c.work_n;
+            if (tr_ran) ctx->tr.work_hint = ct.work_n;
 #ifdef SWR_PROFILE_COUNTERS
             if (ctx->dbg_tiles.p) {
                 const int nu = c.raster_units < 8192 ? (int)c.raster_units : 8192;

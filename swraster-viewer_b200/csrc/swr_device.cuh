@@ -111,7 +111,8 @@ struct FrameCounters {
     uint32_t raster_units;    // entries of the raster work list
     uint32_t raster_unit_refs; // refs per unit chosen for this frame
     uint32_t raster_next;     // work-list cursor of the persistent raster CTAs
-    uint32_t work_n;          // surviving (draw, cluster) pairs (k_cull)
+    uint32_t work_n;          // surviving clusters (k_cull)
+    uint32_t cull_done;       // k_cull blocks finished (the last one scans the block counts)
     uint32_t overflow_sort;   // a tile holds more translucent packets than the in-kernel sort supports
     unsigned long long dbg[8];  // SWR_PROFILE_COUNTERS builds only
 };

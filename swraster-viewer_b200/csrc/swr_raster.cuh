@@ -18,7 +18,12 @@ struct SetupParams {
     const uint32_t *tri_prefix;  // ndraws + 1, local triangle prefix
     const uint32_t *cl_prefix;   // ndraws + 1, cluster prefix (clusters of SWR_CLUSTER_TRIS consecutive triangles)
     uint32_t total_clusters;
-    uint2 *work;                 // surviving (draw, cluster) pairs of this frame (k_cull); counters->work_n entries
+    // k_cull output, in submission order (no atomically appended list: tile lists must stay close to the reference's
+    // front-to-back node order, which is what makes early-Z effective): one keep bit per global cluster, the draw of
+    // every cluster, and per k_cull block (256 clusters = 8 mask words) the exclusive prefix of survivors.
+    uint32_t *cl_mask, *cl_blk, *cl_blk_off, *cl_draw;
+    uint32_t ncull_blocks;
+    uint2 *work;                 // k_compact: the surviving (draw, cluster-in-draw) pairs, in submission order; counters->work_n entries
     float band_lo, band_hi;      // NDC y range of this rank's rows (widened by 2 px); used when use_band != 0 (sort-first)
     int use_band;
     uint32_t ndraws;
@@ -259,13 +264,57 @@ __global__ void __launch_bounds__(256) k_cull(SetupParams P) {
         keep = !out;  // NaNs compare false everywhere: never culled
     }
     const unsigned bm = __ballot_sync(0xFFFFFFFFu, keep);
-    if (bm) {
-        const unsigned lane = threadIdx.x & 31;
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&P.counters->work_n, (uint32_t)__popc(bm));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (keep) P.work[base + __popc(bm & ((1u << lane) - 1u))] = make_uint2(d, cl);
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (i < P.total_clusters) P.cl_draw[i] = d;
+    if (lane == 0) P.cl_mask[i >> 5] = bm;  // the buffer holds 8 words per launched block
+    __shared__ uint32_t s_last, s_warp[8], s_carry;
+    const int cnt = __syncthreads_count(keep);
+    if (threadIdx.x == 0) {
+        P.cl_blk[blockIdx.x] = (uint32_t)cnt;
+        __threadfence();
+        s_last = atomicAdd(&P.counters->cull_done, 1u) == gridDim.x - 1u ? 1u : 0u;
+        s_carry = 0;
     }
+    __syncthreads();
+    if (!s_last) return;
+    // the block that finishes last turns the per-block counts into exclusive offsets (<= a few thousand values)
+    __threadfence();
+    for (uint32_t base = 0; base < gridDim.x; base += 256) {
+        const uint32_t j = base + threadIdx.x;
+        const uint32_t v = j < gridDim.x ? __ldcg(P.cl_blk + j) : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        uint32_t wbase = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) wbase += (w < (int)wid) ? s_warp[w] : 0u;
+        const uint32_t carry = s_carry;
+        if (j < gridDim.x) P.cl_blk_off[j] = carry + wbase + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 255) s_carry = carry + wbase + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        P.cl_blk_off[gridDim.x] = s_carry;
+        P.counters->work_n = s_carry;
+    }
+}
+
+// Ordered compaction of the survivors: block b of k_cull owns mask words 8b..8b+7 and the offset cl_blk_off[b].
+__global__ void __launch_bounds__(256) k_compact(SetupParams P) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t m = __ldg(P.cl_mask + (i >> 5));
+    if (!((m >> lane) & 1u)) return;
+    uint32_t pos = __ldg(P.cl_blk_off + blockIdx.x) + (uint32_t)__popc(m & ((1u << lane) - 1u));
+    for (uint32_t w = 0; w < wid; w++) pos += (uint32_t)__popc(__ldg(P.cl_mask + blockIdx.x * 8u + w));
+    const uint32_t d = __ldg(P.cl_draw + i);
+    P.work[pos] = make_uint2(d, i - __ldg(P.cl_prefix + d));
 }
 
 // K1: persistent over the surviving clusters; one block iteration = one cluster, one thread = one triangle.
@@ -609,18 +658,17 @@ __device__ __forceinline__ void scatter_rect(uint32_t rect, uint32_t id, uint32_
     }
 }
 
-// fan-0 records of the surviving clusters (same work list as k_setup): persistent, one cluster per block iteration
-__global__ void __launch_bounds__(SWR_CLUSTER_TRIS) k_scatter(const uint32_t *rects, const uint2 *work, const uint32_t *tri_prefix, const DevDraw *draws,
-                                                              const DevPrim *prims, uint32_t *tile_cursor, uint32_t *refs, const FrameCounters *counters,
-                                                              int tiles_x) {
-    if (counters->overflow_refs) return;  // lists would not fit: the host grows the buffer and replays the frame
-    const uint32_t nwork = counters->work_n;
+// fan-0 records of the surviving clusters (same ordered work list as k_setup): persistent, one cluster per block iteration
+__global__ void __launch_bounds__(SWR_CLUSTER_TRIS) k_scatter(SetupParams P, uint32_t *tile_cursor, uint32_t *refs) {
+    if (P.counters->overflow_refs) return;  // lists would not fit: the host grows the buffer and replays the frame
+    const uint32_t nwork = P.counters->work_n;
     for (uint32_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
-        const uint2 w = work[wi];
+        const uint2 w = P.work[wi];
+        const uint32_t d = w.x;
         const uint32_t tri = w.y * SWR_CLUSTER_TRIS + threadIdx.x;
-        const uint32_t t = tri_prefix[w.x] + tri;
-        const uint32_t rect = tri < prims[draws[w.x].prim].ntris ? __ldg(rects + t) : 0u;
-        scatter_rect(rect, t * 8u, tile_cursor, refs, tiles_x);
+        const uint32_t t = P.tri_prefix[d] + tri;
+        const uint32_t rect = tri < P.prims[P.draws[d].prim].ntris ? __ldg(P.rects + t) : 0u;
+        scatter_rect(rect, t * 8u, tile_cursor, refs, P.tiles_x);
     }
 }
 
