@@ -543,6 +543,9 @@ class SceneData:
         for nd in self.nodes:
             M = nd.transform.reshape(4, 4).T.astype(F32)
             radius_acc = F32(0.0)
+            # Node::from_gltf (scene.rs:384-386): the sphere starts at the node's LOCAL origin with radius 0 (all nodes of the
+            # procedural scenes are roots, so local == world); grow_by_sphere (scene.rs:44-49) then only grows the radius
+            centre = (M @ np.array([0, 0, 0, 1], F32))[:3].astype(F32)
             if nd.mesh_index >= 0:
                 for prim in self.meshes[nd.mesh_index]:
                     # bounds of the transformed bbox corners are enough for inputs (exact per-vertex for small meshes)
@@ -553,15 +556,14 @@ class SceneData:
                     mn = np.minimum(mn, w[:, :3].min(0))
                     mx = np.maximum(mx, w[:, :3].max(0))
                     bs = prim.bounding_sphere()
-                    # Mat4 * &BoundingSphere (scene.rs:53-63), then grow_by_sphere from a sphere pinned at the origin
+                    # Mat4 * &BoundingSphere (scene.rs:53-63)
                     max_scale = (np.linalg.norm(M[:, 0]) + np.linalg.norm(M[:, 1]) + np.linalg.norm(M[:, 2])) / F32(3.0)
                     c = (M @ np.array([bs[0], bs[1], bs[2], 1], F32))[:3]
                     r = bs[3] * max_scale
-                    dist = F32(np.linalg.norm(c))
+                    dist = F32(np.linalg.norm((centre - c).astype(F32)))
                     if dist + r > radius_acc:
                         radius_acc = F32(dist + r)
-            # BoundingSphere::new() centre stays (0,0,0): grow_by_sphere only grows the radius (scene.rs:36-50)
-            self.node_spheres.append(np.array([0, 0, 0, radius_acc], F32))
+            self.node_spheres.append(np.array([centre[0], centre[1], centre[2], radius_acc], F32))
         self.bounds_min, self.bounds_max = mn.astype(F32), mx.astype(F32)
         self.bounds_center = ((mn + mx) * F32(0.5)).astype(F32)
         self.bounds_diagonal = F32(np.linalg.norm((mx - mn).astype(F32)))
