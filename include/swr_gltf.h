@@ -1,0 +1,68 @@
+/* swr_gltf.h — glTF 2.0 / GLB loader in front of the hot path (C ABI of libswr_host.so).
+ *
+ * Produces the flat swr_scene_desc that swr_upload_scene consumes, following the reference's own loader for every
+ * field the renderer reads (src/scene.rs:145-354 Scene::from_gltf, :383-419 nodes, :440-502 primitives with automatic
+ * normals/tangents :520-646, :648-787 textures/samplers/materials, :789-818 cameras; src/texture.rs:45-128 mip chains,
+ * :897-1010 texel packing). A Rust host keeps using its own `Scene`; this entry point is for hosts
+ * that have no loader of their own (C, C++, Python).
+ *
+ * Not in a glTF file and therefore supplied by the caller: the sky cubemap, the prefiltered specular cubemap, the BRDF
+ * LUT and the GI voxel grid (the reference bakes them from assets/cubemap.jpg at load time).
+ * Images: 8-bit PNG files / data URIs are decoded here; other formats (JPEG) must be registered decoded beforehand.
+ * All functions return 0 / a handle on success, -1 / NULL on error with the message in swrh_last_error() — the wording
+ * follows the reference's SceneError ("Missing data: No positions in primitive", ...). */
+#ifndef SWR_GLTF_H
+#define SWR_GLTF_H
+#include "swr.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct swrh_gltf_env {
+    const swr_texture_desc *cubemap;          /* type SWR_TEX_CUBEMAP, may be NULL (then the scene cannot be rendered) */
+    const swr_texture_desc *cubemap_specular;
+    const swr_texture_desc *brdf_lut;
+    swr_voxel_grid_desc voxel_grid;           /* copied */
+    float light_direction[3];                 /* scene.rs:236-239 */
+    float light_color[3];
+} swrh_gltf_env;
+
+typedef struct swrh_gltf_info {
+    float bounds_min[3], bounds_max[3], bounds_center[3]; /* scene.rs:331-351 */
+    float bounds_diagonal;
+    uint32_t ncameras;
+    uint32_t nfile_textures; /* texture slots that came from the file; the environment follows them */
+} swrh_gltf_info;
+
+/* scene.rs:123-143 SceneCamera: projection parameters + the world transform of the node that carries the camera */
+typedef struct swrh_gltf_camera {
+    int32_t perspective;   /* 1: yfov / aspect, 0: xmag / ymag */
+    float yfov_or_xmag, aspect_or_ymag, znear, zfar;
+    float transform[16];
+} swrh_gltf_camera;
+
+const char *swrh_last_error(void);
+void *swrh_gltf_load(const char *path, const swrh_gltf_env *env);
+void swrh_gltf_free(void *doc);
+const swr_scene_desc *swrh_gltf_scene(void *doc); /* valid until swrh_gltf_free */
+int swrh_gltf_get_info(void *doc, swrh_gltf_info *out);
+int swrh_gltf_get_camera(void *doc, uint32_t index, swrh_gltf_camera *out);
+const char *swrh_gltf_texture_uri(void *doc, uint32_t slot);
+/* Hand in an image the loader cannot decode itself (width*height*4 bytes, R G B A per texel, as image::to_rgba8);
+ * looked up by the exact `uri` string of the glTF image. rgba == NULL removes the entry. */
+int swrh_gltf_register_image(const char *uri, const uint8_t *rgba, uint32_t width, uint32_t height);
+
+/* The pieces of the loader that are useful on their own (and are what the tests pin): */
+int swrh_compute_smooth_normals(const float *positions4, uint32_t nverts, const uint32_t *indices, uint32_t nindices, float *normals4_out);
+int swrh_compute_tangents(const float *positions4, const float *texcoords2, const float *normals4, uint32_t nverts, const uint32_t *indices,
+                          uint32_t nindices, float *tangents4_out);
+/* Type-aware mip chain of one RGBA8 image (texture.rs:45-128). Call with data_out == NULL to get the texel count and the
+ * number of mips; mip_table_out receives 4 x nmips u32: offsets, widths, heights, array strides. */
+int swrh_build_mip_chain(const uint32_t *base_texels, uint32_t width, uint32_t height, uint32_t texture_type, uint32_t *data_out,
+                         uint32_t *ntexels_out, uint32_t *nmips_out, uint32_t *mip_table_out);
+int swrh_decode_png(const uint8_t *file, size_t nbytes, uint8_t *rgba_out, uint32_t *width_out, uint32_t *height_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,178 @@
+"""ctypes face of the native glTF / GLB loader (include/swr_gltf.h, host/swr_gltf.hpp): the step in front of the hot path
+(SURVEY 8f N2). `load_gltf` returns a scene object that Renderer.render_scene and the oracle accept like a SceneData."""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .renderer import load_libraries
+
+
+class GltfEnv(C.Structure):
+    _fields_ = [("cubemap", C.POINTER(abi.TextureDesc)), ("cubemap_specular", C.POINTER(abi.TextureDesc)), ("brdf_lut", C.POINTER(abi.TextureDesc)),
+                ("voxel_grid", abi.VoxelGridDesc), ("light_direction", C.c_float * 3), ("light_color", C.c_float * 3)]
+
+
+class GltfInfo(C.Structure):
+    _fields_ = [("bounds_min", C.c_float * 3), ("bounds_max", C.c_float * 3), ("bounds_center", C.c_float * 3), ("bounds_diagonal", C.c_float),
+                ("ncameras", C.c_uint32), ("nfile_textures", C.c_uint32)]
+
+
+class GltfCamera(C.Structure):
+    _fields_ = [("perspective", C.c_int32), ("yfov_or_xmag", C.c_float), ("aspect_or_ymag", C.c_float), ("znear", C.c_float), ("zfar", C.c_float),
+                ("transform", C.c_float * 16)]
+
+
+_bound = False
+
+
+def _host():
+    global _bound
+    _, host = load_libraries()
+    if not _bound:
+        vp, u32 = C.c_void_p, C.c_uint32
+        host.swrh_gltf_load.restype = vp
+        host.swrh_gltf_load.argtypes = [C.c_char_p, C.POINTER(GltfEnv)]
+        host.swrh_gltf_free.argtypes = [vp]
+        host.swrh_gltf_scene.restype = C.POINTER(abi.SceneDesc)
+        host.swrh_gltf_scene.argtypes = [vp]
+        host.swrh_gltf_get_info.argtypes = [vp, C.POINTER(GltfInfo)]
+        host.swrh_gltf_get_camera.argtypes = [vp, u32, C.POINTER(GltfCamera)]
+        host.swrh_gltf_texture_uri.restype = C.c_char_p
+        host.swrh_gltf_texture_uri.argtypes = [vp, u32]
+        host.swrh_gltf_register_image.argtypes = [C.c_char_p, vp, u32, u32]
+        host.swrh_compute_smooth_normals.argtypes = [vp, u32, vp, u32, vp]
+        host.swrh_compute_tangents.argtypes = [vp, vp, vp, u32, vp, u32, vp]
+        host.swrh_build_mip_chain.argtypes = [vp, u32, u32, u32, vp, C.POINTER(u32), C.POINTER(u32), vp]
+        host.swrh_decode_png.argtypes = [vp, C.c_size_t, vp, C.POINTER(u32), C.POINTER(u32)]
+        host.swrh_last_error.restype = C.c_char_p
+        _bound = True
+    return host
+
+
+class GltfError(RuntimeError):
+    pass
+
+
+def _check(rc, host):
+    if rc != 0:
+        raise GltfError(host.swrh_last_error().decode())
+
+
+class GltfScene:
+    """A loaded document. Owns the native object; `desc()` is the swr_scene_desc view the renderer consumes."""
+
+    def __init__(self, handle, env_keepalive):
+        self._host = _host()
+        self._h = handle
+        self._keep = env_keepalive
+        info = GltfInfo()
+        _check(self._host.swrh_gltf_get_info(self._h, C.byref(info)), self._host)
+        self.bounds_min = np.array(info.bounds_min[:], np.float32)
+        self.bounds_max = np.array(info.bounds_max[:], np.float32)
+        self.bounds_center = np.array(info.bounds_center[:], np.float32)
+        self.bounds_diagonal = np.float32(info.bounds_diagonal)
+        self.nfile_textures = info.nfile_textures
+        self.cameras = []
+        for i in range(info.ncameras):
+            c = GltfCamera()
+            _check(self._host.swrh_gltf_get_camera(self._h, i, C.byref(c)), self._host)
+            self.cameras.append(dict(perspective=bool(c.perspective), yfov_or_xmag=c.yfov_or_xmag, aspect_or_ymag=c.aspect_or_ymag, znear=c.znear,
+                                     zfar=c.zfar, transform=np.array(c.transform[:], np.float32)))
+
+    def desc(self):
+        return self._host.swrh_gltf_scene(self._h).contents
+
+    @property
+    def total_triangles(self):
+        d = self.desc()
+        return sum(sum(d.primitives[p].nindices // 3 for p in range(d.meshes[n.mesh_index].first_primitive,
+                                                                    d.meshes[n.mesh_index].first_primitive + d.meshes[n.mesh_index].num_primitives))
+                   for n in (d.nodes[i] for i in range(d.nnodes)) if n.mesh_index >= 0)
+
+    def texture_uri(self, slot):
+        u = self._host.swrh_gltf_texture_uri(self._h, slot)
+        return u.decode() if u is not None else None
+
+    def close(self):
+        if self._h:
+            self._host.swrh_gltf_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def load_gltf(path, environment=None):
+    """Load `path` (.gltf or .glb). `environment`: a scenes.SceneData whose sky cubemap / prefiltered cubemap / BRDF LUT /
+    voxel grid / light are attached to the loaded scene (a glTF file carries none of them)."""
+    host = _host()
+    env, keep = None, None
+    if environment is not None:
+        sd = environment.desc()
+        env = GltfEnv()
+        env.cubemap = C.pointer(sd.textures[sd.cubemap])
+        env.cubemap_specular = C.pointer(sd.textures[sd.cubemap_specular])
+        env.brdf_lut = C.pointer(sd.textures[sd.brdf_lut])
+        env.voxel_grid = sd.voxel_grid
+        env.light_direction = sd.light_direction
+        env.light_color = sd.light_color
+        keep = (environment, sd)
+    h = host.swrh_gltf_load(str(path).encode(), C.byref(env) if env is not None else None)
+    if not h:
+        raise GltfError(host.swrh_last_error().decode())
+    return GltfScene(h, keep)
+
+
+def register_image(uri, rgba_u8):
+    """Hand the loader a decoded image for `uri` ((H, W, 4) uint8), e.g. a JPEG it cannot decode itself. None removes it."""
+    host = _host()
+    if rgba_u8 is None:
+        _check(host.swrh_gltf_register_image(uri.encode(), None, 0, 0), host)
+        return
+    a = np.ascontiguousarray(rgba_u8, np.uint8)
+    _check(host.swrh_gltf_register_image(uri.encode(), a.ctypes.data, a.shape[1], a.shape[0]), host)
+
+
+def compute_smooth_normals(positions4, indices):
+    host = _host()
+    p = np.ascontiguousarray(positions4, np.float32)
+    i = np.ascontiguousarray(indices, np.uint32)
+    out = np.zeros_like(p)
+    _check(host.swrh_compute_smooth_normals(p.ctypes.data, len(p), i.ctypes.data, len(i), out.ctypes.data), host)
+    return out
+
+
+def compute_tangents(positions4, texcoords2, normals4, indices):
+    host = _host()
+    p, uv, n = (np.ascontiguousarray(a, np.float32) for a in (positions4, texcoords2, normals4))
+    i = np.ascontiguousarray(indices, np.uint32)
+    out = np.zeros_like(p)
+    _check(host.swrh_compute_tangents(p.ctypes.data, uv.ctypes.data, n.ctypes.data, len(p), i.ctypes.data, len(i), out.ctypes.data), host)
+    return out
+
+
+def build_mip_chain(base_u32, width, height, texture_type):
+    """(data, offsets, widths, heights, strides) as Texture::generate_mipmaps builds them (texture.rs:45-128)."""
+    host = _host()
+    b = np.ascontiguousarray(base_u32, np.uint32).reshape(-1)
+    nt, nm = C.c_uint32(), C.c_uint32()
+    _check(host.swrh_build_mip_chain(b.ctypes.data, width, height, texture_type, None, C.byref(nt), C.byref(nm), None), host)
+    data = np.zeros(nt.value, np.uint32)
+    table = np.zeros(4 * nm.value, np.uint32)
+    _check(host.swrh_build_mip_chain(b.ctypes.data, width, height, texture_type, data.ctypes.data, C.byref(nt), C.byref(nm), table.ctypes.data), host)
+    t = table.reshape(4, nm.value)
+    return data, t[0], t[1], t[2], t[3]
+
+
+def decode_png(file_bytes):
+    host = _host()
+    buf = np.frombuffer(file_bytes, np.uint8)
+    w, h = C.c_uint32(), C.c_uint32()
+    _check(host.swrh_decode_png(buf.ctypes.data, len(buf), None, C.byref(w), C.byref(h)), host)
+    out = np.zeros((h.value, w.value, 4), np.uint8)
+    _check(host.swrh_decode_png(buf.ctypes.data, len(buf), out.ctypes.data, C.byref(w), C.byref(h)), host)
+    return out

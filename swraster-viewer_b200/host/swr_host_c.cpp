@@ -1,6 +1,8 @@
 // C exports of the host mirror (swr_host.hpp) so Python tests/bench can drive the
 // same Renderer / RenderCamera code a C++ application would. Links libswr_b200.so.
 #include "swr_host.hpp"
+#include "swr_gltf.hpp"
+#include "../../include/swr_gltf.h"
 
 static thread_local std::string g_err;
 
@@ -82,6 +84,147 @@ int swrh_build_draws(const swr_scene_desc *scene, const swr_camera *cam, swr_dra
         return (int)draws.size();
     } catch (const std::exception &e) {
         g_err = e.what();
+        return -1;
+    }
+}
+
+// ---- glTF loader (include/swr_gltf.h) ---------------------------------------------------------------------------------
+void *swrh_gltf_load(const char *path, const swrh_gltf_env *env) {
+    try {
+        if (!path) throw std::runtime_error("Invalid data: null path");
+        swr::gltf::Environment e;
+        if (env) {
+            e.cubemap = env->cubemap;
+            e.cubemap_specular = env->cubemap_specular;
+            e.brdf_lut = env->brdf_lut;
+            e.voxel_grid = env->voxel_grid;
+            std::memcpy(e.light_direction, env->light_direction, 12);
+            std::memcpy(e.light_color, env->light_color, 12);
+        }
+        return swr::gltf::Document::load(path, e).release();
+    } catch (const std::exception &ex) {
+        g_err = ex.what();
+        return nullptr;
+    }
+}
+void swrh_gltf_free(void *doc) { delete (swr::gltf::Document *)doc; }
+const swr_scene_desc *swrh_gltf_scene(void *doc) { return doc ? &((swr::gltf::Document *)doc)->desc : nullptr; }
+int swrh_gltf_get_info(void *doc, swrh_gltf_info *out) {
+    if (!doc || !out) return -1;
+    const swr::gltf::Document &d = *(swr::gltf::Document *)doc;
+    std::memcpy(out->bounds_min, d.bounds_min, 12);
+    std::memcpy(out->bounds_max, d.bounds_max, 12);
+    std::memcpy(out->bounds_center, d.bounds_center, 12);
+    out->bounds_diagonal = d.bounds_diagonal;
+    out->ncameras = (uint32_t)d.cameras.size();
+    uint32_t nfile = 0;
+    for (const std::string &u : d.texture_uri) nfile += u.empty() || u[0] != '<' ? 1u : 0u;
+    out->nfile_textures = nfile;
+    return 0;
+}
+int swrh_gltf_get_camera(void *doc, uint32_t index, swrh_gltf_camera *out) {
+    if (!doc || !out) return -1;
+    const swr::gltf::Document &d = *(swr::gltf::Document *)doc;
+    if (index >= d.cameras.size()) {
+        g_err = "camera index out of range";
+        return -1;
+    }
+    const swr::gltf::CameraData &c = d.cameras[index];
+    out->perspective = c.perspective ? 1 : 0;
+    out->yfov_or_xmag = c.fov_or_xmag;
+    out->aspect_or_ymag = c.aspect_or_ymag;
+    out->znear = c.znear;
+    out->zfar = c.zfar;
+    std::memcpy(out->transform, c.transform, 64);
+    return 0;
+}
+const char *swrh_gltf_texture_uri(void *doc, uint32_t slot) {
+    if (!doc) return nullptr;
+    const swr::gltf::Document &d = *(swr::gltf::Document *)doc;
+    return slot < d.texture_uri.size() ? d.texture_uri[slot].c_str() : nullptr;
+}
+int swrh_gltf_register_image(const char *uri, const uint8_t *rgba, uint32_t width, uint32_t height) {
+    if (!uri) return -1;
+    auto &m = swr::gltf::Document::registered_images();
+    if (!rgba) {
+        m.erase(uri);
+        return 0;
+    }
+    swr::gltf::Image img;
+    img.width = width;
+    img.height = height;
+    img.rgba.assign(rgba, rgba + (size_t)width * height * 4);
+    m[uri] = std::move(img);
+    return 0;
+}
+int swrh_compute_smooth_normals(const float *positions4, uint32_t nverts, const uint32_t *indices, uint32_t nindices, float *normals4_out) {
+    try {
+        std::vector<float> pos(positions4, positions4 + (size_t)nverts * 4);
+        std::vector<uint32_t> idx(indices, indices + nindices);
+        for (uint32_t i : idx)
+            if (i >= nverts) throw std::runtime_error("Invalid data: vertex index out of range");
+        std::vector<float> n = swr::gltf::compute_smooth_normals(pos, idx);
+        std::memcpy(normals4_out, n.data(), n.size() * 4);
+        return 0;
+    } catch (const std::exception &ex) {
+        g_err = ex.what();
+        return -1;
+    }
+}
+int swrh_compute_tangents(const float *positions4, const float *texcoords2, const float *normals4, uint32_t nverts, const uint32_t *indices,
+                          uint32_t nindices, float *tangents4_out) {
+    try {
+        std::vector<float> pos(positions4, positions4 + (size_t)nverts * 4);
+        std::vector<float> uv(texcoords2, texcoords2 + (size_t)nverts * 2);
+        std::vector<float> nrm(normals4, normals4 + (size_t)nverts * 4);
+        std::vector<uint32_t> idx(indices, indices + nindices);
+        for (uint32_t i : idx)
+            if (i >= nverts) throw std::runtime_error("Invalid data: vertex index out of range");
+        std::vector<float> t = swr::gltf::compute_tangents(pos, uv, nrm, idx);
+        std::memcpy(tangents4_out, t.data(), t.size() * 4);
+        return 0;
+    } catch (const std::exception &ex) {
+        g_err = ex.what();
+        return -1;
+    }
+}
+int swrh_build_mip_chain(const uint32_t *base_texels, uint32_t width, uint32_t height, uint32_t texture_type, uint32_t *data_out, uint32_t *ntexels_out,
+                         uint32_t *nmips_out, uint32_t *mip_table_out) {
+    try {
+        if (!base_texels || !width || !height) throw std::runtime_error("Invalid data: empty image");
+        swr::gltf::TextureData t;
+        const uint32_t slices = texture_type == SWR_TEX_CUBEMAP ? 6u : 1u;
+        t.width = width, t.height = height, t.type = texture_type;
+        t.data.assign(base_texels, base_texels + (size_t)width * height * slices);
+        t.mip_offsets = {0}, t.mip_widths = {width}, t.mip_heights = {height};
+        t.array_stride = {slices > 1 ? width * height : 0u};
+        t.generate_mipmaps();
+        const uint32_t nm = t.max_mip_level() + 1;
+        if (ntexels_out) *ntexels_out = (uint32_t)t.data.size();
+        if (nmips_out) *nmips_out = nm;
+        if (data_out) std::memcpy(data_out, t.data.data(), t.data.size() * 4);
+        if (mip_table_out)
+            for (uint32_t i = 0; i < nm; i++) {
+                mip_table_out[i] = t.mip_offsets[i];
+                mip_table_out[nm + i] = t.mip_widths[i];
+                mip_table_out[2 * nm + i] = t.mip_heights[i];
+                mip_table_out[3 * nm + i] = t.array_stride[i];
+            }
+        return 0;
+    } catch (const std::exception &ex) {
+        g_err = ex.what();
+        return -1;
+    }
+}
+int swrh_decode_png(const uint8_t *file, size_t nbytes, uint8_t *rgba_out, uint32_t *width_out, uint32_t *height_out) {
+    try {
+        swr::gltf::Image img = swr::gltf::decode_png(std::vector<uint8_t>(file, file + nbytes), "<memory>");
+        if (width_out) *width_out = img.width;
+        if (height_out) *height_out = img.height;
+        if (rgba_out) std::memcpy(rgba_out, img.rgba.data(), img.rgba.size());
+        return 0;
+    } catch (const std::exception &ex) {
+        g_err = ex.what();
         return -1;
     }
 }

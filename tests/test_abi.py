@@ -23,6 +23,15 @@ def test_header_symbols_are_exported():
     assert core.swr_abi_version() == 1
 
 
+def test_gltf_header_symbols_are_exported_by_the_host_library():
+    _, host = swr.load_libraries()
+    header = open(os.path.join(ROOT, "include", "swr_gltf.h")).read()
+    declared = set(re.findall(r"\b(swrh_[a-z_0-9]+)\s*\(", header))
+    assert {"swrh_gltf_load", "swrh_gltf_scene", "swrh_gltf_free", "swrh_build_mip_chain", "swrh_decode_png"} <= declared
+    for name in declared:
+        assert hasattr(host, name), f"libswr_host.so does not export {name}"
+
+
 def test_struct_sizes_match_library():
     core, _ = swr.load_libraries()
     for which, T in enumerate([abi.PrimitiveDesc, abi.MeshDesc, abi.NodeDesc, abi.TextureDesc, abi.MaterialDesc,

@@ -299,3 +299,19 @@ def test_cluster_culling_keeps_the_image(configs):
             assert np.array_equal(b[k].reshape(H, W)[y0:y1], g[k].reshape(H, W)[y0:y1]), (row, k)
         culled.append(b["stats"]["clusters_culled"])
     assert min(culled) > g["stats"]["clusters_culled"], (culled, g["stats"]["clusters_culled"])
+
+
+def test_gltf_loaded_scene_matches_the_oracle(tmp_path):
+    """SURVEY 8f N2 through the product path: a scene written as glTF and read back by the native loader (host/swr_gltf.hpp)
+    is uploaded and rendered by the CUDA path exactly as the oracle renders the same loaded scene."""
+    from swraster_viewer_b200 import gltf, scenes
+    from helpers import SMALL
+    sc, spec = scenes.scene_materials_test(**SMALL)
+    scenes.export_gltf(sc, str(tmp_path / "scene"))
+    g = gltf.load_gltf(tmp_path / "scene.gltf", environment=sc)
+    W, H = 320, 192
+    cam = swr.RenderCamera.from_spec(spec, W, H)
+    a, b = render_gpu(g, cam, W, H), render_oracle(g, cam, W, H)
+    assert np.array_equal(a["seq"], b["seq"]) and np.array_equal(a["depth"], b["depth"])
+    assert np.abs(rgba_bytes(a["pixels"]) - rgba_bytes(b["pixels"])).max() <= RGBA_TOL_LSB
+    assert (a["seq"] != 0xFFFFFFFF).mean() > 0.2
