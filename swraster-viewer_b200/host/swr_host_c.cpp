@@ -3,6 +3,7 @@
 #include "swr_host.hpp"
 #include "swr_gltf.hpp"
 #include "../../include/swr_gltf.h"
+#include "../../include/swr_host.h"
 
 static thread_local std::string g_err;
 
@@ -41,7 +42,7 @@ void *swrh_renderer_new(int width, int height, int device) {
     }
 }
 void swrh_renderer_free(void *r) { delete (swr::Renderer *)r; }
-void *swrh_renderer_ctx(void *r) { return ((swr::Renderer *)r)->ctx(); }
+swr_ctx *swrh_renderer_ctx(void *r) { return ((swr::Renderer *)r)->ctx(); }
 
 int swrh_set_reference_rsqrt(void *r, int on) { SWRH_TRY(((swr::Renderer *)r)->set_reference_rsqrt(on != 0)); }
 int swrh_reference_rsqrt_bits(void *r) { return ((swr::Renderer *)r)->reference_rsqrt_bits(); }

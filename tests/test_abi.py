@@ -65,3 +65,26 @@ def test_no_cpu_fallback_without_device():
     assert b"no usable CUDA device" in core.swr_last_error(None) or b"CUDA" in core.swr_last_error(None)
     with pytest.raises(RuntimeError):
         swr.Renderer(64, 64)
+
+
+def test_headers_are_c99_and_the_c_example_builds_and_fails_loudly_without_a_device(tmp_path):
+    """include/*.h must be usable from plain C (the reference-side binding is an FFI, not C++): the example host program
+    compiles with -std=c99 -pedantic -Werror against all three headers, loads a glTF file, and — on a box without a B200 —
+    stops at Renderer::new with the 'no CPU fallback' message instead of producing an image some other way."""
+    import subprocess
+    from swraster_viewer_b200 import scenes
+    lib = os.path.join(ROOT, "swraster-viewer_b200", "lib")
+    exe = str(tmp_path / "render_gltf")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "render_gltf.c"), "-L", lib, "-lswr_host", "-lswr_b200", "-Wl,-rpath," + lib, "-lm", "-o", exe])
+    sc, _ = scenes.scene_c1_sphere(segments=16, bands=8, voxel_dim=4, cube_size=8)
+    scenes.export_gltf(sc, str(tmp_path / "s"))
+    r = subprocess.run([exe, str(tmp_path / "s.gltf"), str(tmp_path / "out.ppm"), "128", "64"], capture_output=True, text=True)
+    assert "1 primitives, 1 nodes, 1 materials" in r.stdout
+    import torch
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and os.path.getsize(tmp_path / "out.ppm") == len("P6\n128 64\n255\n") + 128 * 64 * 3
+    else:
+        assert r.returncode == 3 and "no CPU fallback" in r.stderr and not os.path.exists(tmp_path / "out.ppm")
+    r = subprocess.run([exe, str(tmp_path / "missing.gltf"), str(tmp_path / "out.ppm")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Missing data" in r.stderr
