@@ -145,3 +145,28 @@ def test_parallel_schedule_same_coverage_and_depth():
     assert np.array_equal(a["depth"], b["depth"])
     same = a["seq"] == b["seq"]
     assert same.mean() > 0.999  # only exact depth ties may pick another packet
+
+
+def test_nan_and_infinite_depths_are_never_written():
+    """tilerasterizer.rs:516 `z <= current`: a NaN depth fails the comparison for every pixel (nothing is written, not even
+    over the +INF clear value). A +INF vertex depth ends up the same way: the interpolator is a + b1*(z1-z0) + b2*(z2-z0)
+    (util.rs:169-171) and INF - INF is NaN, so such a triangle never reaches the `INF <= INF` tie with the clear value."""
+    a = [(160, 96), (160, 800), (1500, 800)]
+    b = [(400, 200), (400, 900), (1800, 900)]
+    c = [(96, 320), (96, 960), (900, 960)]
+    tris = [a, b, c]
+    want_ids, want_z = int_raster(tris, [np.nan, np.nan, 0.25], W, H)
+    assert not (want_ids == 0).any() and not (want_ids == 1).any() and (want_ids == 2).any()
+    with np.errstate(invalid="ignore"):
+        got_ids, got_z, o = oracle_ids(tris, [np.nan, np.inf, 0.25])
+    assert np.array_equal(got_ids, want_ids)
+    assert np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32))
+    assert (got_z[got_ids == 2] == np.float32(0.25)).all() and np.isinf(got_z[got_ids == -1]).all()
+    assert o["stats"]["triangles_binned"] == 3  # they are binned like any other triangle; only the depth test rejects them
+    # a NaN in ONE vertex poisons the interpolated depth of the whole triangle; a huge finite depth is an ordinary depth
+    sc = triangle_scene([a, c, b], W, H, depths=[[0.5, np.nan, 0.5], [0.75, 0.75, 0.75], [3.0e38, 3.0e38, 3.0e38]])
+    with np.errstate(invalid="ignore"):
+        o = render_oracle(sc, identity_camera(W, H), W, H)
+    seq = o["seq"].astype(np.int64).reshape(H, W)
+    covered = seq != 0xFFFFFFFF
+    assert not (covered & ((seq >> 3) == 0)).any() and (covered & ((seq >> 3) == 1)).any() and (covered & ((seq >> 3) == 2)).any()
