@@ -26,6 +26,7 @@
 #include <fstream>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <sstream>
 
@@ -56,10 +57,17 @@ struct JVal {
         const JVal *v = get(key);
         return v && v->type == Num ? v->num : dflt;
     }
+    static int64_t to_i64(double d) {  // saturating, NaN -> 0 (a plain cast of an out-of-range double is undefined)
+        if (!(d == d)) return 0;
+        if (d >= 9.0e18) return INT64_MAX;
+        if (d <= -9.0e18) return INT64_MIN;
+        return (int64_t)d;
+    }
     int64_t integer(const char *key, int64_t dflt) const {
         const JVal *v = get(key);
-        return v && v->type == Num ? (int64_t)v->num : dflt;
+        return v && v->type == Num ? to_i64(v->num) : dflt;
     }
+    int64_t as_index() const { return type == Num ? to_i64(num) : -1; }
     std::string string(const char *key, const std::string &dflt = "") const {
         const JVal *v = get(key);
         return v && v->type == Str ? v->str : dflt;
@@ -336,6 +344,7 @@ inline Image decode_png(const std::vector<uint8_t> &file, const std::string &nam
     }
     if (w == 0 || h == 0 || ctype < 0) throw bad("missing IHDR");
     if (depth != 8) throw bad("only 8 bits per channel are supported");
+    if (w > 32768 || h > 32768) throw bad("image larger than 32768 pixels on a side");
     int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
     if (!ch) throw bad("unknown colour type");
     if (ctype == 3 && plte.empty()) throw bad("palette image without PLTE");
@@ -354,6 +363,8 @@ inline Image decode_png(const std::vector<uint8_t> &file, const std::string &nam
         uint32_t pw = w > p.x0 ? (w - p.x0 + p.dx - 1) / p.dx : 0, ph = h > p.y0 ? (h - p.y0 + p.dy - 1) / p.dy : 0;
         if (pw && ph) need += (size_t)ph * ((size_t)pw * ch + 1);
     }
+    // deflate cannot expand by more than ~1032:1: a header that asks for more than the data can hold is corrupt
+    if (need > idat.size() * 1032 + 65536) throw bad("corrupt image data (header larger than the compressed stream)");
     std::vector<uint8_t> raw(need);
     uLongf got = (uLongf)need;
     int zr = uncompress(raw.data(), &got, idat.data(), (uLong)idat.size());
@@ -648,6 +659,10 @@ class Document {
         static std::map<std::string, Image> m;
         return m;
     }
+    static std::mutex &registered_images_mutex() {  // loads may run on any host thread (rayon workers in the reference)
+        static std::mutex mx;
+        return mx;
+    }
 
     static std::unique_ptr<Document> load(const std::string &path, const Environment &env) {
         std::unique_ptr<Document> d(new Document());
@@ -748,10 +763,13 @@ class Document {
         const JVal &v = views[(size_t)view_index];
         const int64_t bi = v.integer("buffer", -1);
         if (bi < 0 || (size_t)bi >= buffers_.size()) throw std::runtime_error("Invalid data: buffer index out of range");
-        const size_t off = (size_t)v.integer("byteOffset", 0) + byte_offset;
-        const size_t vlen = (size_t)v.integer("byteLength", 0);
-        if (stride_out) *stride_out = (size_t)v.integer("byteStride", 0);
-        if (byte_offset + need > vlen || off + need > buffers_[(size_t)bi].size()) throw std::runtime_error("Invalid data: accessor reaches outside its bufferView");
+        const int64_t vo = v.integer("byteOffset", 0), vl = v.integer("byteLength", 0), st = v.integer("byteStride", 0);
+        const size_t bsz = buffers_[(size_t)bi].size();
+        if (vo < 0 || vl < 0 || st < 0 || st > 65536 || (uint64_t)vo > bsz || (uint64_t)vl > bsz - (uint64_t)vo)
+            throw std::runtime_error("Invalid data: bufferView reaches outside its buffer");
+        if (stride_out) *stride_out = (size_t)st;
+        if (byte_offset > (size_t)vl || need > (size_t)vl - byte_offset) throw std::runtime_error("Invalid data: accessor reaches outside its bufferView");
+        const size_t off = (size_t)vo + byte_offset;
         return buffers_[(size_t)bi].data() + off;
     }
     static double read_comp(const uint8_t *p, int ctype) {
@@ -773,7 +791,9 @@ class Document {
         ncomp = type_ncomp(a.string("type"));
         const JVal *nv = a.get("normalized");
         normalized = nv && nv->type == JVal::Bool && nv->b;
-        const size_t count = (size_t)a.integer("count", 0), cs = (size_t)comp_size(ctype), es = cs * (size_t)ncomp;
+        const int64_t count_i = a.integer("count", 0);
+        if (count_i < 0 || count_i > (int64_t)1 << 28) throw std::runtime_error("Invalid data: accessor count out of range");
+        const size_t count = (size_t)count_i, cs = (size_t)comp_size(ctype), es = cs * (size_t)ncomp;
         out.assign(count * (size_t)ncomp, 0.0);
         if (a.has("bufferView") && count) {
             size_t stride = 0;
@@ -786,7 +806,9 @@ class Document {
                 for (int c = 0; c < ncomp; c++) out[i * (size_t)ncomp + (size_t)c] = read_comp(p + i * stride + (size_t)c * cs, ctype);
         }
         if (const JVal *sp = a.get("sparse")) {  // spec 3.6.2.3
-            const size_t n = (size_t)sp->integer("count", 0);
+            const int64_t n_i = sp->integer("count", 0);
+            if (n_i < 0 || (uint64_t)n_i > count) throw std::runtime_error("Invalid data: sparse count out of range");
+            const size_t n = (size_t)n_i;
             const JVal *si = sp->get("indices"), *sv = sp->get("values");
             if (!si || !sv) throw std::runtime_error("Invalid data: sparse accessor without indices/values");
             const int ict = (int)si->integer("componentType", 0);
@@ -897,9 +919,16 @@ class Document {
             td = it->second;
         } else {
             Image img;
-            auto reg = registered_images().find(uri);
-            if (reg != registered_images().end()) {
-                img = reg->second;
+            bool registered = false;
+            {
+                std::lock_guard<std::mutex> lock(registered_images_mutex());
+                auto reg = registered_images().find(uri);
+                if (reg != registered_images().end()) {
+                    img = reg->second;
+                    registered = true;
+                }
+            }
+            if (registered) {
             } else if (uri.compare(0, 5, "data:") == 0) {
                 size_t k = uri.find(";base64,");
                 if (k == std::string::npos) throw std::runtime_error("Invalid data: data URI without base64 payload");
@@ -984,15 +1013,17 @@ class Document {
         return mul(mul(T, mat4_from_quat(Quat{q[0], q[1], q[2], q[3]})), S);  // translation * rotation * scale
     }
 
-    void final_transforms(size_t node, const Mat4 &parent, const std::vector<Mat4> &local, std::vector<int> &guard) {
+    void final_transforms(size_t node, const Mat4 &parent, const std::vector<Mat4> &local, std::vector<int> &guard, int depth = 0) {
         if (guard[node]++) throw std::runtime_error("Invalid data: node hierarchy is not a forest");
+        if (depth > 2048) throw std::runtime_error("Invalid data: node hierarchy deeper than 2048 levels");
         const Mat4 fin = mul(parent, local[node]);  // scene.rs:365
         std::memcpy(nodes[node].transform, fin.m, 64);
         const JVal *ch = array("nodes")[node].get("children");
         for (size_t i = 0; ch && i < ch->size(); i++) {
-            const size_t c = (size_t)(*ch)[i].num;
-            if (c >= nodes.size()) throw std::runtime_error("Invalid data: child index out of range");
-            final_transforms(c, fin, local, guard);
+            const int64_t ci = (*ch)[i].as_index();
+            if (ci < 0 || (size_t)ci >= nodes.size()) throw std::runtime_error("Invalid data: child index out of range");
+            const size_t c = (size_t)ci;
+            final_transforms(c, fin, local, guard, depth + 1);
         }
     }
 
@@ -1057,8 +1088,8 @@ class Document {
             nodes[i] = nd;
             const JVal *ch = jn[i].get("children");
             for (size_t k = 0; ch && k < ch->size(); k++) {
-                const size_t c = (size_t)(*ch)[k].num;
-                if (c < is_child.size()) is_child[c] = 1;
+                const int64_t c = (*ch)[k].as_index();
+                if (c >= 0 && (size_t)c < is_child.size()) is_child[(size_t)c] = 1;
             }
         }
         std::vector<int> guard(jn.size(), 0);

@@ -146,6 +146,7 @@ const char *swrh_gltf_texture_uri(void *doc, uint32_t slot) {
 }
 int swrh_gltf_register_image(const char *uri, const uint8_t *rgba, uint32_t width, uint32_t height) {
     if (!uri) return -1;
+    std::lock_guard<std::mutex> lock(swr::gltf::Document::registered_images_mutex());
     auto &m = swr::gltf::Document::registered_images();
     if (!rgba) {
         m.erase(uri);

@@ -565,3 +565,37 @@ def test_error_wording_follows_the_reference(tmp_path):
     doc["nodes"] = [{"children": [1, 1]}, {"mesh": 0}]
     with pytest.raises(gltf.GltfError, match="not a forest"):
         gltf.load_gltf(write_gltf(tmp_path, doc, "h.gltf"))
+
+
+def test_hostile_sizes_are_rejected_not_trusted(tmp_path):
+    """Offsets, counts and image headers come from the file: negative or absurd values must end in an error, never in an
+    out-of-bounds read or a multi-gigabyte allocation (the loader was also byte- and field-fuzzed under ASan/UBSan)."""
+    for k, (field, value) in enumerate([("byteOffset", -8), ("byteOffset", 2 ** 63), ("byteLength", -1), ("byteLength", 1e30), ("byteStride", -4), ("byteStride", 1e9)]):
+        doc = tri_doc()
+        doc["bufferViews"][0][field] = value
+        with pytest.raises(gltf.GltfError, match="outside"):
+            gltf.load_gltf(write_gltf(tmp_path, doc, f"v{k}.gltf"))
+    for k, value in enumerate([-1, 2 ** 40, 1e300]):
+        doc = tri_doc()
+        doc["accessors"][0]["count"] = value
+        with pytest.raises(gltf.GltfError, match="count out of range|outside"):
+            gltf.load_gltf(write_gltf(tmp_path, doc, f"c{k}.gltf"))
+    doc = tri_doc()
+    doc["accessors"][0]["sparse"] = {"count": -3, "indices": {"bufferView": 1, "componentType": 5123}, "values": {"bufferView": 0}}
+    with pytest.raises(gltf.GltfError, match="sparse count"):
+        gltf.load_gltf(write_gltf(tmp_path, doc, "s.gltf"))
+    doc = tri_doc()
+    doc["nodes"] = [{"children": [i + 1]} for i in range(3000)] + [{"mesh": 0}]
+    with pytest.raises(gltf.GltfError, match="deeper than"):
+        gltf.load_gltf(write_gltf(tmp_path, doc, "deep.gltf"))
+    doc["nodes"][5]["children"] = [-1]
+    with pytest.raises(gltf.GltfError, match="child index"):
+        gltf.load_gltf(write_gltf(tmp_path, doc, "neg.gltf"))
+    rgba = np.zeros((4, 4, 4), np.uint8)
+    png = bytearray(raw_png(rgba, 6, [0]))
+    png[16:24] = struct.pack(">II", 30000, 30000)  # IHDR claims 3.6 GB of pixels for a few dozen compressed bytes (the CRC is not what stops it)
+    with pytest.raises(gltf.GltfError, match="corrupt"):
+        gltf.decode_png(bytes(png))
+    png[16:24] = struct.pack(">II", 2 ** 31, 1)
+    with pytest.raises(gltf.GltfError, match="larger than"):
+        gltf.decode_png(bytes(png))
