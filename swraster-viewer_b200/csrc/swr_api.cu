@@ -416,6 +416,21 @@ int swr_upload_scene(swr_ctx *ctx, const swr_scene_desc *s) {
             ctx->err = "texture has more than 16 mip levels";
             return SWR_ERR_INVALID;
         }
+        if (!t.data || !t.mip_offsets || !t.mip_widths || !t.mip_heights || !t.array_stride || t.width == 0 || t.height == 0 ||
+            t.texture_type > SWR_TEX_LINEAR || t.wrap_s > SWR_WRAP_CLAMP_TO_EDGE || t.wrap_t > SWR_WRAP_CLAMP_TO_EDGE) {
+            ctx->err = "texture " + std::to_string(i) + ": null table, empty image or unknown type / wrap mode";
+            return SWR_ERR_INVALID;
+        }
+        for (uint32_t k = 0; k <= t.max_mip_level; k++) {  // every mip (all six faces of a cubemap) must lie inside the texel array
+            // the sky and the prefiltered sky are sampled as six faces whatever their declared type
+            const uint64_t faces = (t.texture_type == SWR_TEX_CUBEMAP || (int32_t)i == s->cubemap || (int32_t)i == s->cubemap_specular) ? 6 : 1;
+            const uint64_t wh = (uint64_t)t.mip_widths[k] * t.mip_heights[k];
+            const uint64_t last = (uint64_t)t.mip_offsets[k] + (faces - 1) * t.array_stride[k] + wh;
+            if (wh == 0 || last > t.ntexels || (faces > 1 && t.array_stride[k] < wh)) {
+                ctx->err = "texture " + std::to_string(i) + ": mip " + std::to_string(k) + " reaches outside the texel array";
+                return SWR_ERR_INVALID;
+            }
+        }
         DevTex d{};
         uint32_t *data;
         if ((rc = upload(ctx, t.data, t.ntexels, &data))) return rc;

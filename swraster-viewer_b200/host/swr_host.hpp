@@ -266,6 +266,18 @@ inline bool sphere_outside_row_band(const float *model, const float *sphere, con
     return du > radius || dl < -radius;
 }
 
+// The part of the scene description only the host reads (node -> mesh -> primitive ranges, material indices): the
+// reference would panic on a slice access, this mirror throws before anything is indexed.
+inline void validate_scene_ranges(const swr_scene_desc &sc) {
+    for (uint32_t i = 0; i < sc.nmeshes; i++)
+        if ((uint64_t)sc.meshes[i].first_primitive + sc.meshes[i].num_primitives > sc.nprimitives)
+            throw std::runtime_error("scene: mesh " + std::to_string(i) + " names primitives beyond the primitive array");
+    for (uint32_t i = 0; i < sc.nnodes; i++)
+        if (sc.nodes[i].mesh_index >= (int32_t)sc.nmeshes) throw std::runtime_error("scene: node " + std::to_string(i) + " names a mesh that does not exist");
+    for (uint32_t i = 0; i < sc.nprimitives; i++)
+        if (sc.primitives[i].material_index >= sc.nmaterials) throw std::runtime_error("scene: primitive " + std::to_string(i) + " names a material that does not exist");
+}
+
 inline void build_draw_list(const swr_scene_desc &sc, const swr_camera &cam, std::vector<swr_draw> &draws, int shard = 0,
                             int nshards = 1, int band_y0 = 0, int band_y1 = 0, int band_height = 0) {
     std::vector<uint32_t> nodes_by_distance(sc.nnodes);
@@ -401,6 +413,7 @@ class Renderer {
     void render_scene(const Scene &scene, const RenderCamera &camera) { render_scene(scene, camera.to_abi()); }
     void render_scene(const Scene &scene, const swr_camera &cam, bool shade = true, int shard = 0, int nshards = 1) {
         if (scene.desc != uploaded_) {  // immutable scene: upload on first sight (SURVEY §8b ownership)
+            validate_scene_ranges(*scene.desc);
             check(swr_upload_scene(ctx_, scene.desc), "swr_upload_scene");
             uploaded_ = scene.desc;
         }

@@ -55,6 +55,7 @@ int swrh_render_scene(void *r, const swr_scene_desc *scene, const swr_camera *ca
 int swrh_build_draws_band(const swr_scene_desc *scene, const swr_camera *cam, swr_draw *out, int max_draws, int y0, int y1, int height) {
     try {
         std::vector<swr_draw> draws;
+        swr::validate_scene_ranges(*scene);
         swr::build_draw_list(*scene, *cam, draws, 0, 1, y0, y1, height);
         for (size_t i = 0; i < draws.size() && (int)i < max_draws; i++) out[i] = draws[i];
         return (int)draws.size();
@@ -80,6 +81,7 @@ int swrh_wait_blit(void *r, int ticket) { SWRH_TRY(((swr::Renderer *)r)->wait_bl
 int swrh_build_draws(const swr_scene_desc *scene, const swr_camera *cam, swr_draw *out, int max_draws, int shard, int nshards) {
     try {
         std::vector<swr_draw> draws;
+        swr::validate_scene_ranges(*scene);
         swr::build_draw_list(*scene, *cam, draws, shard, nshards);
         for (size_t i = 0; i < draws.size() && (int)i < max_draws; i++) out[i] = draws[i];
         return (int)draws.size();

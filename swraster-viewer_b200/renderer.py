@@ -320,6 +320,8 @@ def build_draws(scene, camera, shard=0, nshards=1, max_draws=1 << 20):
     """Host draw list (renderer.rs:357-468) without touching a device."""
     _, host = load_libraries()
     n = host.swrh_build_draws(C.byref(scene.desc()), C.byref(camera.abi), None, 0, shard, nshards)
+    if n < 0:
+        raise RuntimeError(host.swrh_last_error().decode())
     arr = (abi.Draw * max(n, 1))()
     host.swrh_build_draws(C.byref(scene.desc()), C.byref(camera.abi), arr, n, shard, nshards)
     return arr, n

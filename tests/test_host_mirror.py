@@ -168,3 +168,40 @@ def test_sort_last_key_composite_gloo_world2(tmp_path):
     port = _free_port()
     mp.spawn(_composite_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok").exists()
+
+
+def test_scene_ranges_are_validated_before_they_are_indexed():
+    """node -> mesh -> primitive -> material indices are only read on the host: a bad one must raise, not index out of bounds
+    (the reference would panic on the slice access)."""
+    import copy
+    import ctypes as C
+    from swraster_viewer_b200.renderer import build_draws
+    sc, spec = scenes.scene_c1_sphere(16, 8, **SMALL)
+    cam = swr.RenderCamera.from_spec(spec, 128, 64)
+    good = sc.desc()
+    assert build_draws(sc, cam)[1] == 1
+
+    class Wrapped:
+        def __init__(self, d):
+            self.d = d
+
+        def desc(self):
+            return self.d
+
+    def variant(edit):
+        d = abi.SceneDesc.from_buffer_copy(good)
+        nodes = (abi.NodeDesc * d.nnodes).from_buffer_copy((abi.NodeDesc * d.nnodes).from_address(C.addressof(d.nodes.contents)))
+        meshes = (abi.MeshDesc * d.nmeshes).from_buffer_copy((abi.MeshDesc * d.nmeshes).from_address(C.addressof(d.meshes.contents)))
+        prims = (abi.PrimitiveDesc * d.nprimitives).from_buffer_copy((abi.PrimitiveDesc * d.nprimitives).from_address(C.addressof(d.primitives.contents)))
+        edit(nodes, meshes, prims)
+        d.nodes, d.meshes, d.primitives = nodes, meshes, prims
+        w = Wrapped(d)
+        w.keep = (nodes, meshes, prims)
+        return w
+
+    for edit, msg in [(lambda n, m, p: setattr(n[0], "mesh_index", 7), "mesh that does not exist"),
+                      (lambda n, m, p: setattr(m[0], "num_primitives", 5), "beyond the primitive array"),
+                      (lambda n, m, p: setattr(p[0], "material_index", 3), "material that does not exist")]:
+        with pytest.raises(RuntimeError, match=msg):
+            build_draws(variant(edit), cam)
+    assert build_draws(variant(lambda n, m, p: setattr(n[0], "mesh_index", -1)), cam)[1] == 0  # a node without a mesh draws nothing
