@@ -2,7 +2,7 @@
  *
  *   cc -std=c99 -I include examples/render_gltf.c -L swraster-viewer_b200/lib -lswr_host -lswr_b200 \
  *      -Wl,-rpath,'$ORIGIN/../swraster-viewer_b200/lib' -lm -o render_gltf
- *   ./render_gltf scene.glb out.ppm [width height]
+ *   ./render_gltf scene.glb out.ppm [width height [sky_cross.png]]
  *
  * What a glTF file does not carry (sky, prefiltered sky, BRDF LUT, GI voxels) is filled with small procedural
  * stand-ins here; a real host bakes them the way the reference does (texture.rs:135-552, gi.rs). There is no CPU
@@ -49,37 +49,67 @@ static void make_tex(simple_tex *t, uint32_t w, uint32_t h, uint32_t faces, uint
 
 int main(int argc, char **argv) {
     if (argc < 3) {
-        fprintf(stderr, "usage: %s scene.gltf|scene.glb out.ppm [width height]\n", argv[0]);
+        fprintf(stderr, "usage: %s scene.gltf|scene.glb out.ppm [width height [sky_cross.png]]\n", argv[0]);
         return 2;
     }
     const int W = argc > 4 ? atoi(argv[3]) : 1280, H = argc > 4 ? atoi(argv[4]) : 720;
 
-    /* environment stand-ins: a vertical sky gradient on all six faces, a flat BRDF LUT, one voxel of dim ambient light */
+    /* Environment. With a sky image in the viewer's cross layout (argv[5], PNG) everything is baked on the host the way the
+     * reference does at load time (swrh_env_bake); otherwise small procedural stand-ins: a sky gradient on all six faces, a
+     * flat BRDF LUT, one voxel of dim ambient light. */
     simple_tex sky, spec, lut;
-    make_tex(&sky, 16, 16, 6, SWR_TEX_CUBEMAP);
-    make_tex(&spec, 16, 16, 6, SWR_TEX_CUBEMAP);
-    make_tex(&lut, 16, 16, 1, SWR_TEX_LINEAR);
-    for (uint32_t f = 0; f < 6; f++)
-        for (uint32_t y = 0; y < 16; y++)
-            for (uint32_t x = 0; x < 16; x++) {
-                float t = (float)y / 15.0f;
-                uint32_t c = f == 2 ? pack(0.35f, 0.55f, 0.9f) : f == 3 ? pack(0.25f, 0.22f, 0.2f) : pack(0.35f + 0.3f * t, 0.55f + 0.15f * t, 0.9f - 0.2f * t);
-                sky.texels[(f * 16 + y) * 16 + x] = c;
-                spec.texels[(f * 16 + y) * 16 + x] = c;
-            }
-    for (uint32_t i = 0; i < 256; i++) lut.texels[i] = pack(0.5f, 0.1f, 0.0f);
     float voxel[16];
-    memset(voxel, 0, sizeof(voxel));
-    voxel[0] = voxel[1] = voxel[2] = 0.4f; /* SH band 0, rgb */
-    voxel[3] = 1.0f;                       /* sun visibility */
-
+    void *baked = NULL;
     swrh_gltf_env env;
     memset(&env, 0, sizeof(env));
-    env.cubemap = &sky.desc;
-    env.cubemap_specular = &spec.desc;
-    env.brdf_lut = &lut.desc;
-    env.voxel_grid.dims[0] = env.voxel_grid.dims[1] = env.voxel_grid.dims[2] = 1;
-    env.voxel_grid.gi_sh4 = voxel;
+    memset(&sky, 0, sizeof(sky)), memset(&spec, 0, sizeof(spec)), memset(&lut, 0, sizeof(lut));
+    if (argc > 5) {
+        FILE *pf = fopen(argv[5], "rb");
+        if (!pf) {
+            perror(argv[5]);
+            return 1;
+        }
+        fseek(pf, 0, SEEK_END);
+        long n = ftell(pf);
+        fseek(pf, 0, SEEK_SET);
+        uint8_t *bytes = (uint8_t *)malloc((size_t)n);
+        if (fread(bytes, 1, (size_t)n, pf) != (size_t)n) return 1;
+        fclose(pf);
+        uint32_t cw = 0, ch = 0;
+        if (swrh_decode_png(bytes, (size_t)n, NULL, &cw, &ch)) {
+            fprintf(stderr, "sky image: %s\n", swrh_last_error());
+            return 1;
+        }
+        uint8_t *rgba = (uint8_t *)malloc((size_t)cw * ch * 4);
+        swrh_decode_png(bytes, (size_t)n, rgba, &cw, &ch);
+        baked = swrh_env_bake(rgba, cw, ch, 128, 64, 16, 0.25f, 1.0f, 1.0f); /* texture.rs:216,225 and main.rs:54,280 */
+        free(rgba), free(bytes);
+        if (!baked || swrh_env_get(baked, &env, NULL)) {
+            fprintf(stderr, "environment bake: %s\n", swrh_last_error());
+            return 1;
+        }
+    } else {
+        make_tex(&sky, 16, 16, 6, SWR_TEX_CUBEMAP);
+        make_tex(&spec, 16, 16, 6, SWR_TEX_CUBEMAP);
+        make_tex(&lut, 16, 16, 1, SWR_TEX_LINEAR);
+        for (uint32_t f = 0; f < 6; f++)
+            for (uint32_t y = 0; y < 16; y++)
+                for (uint32_t x = 0; x < 16; x++) {
+                    float t = (float)y / 15.0f;
+                    uint32_t c = f == 2 ? pack(0.35f, 0.55f, 0.9f) : f == 3 ? pack(0.25f, 0.22f, 0.2f) : pack(0.35f + 0.3f * t, 0.55f + 0.15f * t, 0.9f - 0.2f * t);
+                    sky.texels[(f * 16 + y) * 16 + x] = c;
+                    spec.texels[(f * 16 + y) * 16 + x] = c;
+                }
+        for (uint32_t i = 0; i < 256; i++) lut.texels[i] = pack(0.5f, 0.1f, 0.0f);
+        memset(voxel, 0, sizeof(voxel));
+        voxel[0] = voxel[1] = voxel[2] = 0.4f; /* SH band 0, rgb */
+        voxel[3] = 1.0f;                       /* sun visibility */
+        env.cubemap = &sky.desc;
+        env.cubemap_specular = &spec.desc;
+        env.brdf_lut = &lut.desc;
+        env.voxel_grid.dims[0] = env.voxel_grid.dims[1] = env.voxel_grid.dims[2] = 1;
+        env.voxel_grid.gi_sh4 = voxel;
+    }
     { /* scene.rs:236-239 */
         const float d[3] = {-0.2f, 1.0f, 0.5f}, n = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
         for (int c = 0; c < 3; c++) env.light_direction[c] = d[c] * n;
@@ -93,9 +123,8 @@ int main(int argc, char **argv) {
     }
     swrh_gltf_info info;
     swrh_gltf_get_info(doc, &info);
-    /* the voxel grid spans the scene bounds (main.rs:228-235); the descriptor is ours to adjust before the first upload */
+    /* env.voxel_grid carried no extent, so the loader made the grid span the scene bounds (main.rs:228-235) */
     swr_scene_desc scene = *swrh_gltf_scene(doc);
-    for (int c = 0; c < 3; c++) scene.voxel_grid.world_min[c] = info.bounds_min[c], scene.voxel_grid.world_max[c] = info.bounds_max[c];
     printf("%s: %u primitives, %u nodes, %u materials, %u textures, bounds diagonal %.3f\n", argv[1], scene.nprimitives, scene.nnodes, scene.nmaterials,
            scene.ntextures, info.bounds_diagonal);
 
@@ -137,5 +166,6 @@ int main(int argc, char **argv) {
     swrh_renderer_free(r);
     swrh_gltf_free(doc);
     free(sky.texels), free(spec.texels), free(lut.texels);
+    swrh_env_free(baked);
     return 0;
 }

@@ -22,7 +22,7 @@ typedef struct swrh_gltf_env {
     const swr_texture_desc *cubemap;          /* type SWR_TEX_CUBEMAP, may be NULL (then the scene cannot be rendered) */
     const swr_texture_desc *cubemap_specular;
     const swr_texture_desc *brdf_lut;
-    swr_voxel_grid_desc voxel_grid;           /* copied */
+    swr_voxel_grid_desc voxel_grid;           /* copied; world_min == world_max means: span the scene bounds (main.rs:228-235) */
     float light_direction[3];                 /* scene.rs:236-239 */
     float light_color[3];
 } swrh_gltf_env;
@@ -51,6 +51,21 @@ const char *swrh_gltf_texture_uri(void *doc, uint32_t slot);
 /* Hand in an image the loader cannot decode itself (width*height*4 bytes, R G B A per texel, as image::to_rgba8);
  * looked up by the exact `uri` string of the glTF image. rgba == NULL removes the entry. */
 int swrh_gltf_register_image(const char *uri, const uint8_t *rgba, uint32_t width, uint32_t height);
+
+/* Load-time environment bakes, on the host like the reference's (scene.rs:151-231 + main.rs:228-281): from a sky image in
+ * the reference's cross layout (+Y on top; -X +Z +X -Z in the middle row; -Y below; face size = width/4 x height/3) build
+ * the sky cubemap with mips (texture.rs:922-959, :45-128), the GGX-prefiltered specular cubemap (texture.rs:330-420, every
+ * mip at full face resolution, `specular_samples` = 64 in the reference), the irradiance SH4 (texture.rs:289-328), the
+ * BRDF LUT (texture.rs:199-235, `lut_size` = 128) and a voxel grid initialised from the SH (gi.rs:123-149 with main.rs's
+ * irradiance_scale = 0.25, sky_visibility = 1.0; `light_intensity` stands in for the ray-cast sun visibility, N4).
+ * swrh_env_get fills the three texture pointers and voxel_grid.dims / gi_sh4 of `out` (world bounds and light stay the
+ * caller's); they stay valid until swrh_env_free. */
+void *swrh_env_bake(const uint8_t *cross_rgba, uint32_t width, uint32_t height, uint32_t lut_size, uint32_t specular_samples, uint32_t voxel_dim,
+                    float irradiance_scale, float sky_visibility, float light_intensity);
+int swrh_env_get(void *env, swrh_gltf_env *out, float irradiance_sh_out[12]);
+void swrh_env_free(void *env);
+/* one texel's worth of integrate_brdf (texture.rs:167-197): out = (scale, bias) */
+int swrh_integrate_brdf(float ndotv, float roughness, float out[2]);
 
 /* The pieces of the loader that are useful on their own (and are what the tests pin): */
 int swrh_compute_smooth_normals(const float *positions4, uint32_t nverts, const uint32_t *indices, uint32_t nindices, float *normals4_out);

@@ -111,7 +111,15 @@ def load_gltf(path, environment=None):
     voxel grid / light are attached to the loaded scene (a glTF file carries none of them)."""
     host = _host()
     env, keep = None, None
-    if environment is not None:
+    if isinstance(environment, BakedEnvironment):
+        # baked on the host from a sky image; the voxel grid spans the scene bounds, sun and colour as scene.rs:236-239
+        env = GltfEnv.from_buffer_copy(environment.env)
+        d = np.array([-0.2, 1.0, 0.5], np.float32)
+        d = d / np.float32(np.sqrt(np.float32(d[0] * d[0] + d[1] * d[1]) + np.float32(d[2] * d[2])))
+        env.light_direction = (C.c_float * 3)(*d)
+        env.light_color = (C.c_float * 3)(5.0, 5.0, 4.75)
+        keep = environment
+    elif environment is not None:
         sd = environment.desc()
         env = GltfEnv()
         env.cubemap = C.pointer(sd.textures[sd.cubemap])
@@ -176,3 +184,57 @@ def decode_png(file_bytes):
     out = np.zeros((h.value, w.value, 4), np.uint8)
     _check(host.swrh_decode_png(buf.ctypes.data, len(buf), out.ctypes.data, C.byref(w), C.byref(h)), host)
     return out
+
+
+class BakedEnvironment:
+    """Host-side bakes of everything the viewer derives from its sky image (include/swr_gltf.h swrh_env_bake):
+    sky cubemap + mips, GGX-prefiltered cubemap, irradiance SH4, BRDF LUT, SH-initialised voxel grid."""
+
+    def __init__(self, cross_rgba_u8, lut_size=128, specular_samples=64, voxel_dim=16, irradiance_scale=0.25, sky_visibility=1.0, light_intensity=1.0):
+        host = _host()
+        host.swrh_env_bake.restype = C.c_void_p
+        host.swrh_env_bake.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float]
+        host.swrh_env_get.argtypes = [C.c_void_p, C.POINTER(GltfEnv), C.POINTER(C.c_float * 12)]
+        host.swrh_env_free.argtypes = [C.c_void_p]
+        a = np.ascontiguousarray(cross_rgba_u8, np.uint8)
+        assert a.ndim == 3 and a.shape[2] == 4
+        self._host = host
+        self._h = host.swrh_env_bake(a.ctypes.data, a.shape[1], a.shape[0], lut_size, specular_samples, voxel_dim, irradiance_scale, sky_visibility,
+                                     light_intensity)
+        if not self._h:
+            raise GltfError(host.swrh_last_error().decode())
+        self.env = GltfEnv()
+        sh = (C.c_float * 12)()
+        _check(host.swrh_env_get(self._h, C.byref(self.env), C.byref(sh)), host)
+        self.irradiance_sh = np.array(sh[:], np.float32).reshape(4, 3)
+        self.voxel_dim = voxel_dim
+
+    def texture(self, which):
+        """(data, offsets, widths, heights, strides, type) of 'cubemap' | 'cubemap_specular' | 'brdf_lut'."""
+        t = getattr(self.env, which).contents
+        nm = t.max_mip_level + 1
+        arr = lambda p, n: np.ctypeslib.as_array(p, (n,)).copy()
+        return arr(t.data, t.ntexels), arr(t.mip_offsets, nm), arr(t.mip_widths, nm), arr(t.mip_heights, nm), arr(t.array_stride, nm), t.texture_type
+
+    def voxels(self):
+        n = self.voxel_dim ** 3
+        return np.ctypeslib.as_array(self.env.voxel_grid.gi_sh4, (n * 16,)).copy().reshape(n, 4, 4)
+
+    def close(self):
+        if self._h:
+            self._host.swrh_env_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def integrate_brdf(ndotv, roughness):
+    host = _host()
+    host.swrh_integrate_brdf.argtypes = [C.c_float, C.c_float, C.POINTER(C.c_float * 2)]
+    out = (C.c_float * 2)()
+    _check(host.swrh_integrate_brdf(ndotv, roughness, C.byref(out)), host)
+    return float(out[0]), float(out[1])

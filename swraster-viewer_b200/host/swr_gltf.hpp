@@ -1171,6 +1171,11 @@ class Document {
         desc.materials = materials.data(), desc.nmaterials = (uint32_t)materials.size();
         desc.textures = tex_descs.data(), desc.ntextures = (uint32_t)tex_descs.size();
         desc.voxel_grid = env.voxel_grid;
+        if (std::memcmp(desc.voxel_grid.world_min, desc.voxel_grid.world_max, 12) == 0 && !nodes.empty()) {
+            // no extent given: the grid spans the scene bounds, as in main.rs:228-235
+            std::memcpy(desc.voxel_grid.world_min, bounds_min, 12);
+            std::memcpy(desc.voxel_grid.world_max, bounds_max, 12);
+        }
         desc.voxel_grid.gi_sh4 = voxels.empty() ? nullptr : voxels.data();
         desc.cubemap = env_slot[0], desc.cubemap_specular = env_slot[1], desc.brdf_lut = env_slot[2];
         std::memcpy(desc.light_direction, env.light_direction, 12);

@@ -2,6 +2,7 @@
 // same Renderer / RenderCamera code a C++ application would. Links libswr_b200.so.
 #include "swr_host.hpp"
 #include "swr_gltf.hpp"
+#include "swr_bake.hpp"
 #include "../../include/swr_gltf.h"
 #include "../../include/swr_host.h"
 
@@ -231,5 +232,39 @@ int swrh_decode_png(const uint8_t *file, size_t nbytes, uint8_t *rgba_out, uint3
         g_err = ex.what();
         return -1;
     }
+}
+
+// ---- environment bakes (include/swr_gltf.h, host/swr_bake.hpp) ----------------------------------------------------------
+void *swrh_env_bake(const uint8_t *cross_rgba, uint32_t width, uint32_t height, uint32_t lut_size, uint32_t specular_samples, uint32_t voxel_dim,
+                    float irradiance_scale, float sky_visibility, float light_intensity) {
+    try {
+        if (!cross_rgba || !lut_size || !specular_samples || !voxel_dim) throw std::runtime_error("Invalid data: null image or zero size");
+        if (lut_size > 4096 || voxel_dim > 1024 || width > 32768 || height > 32768) throw std::runtime_error("Invalid data: bake size out of range");
+        swr::gltf::Image img;
+        img.width = width;
+        img.height = height;
+        img.rgba.assign(cross_rgba, cross_rgba + (size_t)width * height * 4);
+        return swr::bake::EnvironmentBake::from_cross(img, lut_size, specular_samples, voxel_dim, irradiance_scale, sky_visibility, light_intensity).release();
+    } catch (const std::exception &ex) {
+        g_err = ex.what();
+        return nullptr;
+    }
+}
+int swrh_env_get(void *env, swrh_gltf_env *out, float irradiance_sh_out[12]) {
+    if (!env || !out) return -1;
+    swr::bake::EnvironmentBake &e = *(swr::bake::EnvironmentBake *)env;
+    out->cubemap = &e.descs[0];
+    out->cubemap_specular = &e.descs[1];
+    out->brdf_lut = &e.descs[2];
+    for (int c = 0; c < 3; c++) out->voxel_grid.dims[c] = e.voxel_dims[c];
+    out->voxel_grid.gi_sh4 = e.voxels.data();
+    if (irradiance_sh_out) std::memcpy(irradiance_sh_out, e.irradiance_sh, sizeof(e.irradiance_sh));
+    return 0;
+}
+void swrh_env_free(void *env) { delete (swr::bake::EnvironmentBake *)env; }
+int swrh_integrate_brdf(float ndotv, float roughness, float out[2]) {
+    if (!out) return -1;
+    swr::bake::integrate_brdf(ndotv, roughness, out[0], out[1]);
+    return 0;
 }
 }

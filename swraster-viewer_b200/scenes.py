@@ -258,7 +258,10 @@ def irradiance_sh4(col):
 
 
 def brdf_lut(size=128, samples=128):
-    """generate_brdf_lut (texture.rs:199-235) vectorised; Hammersley + GGX importance sampling."""
+    """generate_brdf_lut (texture.rs:199-235) vectorised in float64; Hammersley + GGX importance sampling. An INPUT builder, not
+    a restatement: it leaves out the tangent frame of importance_sample_ggx (with n = +Z the reference's half vector is rotated by
+    90 degrees about z), so single texels differ from the reference's table by a few LSB. The faithful version is
+    host/swr_bake.hpp (tests/test_bakes.py)."""
     i = np.arange(samples, dtype=np.uint32)
     bits = i.copy()
     bits = (bits << 16) | (bits >> 16)
