@@ -211,42 +211,46 @@ inline TextureData generate_prefiltered_specular_cubemap(const TextureData &cube
     for (uint32_t m = std::max(bw, bh); m >>= 1;) num_mips++;
     const uint32_t max_mip = num_mips - 1;
     t.width = bw, t.height = bh, t.type = SWR_TEX_LINEAR;
-    t.data.reserve((size_t)bw * bh * 6 * num_mips);
+    t.data.assign((size_t)bw * bh * 6 * num_mips, 0u);
     for (uint32_t mip = 0; mip < num_mips; mip++) {
         const float roughness = max_mip > 0 ? (float)mip / (float)max_mip : 0.0f;
-        t.mip_offsets.push_back((uint32_t)t.data.size());
+        const uint32_t mip_offset = mip * bw * bh * 6;
+        t.mip_offsets.push_back(mip_offset);
         t.mip_widths.push_back(bw);
         t.mip_heights.push_back(bh);
         t.array_stride.push_back(bw * bh);
-        for (uint32_t face = 0; face < 6; face++)
-            for (uint32_t y = 0; y < bh; y++) {
-                const float v = (((float)y + 0.5f) / (float)bh) * 2.0f - 1.0f;
-                for (uint32_t x = 0; x < bw; x++) {
-                    const float u = (((float)x + 0.5f) / (float)bw) * 2.0f - 1.0f;
-                    const V3 r = cubemap_face_uv_to_direction(face, u, v);
-                    V3 color;
-                    if (mip == 0) {
-                        color = sample_cubemap_direction_linear(cubemap, r);
-                    } else {
-                        V3 accum{0, 0, 0};
-                        float total = 0.0f;
-                        for (uint32_t i = 0; i < sample_count; i++) {
-                            float xx, xy;
-                            hammersley(i, sample_count, xx, xy);
-                            const V3 h = importance_sample_ggx(xx, xy, r, fmax_rs(roughness, 0.045f));
-                            const V3 l = gltf::normalize(h * (2.0f * gltf::dot(r, h)) - r);
-                            const float ndotl = fmax_rs(gltf::dot(r, l), 0.0f);
-                            if (ndotl > 0.0f) {
-                                accum = accum + sample_cubemap_direction_linear(cubemap, l) * ndotl;
-                                total += ndotl;
-                            }
+        // texels are independent: rows are spread over the host threads (the reference's loop is serial and cached on disk);
+        // every texel is computed exactly as in the serial order, so the result does not depend on the thread count
+#pragma omp parallel for schedule(dynamic, 4)
+        for (int64_t row = 0; row < (int64_t)6 * bh; row++) {
+            const uint32_t face = (uint32_t)(row / bh), y = (uint32_t)(row % bh);
+            const float v = (((float)y + 0.5f) / (float)bh) * 2.0f - 1.0f;
+            for (uint32_t x = 0; x < bw; x++) {
+                const float u = (((float)x + 0.5f) / (float)bw) * 2.0f - 1.0f;
+                const V3 r = cubemap_face_uv_to_direction(face, u, v);
+                V3 color;
+                if (mip == 0) {
+                    color = sample_cubemap_direction_linear(cubemap, r);
+                } else {
+                    V3 accum{0, 0, 0};
+                    float total = 0.0f;
+                    for (uint32_t i = 0; i < sample_count; i++) {
+                        float xx, xy;
+                        hammersley(i, sample_count, xx, xy);
+                        const V3 h = importance_sample_ggx(xx, xy, r, fmax_rs(roughness, 0.045f));
+                        const V3 l = gltf::normalize(h * (2.0f * gltf::dot(r, h)) - r);
+                        const float ndotl = fmax_rs(gltf::dot(r, l), 0.0f);
+                        if (ndotl > 0.0f) {
+                            accum = accum + sample_cubemap_direction_linear(cubemap, l) * ndotl;
+                            total += ndotl;
                         }
-                        color = total > 0.0f ? accum / total : sample_cubemap_direction_linear(cubemap, r);
                     }
-                    const float c4[4] = {color.x, color.y, color.z, 1.0f};
-                    t.data.push_back(gltf::rgba8_pack_vec4(c4));
+                    color = total > 0.0f ? accum / total : sample_cubemap_direction_linear(cubemap, r);
                 }
+                const float c4[4] = {color.x, color.y, color.z, 1.0f};
+                t.data[(size_t)mip_offset + (size_t)face * bw * bh + (size_t)y * bw + x] = gltf::rgba8_pack_vec4(c4);
             }
+        }
     }
     return t;
 }
