@@ -123,6 +123,10 @@ int main(int argc, char **argv) {
     }
     swrh_gltf_info info;
     swrh_gltf_get_info(doc, &info);
+    if (baked && swrh_gltf_bake_sun_visibility(doc)) { /* main.rs:237-246: one ray per voxel near geometry towards the sun */
+        fprintf(stderr, "sun visibility: %s\n", swrh_last_error());
+        return 1;
+    }
     /* env.voxel_grid carried no extent, so the loader made the grid span the scene bounds (main.rs:228-235) */
     swr_scene_desc scene = *swrh_gltf_scene(doc);
     printf("%s: %u primitives, %u nodes, %u materials, %u textures, bounds diagonal %.3f\n", argv[1], scene.nprimitives, scene.nnodes, scene.nmaterials,

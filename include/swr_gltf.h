@@ -64,6 +64,13 @@ void *swrh_env_bake(const uint8_t *cross_rgba, uint32_t width, uint32_t height, 
                     float irradiance_scale, float sky_visibility, float light_intensity);
 int swrh_env_get(void *env, swrh_gltf_env *out, float irradiance_sh_out[12]);
 void swrh_env_free(void *env);
+/* Voxel sun visibility as the reference's default load path computes it (main.rs:237-246; gi.rs:151-314, raytracer.rs,
+ * voxelgrid.rs:371-419): voxels near geometry cast one ray towards scene->light_direction, opaque hits give 0, translucent
+ * hits multiply their transmission, the grid is blurred (3x3x3 mean, squared). out_per_voxel receives dims[0]*dims[1]*dims[2]
+ * floats (index z*w*h + y*w + x); the value belongs into gi_sh4[voxel][0].w. swrh_gltf_bake_sun_visibility does that for
+ * a loaded document in place (call it before the scene is first rendered: uploads are once per scene). */
+int swrh_compute_sun_visibility(const swr_scene_desc *scene, float *out_per_voxel);
+int swrh_gltf_bake_sun_visibility(void *doc);
 /* one texel's worth of integrate_brdf (texture.rs:167-197): out = (scale, bias) */
 int swrh_integrate_brdf(float ndotv, float roughness, float out[2]);
 

@@ -232,6 +232,24 @@ class BakedEnvironment:
             pass
 
 
+def compute_sun_visibility(scene):
+    """Blurred sun visibility per voxel of `scene` (anything with .desc()), shape (d, h, w): gi.rs:151-314 on the host."""
+    host = _host()
+    host.swrh_compute_sun_visibility.argtypes = [C.POINTER(abi.SceneDesc), C.c_void_p]
+    d = scene.desc()
+    w, h, dd = d.voxel_grid.dims[:]
+    out = np.zeros(w * h * dd, np.float32)
+    _check(host.swrh_compute_sun_visibility(C.byref(d), out.ctypes.data), host)
+    return out.reshape(dd, h, w)
+
+
+def bake_sun_visibility(gltf_scene):
+    """Write the sun visibility into a loaded document's voxel grid (gi_sh4[v][0].w) in place, before its first render."""
+    host = _host()
+    host.swrh_gltf_bake_sun_visibility.argtypes = [C.c_void_p]
+    _check(host.swrh_gltf_bake_sun_visibility(gltf_scene._h), host)
+
+
 def integrate_brdf(ndotv, roughness):
     host = _host()
     host.swrh_integrate_brdf.argtypes = [C.c_float, C.c_float, C.POINTER(C.c_float * 2)]

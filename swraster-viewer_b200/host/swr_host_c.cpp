@@ -3,6 +3,7 @@
 #include "swr_host.hpp"
 #include "swr_gltf.hpp"
 #include "swr_bake.hpp"
+#include "swr_sunvis.hpp"
 #include "../../include/swr_gltf.h"
 #include "../../include/swr_host.h"
 
@@ -266,5 +267,32 @@ int swrh_integrate_brdf(float ndotv, float roughness, float out[2]) {
     if (!out) return -1;
     swr::bake::integrate_brdf(ndotv, roughness, out[0], out[1]);
     return 0;
+}
+
+// ---- voxel sun visibility (include/swr_gltf.h, host/swr_sunvis.hpp) ------------------------------------------------------
+int swrh_compute_sun_visibility(const swr_scene_desc *scene, float *out_per_voxel) {
+    try {
+        if (!scene || !out_per_voxel) throw std::runtime_error("Invalid data: null argument");
+        swr::validate_scene_ranges(*scene);
+        std::vector<float> v = swr::sunvis::compute_sun_visibility(*scene, scene->voxel_grid, scene->light_direction);
+        std::memcpy(out_per_voxel, v.data(), v.size() * sizeof(float));
+        return 0;
+    } catch (const std::exception &ex) {
+        g_err = ex.what();
+        return -1;
+    }
+}
+int swrh_gltf_bake_sun_visibility(void *doc) {
+    try {
+        if (!doc) throw std::runtime_error("Invalid data: null document");
+        swr::gltf::Document &d = *(swr::gltf::Document *)doc;
+        if (d.voxels.empty()) throw std::runtime_error("Invalid data: the document has no voxel grid (load it with an environment)");
+        std::vector<float> v = swr::sunvis::compute_sun_visibility(d.desc, d.desc.voxel_grid, d.desc.light_direction);
+        for (size_t i = 0; i < v.size(); i++) d.voxels[i * 16 + 3] = v[i];
+        return 0;
+    } catch (const std::exception &ex) {
+        g_err = ex.what();
+        return -1;
+    }
 }
 }
