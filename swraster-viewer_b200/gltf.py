@@ -232,6 +232,21 @@ class BakedEnvironment:
             pass
 
 
+def load_scene(path, sky_cross_rgba, grid_size=128, lut_size=128, specular_samples=64):
+    """What the viewer's load_scene does before the first frame (main.rs:100-291), for the fields the renderer consumes:
+    parse the glTF / GLB file, bake the environment from the sky image (scene.rs:151-231), span a grid_size^3 voxel grid over
+    the scene bounds (main.rs:228-235), initialise it from the irradiance SH with GI_FALLBACK_SCENE_SH_SCALE = 0.25 and sky
+    visibility 1 (main.rs:54, :280; gi.rs:123-149) and fill in the ray-cast sun visibility (main.rs:237-246).
+    Returns (scene, default camera spec as main.rs:210-224 builds it: (position, look_at, fov, far_plane))."""
+    env = BakedEnvironment(sky_cross_rgba, lut_size=lut_size, specular_samples=specular_samples, voxel_dim=grid_size, irradiance_scale=0.25,
+                           sky_visibility=1.0, light_intensity=1.0)
+    scene = load_gltf(path, environment=env)
+    bake_sun_visibility(scene)
+    c, d = scene.bounds_center, float(scene.bounds_diagonal)
+    camera = ((float(c[0]), float(c[1]), float(c[2]) + d), (float(c[0]), float(c[1]), float(c[2])), float(np.float32(np.pi) / np.float32(4.0)), d * 2.0)
+    return scene, camera
+
+
 def compute_sun_visibility(scene):
     """Blurred sun visibility per voxel of `scene` (anything with .desc()), shape (d, h, w): gi.rs:151-314 on the host."""
     host = _host()

@@ -156,3 +156,24 @@ def test_shadow_reaches_the_frame_through_the_loader(tmp_path):
     lum = lambda o: ((o["pixels"] >> 24) & 255).astype(np.int32) + ((o["pixels"] >> 16) & 255) + ((o["pixels"] >> 8) & 255)
     darker = (lum(a) - lum(b)) > 30
     assert 0.005 < darker.mean() < 0.5, darker.mean()  # a shadow patch on the ground, not the whole frame
+
+
+def test_load_scene_is_the_viewers_load_path_in_one_call(tmp_path):
+    """gltf.load_scene = parse + environment bake + voxel grid over the bounds + SH initialisation + sun visibility
+    (main.rs:100-291); the result renders (oracle) with the default camera of main.rs:210-224."""
+    from test_bakes import cross_from_faces, unpack
+    sc, _ = shadow_scene(False, voxel_dim=4)
+    scenes.export_gltf(sc, str(tmp_path / "s"))
+    tex, _ = scenes.sky_cubemap(8, 3)
+    faces = unpack(tex.data[:6 * 64]).reshape(6, 8, 8, 4).astype(np.uint8)
+    scene, (pos, look, fov, far) = gltf.load_scene(tmp_path / "s.gltf", cross_from_faces(faces), grid_size=24, lut_size=16, specular_samples=8)
+    d = scene.desc()
+    assert tuple(d.voxel_grid.dims[:]) == (24, 24, 24) and np.allclose(d.voxel_grid.world_min[:], scene.bounds_min)
+    vox = np.ctypeslib.as_array(d.voxel_grid.gi_sh4, (24 ** 3 * 16,)).reshape(-1, 4, 4)
+    assert vox[:, 0, 3].min() < 0.1 and vox[:, 0, 3].max() == 1.0 and (vox[:, 1, 3] == 1.0).all()  # sun visibility in, sky visibility 1
+    assert np.array_equal(vox[0, :, :3], vox[-1, :, :3]) and np.abs(vox[0, 0, :3]).min() > 0  # the same scaled SH everywhere
+    assert pos[2] == pytest.approx(float(scene.bounds_center[2]) + float(scene.bounds_diagonal)) and far == pytest.approx(2 * float(scene.bounds_diagonal))
+    W, H = 160, 96
+    cam = swr.RenderCamera(pos, look, fov, W, H, far)
+    o = render_oracle(scene, cam, W, H)
+    assert (o["seq"] != 0xFFFFFFFF).mean() > 0.02
