@@ -242,6 +242,13 @@ def load_scene(path, sky_cross_rgba, grid_size=128, lut_size=128, specular_sampl
                            sky_visibility=1.0, light_intensity=1.0)
     scene = load_gltf(path, environment=env)
     bake_sun_visibility(scene)
+    if scene.cameras:
+        # main.rs:198-209 + RenderCamera::from_gltf (rendercamera.rs:65-76): only the FIRST camera's yfov is used; position,
+        # target and far plane are fixed (the node transform is ignored); an orthographic camera is a load error
+        first = scene.cameras[0]
+        if not first["perspective"]:
+            raise GltfError("Failed to create camera from GLTF: unsupported camera type")
+        return scene, ((0.0, 0.0, 5.0), (0.0, 0.0, 0.0), float(first["yfov_or_xmag"]), 1000.0)
     c, d = scene.bounds_center, float(scene.bounds_diagonal)
     camera = ((float(c[0]), float(c[1]), float(c[2]) + d), (float(c[0]), float(c[1]), float(c[2])), float(np.float32(np.pi) / np.float32(4.0)), d * 2.0)
     return scene, camera

@@ -177,3 +177,22 @@ def test_load_scene_is_the_viewers_load_path_in_one_call(tmp_path):
     cam = swr.RenderCamera(pos, look, fov, W, H, far)
     o = render_oracle(scene, cam, W, H)
     assert (o["seq"] != 0xFFFFFFFF).mean() > 0.02
+
+
+def test_load_scene_camera_rules(tmp_path):
+    """main.rs:198-224: the first glTF camera wins and only its yfov is used; orthographic is a load error; none -> default."""
+    import json
+    from test_bakes import cross_from_faces
+    sc, _ = shadow_scene(False, voxel_dim=4)
+    scenes.export_gltf(sc, str(tmp_path / "s"))
+    sky = cross_from_faces(np.full((6, 4, 4, 4), 200, np.uint8))
+    doc = json.load(open(tmp_path / "s.gltf"))
+    doc["cameras"] = [{"type": "perspective", "perspective": {"yfov": 0.6, "znear": 0.1, "zfar": 50.0}}, {"type": "orthographic", "orthographic": {"xmag": 1, "ymag": 1, "znear": 0.1, "zfar": 5}}]
+    doc["nodes"].append({"camera": 0, "translation": [3, 4, 5]})
+    json.dump(doc, open(tmp_path / "p.gltf", "w"))
+    _, cam = gltf.load_scene(tmp_path / "p.gltf", sky, grid_size=4, lut_size=4, specular_samples=2)
+    assert cam == ((0.0, 0.0, 5.0), (0.0, 0.0, 0.0), pytest.approx(0.6), 1000.0)
+    doc["cameras"].reverse()
+    json.dump(doc, open(tmp_path / "o.gltf", "w"))
+    with pytest.raises(gltf.GltfError, match="unsupported camera type"):
+        gltf.load_scene(tmp_path / "o.gltf", sky, grid_size=4, lut_size=4, specular_samples=2)
