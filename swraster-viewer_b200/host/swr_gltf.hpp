@@ -14,7 +14,8 @@
 // The reference parses with the `gltf` crate (1.4, Cargo.lock) and decodes images with `image` 0.25; neither exists here, so
 // the container / accessor rules below follow the glTF 2.0 specification (what that crate implements): GLB chunks, data:
 // URIs, bufferView strides, sparse accessors, normalised integer texcoords (u8 / 255, u16 / 65535), u8/u16/u32 indices.
-// Images: 8-bit PNG is decoded here (zlib); anything else (JPEG) must be handed in decoded through register_image().
+// Images: PNG is decoded here (zlib; 16-bit samples reduced as image::to_rgba8 does); anything else (JPEG) must be handed in
+// decoded through register_image().
 // The environment (sky cubemap, prefiltered cubemap, BRDF LUT, voxel grid) is not part of a glTF file: the caller supplies
 // it (the reference bakes it from assets/cubemap.jpg).
 // Errors are std::runtime_error with the reference's SceneError wording ("Missing data: No positions in primitive", ...).
@@ -304,7 +305,7 @@ inline std::string dir_of(const std::string &path) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// PNG (8 bits per channel; grey, grey+alpha, RGB, palette (+tRNS), RGBA; non-interlaced and Adam7) -> RGBA8 bytes
+// PNG (every colour type and bit depth of the specification, tRNS, non-interlaced and Adam7) -> RGBA8 bytes
 // ------------------------------------------------------------------------------------------------------------------
 struct Image {
     uint32_t width = 0, height = 0;
@@ -314,7 +315,7 @@ struct Image {
 inline Image decode_png(const std::vector<uint8_t> &file, const std::string &name) {
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
     auto bad = [&](const char *why) -> std::runtime_error { return std::runtime_error("Missing data: Could not load texture '" + name + "': " + why); };
-    if (file.size() < 8 || std::memcmp(file.data(), sig, 8) != 0) throw bad("not a PNG file (only 8-bit PNG is decoded here; register other formats decoded)");
+    if (file.size() < 8 || std::memcmp(file.data(), sig, 8) != 0) throw bad("not a PNG file (only PNG is decoded here; register other formats decoded)");
     auto be32 = [&](size_t o) { return ((uint32_t)file[o] << 24) | ((uint32_t)file[o + 1] << 16) | ((uint32_t)file[o + 2] << 8) | file[o + 3]; };
     uint32_t w = 0, h = 0;
     int depth = 0, ctype = -1, interlace = 0;
@@ -343,7 +344,11 @@ inline Image decode_png(const std::vector<uint8_t> &file, const std::string &nam
         o += 12 + (size_t)len;
     }
     if (w == 0 || h == 0 || ctype < 0) throw bad("missing IHDR");
-    if (depth != 8) throw bad("only 8 bits per channel are supported");
+    // legal (colour type, bit depth) pairs of the PNG specification
+    const bool depth_ok = ctype == 0 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)
+                          : ctype == 3 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8)
+                                       : (depth == 8 || depth == 16);
+    if (!depth_ok) throw bad("illegal bit depth for the colour type");
     if (w > 32768 || h > 32768) throw bad("image larger than 32768 pixels on a side");
     int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
     if (!ch) throw bad("unknown colour type");
@@ -361,7 +366,7 @@ inline Image decode_png(const std::vector<uint8_t> &file, const std::string &nam
     size_t need = 0;
     for (const Pass &p : passes) {
         uint32_t pw = w > p.x0 ? (w - p.x0 + p.dx - 1) / p.dx : 0, ph = h > p.y0 ? (h - p.y0 + p.dy - 1) / p.dy : 0;
-        if (pw && ph) need += (size_t)ph * ((size_t)pw * ch + 1);
+        if (pw && ph) need += (size_t)ph * (((size_t)pw * ch * depth + 7) / 8 + 1);
     }
     // deflate cannot expand by more than ~1032:1: a header that asks for more than the data can hold is corrupt
     if (need > idat.size() * 1032 + 65536) throw bad("corrupt image data (header larger than the compressed stream)");
@@ -378,15 +383,30 @@ inline Image decode_png(const std::vector<uint8_t> &file, const std::string &nam
     for (const Pass &p : passes) {
         uint32_t pw = w > p.x0 ? (w - p.x0 + p.dx - 1) / p.dx : 0, ph = h > p.y0 ? (h - p.y0 + p.dy - 1) / p.dy : 0;
         if (!pw || !ph) continue;
-        const size_t stride = (size_t)pw * ch;
+        const size_t stride = ((size_t)pw * ch * depth + 7) / 8;  // bytes per scanline
+        const size_t bpp = std::max<size_t>(1, (size_t)ch * depth / 8);  // filter distance in bytes
         prev.assign(stride, 0);
         cur.resize(stride);
+        // sample k of the scanline as 8 bits: sub-byte grey is scaled to 0..255, 16 bits are reduced as image::to_rgba8
+        // does ((v + 128) / 257, the rounded v * 255 / 65535); palette indices stay indices
+        auto sample = [&](size_t k) -> uint32_t {
+            if (depth == 8) return cur[k];
+            if (depth == 16) return ((uint32_t)cur[2 * k] << 8) | cur[2 * k + 1];
+            const size_t bit = k * (size_t)depth;
+            return (uint32_t)(cur[bit >> 3] >> (8 - depth - (bit & 7))) & ((1u << depth) - 1u);
+        };
+        auto to8 = [&](uint32_t v) -> uint8_t {
+            if (depth == 8) return (uint8_t)v;
+            if (depth == 16) return (uint8_t)((v + 128u) / 257u);
+            return (uint8_t)(v * (255u / ((1u << depth) - 1u)));
+        };
+        auto trns16 = [&](size_t i) -> uint32_t { return ((uint32_t)trns[2 * i] << 8) | trns[2 * i + 1]; };
         for (uint32_t y = 0; y < ph; y++) {
             const uint8_t ft = raw[pos++];
             const uint8_t *src = &raw[pos];
             pos += stride;
             for (size_t i = 0; i < stride; i++) {
-                const int a = i >= (size_t)ch ? cur[i - ch] : 0, b = prev[i], c = i >= (size_t)ch ? prev[i - ch] : 0;
+                const int a = i >= bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
                 int v = src[i];
                 switch (ft) {
                     case 0: break;
@@ -404,25 +424,29 @@ inline Image decode_png(const std::vector<uint8_t> &file, const std::string &nam
             }
             for (uint32_t x = 0; x < pw; x++) {
                 uint8_t *dst = &img.rgba[(((size_t)p.y0 + (size_t)y * p.dy) * w + p.x0 + (size_t)x * p.dx) * 4];
-                const uint8_t *s = &cur[(size_t)x * ch];
+                const size_t k0 = (size_t)x * ch;
                 switch (ctype) {
-                    case 0:
-                        dst[0] = dst[1] = dst[2] = s[0];
-                        if (trns.size() >= 2 && trns[1] == s[0] && trns[0] == 0) dst[3] = 0;
+                    case 0: {
+                        const uint32_t g = sample(k0);
+                        dst[0] = dst[1] = dst[2] = to8(g);
+                        if (trns.size() >= 2 && trns16(0) == g) dst[3] = 0;  // tRNS holds the transparent grey level in file precision
                         break;
-                    case 2:
-                        dst[0] = s[0], dst[1] = s[1], dst[2] = s[2];
-                        if (trns.size() >= 6 && trns[0] == 0 && trns[2] == 0 && trns[4] == 0 && trns[1] == s[0] && trns[3] == s[1] && trns[5] == s[2]) dst[3] = 0;
+                    }
+                    case 2: {
+                        const uint32_t r = sample(k0), g = sample(k0 + 1), bl = sample(k0 + 2);
+                        dst[0] = to8(r), dst[1] = to8(g), dst[2] = to8(bl);
+                        if (trns.size() >= 6 && trns16(0) == r && trns16(1) == g && trns16(2) == bl) dst[3] = 0;
                         break;
+                    }
                     case 3: {
-                        const size_t k = s[0];
+                        const size_t k = sample(k0);
                         if (k * 3 + 2 >= plte.size()) throw bad("palette index out of range");
                         dst[0] = plte[k * 3], dst[1] = plte[k * 3 + 1], dst[2] = plte[k * 3 + 2];
                         if (k < trns.size()) dst[3] = trns[k];
                         break;
                     }
-                    case 4: dst[0] = dst[1] = dst[2] = s[0], dst[3] = s[1]; break;
-                    case 6: dst[0] = s[0], dst[1] = s[1], dst[2] = s[2], dst[3] = s[3]; break;
+                    case 4: dst[0] = dst[1] = dst[2] = to8(sample(k0)), dst[3] = to8(sample(k0 + 1)); break;
+                    case 6: dst[0] = to8(sample(k0)), dst[1] = to8(sample(k0 + 1)), dst[2] = to8(sample(k0 + 2)), dst[3] = to8(sample(k0 + 3)); break;
                 }
             }
             std::swap(prev, cur);

@@ -599,3 +599,68 @@ def test_hostile_sizes_are_rejected_not_trusted(tmp_path):
     png[16:24] = struct.pack(">II", 2 ** 31, 1)
     with pytest.raises(gltf.GltfError, match="larger than"):
         gltf.decode_png(bytes(png))
+
+
+def raw_png_bits(samples, ctype, depth):
+    """Encoder for any legal bit depth, filter 0: samples is (h, w, channels) of integers in file precision."""
+    h, w, ch = samples.shape
+    out = bytearray()
+    for y in range(h):
+        row = samples[y].reshape(-1).astype(np.uint32)
+        if depth == 16:
+            data = row.astype(">u2").tobytes()
+        elif depth == 8:
+            data = row.astype(np.uint8).tobytes()
+        else:
+            bits = "".join(format(int(v), f"0{depth}b") for v in row)
+            bits += "0" * (-len(bits) % 8)
+            data = int(bits, 2).to_bytes(len(bits) // 8, "big")
+        out += b"\x00" + data
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
+    return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(bytes(out))) + chunk(b"IEND", b"")
+
+
+def test_png_decoder_other_bit_depths():
+    """1/2/4-bit grey and palette, 16-bit grey / RGB / RGBA. 16 -> 8 bits as image::to_rgba8: (v + 128) / 257."""
+    from PIL import Image
+    rng = np.random.default_rng(21)
+    w, h = 13, 5  # scanlines that do not end on a byte boundary
+    for depth in (1, 2, 4):
+        g = rng.integers(0, 1 << depth, (h, w, 1))
+        got = gltf.decode_png(raw_png_bits(g, 0, depth))
+        want8 = (g[..., 0] * (255 // ((1 << depth) - 1))).astype(np.uint8)
+        assert np.array_equal(got, np.stack([want8] * 3 + [np.full((h, w), 255, np.uint8)], -1)), depth
+    for depth, mode in ((16, None),):
+        g = rng.integers(0, 65536, (h, w, 1))
+        got = gltf.decode_png(raw_png_bits(g, 0, 16))
+        assert np.array_equal(got[..., 0], ((g[..., 0] + 128) // 257).astype(np.uint8)) and (got[..., 3] == 255).all()
+        rgb = rng.integers(0, 65536, (h, w, 3))
+        got = gltf.decode_png(raw_png_bits(rgb, 2, 16))
+        assert np.array_equal(got[..., :3], ((rgb + 128) // 257).astype(np.uint8))
+        rgba = rng.integers(0, 65536, (h, w, 4))
+        got = gltf.decode_png(raw_png_bits(rgba, 6, 16))
+        assert np.array_equal(got, ((rgba + 128) // 257).astype(np.uint8))
+        ga = rng.integers(0, 65536, (h, w, 2))
+        got = gltf.decode_png(raw_png_bits(ga, 4, 16))
+        assert np.array_equal(got[..., 0], ((ga[..., 0] + 128) // 257).astype(np.uint8)) and np.array_equal(got[..., 3], ((ga[..., 1] + 128) // 257).astype(np.uint8))
+    # against PIL's own writer and reader: bilevel, small palettes (PIL packs them into 1/2/4 bits), 16-bit grey
+    bil = Image.fromarray((rng.integers(0, 2, (h, w)) * 255).astype(np.uint8), "L").convert("1")
+    buf = io.BytesIO()
+    bil.save(buf, "PNG")
+    assert np.array_equal(gltf.decode_png(buf.getvalue()), np.asarray(bil.convert("RGBA")))
+    for ncol, bits in ((2, 1), (4, 2), (16, 4)):
+        idx = rng.integers(0, ncol, (h, w)).astype(np.uint8)
+        im = Image.fromarray(idx, "P")
+        im.putpalette([int(v) for v in rng.integers(0, 256, ncol * 3)])
+        buf = io.BytesIO()
+        im.save(buf, "PNG", bits=bits)
+        assert buf.getvalue()[24] == bits  # IHDR bit depth
+        assert np.array_equal(gltf.decode_png(buf.getvalue()), np.asarray(im.convert("RGBA"))), bits
+    g16 = rng.integers(0, 65536, (h, w)).astype(np.uint16)
+    buf = io.BytesIO()
+    Image.fromarray(g16).save(buf, "PNG")
+    assert np.array_equal(gltf.decode_png(buf.getvalue())[..., 0], ((g16.astype(np.uint32) + 128) // 257).astype(np.uint8))
+    with pytest.raises(gltf.GltfError, match="illegal bit depth"):
+        gltf.decode_png(raw_png_bits(rng.integers(0, 4, (h, w, 3)), 2, 2))
