@@ -664,3 +664,50 @@ def test_png_decoder_other_bit_depths():
     assert np.array_equal(gltf.decode_png(buf.getvalue())[..., 0], ((g16.astype(np.uint32) + 128) // 257).astype(np.uint8))
     with pytest.raises(gltf.GltfError, match="illegal bit depth"):
         gltf.decode_png(raw_png_bits(rng.integers(0, 4, (h, w, 3)), 2, 2))
+
+
+def test_mutated_files_never_crash_the_loader(tmp_path):
+    """Regression guard for the ASan/UBSan fuzzing done offline (40 k mutations): byte-level damage to a valid .gltf, .glb and
+    .png must end in GltfError or in a successful load, never in a crash (a segfault would take the test process down)."""
+    rng = np.random.default_rng(2024)
+    sc, _ = scenes.scene_materials_test(**SMALL)
+    scenes.export_gltf(sc, str(tmp_path / "seed"))
+    seeds = {"gltf": (tmp_path / "seed.gltf").read_bytes(), "png": (tmp_path / "seed_tex0.png").read_bytes()}
+    g = json.loads(seeds["gltf"])
+    blob = (tmp_path / "seed.bin").read_bytes()
+    for k in ("images", "textures", "samplers"):
+        g.pop(k, None)
+    for m in g["materials"]:
+        for kk in [k for k in m.get("pbrMetallicRoughness", {}) if k.endswith("Texture")]:
+            del m["pbrMetallicRoughness"][kk]
+        for kk in [k for k in m if k.endswith("Texture")]:
+            del m[kk]
+    del g["buffers"][0]["uri"]
+    js = json.dumps(g).encode()
+    js += b" " * (-len(js) % 4)
+    seeds["glb"] = b"glTF" + struct.pack("<II", 2, 20 + len(js) + 8 + len(blob)) + struct.pack("<II", len(js), 0x4E4F534A) + js + struct.pack("<II", len(blob), 0x004E4942) + blob
+    outcomes = {"ok": 0, "rejected": 0}
+    for it in range(240):
+        kind = ("gltf", "glb", "png")[it % 3]
+        data = bytearray(seeds[kind])
+        for _ in range(int(rng.integers(1, 4))):
+            pos = int(rng.integers(0, len(data)))
+            op = int(rng.integers(0, 4))
+            if op == 0:
+                data[pos] ^= 1 << int(rng.integers(0, 8))
+            elif op == 1:
+                data[pos] = int(rng.integers(0, 256))
+            elif op == 2:
+                del data[pos:pos + int(rng.integers(1, 16))]
+            else:
+                data.insert(pos, b"0123456789-{}[],:\"e."[int(rng.integers(0, 20))])
+        try:
+            if kind == "png":
+                gltf.decode_png(bytes(data))
+            else:
+                (tmp_path / f"case.{kind}").write_bytes(bytes(data))
+                gltf.load_gltf(tmp_path / f"case.{kind}").close()
+            outcomes["ok"] += 1
+        except gltf.GltfError:
+            outcomes["rejected"] += 1
+    assert outcomes["ok"] + outcomes["rejected"] == 240 and outcomes["rejected"] > 50
