@@ -88,3 +88,35 @@ def test_headers_are_c99_and_the_c_example_builds_and_fails_loudly_without_a_dev
         assert r.returncode == 3 and "no CPU fallback" in r.stderr and not os.path.exists(tmp_path / "out.ppm")
     r = subprocess.run([exe, str(tmp_path / "missing.gltf"), str(tmp_path / "out.ppm")], capture_output=True, text=True)
     assert r.returncode == 1 and "Missing data" in r.stderr
+
+
+def test_every_entry_point_survives_a_null_context():
+    """The FFI caller may hold a failed (NULL) context: every entry point must return an error / NULL, not dereference it.
+    Runs in a child process so that a regression shows up as a failure instead of killing the test run."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, sys
+sys.path.insert(0, %r)
+import swraster_viewer_b200 as swr
+from swraster_viewer_b200 import abi
+core, _ = swr.load_libraries()
+core.swr_resolve_async.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+core.swr_wait_pixels.argtypes = [C.c_void_p, C.c_int]
+args = {"swr_set_rsqrt_table": (None, None, 10), "swr_set_tile_rows": (None, 0, 1), "swr_upload_scene": (None, None), "swr_render": (None, None, None, 0, 1),
+        "swr_shade": (None, None), "swr_shade_composited": (None, None, 0, 0), "swr_resolve": (None, 2.0, None), "swr_resolve_async": (None, 2.0, None, None),
+        "swr_wait_pixels": (None, 0), "swr_read_tile_luminance": (None, None), "swr_read_tile_costs": (None, None, None),
+        "swr_read_visbuffer": (None, None, None, None, None), "swr_read_color": (None, None), "swr_get_stats": (None, None), "swr_peer_export": (None, None),
+        "swr_peer_open": (None, None), "swr_peer_attach": (None, None), "swr_resolve_peer": (None, 2.0, 1), "swr_peer_collect": (None, 1, 1),
+        "swr_peer_release": (None, 1)}
+skip = {"swr_abi_version", "swr_last_error", "swr_create", "swr_sizeof"}
+for name in abi.EXPORTS:
+    if name in skip:
+        continue
+    r = getattr(core, name)(*args.get(name, (None,)))
+    ok = r is None or r == 0 if name in ("swr_destroy", "swr_device_pixels", "swr_device_keys", "swr_device_keys_bytes", "swr_device_bary", "swr_cuda_stream") else r < 0
+    assert ok, (name, r)
+print("NULL-SAFE", len(abi.EXPORTS) - len(skip))
+''' % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "NULL-SAFE" in r.stdout, r.stderr[-2000:]
