@@ -120,3 +120,40 @@ print("NULL-SAFE", len(abi.EXPORTS) - len(skip))
 ''' % ROOT
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "NULL-SAFE" in r.stdout, r.stderr[-2000:]
+
+
+def test_host_entry_points_survive_null_arguments():
+    """Same for the host mirror's C API (include/swr_host.h, include/swr_gltf.h): NULL handles and pointers are errors."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, sys
+sys.path.insert(0, %r)
+import swraster_viewer_b200 as swr
+_, h = swr.load_libraries()
+h.swrh_auto_exposure.restype = C.c_float
+h.swrh_renderer_ctx.restype = C.c_void_p
+h.swrh_gltf_load.restype = C.c_void_p
+h.swrh_gltf_scene.restype = C.c_void_p
+h.swrh_gltf_texture_uri.restype = C.c_char_p
+h.swrh_env_bake.restype = C.c_void_p
+f = C.c_float
+neg = {"swrh_camera_build": (None, None, f(1), f(64), f(64), f(10), None), "swrh_camera_build_rotated": (None, None, f(0), f(0), f(1), f(64), f(64), f(10), None),
+       "swrh_set_reference_rsqrt": (None, 1), "swrh_reference_rsqrt_bits": (None,), "swrh_set_tile_rows": (None, 0, 1),
+       "swrh_render_scene": (None, None, None, 1, 0, 1), "swrh_num_draws": (None,), "swrh_update_auto_exposure": (None, f(0)),
+       "swrh_blit_to_buffer": (None, None, 64, 64), "swrh_blit_to_buffer_async": (None, None, 64, 64, None), "swrh_wait_blit": (None, 0),
+       "swrh_build_draws": (None, None, None, 0, 0, 1), "swrh_build_draws_band": (None, None, None, 0, 0, 64, 64),
+       "swrh_gltf_get_info": (None, None), "swrh_gltf_get_camera": (None, 0, None), "swrh_gltf_register_image": (None, None, 0, 0),
+       "swrh_gltf_bake_sun_visibility": (None,), "swrh_compute_sun_visibility": (None, None), "swrh_env_get": (None, None, None), "swrh_integrate_brdf": (f(0.5), f(0.5), None)}
+for name, a in neg.items():
+    r = getattr(h, name)(*a)
+    assert r < 0, (name, r)
+for name, a in {"swrh_renderer_ctx": (None,), "swrh_gltf_load": (None, None), "swrh_gltf_scene": (None,), "swrh_gltf_texture_uri": (None, 0),
+                "swrh_env_bake": (None, 4, 3, 4, 4, 1, f(1), f(1), f(1))}.items():
+    assert getattr(h, name)(*a) is None, name
+h.swrh_renderer_free(None); h.swrh_gltf_free(None); h.swrh_env_free(None)
+assert h.swrh_auto_exposure(None) == 0.0
+print("NULL-SAFE", len(neg))
+''' % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "NULL-SAFE" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
