@@ -8,7 +8,8 @@
  *
  * Not in a glTF file and therefore supplied by the caller: the sky cubemap, the prefiltered specular cubemap, the BRDF
  * LUT and the GI voxel grid (the reference bakes them from assets/cubemap.jpg at load time).
- * Images: 8-bit PNG files / data URIs are decoded here; other formats (JPEG) must be registered decoded beforehand.
+ * Images: PNG and JPEG files / data URIs are decoded here (host/swr_gltf.hpp, host/swr_jpeg.hpp); other formats can be
+ * registered decoded beforehand.
  * All functions return 0 / a handle on success, -1 / NULL on error with the message in swrh_last_error() — the wording
  * follows the reference's SceneError ("Missing data: No positions in primitive", ...). */
 #ifndef SWR_GLTF_H
@@ -82,6 +83,7 @@ int swrh_compute_tangents(const float *positions4, const float *texcoords2, cons
  * number of mips; mip_table_out receives 4 x nmips u32: offsets, widths, heights, array strides. */
 int swrh_build_mip_chain(const uint32_t *base_texels, uint32_t width, uint32_t height, uint32_t texture_type, uint32_t *data_out,
                          uint32_t *ntexels_out, uint32_t *nmips_out, uint32_t *mip_table_out);
+/* PNG or JPEG (by signature) -> RGBA8; call with rgba_out == NULL for the size. (The name predates the JPEG decoder.) */
 int swrh_decode_png(const uint8_t *file, size_t nbytes, uint8_t *rgba_out, uint32_t *width_out, uint32_t *height_out);
 
 #ifdef __cplusplus

@@ -14,8 +14,8 @@
 // The reference parses with the `gltf` crate (1.4, Cargo.lock) and decodes images with `image` 0.25; neither exists here, so
 // the container / accessor rules below follow the glTF 2.0 specification (what that crate implements): GLB chunks, data:
 // URIs, bufferView strides, sparse accessors, normalised integer texcoords (u8 / 255, u16 / 65535), u8/u16/u32 indices.
-// Images: PNG is decoded here (zlib; 16-bit samples reduced as image::to_rgba8 does); anything else (JPEG) must be handed in
-// decoded through register_image().
+// Images: PNG (zlib; 16-bit samples reduced as image::to_rgba8 does) and JPEG (swr_jpeg.hpp) are decoded here; anything else
+// can be handed in decoded through register_image().
 // The environment (sky cubemap, prefiltered cubemap, BRDF LUT, voxel grid) is not part of a glTF file: the caller supplies
 // it (the reference bakes it from assets/cubemap.jpg).
 // Errors are std::runtime_error with the reference's SceneError wording ("Missing data: No positions in primitive", ...).
@@ -32,6 +32,7 @@
 #include <sstream>
 
 #include "swr_host.hpp"
+#include "swr_jpeg.hpp"
 
 namespace swr {
 namespace gltf {
@@ -315,7 +316,7 @@ struct Image {
 inline Image decode_png(const std::vector<uint8_t> &file, const std::string &name) {
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
     auto bad = [&](const char *why) -> std::runtime_error { return std::runtime_error("Missing data: Could not load texture '" + name + "': " + why); };
-    if (file.size() < 8 || std::memcmp(file.data(), sig, 8) != 0) throw bad("not a PNG file (only PNG is decoded here; register other formats decoded)");
+    if (file.size() < 8 || std::memcmp(file.data(), sig, 8) != 0) throw bad("neither a PNG nor a JPEG file (register other formats decoded)");
     auto be32 = [&](size_t o) { return ((uint32_t)file[o] << 24) | ((uint32_t)file[o + 1] << 16) | ((uint32_t)file[o + 2] << 8) | file[o + 3]; };
     uint32_t w = 0, h = 0;
     int depth = 0, ctype = -1, interlace = 0;
@@ -453,6 +454,18 @@ inline Image decode_png(const std::vector<uint8_t> &file, const std::string &nam
         }
     }
     return img;
+}
+
+// PNG or JPEG by signature (what image::open does for the two formats glTF allows)
+inline Image decode_image(const std::vector<uint8_t> &file, const std::string &name) {
+    if (file.size() >= 2 && file[0] == 0xFF && file[1] == 0xD8) {
+        jpeg::DecodedImage j = jpeg::decode(file.data(), file.size(), name);
+        Image img;
+        img.width = j.width, img.height = j.height;
+        img.rgba.swap(j.rgba);
+        return img;
+    }
+    return decode_png(file, name);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -956,7 +969,7 @@ class Document {
             } else if (uri.compare(0, 5, "data:") == 0) {
                 size_t k = uri.find(";base64,");
                 if (k == std::string::npos) throw std::runtime_error("Invalid data: data URI without base64 payload");
-                img = decode_png(base64_decode(uri.data() + k + 8, uri.size() - k - 8), "data:");
+                img = decode_image(base64_decode(uri.data() + k + 8, uri.size() - k - 8), "data:");
             } else {
                 std::vector<uint8_t> bytes;
                 try {
@@ -964,7 +977,7 @@ class Document {
                 } catch (const std::exception &) {
                     throw std::runtime_error("Missing data: Could not load texture '" + uri + "' from path '" + base_dir_ + "/" + uri + "'");
                 }
-                img = decode_png(bytes, uri);
+                img = decode_image(bytes, uri);
             }
             td = std::make_shared<TextureData>(TextureData::from_rgba8(img, type));
             td->generate_mipmaps();

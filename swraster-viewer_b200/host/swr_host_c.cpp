@@ -235,7 +235,8 @@ int swrh_build_mip_chain(const uint32_t *base_texels, uint32_t width, uint32_t h
 }
 int swrh_decode_png(const uint8_t *file, size_t nbytes, uint8_t *rgba_out, uint32_t *width_out, uint32_t *height_out) {
     try {
-        swr::gltf::Image img = swr::gltf::decode_png(std::vector<uint8_t>(file, file + nbytes), "<memory>");
+        if (!file) throw std::runtime_error("Invalid data: null image");
+        swr::gltf::Image img = swr::gltf::decode_image(std::vector<uint8_t>(file, file + nbytes), "<memory>");
         if (width_out) *width_out = img.width;
         if (height_out) *height_out = img.height;
         if (rgba_out) std::memcpy(rgba_out, img.rgba.data(), img.rgba.size());
