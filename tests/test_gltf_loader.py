@@ -482,8 +482,8 @@ def test_png_decoder_all_colour_types_filters_and_interlace():
         for inter in (False, True):
             data, want = png_bytes(rgba, mode, inter)
             assert np.array_equal(gltf.decode_png(data), want), (mode, inter)
-    with pytest.raises(gltf.GltfError, match="not a PNG"):
-        gltf.decode_png(b"\xff\xd8\xff\xe0" + b"\0" * 32)  # a JPEG header
+    with pytest.raises(gltf.GltfError, match="neither a PNG nor a JPEG"):
+        gltf.decode_png(b"GIF89a" + b"\0" * 32)
     bad = bytearray(raw_png(rgba, 6, [0]))
     bad[60] ^= 0xFF
     with pytest.raises(gltf.GltfError, match="inflate|corrupt"):
