@@ -23,13 +23,24 @@ def test_header_symbols_are_exported():
     assert core.swr_abi_version() == 1
 
 
-def test_gltf_header_symbols_are_exported_by_the_host_library():
+def test_gltf_and_host_header_symbols_are_exported_by_the_host_library():
     _, host = swr.load_libraries()
-    header = open(os.path.join(ROOT, "include", "swr_gltf.h")).read()
-    declared = set(re.findall(r"\b(swrh_[a-z_0-9]+)\s*\(", header))
-    assert {"swrh_gltf_load", "swrh_gltf_scene", "swrh_gltf_free", "swrh_build_mip_chain", "swrh_decode_png"} <= declared
-    for name in declared:
-        assert hasattr(host, name), f"libswr_host.so does not export {name}"
+    total = set()
+    for hdr, must in (("swr_gltf.h", {"swrh_gltf_load", "swrh_gltf_scene", "swrh_gltf_free", "swrh_build_mip_chain", "swrh_decode_png", "swrh_env_bake",
+                                      "swrh_compute_sun_visibility"}),
+                      ("swr_host.h", {"swrh_renderer_new", "swrh_render_scene", "swrh_blit_to_buffer", "swrh_update_auto_exposure", "swrh_camera_build",
+                                      "swrh_build_draws"})):
+        header = open(os.path.join(ROOT, "include", hdr)).read()
+        declared = set(re.findall(r"\b(swrh_[a-z_0-9]+)\s*\(", header))
+        assert must <= declared, must - declared
+        for name in declared:
+            assert hasattr(host, name), f"libswr_host.so does not export {name} ({hdr})"
+        total |= declared
+    # and nothing the library exports is left undeclared: every swrh_ symbol of the .so appears in one of the two headers
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "swraster-viewer_b200", "lib", "libswr_host.so")], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\b(swrh_[a-z_0-9]+)\b", out))
+    assert exported == total, exported ^ total
 
 
 def test_struct_sizes_match_library():
