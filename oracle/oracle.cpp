@@ -322,9 +322,17 @@ struct Draw {
     uint32_t primitive, mesh, flags, first_triangle;
 };
 
-struct Stats {
-    std::atomic<uint64_t> tris_binned{0}, tris_clipped{0}, packets{0}, packets_dup{0};
+// Frame counters. The reference keeps none on this path (renderer.rs:668-846 pushes packets and nothing else), so they
+// must not cost the timed parallel bin phase anything: one cache-line-sized slot per worker thread, folded after the
+// phase (a shared atomic here would serialise the workers on one line and handicap the CPU baseline).
+struct alignas(64) ThreadStats {
+    uint64_t tris_binned = 0, tris_clipped = 0, packets = 0, packets_dup = 0;
+    uint64_t pad[4];
 };
+struct Stats {
+    uint64_t tris_binned = 0, tris_clipped = 0, packets = 0, packets_dup = 0;
+};
+static const int MAX_THREADS = 1024;
 
 struct Oracle {
     int W, H, tiles_x, tiles_y;
@@ -333,6 +341,8 @@ struct Oracle {
     std::vector<Tile *> tiles;
     std::vector<Draw> draws;
     Stats stats;
+    std::vector<ThreadStats> tstats;  // indexed by omp_get_thread_num()
+    bool track_written = true;        // per-lane "written" bookkeeping is only needed when the caller reads seq back
     int nthreads;
     uint64_t tris_submitted = 0, verts_submitted = 0;
     double ms_clipbin = 0, ms_raster = 0;
@@ -743,7 +753,7 @@ static void fine_raster(const Oracle &o, Tile &tile, const RasterParams &rp, int
                     for (int l = 0; l < 4; l++)
                         if (bm & (1 << l)) {
                             tile.packet_index[index].v[l] = rp.packet_index;
-                            tile.written[index].v[l] = 1;
+                            if (o.track_written) tile.written[index].v[l] = 1;
                         }
                     tile.bary1[index] = select(m, bary1, tile.bary1[index]);
                     tile.bary2[index] = select(m, bary2, tile.bary2[index]);
@@ -899,6 +909,7 @@ static inline bool of_less(float a, float b) {
 
 static void render_tile(Oracle &o, Tile &tile, bool shade) {  // :72-111
     std::fill(tile.depth.begin(), tile.depth.end(), splat(INFINITY));
+    if (o.track_written) std::fill(tile.written.begin(), tile.written.end(), U4{{0, 0, 0, 0}});
     uint32_t n = tile.packets_opaque.len();
     for (uint32_t i = 0; i < n; i++) {
         RasterPacket packet = tile.packets_opaque.get(i);
@@ -1033,9 +1044,10 @@ static void bin_triangle(Oracle &o, const Vertex tri[3], uint32_t mesh_index, ui
         }
     }
     if (opaque) {  // the reported counters describe the opaque pass (what the BASELINE configs exercise)
-        if (any) o.stats.tris_binned.fetch_add(1, std::memory_order_relaxed);
-        o.stats.packets.fetch_add(npk, std::memory_order_relaxed);
-        o.stats.packets_dup.fetch_add(ndup, std::memory_order_relaxed);
+        ThreadStats &ts = o.tstats[omp_get_thread_num()];
+        ts.tris_binned += any ? 1 : 0;
+        ts.packets += npk;
+        ts.packets_dup += ndup;
     }
 }
 
@@ -1096,7 +1108,7 @@ static void clip_against_frustum(Oracle &o, const Vertex tri[3], uint32_t mesh_i
         n = m;
     }
     if (n < 3) return;
-    if (touched && opaque) o.stats.tris_clipped.fetch_add(1, std::memory_order_relaxed);
+    if (touched && opaque) o.tstats[omp_get_thread_num()].tris_clipped++;
     for (int i = 1; i < n - 1; i++) {
         Vertex t[3] = {poly[0], poly[i], poly[i + 1]};
         bin_triangle(o, t, mesh_index, primitive_index, seq_base + (uint32_t)(i - 1), opaque);
@@ -1227,6 +1239,12 @@ static void render_scene(Oracle &o, bool shade) {  // renderer.rs:201-220
             for (uint32_t t = bt.t0; t < bt.t1; t++) process_triangle(o, o.draws[bt.draw], t);
         }
     }
+    for (const ThreadStats &ts : o.tstats) {
+        o.stats.tris_binned += ts.tris_binned;
+        o.stats.tris_clipped += ts.tris_clipped;
+        o.stats.packets += ts.packets;
+        o.stats.packets_dup += ts.packets_dup;
+    }
     double t1 = now_ms();
     // rayon fan-out #3 (renderer.rs:216): one job per tile
 #pragma omp parallel for schedule(dynamic, 1) num_threads(o.nthreads > 1 ? o.nthreads : 1)
@@ -1294,14 +1312,13 @@ int orc_render(void *h, const swr_scene_desc *scene, const swr_camera *cam, int 
     o.scene = scene;
     o.cam = cam;
     o.nthreads = nthreads;
-    o.stats.tris_binned = 0;
-    o.stats.tris_clipped = 0;
-    o.stats.packets = 0;
-    o.stats.packets_dup = 0;
+    o.stats = Stats();
+    o.tstats.assign((size_t)std::min(std::max(std::max(nthreads, omp_get_max_threads()), 1), MAX_THREADS), ThreadStats());
+    const bool any_output = depth_bits || seq || bary1 || bary2 || color_rgb;
+    o.track_written = seq != nullptr;
     for (Tile *t : o.tiles) {
         t->packets_opaque.reset();
         t->packets_translucent.reset();
-        std::fill(t->written.begin(), t->written.end(), U4{{0, 0, 0, 0}});
         if (fresh) {
             std::fill(t->packet_index.begin(), t->packet_index.end(), U4{{0, 0, 0, 0}});
             std::fill(t->bary1.begin(), t->bary1.end(), splat(0.0f));
@@ -1312,6 +1329,7 @@ int orc_render(void *h, const swr_scene_desc *scene, const swr_camera *cam, int 
     for (size_t ti = 0; ti < o.tiles.size(); ti++) {
         Tile &t = *o.tiles[ti];
         if (tile_luminance) tile_luminance[ti] = t.center_luminance;
+        if (!any_output) continue;  // timed runs pass no output arrays: nothing to copy out
         for (int qy = 0; qy < TILE / 2; qy++)
             for (int qx = 0; qx < TILE / 2; qx++) {
                 size_t qi = (size_t)qy * (TILE / 2) + qx;

@@ -726,7 +726,21 @@ struct TileBatch {
     uint32_t zmin_hi[RASTER_THREADS];  // orderable lower bound of every fragment depth of the packet (0 = unknown)
     uint16_t prefix[RASTER_THREADS + 2];  // item prefix (<= 256 * 165 items per batch)
     uint32_t wsum[RASTER_WARPS];
+    // Hierarchical Z: per 8x8-pixel block of the tile, an upper bound of the orderable depth (key high word) of its 64
+    // pixels. Keys only ever decrease, so a stale value stays an upper bound; refreshed once per batch.
+    uint32_t zmax[64];
 };
+
+// Shared-memory key layout: pixel (x, y) of the tile lives at y * 64 + (x ^ swz(y)), swz(y) = ((y >> 1) & 7) << 1.
+// Lanes of a warp walk different quad rows at the same x; without the swizzle their key addresses differ by multiples
+// of 1 KiB and all hit one bank. The XOR is even, so the two pixels of a quad row stay an aligned 16-byte pair.
+__device__ __forceinline__ int key_swz(int y) { return ((y >> 1) & 7) << 1; }
+__device__ __forceinline__ int key_index(int x, int y) { return y * SWR_TILE + (x ^ key_swz(y)); }
+__device__ __forceinline__ uint4 lds_volatile_v4(const void *p) {
+    uint4 v;
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
 
 // Per-warp queue of covered pixels waiting for the depth computation: coverage is found by lanes walking different
 // quad rows (divergent by nature); the expensive part — perspective depth, 64-bit min — then runs up to 32 wide.
@@ -838,8 +852,10 @@ __device__ __forceinline__ int drain_queue(const RP &P, unsigned long long *skey
 struct RowState {
     float v[4][3];
     float step[3];
-    int len;  // quads in the row
-    int pix;  // tile pixel index of lane 0 of the current quad
+    int len;   // quads in the row
+    int ybase; // (tile-local y of the quad's upper row) * 64
+    int x;     // tile-local x of lane 0 of the current quad (even)
+    int swz;   // key_swz(y): the same for both rows of a quad
     int pk;
     uint32_t zmin_hi;
 };
@@ -871,7 +887,21 @@ __device__ __forceinline__ void row_setup(const TileBatch &tb, int pk, uint32_t 
         c[e] = tb.c[e][pk];
         st.step[e] = i2f(wmul(a[e], 32));
     }
-    st.pix = (yq + qy) * 2 * SWR_TILE + (xq + qx0) * 2;
+    st.ybase = (yq + qy) * 2 * SWR_TILE;
+    st.x = (xq + qx0) * 2;
+    st.swz = key_swz((yq + qy) * 2);
+    {
+        // hierarchical Z: the row lies in one band of 8x8 blocks and touches at most three of them
+        const int by = ((yq + qy) * 2) >> 3, bx0 = st.x >> 3, bx1 = (st.x + st.len * 2 - 1) >> 3;
+        const volatile uint32_t *zm = tb.zmax + by * 8;
+        uint32_t zmx = zm[bx0];
+        if (bx1 > bx0) zmx = max(zmx, zm[bx0 + 1]);
+        if (bx1 > bx0 + 1) zmx = max(zmx, zm[bx1]);
+        if (st.zmin_hi > zmx) {  // every pixel of the row already holds something nearer than the packet can produce
+            st.len = 0;
+            return;
+        }
+    }
     if (exact) {
         // integer edge functions at the pixel centres of the first quad (== the f32 chain values, all exact)
         const int sx = xs + qx0 * 32 + 8, sy = ys + qy * 32 + 8;
@@ -960,6 +990,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
     const uint32_t unit_refs = P.tile_unit[tile];
     const bool split = tile_end - tile_beg > unit_refs;  // several CTAs share this tile: merge with atomics at the end
     for (int i = tid; i < SWR_TILE_PIXELS; i += RASTER_THREADS) skeys[i] = SWR_KEY_EMPTY;
+    if (tid < 64) tb.zmax[tid] = 0xFFFFFFFFu;
 #ifdef SWR_PROFILE_COUNTERS
     const long long dbg_t0 = clock64();
     unsigned long long dbg_items = 0;
@@ -980,6 +1011,19 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
     if (beg + RASTER_THREADS + tid < end) slot_next2 = __ldg(P.refs + beg + RASTER_THREADS + tid);
     for (uint32_t base = beg; base < end; base += RASTER_THREADS) {
         __syncthreads();  // previous batch fully consumed (and key init done)
+        if (base != beg) {
+            // Hi-Z refresh: warp w takes blocks 8w..8w+7 (one band), two pixels per lane. Nobody writes keys until the item
+            // phase, and readers of zmax in the packet phase below may see the old or the new value: both are upper bounds.
+#pragma unroll
+            for (int bb = 0; bb < 8; bb++) {
+                const int bx = bb, by = wid;
+                const int x = bx * 8 + (lane & 7), y0 = by * 8 + (lane >> 3);
+                const uint32_t h0 = reinterpret_cast<const uint32_t *>(skeys)[2 * key_index(x, y0) + 1];
+                const uint32_t h1 = reinterpret_cast<const uint32_t *>(skeys)[2 * key_index(x, y0 + 4) + 1];
+                const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, max(h0, h1));
+                if (lane == 0) tb.zmax[by * 8 + bx] = m;
+            }
+        }
         const uint32_t ri = base + tid;
         uint32_t nitems = 0;
         const uint32_t slot = slot_next;
@@ -1033,6 +1077,15 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
                     if (lo == lo && fabsf(lo) < 3.0e38f) zhi = depth_orderable(lo);
                 }
                 tb.zmin_hi[tid] = zhi;
+                // Hi-Z at packet level: a packet whose region touches at most 2x2 blocks and whose depth lower bound is behind
+                // all of them produces no fragment that could win: it contributes no items at all.
+                const int rx0 = (ps.xs >> 4) - tile_x0, ry0 = (ps.ys >> 4) - tile_y0;
+                const int bx0 = rx0 >> 3, bx1 = (rx0 + ps.nqx * 2 - 1) >> 3, by0 = ry0 >> 3, by1 = (ry0 + ps.nqy * 2 - 1) >> 3;
+                if (zhi != 0u && bx1 - bx0 <= 1 && by1 - by0 <= 1) {
+                    const volatile uint32_t *zm = tb.zmax;
+                    const uint32_t zmx = max(max(zm[by0 * 8 + bx0], zm[by0 * 8 + bx1]), max(zm[by1 * 8 + bx0], zm[by1 * 8 + bx1]));
+                    if (zhi > zmx) nitems = 0;
+                }
             }
         }
         // CTA-wide exclusive prefix of item counts
@@ -1064,8 +1117,11 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
             const uint32_t it = it0 + lane;
             RowState st;
             st.len = 0;
-            st.pix = 0;
+            st.ybase = 0;
+            st.x = 0;
+            st.swz = 0;
             st.pk = 0;
+            st.zmin_hi = 0;
             if (it < total) {
                 int lo = 0, hi = RASTER_THREADS;
 #pragma unroll
@@ -1084,32 +1140,50 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
             if (lane == 0) dbg_maxsteps += maxlen;
 #endif
             for (int s = 0; s < maxlen; s++) {
-                const bool act = s < st.len;
+                // coverage of the quad's four pixels: all three edge values >= 0. The chain values are sums and products of
+                // finite integers-as-floats with positive coordinates: never NaN, never -0, so ">= 0" is "sign bit clear".
+                uint32_t m4 = 0;
+                if (s < st.len) {
 #pragma unroll
-                for (int l = 0; l < 4; l++) {
-                    bool cov = act && st.v[l][0] >= 0.0f && st.v[l][1] >= 0.0f && st.v[l][2] >= 0.0f;
+                    for (int l = 0; l < 4; l++) {
+                        const uint32_t sg = __float_as_uint(st.v[l][0]) | __float_as_uint(st.v[l][1]) | __float_as_uint(st.v[l][2]);
+                        m4 |= ((sg >> 31) ^ 1u) << l;
+                    }
+                }
+                const int phys = st.ybase + (st.x ^ st.swz);  // key index of lane 0; lane 1 = +1, lanes 2,3 = +64
+                if (m4) {
                     // early-Z: the packet's depth lower bound is already behind what the pixel holds -> it cannot win
-                    if (cov) cov = st.zmin_hi <= reinterpret_cast<volatile uint32_t *>(skeys)[2 * (st.pix + (l & 1) + (l >> 1) * SWR_TILE) + 1];
-                    const unsigned m = __ballot_sync(0xFFFFFFFFu, cov);
-                    if (m) {
-                        if (cov) {
-                            const int pos = qn + __popc(m & lt_mask);
-                            fq.pkpix[pos] = ((uint32_t)st.pk << 16) | (uint32_t)(st.pix + (l & 1) + (l >> 1) * SWR_TILE);
-                            fq.w1[pos] = st.v[l][1];
-                            fq.w2[pos] = st.v[l][2];
-                        }
-                        qn += __popc(m);
+                    const uint4 k0 = lds_volatile_v4(skeys + phys), k1 = lds_volatile_v4(skeys + phys + SWR_TILE);
+                    if (st.zmin_hi > k0.y) m4 &= ~1u;
+                    if (st.zmin_hi > k0.w) m4 &= ~2u;
+                    if (st.zmin_hi > k1.y) m4 &= ~4u;
+                    if (st.zmin_hi > k1.w) m4 &= ~8u;
+                }
+                if (__any_sync(0xFFFFFFFFu, m4 != 0u)) {
+#pragma unroll
+                    for (int l = 0; l < 4; l++) {
+                        const bool cov = (m4 >> l) & 1u;
+                        const unsigned m = __ballot_sync(0xFFFFFFFFu, cov);
+                        if (m) {
+                            if (cov) {
+                                const int pos = qn + __popc(m & lt_mask);
+                                fq.pkpix[pos] = ((uint32_t)st.pk << 16) | (uint32_t)(phys + (l & 1) + (l >> 1) * SWR_TILE);
+                                fq.w1[pos] = st.v[l][1];
+                                fq.w2[pos] = st.v[l][2];
+                            }
+                            qn += __popc(m);
 #ifdef SWR_PROFILE_COUNTERS
-                        if (lane == 0) dbg_frags += __popc(m);
+                            if (lane == 0) dbg_frags += __popc(m);
 #endif
-                        if (qn >= FRAGQ_DRAIN) qn = drain_queue(P, skeys, tb, fq, qn, lane);
+                            if (qn >= FRAGQ_DRAIN) qn = drain_queue(P, skeys, tb, fq, qn, lane);
+                        }
                     }
                 }
 #pragma unroll
                 for (int l = 0; l < 4; l++)
 #pragma unroll
                     for (int e = 0; e < 3; e++) st.v[l][e] = fadd(st.v[l][e], st.step[e]);  // one quad to the right
-                st.pix += 2;
+                st.x += 2;
             }
         }
         while (qn > 0) qn = drain_queue(P, skeys, tb, fq, qn, lane);  // fragments reference this batch's packets
@@ -1124,10 +1198,10 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
     __syncthreads();
     unsigned long long *out = P.keys + (size_t)tile * SWR_TILE_PIXELS;
     if (!split) {
-        for (int i = tid; i < SWR_TILE_PIXELS; i += RASTER_THREADS) out[i] = skeys[i];
+        for (int i = tid; i < SWR_TILE_PIXELS; i += RASTER_THREADS) out[i] = skeys[key_index(i & (SWR_TILE - 1), i >> 6)];
     } else {  // the key buffer was reset to EMPTY before the launch
         for (int i = tid; i < SWR_TILE_PIXELS; i += RASTER_THREADS) {
-            const unsigned long long k = skeys[i];
+            const unsigned long long k = skeys[key_index(i & (SWR_TILE - 1), i >> 6)];
             if (k != SWR_KEY_EMPTY) atomicMin(&out[i], k);
         }
     }
