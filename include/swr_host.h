@@ -26,6 +26,9 @@ swr_ctx *swrh_renderer_ctx(void *renderer); /* the device context underneath, fo
  * the host and enqueues the frame. shade = 0 stops after the visibility buffer; shard / nshards select every nshards-th
  * draw (sort-last), 0 / 1 for everything. */
 int swrh_render_scene(void *renderer, const swr_scene_desc *scene, const swr_camera *camera, int shade, int shard, int nshards);
+/* The scene upload is cached by descriptor address (the reference's Scene is immutable, scene.rs:65-77). Call this when
+ * the same address now describes a different scene: the next swrh_render_scene uploads again. */
+int swrh_invalidate_scene(void *renderer);
 /* Renderer::update_auto_exposure(delta_time) (renderer.rs:258) and the exposure blit_to_buffer applies */
 int swrh_update_auto_exposure(void *renderer, float delta_time);
 float swrh_auto_exposure(void *renderer);

@@ -52,7 +52,10 @@ struct Staging {  // pinned host mirror of the per-frame draw table, rotated so 
 // translucent ones (forward-shaded afterwards, tilerasterizer.rs:92-101).
 struct GeomSet {
     DevBuf<DevDraw> draws;
-    DevBuf<uint32_t> tri_prefix, cl_prefix;
+    DevBuf<uint32_t> tri_prefix;  // ndraws + 1 triangle prefix, then ndraws + 1 cluster prefix
+    // second copy of both tables: frame N+1's tables are uploaded (on the upload stream) while frame N's kernels still read theirs
+    DevBuf<DevDraw> draws_alt;
+    DevBuf<uint32_t> tri_prefix_alt;
     DevBuf<uint32_t> cull;  // k_cull output: keep mask, per-block counts and offsets, draw of every cluster
     DevBuf<uint2> work;     // k_compact output: surviving (draw, cluster) pairs in submission order
     DevBuf<TriRecord> records;
@@ -64,7 +67,7 @@ struct GeomSet {
     DevBuf<uint32_t> tile_count, tile_offset, tile_cursor;
     DevBuf<uint32_t> refs;
     DevBuf<FrameCounters> counters;
-    FrameCounters *h_counters = nullptr;  // pinned
+    FrameCounters *h_counters = nullptr;  // where this frame's counters are copied: the current FrameSlot's pinned block (not owned)
     Staging staging[4];
     int staging_next = 0;
     std::vector<swr_draw> last_draws;
@@ -76,13 +79,37 @@ struct GeomSet {
     bool rendered_once = false;
 };
 
+// Two frames may be in flight on the stream: the host enqueues frame N+1 while frame N still runs, and a frame's device
+// counters (buffer overflow flags, statistics) are only looked at when somebody needs that frame — the next-but-one
+// swr_render, swr_wait_pixels, or any synchronising call. A slot keeps what a replay needs if a buffer turned out too small.
+#define SWR_FRAMES_IN_FLIGHT 2
+struct FrameSlot {
+    bool pending = false;
+    std::vector<swr_draw> op_draws, tr_draws;
+    swr_camera cam{};
+    int shade = 0;
+    bool tr_ran = false;      // the translucent geometry pass was launched (its counters are valid)
+    int resolve_kind = 0;     // queued behind the frame: 0 nothing, 1 device-only resolve, 2 resolve + read-back (swr_resolve_async)
+    int resolve_idx = 0;
+    float resolve_exposure = 0.0f;
+    uint32_t *resolve_host = nullptr;
+    FrameCounters *h_op = nullptr, *h_tr = nullptr;  // pinned
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // phase timing: begin, geometry done, raster done, shade done
+    cudaEvent_t done = nullptr;                                // both counter blocks are on the host
+    uint32_t total_tris = 0, clusters = 0;
+    uint64_t total_verts = 0;
+};
+
 struct swr_ctx {
     int device = 0;
     int num_sms = 148;
     int W = 0, H = 0, tiles_x = 0, tiles_y = 0, ntiles = 0;
     int row_begin = 0, row_end = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t upload_stream = nullptr;  // per-frame draw tables: issued at enqueue time, ahead of the frame that needs them
+    FrameSlot slots[SWR_FRAMES_IN_FLIGHT];
+    int slot_head = 0, slots_pending = 0;  // ring: oldest pending slot, number pending
+    FrameSlot *cur = nullptr;              // slot of the frame being (or last) enqueued
     cudaEvent_t ev_res[2] = {nullptr, nullptr};
     std::string err;
 
@@ -106,12 +133,6 @@ struct swr_ctx {
     cudaEvent_t ev_resolved[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     bool copy_pending[2] = {false, false};
     int pix_cur = 0;
-    struct {
-        bool valid = false;
-        int idx = 0;
-        float exposure = 0.0f;
-        uint32_t *host = nullptr;
-    } last_async;
     DevBuf<float> lum;
     DevBuf<float2> bary;
     bool composited = false;
@@ -120,12 +141,7 @@ struct swr_ctx {
     DevBuf<uint32_t> rsqrt_tab;
     int rsqrt_bits = 0;
     bool rsqrt_on = false;
-    DevBuf<unsigned long long> tsort_keys;  // translucent pass: per-tile sorted (avg_z desc, seq) keys
-    DevBuf<uint32_t> tsort_ids;
-    // replay info
     swr_camera last_cam{};
-    int last_shade = 0;
-    bool frame_pending = false;
     // peer frame assembly (swr_peer_*): mapping of the assembling rank's pixel buffer + local bookkeeping
     uint32_t *peer_pixels = nullptr;   // assembler's pixels as seen from this context (own buffer on the assembler)
     void *peer_ipc_base = nullptr;     // non-null when opened through an IPC handle (closed on destroy)
@@ -203,11 +219,16 @@ swr_ctx *swr_create(int width, int height, int device) {
         delete ctx;
         return nullptr;
     }
-    bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; ok && i < 5; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (FrameSlot &f : ctx->slots) {
+        for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&f.ev[i]) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaMallocHost(&f.h_op, sizeof(FrameCounters)) == cudaSuccess && cudaMallocHost(&f.h_tr, sizeof(FrameCounters)) == cudaSuccess;
+    }
+    ctx->cur = &ctx->slots[0];
     for (int i = 0; ok && i < 2; i++) ok = cudaEventCreate(&ctx->ev_res[i]) == cudaSuccess;
     for (int i = 0; ok && i < 4; i++) ok = cudaEventCreateWithFlags(&ctx->op.staging[i].done, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaMallocHost(&ctx->op.h_counters, sizeof(FrameCounters)) == cudaSuccess;
     ok = ok && ctx->op.tile_count.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->op.tile_offset.reserve(ctx->ntiles + 1) == cudaSuccess &&
          ctx->op.tile_cursor.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_cycles.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_cycles_prev.reserve(ctx->ntiles + 1) == cudaSuccess &&
          ctx->tile_count_prev.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_unit.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->unit_list.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->keys.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess &&
@@ -246,6 +267,8 @@ void swr_destroy(swr_ctx *ctx) {
     for (GeomSet *g : {&ctx->op, &ctx->tr}) {
         g->draws.release();
         g->tri_prefix.release();
+        g->draws_alt.release();
+        g->tri_prefix_alt.release();
         g->cull.release();
         g->work.release();
         g->records.release();
@@ -260,7 +283,6 @@ void swr_destroy(swr_ctx *ctx) {
         g->tile_cursor.release();
         g->refs.release();
         g->counters.release();
-        if (g->h_counters) cudaFreeHost(g->h_counters);
         for (auto &st : g->staging) {
             if (st.host) cudaFreeHost(st.host);
             if (st.done) cudaEventDestroy(st.done);
@@ -286,10 +308,16 @@ void swr_destroy(swr_ctx *ctx) {
     ctx->bary.release();
     ctx->rsqrt_tab.release();
     ctx->dbg_tiles.release();
-    for (auto &e : ctx->ev)
-        if (e) cudaEventDestroy(e);
+    for (FrameSlot &f : ctx->slots) {
+        for (auto &e : f.ev)
+            if (e) cudaEventDestroy(e);
+        if (f.done) cudaEventDestroy(f.done);
+        if (f.h_op) cudaFreeHost(f.h_op);
+        if (f.h_tr) cudaFreeHost(f.h_tr);
+    }
     for (auto &e : ctx->ev_res)
         if (e) cudaEventDestroy(e);
+    if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -485,6 +513,7 @@ int swr_upload_scene(swr_ctx *ctx, const swr_scene_desc *s) {
         sc.gdim[k] = g.dims[k];
         sc.gmin[k] = g.world_min[k];
         sc.gmax[k] = g.world_max[k];
+        sc.gvs[k] = (g.world_max[k] - g.world_min[k]) / (float)g.dims[k];  // one IEEE f32 divide, the same on host and device
         sc.light_dir[k] = s->light_direction[k];
         sc.light_color[k] = s->light_color[k];
     }
@@ -500,6 +529,10 @@ int swr_upload_scene(swr_ctx *ctx, const swr_scene_desc *s) {
 static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
     const std::vector<swr_draw> &draws = g.last_draws;
     const uint32_t nd = (uint32_t)draws.size();
+    // the previous frame may still be reading its draw table: this frame gets the other copy (the frame before that has
+    // been settled, shading included, before this one is enqueued)
+    std::swap(g.draws, g.draws_alt);
+    std::swap(g.tri_prefix, g.tri_prefix_alt);
     size_t bytes = (size_t)nd * sizeof(DevDraw) + 2 * (size_t)(nd + 1) * sizeof(uint32_t);
     Staging &st = g.staging[g.staging_next];
     g.staging_next = (g.staging_next + 1) & 3;
@@ -559,7 +592,6 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
               g.rects.reserve(slots + 1) == cudaSuccess && g.tile_count.reserve(ctx->ntiles + 1) == cudaSuccess &&
               g.tile_offset.reserve(ctx->ntiles + 1) == cudaSuccess && g.tile_cursor.reserve(ctx->ntiles + 1) == cudaSuccess &&
               g.counters.reserve(1) == cudaSuccess && (!translucent || g.avgz.reserve(slots + 1) == cudaSuccess);
-    if (ok && !g.h_counters) ok = cudaMallocHost(&g.h_counters, sizeof(FrameCounters)) == cudaSuccess;
     if (!ok) {
         ctx->err = "out of device memory for per-frame triangle records";
         return SWR_ERR_OOM;
@@ -581,9 +613,12 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
         return SWR_ERR_OOM;
 
     cudaStream_t s = ctx->stream;
-    if (nd) CK(cudaMemcpyAsync(g.draws.p, hd, (size_t)nd * sizeof(DevDraw), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(g.tri_prefix.p, hp, 2 * (size_t)(nd + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    CK(cudaEventRecord(st.done, s));
+    // Upload on its own stream, now: the frame in front is still running and the PCIe link is quiet. Issued in stream
+    // order behind that frame it would share the link with the frame's 33 MB read-back and take ~0.1 ms instead of ~10 us.
+    if (nd) CK(cudaMemcpyAsync(g.draws.p, hd, (size_t)nd * sizeof(DevDraw), cudaMemcpyHostToDevice, ctx->upload_stream));
+    CK(cudaMemcpyAsync(g.tri_prefix.p, hp, 2 * (size_t)(nd + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->upload_stream));
+    CK(cudaEventRecord(st.done, ctx->upload_stream));
+    CK(cudaStreamWaitEvent(s, st.done, 0));
     CK(cudaMemsetAsync(g.tile_count.p, 0, (ctx->ntiles + 1) * sizeof(uint32_t), s));
     CK(cudaMemsetAsync(g.counters.p, 0, sizeof(FrameCounters), s));
 
@@ -665,7 +700,7 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
 static int launch_frame(swr_ctx *ctx) {
     cudaStream_t s = ctx->stream;
     GeomSet &g = ctx->op;
-    CK(cudaEventRecord(ctx->ev[0], s));
+    CK(cudaEventRecord(ctx->cur->ev[0], s));
     // raster cycles of the previous frame become the history that sizes this frame's work units
     std::swap(ctx->tile_cycles.p, ctx->tile_cycles_prev.p);
     CK(cudaMemsetAsync(ctx->tile_cycles.p, 0, (ctx->ntiles + 1) * sizeof(uint32_t), s));
@@ -673,7 +708,7 @@ static int launch_frame(swr_ctx *ctx) {
     if (rc) return rc;
     const int rb = ctx->row_begin, re = ctx->row_end;
     const uint32_t cta_slots = (uint32_t)ctx->num_sms * 4u;
-    CK(cudaEventRecord(ctx->ev[1], s));
+    CK(cudaEventRecord(ctx->cur->ev[1], s));
     if (re > rb) {
         RasterParams rp{};
         rp.records = g.records.p;
@@ -703,7 +738,7 @@ static int launch_frame(swr_ctx *ctx) {
         CK(cudaMemsetAsync(ctx->keys.p + (size_t)rb * ctx->tiles_x * SWR_TILE_PIXELS, 0xFF, (size_t)(re - rb) * ctx->tiles_x * SWR_TILE_PIXELS * 8, s));
         k_raster_tiles<<<cta_slots, RASTER_THREADS, raster_smem_bytes(), s>>>(rp);  // persistent: one CTA per resident slot
     }
-    CK(cudaEventRecord(ctx->ev[2], s));
+    CK(cudaEventRecord(ctx->cur->ev[2], s));
     CK(cudaMemcpyAsync(g.h_counters, g.counters.p, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
     CK(cudaGetLastError());
     return SWR_OK;
@@ -753,11 +788,12 @@ static int launch_shade(swr_ctx *ctx) {
             fp.counters = t.counters.p;
             k_forward_translucent<<<grid, SHADE_BLOCK, 0, s>>>(fp);
             CK(cudaMemcpyAsync(t.h_counters, t.counters.p, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
+            ctx->cur->tr_ran = true;
         }
         const int t0 = rb * ctx->tiles_x, t1 = re * ctx->tiles_x;
         k_luminance<<<(t1 - t0 + 127) / 128, 128, 0, s>>>(ctx->color.p, ctx->lum.p, sp.Wp, sp.Hp, ctx->tiles_x, ctx->ntiles, t0, t1);
     }
-    CK(cudaEventRecord(ctx->ev[3], s));
+    CK(cudaEventRecord(ctx->cur->ev[3], s));
     CK(cudaGetLastError());
     return SWR_OK;
 }
@@ -772,29 +808,66 @@ static void set_camera(swr_ctx *ctx, const swr_camera *cam) {
 
 static int issue_resolve_copy(swr_ctx *ctx, int idx, float exposure, uint32_t *host);
 
-// Synchronise, and if a device-side buffer overflowed grow it and replay the frame.
-static int finish_frame(swr_ctx *ctx) {
-    CK(cudaSetDevice(ctx->device));
+static int resolve_into(swr_ctx *ctx, uint32_t *dst, float exposure);
+
+// Enqueue (or re-enqueue) everything a slot describes: opaque pass, shading, and the resolve that was queued behind it.
+static int enqueue_slot(swr_ctx *ctx, FrameSlot &f) {
+    ctx->cur = &f;
+    ctx->op.h_counters = f.h_op;
+    ctx->tr.h_counters = f.h_tr;
+    ctx->op.last_draws = f.op_draws;
+    ctx->tr.last_draws = f.tr_draws;
+    set_camera(ctx, &f.cam);
+    f.tr_ran = false;
+    int rc;
+    if ((rc = launch_frame(ctx))) return rc;
+    if (f.shade && (rc = launch_shade(ctx))) return rc;
+    f.total_tris = ctx->op.total_tris;
+    f.total_verts = ctx->op.total_verts;
+    f.clusters = ctx->op.clusters;
+    CK(cudaEventRecord(f.done, ctx->stream));
+    if (f.resolve_kind == 1) return resolve_into(ctx, f.resolve_idx ? ctx->pixels_alt.p : ctx->pixels.p, f.resolve_exposure);
+    if (f.resolve_kind == 2) return issue_resolve_copy(ctx, f.resolve_idx, f.resolve_exposure, f.resolve_host);
+    return SWR_OK;
+}
+
+static bool overflowed(const FrameSlot &f) {
+    const FrameCounters &c = *f.h_op;
+    if (c.overflow_refs || c.overflow_clip || c.overflow_ext) return true;
+    if (f.tr_ran) {
+        const FrameCounters &t = *f.h_tr;
+        if (t.overflow_refs || t.overflow_clip || t.overflow_ext) return true;
+    }
+    return false;
+}
+
+// Wait for the OLDEST pending frame's counters. Fine -> publish its statistics. A buffer was too small -> drain the stream,
+// grow the buffers and re-enqueue every pending frame in order (their resolves included), then look again.
+static int settle_oldest(swr_ctx *ctx) {
     for (int attempt = 0; attempt < 4; attempt++) {
-        CK(cudaStreamSynchronize(ctx->stream));
-        if (!ctx->frame_pending) return SWR_OK;
-        const FrameCounters c = *ctx->op.h_counters;
+        if (ctx->slots_pending == 0) return SWR_OK;
+        FrameSlot &f = ctx->slots[ctx->slot_head];
+        CK(cudaEventSynchronize(f.done));
+        const FrameCounters c = *f.h_op;
         FrameCounters ct{};
-        const bool tr_ran = ctx->last_shade && !ctx->tr.last_draws.empty() && ctx->tr.h_counters;
-        if (tr_ran) ct = *ctx->tr.h_counters;
+        if (f.tr_ran) ct = *f.h_tr;
         if (ct.overflow_sort) {
             ctx->err = "a tile holds more than 4096 translucent triangles: the in-kernel back-to-front sort does not support that";
-            ctx->frame_pending = false;
+            f.pending = false;
+            ctx->slot_head = (ctx->slot_head + 1) % SWR_FRAMES_IN_FLIGHT;
+            ctx->slots_pending--;
             return SWR_ERR_INVALID;
         }
-        if (!c.overflow_refs && !c.overflow_clip && !c.overflow_ext && !ct.overflow_refs && !ct.overflow_clip && !ct.overflow_ext) {
-            ctx->tr.rendered_once = ctx->tr.rendered_once || tr_ran;
-            ctx->frame_pending = false;
+        if (!overflowed(f)) {
+            f.pending = false;
+            ctx->slot_head = (ctx->slot_head + 1) % SWR_FRAMES_IN_FLIGHT;
+            ctx->slots_pending--;
+            ctx->tr.rendered_once = ctx->tr.rendered_once || f.tr_ran;
             ctx->frame_valid = true;
             ctx->op.rendered_once = true;
             swr_frame_stats &st = ctx->stats;
-            st.triangles_submitted = ctx->op.total_tris;
-            st.vertices_submitted = ctx->op.total_verts;
+            st.triangles_submitted = f.total_tris;
+            st.vertices_submitted = f.total_verts;
             uint64_t binned = 0, uncovered = 0;
             for (int k = 0; k < 32; k++) {
                 binned += c.tris_binned[k];
@@ -805,9 +878,9 @@ static int finish_frame(swr_ctx *ctx) {
             st.tile_refs = c.tile_refs + uncovered;  // the reference's R: every (triangle, tile) packet it would push
             ctx->op.refs_emitted = c.tile_refs;
             st.tiles = (uint32_t)ctx->ntiles;
-            st.clusters_culled = ctx->op.clusters - c.work_n;
+            st.clusters_culled = f.clusters - c.work_n;
             ctx->op.work_hint = c.work_n;
-            if (tr_ran) ctx->tr.work_hint = ct.work_n;
+            if (f.tr_ran) ctx->tr.work_hint = ct.work_n;
 #ifdef SWR_PROFILE_COUNTERS
             if (ctx->dbg_tiles.p) {
                 const int nu = c.raster_units < 8192 ? (int)c.raster_units : 8192;
@@ -831,41 +904,57 @@ static int finish_frame(swr_ctx *ctx) {
             }
             fprintf(stderr, "[swr dbg] items %llu batches %llu quad-steps %llu fragments %llu warp-iters %llu\n", c.dbg[0], c.dbg[1], c.dbg[2], c.dbg[3], c.dbg[4]);
 #endif
-            cudaEventElapsedTime(&st.ms_setup_bin, ctx->ev[0], ctx->ev[1]);
-            cudaEventElapsedTime(&st.ms_raster, ctx->ev[1], ctx->ev[2]);
+            cudaEventElapsedTime(&st.ms_setup_bin, f.ev[0], f.ev[1]);
+            cudaEventElapsedTime(&st.ms_raster, f.ev[1], f.ev[2]);
             st.ms_shade = 0.0f;
-            if (ctx->last_shade) cudaEventElapsedTime(&st.ms_shade, ctx->ev[2], ctx->ev[3]);
+            if (f.shade) cudaEventElapsedTime(&st.ms_shade, f.ev[2], f.ev[3]);
             return SWR_OK;
         }
-        struct Grow {
-            GeomSet *g;
-            const FrameCounters *c;
-        } grow[2] = {{&ctx->op, &c}, {&ctx->tr, &ct}};
-        for (const Grow &gw : grow) {
-            if (gw.c->overflow_refs) {
-                size_t want = (size_t)gw.c->tile_refs + (size_t)gw.c->tile_refs / 4 + 4096;
-                if (gw.g->refs.reserve(want) != cudaSuccess) {
-                    ctx->err = "out of device memory growing tile lists";
-                    return SWR_ERR_OOM;
+        // growth: nothing may be in flight while buffers are reallocated
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
+        for (int k = 0; k < ctx->slots_pending; k++) {
+            const FrameSlot &g = ctx->slots[(ctx->slot_head + k) % SWR_FRAMES_IN_FLIGHT];
+            struct Grow {
+                GeomSet *g;
+                const FrameCounters *c;
+            } grow[2] = {{&ctx->op, g.h_op}, {&ctx->tr, g.tr_ran ? g.h_tr : nullptr}};
+            for (const Grow &gw : grow) {
+                if (!gw.c) continue;
+                if (gw.c->overflow_refs) {
+                    size_t want = (size_t)gw.c->tile_refs + (size_t)gw.c->tile_refs / 4 + 4096;
+                    if (gw.g->refs.reserve(want) != cudaSuccess) {
+                        ctx->err = "out of device memory growing tile lists";
+                        return SWR_ERR_OOM;
+                    }
                 }
-            }
-            if (gw.c->overflow_ext) gw.g->ext_cap = (size_t)gw.c->ext_records + (size_t)gw.c->ext_records / 4 + 4096;
-            if (gw.c->overflow_clip) {
-                size_t want = (size_t)gw.c->clip_verts + (size_t)gw.c->clip_verts / 4 + 4096;
-                if (gw.g->clip_verts.reserve(want) != cudaSuccess) {
-                    ctx->err = "out of device memory growing clip vertex buffer";
-                    return SWR_ERR_OOM;
+                if (gw.c->overflow_ext) gw.g->ext_cap = std::max(gw.g->ext_cap, (size_t)gw.c->ext_records + (size_t)gw.c->ext_records / 4 + 4096);
+                if (gw.c->overflow_clip) {
+                    size_t want = (size_t)gw.c->clip_verts + (size_t)gw.c->clip_verts / 4 + 4096;
+                    if (gw.g->clip_verts.reserve(want) != cudaSuccess) {
+                        ctx->err = "out of device memory growing clip vertex buffer";
+                        return SWR_ERR_OOM;
+                    }
                 }
             }
         }
-        int rc = launch_frame(ctx);
-        if (rc) return rc;
-        if (ctx->last_shade && (rc = launch_shade(ctx))) return rc;
-        // an asynchronous resolve + read-back was already queued behind the frame that just got replayed: redo it
-        if (ctx->last_async.valid && (rc = issue_resolve_copy(ctx, ctx->last_async.idx, ctx->last_async.exposure, ctx->last_async.host))) return rc;
+        for (int k = 0; k < ctx->slots_pending; k++) {
+            int rc = enqueue_slot(ctx, ctx->slots[(ctx->slot_head + k) % SWR_FRAMES_IN_FLIGHT]);
+            if (rc) return rc;
+        }
     }
     ctx->err = "frame did not fit after growing buffers";
     return SWR_ERR_OOM;
+}
+
+// Settle every pending frame and leave the stream idle.
+static int finish_frame(swr_ctx *ctx) {
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    while (ctx->slots_pending > 0)
+        if ((rc = settle_oldest(ctx))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SWR_OK;
 }
 
 int swr_render(swr_ctx *ctx, const swr_camera *camera, const swr_draw *draws, int ndraws, int shade) {
@@ -876,17 +965,19 @@ int swr_render(swr_ctx *ctx, const swr_camera *camera, const swr_draw *draws, in
     }
     CK(cudaSetDevice(ctx->device));
     int rc;
-    if (ctx->frame_pending && (rc = finish_frame(ctx))) return rc;  // settle a previous frame's growth before reusing buffers
-    ctx->last_async.valid = false;
-    ctx->op.last_draws.clear();
-    ctx->tr.last_draws.clear();
-    for (int i = 0; i < ndraws; i++) ((draws[i].flags & SWR_DRAW_TRANSLUCENT) ? ctx->tr : ctx->op).last_draws.push_back(draws[i]);
-    set_camera(ctx, camera);
-    ctx->last_shade = shade;
-    if ((rc = launch_frame(ctx))) return rc;
-    if (shade && (rc = launch_shade(ctx))) return rc;
-    ctx->frame_pending = true;
-    return SWR_OK;
+    // at most SWR_FRAMES_IN_FLIGHT frames are unsettled; until the first frame has sized the buffers, one at a time
+    while (ctx->slots_pending >= (ctx->op.rendered_once ? SWR_FRAMES_IN_FLIGHT : 1))
+        if ((rc = settle_oldest(ctx))) return rc;
+    FrameSlot &f = ctx->slots[(ctx->slot_head + ctx->slots_pending) % SWR_FRAMES_IN_FLIGHT];
+    f.op_draws.clear();
+    f.tr_draws.clear();
+    for (int i = 0; i < ndraws; i++) ((draws[i].flags & SWR_DRAW_TRANSLUCENT) ? f.tr_draws : f.op_draws).push_back(draws[i]);
+    f.cam = *camera;
+    f.shade = shade;
+    f.resolve_kind = 0;
+    f.pending = true;
+    ctx->slots_pending++;
+    return enqueue_slot(ctx, f);
 }
 
 int swr_shade(swr_ctx *ctx, const swr_camera *camera) {
@@ -896,8 +987,9 @@ int swr_shade(swr_ctx *ctx, const swr_camera *camera) {
     int rc;
     if ((rc = finish_frame(ctx))) return rc;
     set_camera(ctx, camera);
-    ctx->last_shade = 1;
-    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    ctx->cur->shade = 1;  // not pending any more: only its phase events and counter block are reused
+    ctx->tr.h_counters = ctx->cur->h_tr;
+    CK(cudaEventRecord(ctx->cur->ev[2], ctx->stream));
     return launch_shade(ctx);
 }
 
@@ -943,27 +1035,50 @@ void *swr_device_bary(swr_ctx *ctx) {
     return ctx->bary.p;
 }
 
-int swr_resolve(swr_ctx *ctx, float exposure, uint32_t *out_pixels) {
-    if (!ctx) return SWR_ERR_INVALID;
-    CK(cudaSetDevice(ctx->device));
-    int rc;
-    // a pending frame may still need a replay; only the synchronising form (host output) or an explicit
-    // swr_synchronize settles it, so the device-only form stays asynchronous.
-    if (out_pixels && (rc = finish_frame(ctx))) return rc;
+// k_resolve of the owned rows into `dst` on the main stream
+static int resolve_into(swr_ctx *ctx, uint32_t *dst, float exposure) {
     cudaStream_t s = ctx->stream;
     const size_t W = ctx->W;
     size_t y0 = (size_t)ctx->row_begin * SWR_TILE, y1 = (size_t)ctx->row_end * SWR_TILE;
     if (y1 > (size_t)ctx->H) y1 = ctx->H;
     CK(cudaEventRecord(ctx->ev_res[0], s));
     if (y1 > y0) {
+        const int idx = dst == ctx->pixels_alt.p ? 1 : 0;
         dim3 grid((unsigned)((W + 255) / 256), (unsigned)((y1 - y0 + 3) / 4));
-        if (ctx->copy_pending[ctx->pix_cur]) CK(cudaStreamWaitEvent(s, ctx->ev_copied[ctx->pix_cur], 0));
-        k_resolve<<<grid, 256, 0, s>>>(ctx->color.p, ctx->tiles_x * SWR_TILE, (uint32_t *)swr_device_pixels(ctx), ctx->W, (int)y0, (int)y1, exposure);
+        if (ctx->copy_pending[idx]) CK(cudaStreamWaitEvent(s, ctx->ev_copied[idx], 0));
+        k_resolve<<<grid, 256, 0, s>>>(ctx->color.p, ctx->tiles_x * SWR_TILE, dst, ctx->W, (int)y0, (int)y1, exposure);
     }
     CK(cudaEventRecord(ctx->ev_res[1], s));
     CK(cudaGetLastError());
+    return SWR_OK;
+}
+
+static FrameSlot *newest_pending(swr_ctx *ctx) {
+    return ctx->slots_pending ? &ctx->slots[(ctx->slot_head + ctx->slots_pending - 1) % SWR_FRAMES_IN_FLIGHT] : nullptr;
+}
+
+int swr_resolve(swr_ctx *ctx, float exposure, uint32_t *out_pixels) {
+    if (!ctx) return SWR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    // The host form settles the frame first (a buffer-growth replay must happen before pixels are handed out). The
+    // device-only form stays asynchronous: it is noted in the frame's slot so that a replay re-issues it.
+    if (out_pixels && (rc = finish_frame(ctx))) return rc;
+    uint32_t *dst = (uint32_t *)swr_device_pixels(ctx);
+    if (!out_pixels) {
+        if (FrameSlot *f = newest_pending(ctx)) {
+            f->resolve_kind = 1;
+            f->resolve_idx = ctx->pix_cur;
+            f->resolve_exposure = exposure;
+        }
+    }
+    if ((rc = resolve_into(ctx, dst, exposure))) return rc;
     if (out_pixels) {
-        if (y1 > y0) CK(cudaMemcpyAsync(out_pixels + y0 * W, (uint32_t *)swr_device_pixels(ctx) + y0 * W, (y1 - y0) * W * 4, cudaMemcpyDeviceToHost, s));
+        cudaStream_t s = ctx->stream;
+        const size_t W = ctx->W;
+        size_t y0 = (size_t)ctx->row_begin * SWR_TILE, y1 = (size_t)ctx->row_end * SWR_TILE;
+        if (y1 > (size_t)ctx->H) y1 = ctx->H;
+        if (y1 > y0) CK(cudaMemcpyAsync(out_pixels + y0 * W, dst + y0 * W, (y1 - y0) * W * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         cudaEventElapsedTime(&ctx->stats.ms_resolve, ctx->ev_res[0], ctx->ev_res[1]);
     }
@@ -1029,6 +1144,11 @@ int swr_resolve_peer(swr_ctx *ctx, float exposure, uint32_t frame) {
         return SWR_ERR_INVALID;
     }
     CK(cudaSetDevice(ctx->device));
+    // A contribution cannot be taken back once it is signalled, so the frame must be known good first: wait for its
+    // counters (one event wait, no full drain) and replay it here if a buffer had to grow.
+    int rc;
+    while (ctx->slots_pending > 0)
+        if ((rc = settle_oldest(ctx))) return rc;
     cudaStream_t s = ctx->stream;
     const size_t W = ctx->W;
     size_t y0 = (size_t)ctx->row_begin * SWR_TILE, y1 = (size_t)ctx->row_end * SWR_TILE;
@@ -1106,10 +1226,12 @@ int swr_resolve_async(swr_ctx *ctx, float exposure, uint32_t *out_pixels, int *t
     int rc = issue_resolve_copy(ctx, idx, exposure, out_pixels);
     if (rc) return rc;
     ctx->pix_cur = idx;
-    ctx->last_async.valid = true;
-    ctx->last_async.idx = idx;
-    ctx->last_async.exposure = exposure;
-    ctx->last_async.host = out_pixels;
+    if (FrameSlot *f = newest_pending(ctx)) {  // re-issued if the frame has to be replayed
+        f->resolve_kind = 2;
+        f->resolve_idx = idx;
+        f->resolve_exposure = exposure;
+        f->resolve_host = out_pixels;
+    }
     *ticket = idx;
     return SWR_OK;
 }
@@ -1118,8 +1240,17 @@ int swr_wait_pixels(swr_ctx *ctx, int ticket) {
     if (!ctx || ticket < 0 || ticket > 1) return SWR_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     int rc;
-    // the frame behind the newest ticket may still need a buffer-growth replay (which re-issues its resolve + copy)
-    if (ctx->frame_pending && ctx->last_async.valid && ctx->last_async.idx == ticket && (rc = finish_frame(ctx))) return rc;
+    // the frame behind this ticket may still need a buffer-growth replay (which re-issues its resolve + copy): settle the
+    // pending frames up to and including it, oldest first
+    for (;;) {
+        bool mine = false;
+        for (int k = 0; k < ctx->slots_pending; k++) {
+            const FrameSlot &f = ctx->slots[(ctx->slot_head + k) % SWR_FRAMES_IN_FLIGHT];
+            if (f.resolve_kind == 2 && f.resolve_idx == ticket) mine = true;
+        }
+        if (!mine) break;
+        if ((rc = settle_oldest(ctx))) return rc;
+    }
     if (ctx->copy_pending[ticket]) CK(cudaEventSynchronize(ctx->ev_copied[ticket]));
     return SWR_OK;
 }

@@ -86,6 +86,7 @@ struct DevScene {
     const float4 *gi;  // voxels x 4 coefficients
     uint32_t gdim[3];
     float gmin[3], gmax[3];
+    float gvs[3];  // voxel size (gmax - gmin) / gdim in f32, as VoxelGrid::new computes it (voxelgrid.rs:154-161)
     int cubemap, cubemap_specular, brdf_lut;
     float light_dir[3], light_color[3];
 };
@@ -284,6 +285,45 @@ __device__ __forceinline__ float frag_depth(const TriRecord &r, float w1, float 
     float wp = frcp(q);
     float zz = fadd(fadd(r.zw0, fmul(b1, zwda)), fmul(b2, zwdb));
     return fmul(zz, wp);
+}
+
+// Edge values w1, w2 of a pixel its packet is KNOWN to cover (the key's owner): same chain as eval_chain, but neither the
+// coarse reject nor edge 0 (both only decide coverage) is evaluated.
+__device__ __forceinline__ void eval_chain_owner(const PacketSetup &p, int qx, int qy, int lx, int ly, float &w1, float &w2) {
+    int bx = p.xs, by = p.ys, i = qx, j = qy;
+    if (p.coarse) {
+        bx = p.xs + (qx >> 3) * 256;
+        by = p.ys + (qy >> 3) * 256;
+        i = qx & 7;
+        j = qy & 7;
+    }
+    const float x = i2f(bx + 8 + 16 * lx), y = i2f(by + 8 + 16 * ly);
+    float v[2];
+#pragma unroll
+    for (int e = 1; e < 3; e++) {
+        float t = fadd(fadd(fmul(i2f(p.a[e]), x), fmul(i2f(p.b[e]), y)), i2f(p.c[e]));
+        const float sy = i2f(wmul(p.b[e], 32)), sx = i2f(wmul(p.a[e], 32));
+        for (int k = 0; k < j; k++) t = fadd(t, sy);
+        for (int k = 0; k < i; k++) t = fadd(t, sx);
+        v[e - 1] = t;
+    }
+    w1 = v[0];
+    w2 = v[1];
+}
+
+// Barycentrics and depth of a pixel for the record that owns its key (shading): no coverage re-test.
+__device__ __forceinline__ float resolve_owner(const TriRecord &r, int W, int H, int px, int py, float &b1, float &b2) {
+    PacketSetup p;
+    packet_setup(r, W, H, px & ~(SWR_TILE - 1), py & ~(SWR_TILE - 1), p);
+    float w1, w2;
+    if (p.exact) {
+        const int sx = px * 16 + 8, sy = py * 16 + 8;
+        w1 = i2f(p.a[1] * sx + p.b[1] * sy + p.c[1]);
+        w2 = i2f(p.a[2] * sx + p.b[2] * sy + p.c[2]);
+    } else {
+        eval_chain_owner(p, ((px & ~1) * 16 - p.xs) >> 5, ((py & ~1) * 16 - p.ys) >> 5, px & 1, py & 1, w1, w2);
+    }
+    return frag_depth(r, w1, w2, b1, b2);
 }
 
 // Full re-evaluation of one pixel against one record (used after the key buffer is final: shading and

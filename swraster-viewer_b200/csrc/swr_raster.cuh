@@ -744,8 +744,7 @@ __device__ __forceinline__ uint4 lds_volatile_v4(const void *p) {
 
 // Per-warp queue of covered pixels waiting for the depth computation: coverage is found by lanes walking different
 // quad rows (divergent by nature); the expensive part — perspective depth, 64-bit min — then runs up to 32 wide.
-#define FRAGQ_CAP 44
-#define FRAGQ_DRAIN 12
+#define FRAGQ_CAP 44  // a drain takes min(qn, 32) entries, leaving <= 12: the next plane of <= 32 fragments always fits
 struct FragQueue {
     uint32_t pkpix[FRAGQ_CAP];  // packet index in the batch << 16 | pixel index in the tile
     float w1[FRAGQ_CAP], w2[FRAGQ_CAP];
@@ -984,7 +983,8 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long unit_t0 = clock64();
     FragQueue &fq = fqs[wid];
-    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned lt_mask;  // one S2R when the compiler rematerialises it (it does, at 64 registers)
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
 
     const uint32_t tile_beg = P.tile_offset[tile], tile_end = P.tile_offset[tile + 1];
     const uint32_t unit_refs = P.tile_unit[tile];
@@ -1165,6 +1165,8 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
                         const bool cov = (m4 >> l) & 1u;
                         const unsigned m = __ballot_sync(0xFFFFFFFFu, cov);
                         if (m) {
+                            // lazy drain: only when this plane's fragments would not fit, so drains run (nearly) 32 wide
+                            if (qn + __popc(m) > FRAGQ_CAP) qn = drain_queue(P, skeys, tb, fq, qn, lane);
                             if (cov) {
                                 const int pos = qn + __popc(m & lt_mask);
                                 fq.pkpix[pos] = ((uint32_t)st.pk << 16) | (uint32_t)(phys + (l & 1) + (l >> 1) * SWR_TILE);
@@ -1175,7 +1177,6 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
 #ifdef SWR_PROFILE_COUNTERS
                             if (lane == 0) dbg_frags += __popc(m);
 #endif
-                            if (qn >= FRAGQ_DRAIN) qn = drain_queue(P, skeys, tb, fq, qn, lane);
                         }
                     }
                 }

@@ -51,9 +51,11 @@ __device__ __forceinline__ float rsqrt_ref(float x, Rsq q) {
     if (q.tab == nullptr) return rsqrtf(x);
     const uint32_t b = __float_as_uint(x);
     const uint32_t e = (b >> 23) & 0xFFu;
-    if (e == 0u) return __uint_as_float((b & 0x80000000u) | 0x7F800000u);
-    if (e == 255u) return (b & 0x007FFFFFu) ? __uint_as_float(b | 0x00400000u) : ((b >> 31) ? __uint_as_float(0xFFC00000u) : 0.0f);
-    if (b >> 31) return __uint_as_float(0xFFC00000u);
+    if (b - 0x00800000u >= 0x7F000000u) {  // not a positive normal number: zero / denormal, inf / NaN, negative
+        if (e == 0u) return __uint_as_float((b & 0x80000000u) | 0x7F800000u);
+        if (e == 255u) return (b & 0x007FFFFFu) ? __uint_as_float(b | 0x00400000u) : ((b >> 31) ? __uint_as_float(0xFFC00000u) : 0.0f);
+        return __uint_as_float(0xFFC00000u);
+    }
     const int ue = (int)e - 127;
     const int p = ue & 1;
     const int k = (ue - p) >> 1;
@@ -112,7 +114,7 @@ __device__ __forceinline__ V3 sample_bilinear_rgb0(const DevTex &t, float u, flo
 __device__ __forceinline__ uint32_t f2usize_clamped(float f, uint32_t hi) { return min(__float2uint_rz(f), hi); }
 __device__ __forceinline__ void sample_gi(const DevScene &s, V3 pos, V3 rgb[4], float w[4]) {
     const uint32_t W = s.gdim[0], H = s.gdim[1], D = s.gdim[2];
-    float vsx = (s.gmax[0] - s.gmin[0]) / (float)W, vsy = (s.gmax[1] - s.gmin[1]) / (float)H, vsz = (s.gmax[2] - s.gmin[2]) / (float)D;
+    const float vsx = s.gvs[0], vsy = s.gvs[1], vsz = s.gvs[2];  // (world_max - world_min) / dims, voxelgrid.rs:154-161
     float vx = (pos.x - s.gmin[0]) / vsx, vy = (pos.y - s.gmin[1]) / vsy, vz = (pos.z - s.gmin[2]) / vsz;
     float x0f = floorf(vx), y0f = floorf(vy), z0f = floorf(vz);
     uint32_t x0 = f2usize_clamped(x0f, W - 1), y0 = f2usize_clamped(y0f, H - 1), z0 = f2usize_clamped(z0f, D - 1);
@@ -377,8 +379,9 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SWR_SHADE_MINB) k_shade(ShadePara
             foreign = true;
         } else {
             rec = P.records[record_of_id(slot, P.clip_ext)];
-            float z;
-            if (resolve_pixel(rec, P.W, P.H, px, py, b1, b2, z)) covered = __float_as_uint(z) != SWR_INF_BITS;  // depth.cmpne(INF)
+            // the key's owner covers the pixel (k_read_vis re-checks that in the parity read-back): barycentrics only
+            const float z = resolve_owner(rec, P.W, P.H, px, py, b1, b2);
+            covered = __float_as_uint(z) != SWR_INF_BITS;  // depth.cmpne(INF)
         }
     }
     if (P.ext_bary != nullptr && inside && px < P.W && py < P.H) {
@@ -399,13 +402,16 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SWR_SHADE_MINB) k_shade(ShadePara
     }
     if (covered) {
         const float iwda = rec.iw1 - rec.iw0, iwdb = rec.iw2 - rec.iw0;
-        float wq[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) wq[j] = 1.0f / interp1(rec.iw0, iwda, iwdb, qb1[j], qb2[j]);  // shader.rs:123
         ShadePacket sp;
         build_shade_packet(P, rec, sp);
-        float dd[4] = {sp.du_dv[0] * wq[0], sp.du_dv[1] * wq[1], sp.du_dv[2] * wq[2], sp.du_dv[3] * wq[3]};
-        const float w = sub == 0 ? wq[0] : (sub == 1 ? wq[1] : (sub == 2 ? wq[2] : wq[3]));
+        const float w = 1.0f / interp1(rec.iw0, iwda, iwdb, b1, b2);  // shader.rs:123, my lane
+        float dd[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        const DevMat &mat = P.scene.mats[sp.material];
+        if ((mat.tex_base & mat.tex_mr & mat.tex_normal & mat.tex_emissive & mat.tex_occlusion) >= 0) {
+            // du_dv * w is lane-wise over the quad (shader.rs:130) and only texture sampling (mip selection) reads it
+#pragma unroll
+            for (int j = 0; j < 4; j++) dd[j] = sp.du_dv[j] * (1.0f / interp1(rec.iw0, iwda, iwdb, qb1[j], qb2[j]));
+        }
         out = pbr_shader(P, sp, b1, b2, w, dd);
     }
     bool wrote = covered;

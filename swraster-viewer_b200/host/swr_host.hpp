@@ -408,6 +408,9 @@ class Renderer {
         row0_ = r0;
         row1_ = r1;
     }
+    // The upload is cached by descriptor address (the reference's Scene is immutable and outlives the renderer). A caller
+    // that reuses an address for different contents says so here; the next render_scene uploads again.
+    void invalidate_scene() { uploaded_ = nullptr; }
 
     // render_scene(&mut self, scene, camera) — renderer.rs:201
     void render_scene(const Scene &scene, const RenderCamera &camera) { render_scene(scene, camera.to_abi()); }
@@ -427,10 +430,17 @@ class Renderer {
     void update_auto_exposure(float delta_time) {
         swr_frame_stats st;
         check(swr_get_stats(ctx_, &st), "swr_get_stats");
-        size_t n = st.tiles;
-        if (n == 0) return;
-        std::vector<float> lum(n);
+        if (st.tiles == 0) return;
+        std::vector<float> lum(st.tiles);
         check(swr_read_tile_luminance(ctx_, lum.data()), "swr_read_tile_luminance");
+        // sort-first: only the tiles of the rows this renderer owns were shaded; the others hold no metering value
+        if (row1_ > row0_) {
+            const size_t tiles_x = (size_t)(width_ + SWR_TILE_SIZE - 1) / SWR_TILE_SIZE;
+            const size_t t0 = std::min((size_t)row0_ * tiles_x, lum.size()), t1 = std::min((size_t)row1_ * tiles_x, lum.size());
+            lum = std::vector<float>(lum.begin() + t0, lum.begin() + t1);
+        }
+        const size_t n = lum.size();
+        if (n == 0) return;
         for (float &v : lum) v = std::log2(std::fmax(v, 1e-4f));
         std::sort(lum.begin(), lum.end());
         size_t trim = (size_t)std::floor((float)n * 0.10f);

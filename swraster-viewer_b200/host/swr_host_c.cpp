@@ -77,6 +77,7 @@ int swrh_build_draws_band(const swr_scene_desc *scene, const swr_camera *cam, sw
         return -1;
     }
 }
+int swrh_invalidate_scene(void *r) { SWRH_TRY(need(r).invalidate_scene()); }
 int swrh_num_draws(void *r) { return r ? (int)((swr::Renderer *)r)->draws().size() : -1; }
 int swrh_update_auto_exposure(void *r, float dt) { SWRH_TRY(need(r).update_auto_exposure(dt)); }
 float swrh_auto_exposure(void *r) { return r ? ((swr::Renderer *)r)->auto_exposure() : 0.0f; }

@@ -83,6 +83,7 @@ def load_libraries():
     host.swrh_renderer_ctx.restype = vp
     host.swrh_renderer_ctx.argtypes = [vp]
     host.swrh_set_tile_rows.argtypes = [vp, i32, i32]
+    host.swrh_invalidate_scene.argtypes = [vp]
     host.swrh_set_reference_rsqrt.argtypes = [vp, i32]
     host.swrh_reference_rsqrt_bits.argtypes = [vp]
     host.swrh_render_scene.argtypes = [vp, C.POINTER(abi.SceneDesc), C.POINTER(abi.Camera), i32, i32, i32]
@@ -201,8 +202,12 @@ class Renderer:
 
     def render_scene(self, scene, camera, shade=True, shard=0, nshards=1):
         """scene: scenes.SceneData; camera: RenderCamera."""
+        desc = scene.desc()
+        if scene is not self._scene:
+            # a new SceneData may be handed a descriptor at a recycled address: never trust pointer identity across scenes
+            self._check(self.host.swrh_invalidate_scene(self._h))
+        self._check(self.host.swrh_render_scene(self._h, C.byref(desc), C.byref(camera.abi), int(shade), shard, nshards))
         self._scene = scene  # keep the arrays alive while the context references the descriptor
-        self._check(self.host.swrh_render_scene(self._h, C.byref(scene.desc()), C.byref(camera.abi), int(shade), shard, nshards))
 
     @property
     def num_draws(self):
