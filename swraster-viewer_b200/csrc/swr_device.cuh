@@ -153,8 +153,10 @@ __device__ __forceinline__ float3 mul_mat3(const float *m, float3 v) {
 // __float2int_rz saturates and maps NaN to 0 exactly like Rust's `as i32`.
 __device__ __forceinline__ void snap_vertex(float4 c, float Wf, float Hf, int &X, int &Y) {
     float nx = fdiv(c.x, c.w), ny = fdiv(c.y, c.w);
-    float sx = fdiv(fmul(fadd(nx, 1.0f), Wf), 2.0f);
-    float sy = fdiv(fmul(fsub(1.0f, ny), Hf), 2.0f);
+    // "/ 2.0" (renderer.rs:838-839) as "* 0.5": identical bits for every input (a power-of-two scale is exact in binary
+    // floating point, subnormal results included), without the IEEE division sequence
+    float sx = fmul(fmul(fadd(nx, 1.0f), Wf), 0.5f);
+    float sy = fmul(fmul(fsub(1.0f, ny), Hf), 0.5f);
     X = __float2int_rz(roundf(fmul(sx, 16.0f)));
     Y = __float2int_rz(roundf(fmul(sy, 16.0f)));
 }

@@ -616,20 +616,35 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
     }
     __syncthreads();
     if (counters->overflow_refs) return;
-    // one warp per tile: a hot tile has hundreds of units, emitted 32 at a time instead of one by one
-    for (int i = tile_begin + wid; i < tile_end; i += 32) {
+    // one thread per tile; a tile split into many units (a hot tile has hundreds) is left to a whole warp afterwards
+    for (int i = tile_begin + tid; i < tile_end; i += 1024) {
         const uint32_t v = tile_count[i];
         const uint32_t ut = tile_unit[i];
         const uint32_t nfull = v / ut, rem = v % ut;
-        uint32_t base = 0, tail = 0;
-        if (lane == 0) {
-            if (nfull) base = atomicAdd(&s_cur[32 - __clz(ut)], nfull);
-            if (rem || !nfull) tail = atomicAdd(&s_cur[rem ? 32 - __clz(rem) : 0], 1u);
-            prev_count[i] = v;  // history for the next frame
+        prev_count[i] = v;  // history for the next frame
+        if (rem || !nfull) unit_list[atomicAdd(&s_cur[rem ? 32 - __clz(rem) : 0], 1u)] = ((uint32_t)i << 14) | nfull;
+        if (nfull && nfull <= 8u) {
+            const uint32_t base = atomicAdd(&s_cur[32 - __clz(ut)], nfull);
+            for (uint32_t k = 0; k < nfull; k++) unit_list[base + k] = ((uint32_t)i << 14) | k;
         }
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        for (uint32_t k = lane; k < nfull; k += 32) unit_list[base + k] = ((uint32_t)i << 14) | k;
-        if (lane == 0 && (rem || !nfull)) unit_list[tail] = ((uint32_t)i << 14) | nfull;
+    }
+    for (int i0 = tile_begin + wid * 32; i0 < tile_end; i0 += 1024) {  // warp-uniform trip count
+        const int i = i0 + lane;
+        uint32_t nfull = 0, ut = 1;
+        if (i < tile_end) {
+            ut = tile_unit[i];
+            nfull = tile_count[i] / ut;
+        }
+        unsigned big = __ballot_sync(0xFFFFFFFFu, nfull > 8u);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const uint32_t n = __shfl_sync(0xFFFFFFFFu, nfull, src), u = __shfl_sync(0xFFFFFFFFu, ut, src);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&s_cur[32 - __clz(u)], n);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            for (uint32_t k = lane; k < n; k += 32) unit_list[base + k] = ((uint32_t)(i0 + src) << 14) | k;
+        }
     }
 }
 

@@ -31,6 +31,22 @@ struct ShadeParams {
     int sky_row_begin, sky_row_end;
 };
 
+// Value-domain arithmetic. The translation unit is built with -fmad=false and everything that decides an ADDRESS (texel,
+// mip level, voxel cell, cubemap face, LUT cell) keeps the reference's unfused operation order, so those decisions are bit
+// for bit the reference's. Arithmetic whose result is only ever a colour VALUE (trilinear SH blend, BRDF terms, colour
+// sums) may contract a*b+c into one FMA: the result moves by <= 1 ulp per operation, far inside the +-1 LSB RGBA8 budget
+// (measured max / mean error: DESIGN.md 5). -DSWR_SHADE_FMA=0 restores the unfused form (then RGBA8 is bit-exact).
+#ifndef SWR_SHADE_FMA
+#define SWR_SHADE_FMA 1
+#endif
+__device__ __forceinline__ float vfma(float a, float b, float c) {  // a * b + c in the value domain
+#if SWR_SHADE_FMA
+    return __fmaf_rn(a, b, c);
+#else
+    return a * b + c;
+#endif
+}
+
 struct V3 {
     float x, y, z;
 };
@@ -41,6 +57,9 @@ __device__ __forceinline__ V3 operator*(V3 a, V3 b) { return V3{a.x * b.x, a.y *
 __device__ __forceinline__ V3 operator*(V3 a, float b) { return V3{a.x * b, a.y * b, a.z * b}; }
 __device__ __forceinline__ V3 operator+(V3 a, float b) { return V3{a.x + b, a.y + b, a.z + b}; }
 __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  // math.rs:88-90
+__device__ __forceinline__ float vdot(V3 a, V3 b) { return vfma(a.z, b.z, vfma(a.y, b.y, a.x * b.x)); }  // value domain
+__device__ __forceinline__ V3 vfma3(V3 a, V3 b, V3 c) { return V3{vfma(a.x, b.x, c.x), vfma(a.y, b.y, c.y), vfma(a.z, b.z, c.z)}; }
+__device__ __forceinline__ V3 vfma3(V3 a, float b, V3 c) { return V3{vfma(a.x, b, c.x), vfma(a.y, b, c.y), vfma(a.z, b, c.z)}; }
 // math.rs:34-39 rsqrt_vec. With a host table: exact emulation of _mm_rsqrt_ps (value = table[parity][top mantissa
 // bits] scaled by the even part of the exponent; zero/denormal -> inf, negative -> NaN, inf -> 0).
 struct Rsq {
@@ -67,7 +86,8 @@ __device__ __forceinline__ V3 normalize(V3 a, Rsq q) {  // math.rs:101-108
     return V3{a.x * r, a.y * r, a.z * r};
 }
 __device__ __forceinline__ V3 cross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
-__device__ __forceinline__ V3 srgb_to_linear_fast(V3 x) { return x * (x * (x * 0.305306011f + 0.682171111f) + 0.012522878f); }
+__device__ __forceinline__ float srgb1(float x) { return x * vfma(x, vfma(x, 0.305306011f, 0.682171111f), 0.012522878f); }
+__device__ __forceinline__ V3 srgb_to_linear_fast(V3 x) { return V3{srgb1(x.x), srgb1(x.y), srgb1(x.z)}; }  // util.rs:111-113
 
 __device__ __forceinline__ V3 sample_cubemap_rgb(const DevTex &t, V3 n, uint32_t mip) {  // texture.rs:593-663
     float ax = fabsf(n.x), ay = fabsf(n.y), az = fabsf(n.z);
@@ -93,7 +113,7 @@ __device__ __forceinline__ V3 sample_cubemap_trilinear_rgb(const DevTex &t, V3 n
     float m0 = floorf(mip), m1 = sse_min(m0 + 1.0f, maxm), tt = mip - m0;
     V3 c0 = sample_cubemap_rgb(t, n, __float2uint_rz(m0));
     V3 c1 = sample_cubemap_rgb(t, n, __float2uint_rz(m1));
-    return v3(c0.x + (c1.x - c0.x) * tt, c0.y + (c1.y - c0.y) * tt, c0.z + (c1.z - c0.z) * tt);
+    return v3(vfma(c1.x - c0.x, tt, c0.x), vfma(c1.y - c0.y, tt, c0.y), vfma(c1.z - c0.z, tt, c0.z));
 }
 __device__ __forceinline__ V3 sample_bilinear_rgb0(const DevTex &t, float u, float v) {  // texture.rs:730-790, mip 0 slice 0
     float wf = (float)t.mip_w[0], hf = (float)t.mip_h[0];
@@ -106,8 +126,8 @@ __device__ __forceinline__ V3 sample_bilinear_rgb0(const DevTex &t, float u, flo
     float4 p00 = fetch_texel(t, off + y0i * wi + x0i), p10 = fetch_texel(t, off + y0i * wi + x1i);
     float4 p01 = fetch_texel(t, off + y1i * wi + x0i), p11 = fetch_texel(t, off + y1i * wi + x1i);
     float w00 = omfx * omfy, w10 = fx * omfy, w01 = omfx * fy, w11 = fx * fy;
-    return v3(p00.x * w00 + p10.x * w10 + p01.x * w01 + p11.x * w11, p00.y * w00 + p10.y * w10 + p01.y * w01 + p11.y * w11,
-              p00.z * w00 + p10.z * w10 + p01.z * w01 + p11.z * w11);
+    return v3(vfma(p11.x, w11, vfma(p01.x, w01, vfma(p10.x, w10, p00.x * w00))), vfma(p11.y, w11, vfma(p01.y, w01, vfma(p10.y, w10, p00.y * w00))),
+              vfma(p11.z, w11, vfma(p01.z, w01, vfma(p10.z, w10, p00.z * w00))));
 }
 
 // voxelgrid.rs:264-368 for one position.
@@ -132,10 +152,10 @@ __device__ __forceinline__ void sample_gi(const DevScene &s, V3 pos, V3 rgb[4], 
         float4 v100 = __ldg(g100 + c), v101 = __ldg(g101 + c), v110 = __ldg(g110 + c), v111 = __ldg(g111 + c);
 #define SWR_TRI(F)                                                                                   \
     ({                                                                                               \
-        float v00 = v000.F * ox + v100.F * fx, v01 = v001.F * ox + v101.F * fx;                      \
-        float v10 = v010.F * ox + v110.F * fx, v11 = v011.F * ox + v111.F * fx;                      \
-        float v0 = v00 * oy + v10 * fy, v1 = v01 * oy + v11 * fy;                                    \
-        v0 * oz + v1 * fz;                                                                           \
+        float v00 = vfma(v100.F, fx, v000.F * ox), v01 = vfma(v101.F, fx, v001.F * ox);              \
+        float v10 = vfma(v110.F, fx, v010.F * ox), v11 = vfma(v111.F, fx, v011.F * ox);              \
+        float v0 = vfma(v10, fy, v00 * oy), v1 = vfma(v11, fy, v01 * oy);                            \
+        vfma(v1, fz, v0 * oz);                                                                       \
     })
         rgb[c] = v3(SWR_TRI(x), SWR_TRI(y), SWR_TRI(z));
         if (c < 2) w[c] = SWR_TRI(w);  // only the .w of coefficients 0 and 1 is consumed (shader.rs:172-173)
@@ -252,11 +272,11 @@ __device__ __forceinline__ V3 pbr_shader(const ShadeParams &P, const ShadePacket
     V3 view_dir = v3(P.cam.position[0], P.cam.position[1], P.cam.position[2]) - pos_world;
     V3 view_normal = normalize(view_dir, rq);
 
-    float n_dot_l = sse_max(dot(normal_world, light_dir), 0.0f);
+    float n_dot_l = sse_max(vdot(normal_world, light_dir), 0.0f);
     V3 half_vector = normalize(light_dir + view_normal, rq);
-    float n_dot_h = sse_max(dot(normal_world, half_vector), 0.0f);
-    float n_dot_v = sse_max(dot(normal_world, view_normal), 1.0e-4f);
-    float v_dot_h = sse_max(dot(view_normal, half_vector), 0.0f);
+    float n_dot_h = sse_max(vdot(normal_world, half_vector), 0.0f);
+    float n_dot_v = sse_max(dot(normal_world, view_normal), 1.0e-4f);  // addresses the BRDF LUT: unfused
+    float v_dot_h = sse_max(vdot(view_normal, half_vector), 0.0f);
 
     V3 gi_rgb[4];
     float gi_w[4];
@@ -280,27 +300,27 @@ __device__ __forceinline__ V3 pbr_shader(const ShadeParams &P, const ShadePacket
     float ao = 1.0f;
     if (mat.tex_occlusion >= 0) {
         ao = sample4(sc.texs[mat.tex_occlusion], uv_x, uv_y, du_dv).x;
-        ao = 1.0f + (ao - 1.0f) * mat.occlusion_strength;
+        ao = vfma(ao - 1.0f, mat.occlusion_strength, 1.0f);
     }
-    V3 f0 = v3(0.04f + (base.x - 0.04f) * metallic, 0.04f + (base.y - 0.04f) * metallic, 0.04f + (base.z - 0.04f) * metallic);
+    V3 f0 = v3(vfma(base.x - 0.04f, metallic, 0.04f), vfma(base.y - 0.04f, metallic, 0.04f), vfma(base.z - 0.04f, metallic, 0.04f));
     float omvh = 1.0f - v_dot_h;
     float omvh2 = omvh * omvh;
     float omvh4 = omvh2 * omvh2;
     float omvh5 = omvh4 * omvh;
     V3 one3 = v3(1.0f, 1.0f, 1.0f);
-    V3 brdf_f_direct = f0 + (one3 - f0) * omvh5;
+    V3 brdf_f_direct = vfma3(one3 - f0, omvh5, f0);
 
     float alpha = roughness * roughness;
     float alpha_2 = alpha * alpha;
     float ndh_2 = n_dot_h * n_dot_h;
-    float denom_d = ndh_2 * (alpha_2 - 1.0f) + 1.0f;
-    float brdf_d = alpha_2 / (PI * (denom_d * denom_d) + EPS);
+    float denom_d = vfma(ndh_2, alpha_2 - 1.0f, 1.0f);
+    float brdf_d = alpha_2 / vfma(PI, denom_d * denom_d, EPS);
     float k = roughness + 1.0f;
     k = (k * k) * 0.125f;
-    float gv = n_dot_v / ((n_dot_v * (1.0f - k) + k) + EPS);
-    float gl = n_dot_l / ((n_dot_l * (1.0f - k) + k) + EPS);
+    float gv = n_dot_v / (vfma(n_dot_v, 1.0f - k, k) + EPS);
+    float gl = n_dot_l / (vfma(n_dot_l, 1.0f - k, k) + EPS);
     float brdf_g = gv * gl;
-    float specular_dg = (brdf_d * brdf_g) / (4.0f * n_dot_l * n_dot_v + EPS);
+    float specular_dg = (brdf_d * brdf_g) / vfma(4.0f * n_dot_l, n_dot_v, EPS);
     V3 k_d_direct = (one3 - brdf_f_direct) * (1.0f - metallic);
     const float INV_PI = 1.0f / 3.14159265358979323846f;
     V3 lambert = base * INV_PI;
@@ -308,7 +328,7 @@ __device__ __forceinline__ V3 pbr_shader(const ShadeParams &P, const ShadePacket
     V3 color_direct_specular = light_color * brdf_f_direct * specular_dg * n_dot_l * voxel_light_intensity;
 
     V3 k_d_indirect = (one3 - f0) * (1.0f - metallic);
-    V3 irr = gi_rgb[0] + gi_rgb[1] * normal_world.y + gi_rgb[2] * normal_world.z + gi_rgb[3] * normal_world.x;  // shader.rs:102-108
+    V3 irr = vfma3(gi_rgb[3], normal_world.x, vfma3(gi_rgb[2], normal_world.z, vfma3(gi_rgb[1], normal_world.y, gi_rgb[0])));  // shader.rs:102-108
     irr = v3(sse_max(irr.x, 0.0f), sse_max(irr.y, 0.0f), sse_max(irr.z, 0.0f));
     V3 color_indirect_diffuse = irr * base * k_d_indirect * INV_PI;
 
@@ -317,10 +337,9 @@ __device__ __forceinline__ V3 pbr_shader(const ShadeParams &P, const ShadePacket
     const DevTex &spec = sc.texs[sc.cubemap_specular];
     V3 prefiltered_env = sample_cubemap_trilinear_rgb(spec, reflect_dir, roughness * (float)spec.max_mip);
     V3 lut = sample_bilinear_rgb0(sc.texs[sc.brdf_lut], sse_clamp(n_dot_v, 0.0f, 1.0f), sse_clamp(roughness, 0.0f, 1.0f));
-    V3 brdf_spec_factor = f0 * lut.x;
-    brdf_spec_factor = brdf_spec_factor + lut.y;
+    V3 brdf_spec_factor = v3(vfma(f0.x, lut.x, lut.y), vfma(f0.y, lut.x, lut.y), vfma(f0.z, lut.x, lut.y));
     V3 color_indirect_specular = prefiltered_env * brdf_spec_factor;
-    float ao_spec = 1.0f + (ao - 1.0f) * 0.5f;
+    float ao_spec = vfma(ao - 1.0f, 0.5f, 1.0f);
     color_indirect_specular = color_indirect_specular * (ao_spec * sky_visibility);
 
     V3 color;
@@ -339,7 +358,7 @@ __device__ __forceinline__ V3 pbr_shader(const ShadeParams &P, const ShadePacket
         float4 s = sample4(sc.texs[mat.tex_emissive], uv_x, uv_y, du_dv);
         emissive_mat = srgb_to_linear_fast(v3(s.x, s.y, s.z));
     }
-    color = color + emissive_mat * v3(mat.emissive[0], mat.emissive[1], mat.emissive[2]);
+    color = vfma3(emissive_mat, v3(mat.emissive[0], mat.emissive[1], mat.emissive[2]), color);
     return color;
 }
 
