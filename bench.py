@@ -1,43 +1,74 @@
 #!/usr/bin/env python
-"""bench.py — frames/s and Mtriangles/s of the rasterisation hot path at 3840x2160 (BASELINE.json metric).
+"""bench.py — frames/s and Mtriangles/s of the rasterisation hot path (BASELINE.json metric).
 
-Workload (config.workload): C3 = BASELINE.json configs[2], the configuration the metric is quoted on:
-procedural ~10 M-triangle instanced scene (3 base meshes, seeded scatter, camera inside the cloud, heavy
-clipping), 3840x2160. One step = one frame = Renderer.render_scene + blit (set-up, clip, bin, raster,
-vis-buffer shading, resolve).
+  --config c3 (default)  BASELINE.json configs[2], the configuration the metric is quoted on: procedural ~10 M-triangle
+                         instanced scene, 3840x2160, sort-first over N GPUs.
+  --config c1|c2|c4|c5   the other BASELINE configs: 100 K-triangle sphere and 1 M-triangle textured terrain
+                         at 1920x1080, 50 M micro-triangles at 3840x2160 (sort-first), 8 x 25 M-triangle shards at 7680x4320
+                         (sort-last: shard by draw, u64-min key composite over NCCL).
+One step = one frame = Renderer.render_scene + blit (set-up, clip, bin, raster, vis-buffer shading, resolve).
 
-  value     device-resident throughput: swr_render + swr_resolve(NULL) timed with CUDA events on the
-            library's stream, inputs already in HBM, L2 flushed between frames (256 MiB write).
-  e2e       the same frames through the public host API (Renderer.render_scene + blit_to_buffer into a pinned
-            host buffer): draw-list build + H2D of camera/draw table + all kernels + D2H of the RGBA8 frame,
-            wall clock, max over ranks.
-  N > 1     sort-first: every rank holds the scene and owns a contiguous range of tile rows; each rank's resolve kernel
-            stores its RGBA8 rows straight into rank 0's frame over NVLink peer memory (swr_peer_*), inside the timed
-            region ("scaling": "strong" — total work fixed).
-  --impl reference   the reference's CPU path (oracle port: C++ restatement with the reference's parallel
-            structure, all host threads) on the same config, rank 0 only.
+  value     device-resident throughput: swr_render + swr_resolve(NULL) timed with CUDA events on the library's stream,
+            inputs already in HBM, L2 flushed between frames (256 MiB write).
+  e2e       the same frames through the public host API (Renderer.render_scene + blit_to_buffer into pinned host memory):
+            draw-list build + H2D of camera/draw table + all kernels + D2H of the RGBA8 frame, wall clock, max over ranks.
+            N = 1: pipelined like the reference's App (read-back of frame N overlaps frame N+1). N > 1, sort-first: every
+            rank reads ITS rows back over its own PCIe link into one host frame shared by all ranks (POSIX shared memory,
+            page-locked by every rank) — no GPU-to-GPU hop on the e2e path.
+  N > 1     sort-first (c1-c4): every rank holds the scene and owns a contiguous, cost-balanced range of tile rows; for
+            `value` each rank's resolve kernel stores its RGBA8 rows straight into rank 0's frame over NVLink peer memory
+            (swr_peer_*), inside the timed region. sort-last (c5): see multigpu.sort_last_frame. "scaling": "strong".
+  --impl reference   the reference's CPU path (oracle port: C++ restatement with the reference's parallel structure, all
+            host threads) on the same config, rank 0 only. Loads neither torch nor the product libraries.
 """
 import argparse
 import json
-
-import numpy as np
 import os
 import subprocess
 import sys
 import threading
 import time
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H = 3840, 2160
-WORKLOAD = "C3: procedural 10M-triangle instanced scene (icosphere 20480 / torus 8192 / box-grid 1200 tris, seeded scatter, scales 0.05-4, camera inside the cloud, heavy clipping), 3840x2160"
-KERNELS_PER_FRAME = 11  # k_cull, k_compact, k_setup, k_clip, k_scan_tiles, k_scatter, k_scatter_list, k_raster_tiles, k_shade, k_luminance, k_resolve
+CONFIGS = {
+    "c1": {"W": 1920, "H": 1080, "mode": "sort-first", "builder": "scene_c1_sphere", "args": {},
+           "workload": "C1: procedural 99,904-triangle UV sphere (224 x 224), untextured, one default material, reference default camera, 1920x1080"},
+    "c2": {"W": 1920, "H": 1080, "mode": "sort-first", "builder": "scene_c2_terrain", "args": {},
+           "workload": "C2: procedural 999,698-triangle textured height-field (708 x 708 vertices, 2048^2 sRGB texture, mips 0-5 hit), low-oblique camera, 1920x1080"},
+    "c3": {"W": 3840, "H": 2160, "mode": "sort-first", "builder": "scene_c3_instanced", "args": {},
+           "workload": "C3: procedural 10M-triangle instanced scene (icosphere 20480 / torus 8192 / box-grid 1200 tris, seeded scatter, scales 0.05-4, camera inside the cloud, heavy clipping), 3840x2160"},
+    "c4": {"W": 3840, "H": 2160, "mode": "sort-first", "builder": "scene_c4_micro", "args": {},
+           "workload": "C4: procedural 50.0M-triangle dense micro-triangle grid (5001 x 5001 vertices, ~0.3 px^2 per triangle, binning-bound), 3840x2160"},
+    "c5": {"W": 7680, "H": 4320, "mode": "sort-last", "builder": "scene_c5_shards", "args": {"nshards": 8},
+           "workload": "C5: procedural 200M-triangle scene, 8 shards of 25M-triangle grids at different depths, sharded by primitive with u64-min depth composite, 7680x4320"},
+}
+CAMERA_FIXTURE = os.path.join(ROOT, "tests", "golden", "bench_cameras.json")
 
 
-def build_scene():
+def build_scene(name):
     from swraster_viewer_b200 import scenes
-    return scenes.scene_c3_instanced(voxel_dim=128, cube_size=256)
+    cfg = CONFIGS[name]
+    return getattr(scenes, cfg["builder"])(voxel_dim=128, cube_size=256, **cfg["args"])
+
+
+def camera_spec(name):
+    return build_scene(name)[1]
+
+
+def fixture_camera(name, spec):
+    """The config's swr_camera block from the committed fixture (tests/golden/make_bench_cameras.py): lets the CPU arm run
+    without the product libraries. The fixture's spec must be the scene's spec."""
+    from swraster_viewer_b200 import abi
+    fx = json.load(open(CAMERA_FIXTURE))[name]
+    same = (np.allclose(fx["position"], spec.position, rtol=0, atol=0) and np.allclose(fx["look_at"], spec.look_at, rtol=0, atol=0)
+            and fx["fov"] == spec.fov and fx["far_plane"] == spec.far_plane)
+    if not same:
+        raise SystemExit(f"tests/golden/bench_cameras.json is stale for {name}: rerun tests/golden/make_bench_cameras.py")
+    return abi.Camera.from_buffer_copy(bytes.fromhex(fx["camera_hex"]))
 
 
 def peaks():
@@ -93,7 +124,14 @@ def algorithmic_bytes(st, w, h):
     return 12 * st["triangles_submitted"] + 16 * st["vertices_submitted"] + 8 * st["tile_refs"] + 12 * w * h
 
 
-def cpu_frame_times(scene, cam_abi, steps, warmup, nthreads):
+def metric_name(cfg):
+    return f"frames_per_sec_{cfg['W']}x{cfg['H']}"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_frame_times(scene, cam_abi, W, H, steps, warmup, nthreads):
     """Times the oracle (CPU port of the reference path, reference's parallel structure) on full frames."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as orc
@@ -113,27 +151,30 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import swraster_viewer_b200 as swr
-    scene, spec = build_scene()
-    cam = swr.RenderCamera.from_spec(spec, W, H)
+    cfg = CONFIGS[args.config]
+    W, H = cfg["W"], cfg["H"]
+    scene, spec = build_scene(args.config)
+    cam_abi = fixture_camera(args.config, spec)
     ncores = os.cpu_count() or 1
     steps = max(1, args.steps)
     warmup = max(0, args.warmup)
     # bounded: keep the whole run within a few minutes whatever K/W the driver passes
-    probe, st = cpu_frame_times(scene, cam.abi, 1, 0, ncores)
+    probe, st = cpu_frame_times(scene, cam_abi, W, H, 1, 0, ncores)
     budget = 150.0
     per = probe[0]
     steps_eff = max(1, min(steps, int(budget / per)))
     warm_eff = min(warmup, 1)
-    times, st = cpu_frame_times(scene, cam.abi, steps_eff, warm_eff, ncores)
+    if per * (steps_eff + warm_eff) > budget:  # huge configs (C4 / C5): the probe frame is the warm-up
+        warm_eff = 0
+    times, st = cpu_frame_times(scene, cam_abi, W, H, steps_eff, warm_eff, ncores)
     ms = 1e3 * sum(times) / len(times)
     fps = 1e3 / ms
     T = st["triangles_submitted"]
     line = {
-        "impl": "reference", "metric": "frames_per_sec_3840x2160", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(cfg), "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": steps_eff, "warmup": warm_eff, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "mtriangles_per_sec": fps * T / 1e6,
-        "config": {"workload": WORKLOAD, "width": W, "height": H, "triangles_submitted": T, "scene_triangles": scene.total_triangles},
+        "config": {"workload": cfg["workload"], "width": W, "height": H, "triangles_submitted": T, "scene_triangles": scene.total_triangles},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": ncores, "kind": "port",
                          "sample": f"{steps_eff} full frames of the same workload (C++ restatement of swraster-viewer's rayon+glam path; Rust toolchain unavailable)",
                          "ms_per_frame": ms, "ms_clipbin": st["ms_clipbin"], "ms_raster_shade": st["ms_raster"], "ms_resolve": st["ms_resolve"]},
@@ -143,13 +184,18 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------------------------------------------------
 def run_gpu(args):
     import torch
     import torch.distributed as dist
     import swraster_viewer_b200 as swr
-    from swraster_viewer_b200 import abi
-    from swraster_viewer_b200.multigpu import tile_row_ranges, balanced_row_ranges, PeerAssembly, device_tensor
+    from swraster_viewer_b200.multigpu import (tile_row_ranges, balanced_row_ranges, PeerAssembly, SharedHostFrame, device_tensor,
+                                               sort_last_frame)
 
+    cfg = CONFIGS[args.config]
+    W, H = cfg["W"], cfg["H"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -159,54 +205,51 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = f"cuda:{local}"
+    sort_last = cfg["mode"] == "sort-last" and world > 1
 
-    scene, spec = build_scene()
+    scene, spec = build_scene(args.config)
     cam = swr.RenderCamera.from_spec(spec, W, H)
     r = swr.Renderer(W, H, device=local)
     tiles_y = r.tiles_y
     ranges = tile_row_ranges(tiles_y, world)
-    if world > 1:
+    if world > 1 and not sort_last:
         # probe frame on every rank (full screen, identical everywhere) -> cost-balanced contiguous row bands
         for _ in range(3):
             r.render_scene(scene, cam, shade=False)
-        cyc = torch.from_numpy(r.read_tile_costs()[1].astype(np.int64)).to(f"cuda:{local}")
+        cyc = torch.from_numpy(r.read_tile_costs()[1].astype(np.int64)).to(dev)
         dist.broadcast(cyc, src=0)  # measured cycles differ slightly per rank: everybody uses rank 0's
         ranges = balanced_row_ranges(cyc.cpu().numpy(), world)
         r.set_tile_rows(*ranges[rank])
-    buf = swr.RenderBuffer(W, H, pinned=True)
     stream = torch.cuda.ExternalStream(r.cuda_stream(), device=local)
-    pix = device_tensor(r.device_pixels_ptr(), W * H * 4, torch.int32, f"cuda:{local}").view(H, W)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # N > 1: the frame is assembled in rank 0's pixel buffer by the other ranks' resolve kernels (peer stores over NVLink
-    # + a device-side handshake, include/swr.h swr_peer_*): no collective on the data path
-    pa = PeerAssembly(r, dst=0) if world > 1 else None
+    # N > 1, sort-first: the frame is assembled in rank 0's pixel buffer by the other ranks' resolve kernels (peer stores over
+    # NVLink + a device-side handshake, include/swr.h swr_peer_*): no collective on the data path
+    pa = PeerAssembly(r, dst=0) if (world > 1 and not sort_last) else None
+    # host frame(s) of the e2e path: pinned; shared between the ranks at N > 1
+    if world > 1:
+        hosts = [SharedHostFrame(W, H, tag=f"swr_bench_{os.environ.get('MASTER_PORT', '0')}_{k}") for k in range(2)]
+        bufs = [swr.RenderBuffer(W, H, pixels=h.pixels) for h in hosts]
+    else:
+        hosts = None
+        bufs = [swr.RenderBuffer(W, H, pinned=True), swr.RenderBuffer(W, H, pinned=True)]
 
     def step_device():
+        if sort_last:
+            sort_last_frame(r, scene, cam, rank, world, stream)
+            return
         r.render_scene(scene, cam)
         if world > 1:
             pa.frame(2.0)
             pa.release()
         else:
             r.resolve_device_only(2.0)
-
-    def step_e2e():
-        r.render_scene(scene, cam)
-        if world > 1:
-            pa.frame(2.0)
-            if rank == 0:
-                # D2H of the assembled frame on rank 0 (the caller's RenderBuffer), then hand the buffer back
-                with torch.cuda.stream(stream):
-                    buf._t.view(H, W).copy_(pix, non_blocking=True)
-            pa.release()
-            stream.synchronize()
-        else:
-            r.blit_to_buffer(buf)
 
     # ---- warm-up (also settles buffer growth) -------------------------------------------------------------
     for _ in range(max(3, args.warmup)):
@@ -219,9 +262,11 @@ def run_gpu(args):
     barrier()
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    K = args.steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     phase = {"ms_setup_bin": 0.0, "ms_raster": 0.0, "ms_shade": 0.0}
-    for i in range(args.steps):
+    launches0 = r.launch_count
+    for i in range(K):
         with torch.cuda.stream(stream):
             flush.fill_(i & 0xFF)  # evict L2 (126 MB) between timed frames
             ev[i][0].record(stream)
@@ -232,91 +277,121 @@ def run_gpu(args):
         for k in phase:
             phase[k] += s[k]
     barrier()
+    launches_dev = r.launch_count - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     # ---- end-to-end timing: public API, host buffers, wall clock ---------------------------------------------
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    if world == 1:
-        # pipelined like the reference's App (present N-1 || render N, main.rs:526-597): every step still uploads its draw
-        # table and reads its own 33 MB frame back into pinned host memory; the read-back of frame N overlaps frame N+1
-        bufs = [buf, swr.RenderBuffer(W, H, pinned=True)]
-        prev = None
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            r.render_scene(scene, cam)
-            tk = r.blit_to_buffer_async(bufs[i & 1])
-            if prev is not None:
-                r.wait_blit(prev)
-            prev = tk
-        r.wait_blit(prev)
-        e2e_s = time.perf_counter() - t0
-        # and the strictly synchronous form (render, blit, wait) for reference
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
-        e2e_sync_s = time.perf_counter() - t0
+    if sort_last:
+        pix_host = torch.empty(W * H, dtype=torch.int32).pin_memory()
+
+        def e2e_loop(n):
+            for _ in range(n):
+                pix = sort_last_frame(r, scene, cam, rank, world, stream)
+                if rank == 0:
+                    with torch.cuda.stream(stream):
+                        pix_host.copy_(pix, non_blocking=True)
+                stream.synchronize()
+            barrier()
+        e2e_mode = "sort-last composite over NCCL, then D2H of the composited frame on rank 0 (synchronous)"
     else:
+        def e2e_loop(n):
+            # pipelined like the reference's App (present N-1 || render N, main.rs:526-597): every step still uploads its draw
+            # table and reads its own pixels back into pinned host memory; the read-back of frame N overlaps frame N+1.
+            # N > 1: each rank's rows go over its own PCIe link into the host frame all ranks share; the frame is complete
+            # when every rank has waited for its copy (hosts[k].arrive / wait_all: flags in the same shared segment).
+            prev = None
+            for i in range(n):
+                r.render_scene(scene, cam)
+                tk = r.blit_to_buffer_async(bufs[i & 1])
+                if prev is not None:
+                    r.wait_blit(prev[0])
+                    if hosts:
+                        hosts[prev[1]].arrive(rank, prev[2])
+                        if rank == 0:
+                            hosts[prev[1]].wait_all(world, prev[2])
+                prev = (tk, i & 1, i + 1)
+            r.wait_blit(prev[0])
+            if hosts:
+                hosts[prev[1]].arrive(rank, prev[2])
+                if rank == 0:
+                    hosts[prev[1]].wait_all(world, prev[2])
+        e2e_mode = ("pipelined: read-back of frame N overlaps frame N+1 (swr_resolve_async)" if world == 1 else
+                    "pipelined; every rank reads its own rows back over its own PCIe link into one page-locked host frame shared by all ranks")
+    for h in hosts or []:
+        h.reset()
+    e2e_loop(2)
+    for h in hosts or []:
+        h.reset()
+    barrier()
+    launches1 = r.launch_count
+    t0 = time.perf_counter()
+    e2e_loop(K)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    launches2 = r.launch_count
+    e2e_sync_s = None
+    if world == 1:
+        # the strictly synchronous form (render, blit, wait) for reference
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
-        barrier()
-        e2e_s = time.perf_counter() - t0
-        e2e_sync_s = e2e_s
+        for _ in range(K):
+            r.render_scene(scene, cam)
+            r.blit_to_buffer(bufs[0])
+        e2e_sync_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=f"cuda:{local}")
-    cnt = torch.tensor([st0["tile_refs"], st0["triangles_binned"]], dtype=torch.float64, device=f"cuda:{local}")
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([st0["tile_refs"], st0["triangles_binned"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     dev_ms, e2e_s = float(t[0]), float(t[1])
     if rank == 0:
-        K = args.steps
         ms = dev_ms / K
         fps = 1e3 / ms
-        T = st0["triangles_submitted"]
+        T = scene_triangles_submitted(st0, sort_last, scene)
         stats_all = dict(st0)
         stats_all["tile_refs"] = int(cnt[0])
+        stats_all["triangles_submitted"] = T
         B = algorithmic_bytes(stats_all, W, H)
         peak, peak_src = peaks()
         # dominant kernel of the step on this rank
         dom = max(phase, key=lambda k: phase[k])
         dom_ms = phase[dom] / K
-        kname = {"ms_setup_bin": "k_setup+k_scan_tiles+k_scatter", "ms_raster": "k_raster_tiles", "ms_shade": "k_shade"}[dom]
-        kbytes = {"ms_setup_bin": 12 * T + 16 * st0["vertices_submitted"] + 4 * st0["tile_refs"],
-                  "ms_raster": 4 * st0["tile_refs"] + 8 * W * H // world,
+        kname = {"ms_setup_bin": "k_setup+k_clip+k_scan_tiles+k_scatter", "ms_raster": "k_raster_tiles", "ms_shade": "k_shade"}[dom]
+        kbytes = {"ms_setup_bin": 12 * st0["triangles_submitted"] + 16 * st0["vertices_submitted"] + 4 * st0["tile_refs"],
+                  "ms_raster": 4 * st0["tile_refs"] + 8 * W * H // (1 if sort_last else world),
                   "ms_shade": 4 * W * H // world}[dom]
         achieved = kbytes / (dom_ms * 1e-3) / 1e9
-        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this same command (N=1)
-        traffic = None
-        tj = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if world == 1 and os.path.exists(tj):
-            traffic = json.load(open(tj)).get(kname.split("+")[0])
-        # What really bounds these kernels is instruction issue, not HBM: warp instructions per launch from the
-        # same committed ncu capture against the SM issue rate (4 schedulers x 1 warp instruction / clock / SM).
-        issue = None
-        ij = os.path.join(ROOT, "profiles", "r01_warp_inst.json")
-        if world == 1 and os.path.exists(ij) and clocks and clocks.get("sm_mhz"):
-            winst = json.load(open(ij)).get(kname.split("+")[0])
-            if winst:
-                ipeak = torch.cuda.get_device_properties(local).multi_processor_count * 4 * clocks["sm_mhz"] * 1e6 / 1e9
-                issue = {"warp_inst_per_launch": winst, "achieved": winst / (dom_ms * 1e-3) / 1e9, "peak": ipeak, "unit": "G warp-inst/s",
-                         "frac": winst / (dom_ms * 1e-3) / 1e9 / ipeak, "source": "smsp__inst_executed.sum (profiles/r01_warp_inst.json) / live kernel time"}
+        # DRAM traffic / warp instructions of the dominant kernel from the committed `ncu --set full` capture of this same
+        # command (C3, N=1 only): profiles/r02_traffic.json, r02_warp_inst.json
+        traffic, issue = None, None
+        tj, ij = os.path.join(ROOT, "profiles", "r02_traffic.json"), os.path.join(ROOT, "profiles", "r02_warp_inst.json")
+        if world == 1 and args.config == "c3":
+            if os.path.exists(tj):
+                traffic = json.load(open(tj)).get(kname.split("+")[0])
+            if os.path.exists(ij) and clocks and clocks.get("sm_mhz"):
+                winst = json.load(open(ij)).get(kname.split("+")[0])
+                if winst:
+                    ipeak = torch.cuda.get_device_properties(local).multi_processor_count * 4 * clocks["sm_mhz"] * 1e6 / 1e9
+                    issue = {"warp_inst_per_launch": winst, "achieved": winst / (dom_ms * 1e-3) / 1e9, "peak": ipeak, "unit": "G warp-inst/s",
+                             "frac": winst / (dom_ms * 1e-3) / 1e9 / ipeak, "source": "smsp__inst_executed.sum (profiles/r02_warp_inst.json) / live kernel time"}
         h2d = r.num_draws * (144 + 4) + 4
+        if sort_last:
+            par = f"sort-last x{world}: draws dealt round-robin, u64-min key all-reduce + barycentric / RGBA8 sum all-reduce over NCCL, every rank shades the pixels whose winner it owns"
+        elif world > 1:
+            par = f"sort-first x{world}: cost-balanced contiguous tile-row bands {ranges}, per-band draw + cluster culling, peer-store frame assembly on rank 0 (NVLink P2P, no collective)"
+        else:
+            par = "single GPU"
         line = {
-            "metric": "frames_per_sec_3840x2160", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
+            "metric": metric_name(cfg), "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "mtriangles_per_sec": fps * T / 1e6,
-            "config": {"workload": WORKLOAD, "width": W, "height": H, "triangles_submitted": T, "scene_triangles": scene.total_triangles,
+            "config": {"workload": cfg["workload"], "width": W, "height": H, "triangles_submitted": T, "scene_triangles": scene.total_triangles,
                        "vertices_submitted": st0["vertices_submitted"], "tile_refs": int(cnt[0]), "triangles_binned": int(cnt[1]),
-                       "l2": "256 MiB device write between timed frames (L2 flush)", "parallelism": (f"sort-first x{world}: cost-balanced contiguous tile-row bands {ranges}, per-band draw culling, peer-store frame assembly on rank 0 (NVLink P2P, no collective)" if world > 1 else "single GPU")},
+                       "l2": "256 MiB device write between timed frames (L2 flush)", "parallelism": par},
             "e2e": {"value": K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": W * H * 4, "ms_per_step": 1e3 * e2e_s / K,
-                    "mode": "pipelined: read-back of frame N overlaps frame N+1 (swr_resolve_async)" if world == 1 else "synchronous + peer-store frame assembly on rank 0 (NVLink P2P, no collective)",
-                    "synchronous_value": K / e2e_sync_s},
-            # our kernels launched inside the timed regions on this rank: K device-timed frames + K e2e frames (+ K synchronous e2e frames at N=1;
-            # + k_peer_wait / k_peer_release per frame on the assembling rank at N>1)
-            "gpu_launches": (KERNELS_PER_FRAME * 3 * K) if world == 1 else ((KERNELS_PER_FRAME + 2) * 2 * K),
+                    "mode": e2e_mode, "synchronous_value": (K / e2e_sync_s) if e2e_sync_s else None},
+            # kernels of ours launched on this rank inside the two timed regions, counted by the library (swr_launch_count)
+            "gpu_launches": launches_dev + (launches2 - launches1),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel_ms": dom_ms, "kernel_algorithmic_bytes": kbytes,
@@ -325,12 +400,12 @@ def run_gpu(args):
         }
         if world == 1 and not args.no_cpu:
             # The CPU port is timed in a fresh interpreter: inside this process (torch and its OpenMP runtime loaded, CUDA
-            # context alive) the same code runs about 1.5x slower, which would flatter the GPU arm.
+            # context alive) the same code runs slower, which would flatter the GPU arm.
             env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
             ref = None
             try:
-                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1"], env=env,
-                                     capture_output=True, text=True, timeout=600)
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", args.config, "--steps", "3", "--warmup", "1"],
+                                     env=env, capture_output=True, text=True, timeout=900)
                 for ln in out.stdout.splitlines():
                     if ln.startswith("{"):
                         ref = json.loads(ln)
@@ -338,20 +413,20 @@ def run_gpu(args):
                 ref = None
             if ref is not None:
                 line["cpu_baseline"] = dict(ref["cpu_baseline"])
-                line["cpu_baseline"]["sample"] = ("2 full frames (+1 warm-up) of the same workload on the host CPU, separate torch-free process: C++ restatement "
-                                                  "of swraster-viewer's rayon+glam path (Rust toolchain unavailable)")
-            else:  # the baseline must not cost the bench line: time it here instead
-                ncores = os.cpu_count() or 1
-                times, ost = cpu_frame_times(scene, cam.abi, 2, 1, ncores)
-                cfps = len(times) / sum(times)
-                line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": ncores, "kind": "port",
-                                        "sample": "2 full frames (+1 warm-up) of the same workload on the host CPU, inside the bench process (the separate process failed)",
-                                        "ms_per_frame": 1e3 / cfps, "ms_clipbin": ost["ms_clipbin"], "ms_raster_shade": ost["ms_raster"], "ms_resolve": ost["ms_resolve"]}
+                line["cpu_baseline"]["sample"] = (f"{ref['steps']} full frames (+{ref['warmup']} warm-up) of the same workload on the host CPU, separate torch-free process: C++ "
+                                                  "restatement of swraster-viewer's rayon+glam path (Rust toolchain unavailable)")
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": "the CPU leg failed to run"}
         print(json.dumps(line), flush=True)
     # orderly teardown: torch tensors that were used on the library's stream must die before the stream does
     torch.cuda.synchronize()
-    del ev, flush, pix, stream
-    buf = None
+    del ev, flush, stream
+    e2e_loop = step_device = None  # closures hold tensors that live on the library's stream
+    if sort_last:
+        del pix_host
+    bufs = None
+    for h in hosts or []:
+        h.close(unlink=(rank == 0))
     import gc
     gc.collect()
     torch.cuda.empty_cache()
@@ -359,6 +434,12 @@ def run_gpu(args):
         dist.barrier()
         dist.destroy_process_group()
     r.close()
+
+
+def scene_triangles_submitted(st0, sort_last, scene):
+    """T of the frame: this rank's submitted triangles (sort-first ranks all submit the same draw list before culling);
+    for sort-last the shards partition the scene, so the frame's T is the whole scene's."""
+    return scene.total_triangles if sort_last else st0["triangles_submitted"]
 
 
 def main():
@@ -371,11 +452,12 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     import __graft_entry__ as g
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
-        g.build()
+        g.build(load=args.impl != "reference")  # the CPU arm builds the checker but never maps the product libraries
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -273,6 +273,8 @@ int swr_read_color(swr_ctx *ctx, float *rgb);
 
 int swr_synchronize(swr_ctx *ctx);
 int swr_get_stats(swr_ctx *ctx, swr_frame_stats *out);
+/* Number of CUDA kernels this context has launched since swr_create (monotonic; what bench.py reports as gpu_launches). */
+uint64_t swr_launch_count(swr_ctx *ctx);
 
 /* Sort-first frame assembly over NVLink peer memory: instead of resolving locally and gathering strips with a
  * collective, every contributing rank's resolve kernel stores its rows straight into the assembling rank's pixel buffer

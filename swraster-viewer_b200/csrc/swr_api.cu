@@ -112,6 +112,7 @@ struct swr_ctx {
     FrameSlot *cur = nullptr;              // slot of the frame being (or last) enqueued
     cudaEvent_t ev_res[2] = {nullptr, nullptr};
     std::string err;
+    uint64_t launches = 0;  // kernels this context has launched (swr_launch_count)
 
     // scene
     bool have_scene = false;
@@ -404,6 +405,7 @@ int swr_upload_scene(swr_ctx *ctx, const swr_scene_desc *s) {
             float4 *sph = nullptr;
             CK(cudaMalloc(&sph, (size_t)d.ncl * sizeof(float4)));
             ctx->scene_allocs.push_back(sph);
+            ctx->launches++;
             k_cluster_bounds<<<(d.ncl + 7) / 8, 256, 0, ctx->stream>>>(pos, idx, d.ntris, sph, d.ncl);
             d.cl_sphere = sph;
         }
@@ -667,30 +669,40 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
         const uint64_t guess = g.work_hint ? (uint64_t)g.work_hint + g.work_hint / 8 + 64 : clusters;
         const unsigned geom_grid = (unsigned)std::min<uint64_t>(clusters, std::max<uint64_t>(guess, (uint64_t)ctx->num_sms * 16u));
         g.geom_grid = geom_grid;
+        ctx->launches++;
         k_cull<<<sp.ncull_blocks, 256, 0, s>>>(sp);
+        ctx->launches++;
         k_compact<<<sp.ncull_blocks, 256, 0, s>>>(sp);
+        ctx->launches++;
         k_setup<<<geom_grid, SETUP_THREADS, 0, s>>>(sp);
         if (clip_tris > 0) {
             uint64_t want = (clip_tris + CLIP_GROUPS - 1) / CLIP_GROUPS;
             // many short CTAs: an iteration lasts as long as its slowest polygon (block barriers in the accounting), so fine grains win
             const uint64_t cap = (uint64_t)ctx->num_sms * 8u;
+            ctx->launches++;
             k_clip<<<(unsigned)(want < cap ? want : cap), CLIP_THREADS, 0, s>>>(sp);
         }
     }
     if (translucent) {
+        ctx->launches++;
         k_scan_simple<<<1, 1024, 0, s>>>(g.tile_count.p, g.tile_offset.p, g.tile_cursor.p, ctx->ntiles, g.counters.p, (uint32_t)g.refs.cap);
     } else {
         const size_t unit_cap = (size_t)ctx->ntiles + g.refs.cap / RASTER_UNIT_MIN + 1;
         const uint32_t cta_slots = (uint32_t)ctx->num_sms * 4u;  // k_raster_tiles: 4 CTAs per SM
         if (ctx->unit_list.reserve(unit_cap) != cudaSuccess) return SWR_ERR_OOM;
+        ctx->launches++;
         k_scan_tiles<<<1, 1024, 0, s>>>(g.tile_count.p, g.tile_offset.p, g.tile_cursor.p, ctx->ntiles, g.counters.p, (uint32_t)g.refs.cap, ctx->unit_list.p,
                                         (uint32_t)unit_cap, rb * ctx->tiles_x, re * ctx->tiles_x, cta_slots, ctx->tile_unit.p, ctx->tile_count_prev.p,
                                         ctx->tile_cycles_prev.p, ctx->have_history ? 1 : 0);
         ctx->have_history = true;
     }
     if (tris > 0) {
+        ctx->launches++;
         k_scatter<<<g.geom_grid, SWR_CLUSTER_TRIS, 0, s>>>(sp, g.tile_cursor.p, g.refs.p);
-        if (clip_tris > 0) k_scatter_list<<<148, 256, 0, s>>>(g.rects.p, g.clip_list.p, g.clip_ext.p, g.tile_cursor.p, g.refs.p, g.counters.p, ctx->tiles_x);
+        if (clip_tris > 0) {
+            ctx->launches++;
+            k_scatter_list<<<148, 256, 0, s>>>(g.rects.p, g.clip_list.p, g.clip_ext.p, g.tile_cursor.p, g.refs.p, g.counters.p, ctx->tiles_x);
+        }
     }
     CK(cudaGetLastError());
     return SWR_OK;
@@ -736,6 +748,7 @@ static int launch_frame(swr_ctx *ctx) {
         rp.row_end = re;
         // keys of the owned rows start EMPTY: tiles split over several CTAs merge into them with atomicMin
         CK(cudaMemsetAsync(ctx->keys.p + (size_t)rb * ctx->tiles_x * SWR_TILE_PIXELS, 0xFF, (size_t)(re - rb) * ctx->tiles_x * SWR_TILE_PIXELS * 8, s));
+        ctx->launches++;
         k_raster_tiles<<<cta_slots, RASTER_THREADS, raster_smem_bytes(), s>>>(rp);  // persistent: one CTA per resident slot
     }
     CK(cudaEventRecord(ctx->cur->ev[2], s));
@@ -774,23 +787,27 @@ static int launch_shade(swr_ctx *ctx) {
         ShadeParams sp{};
         fill_shade_params(ctx, ctx->op, sp);
         dim3 grid(sp.Wp / 16, (re - rb) * SWR_TILE / SHADE_ROWS);
+        ctx->launches++;
         k_shade<<<grid, SHADE_BLOCK, 0, s>>>(sp);
         if (!ctx->tr.last_draws.empty() && !ctx->composited) {
             // translucent pass (tilerasterizer.rs:92-101): own geometry set, per-tile back-to-front sort, forward shading
             int rc = launch_geometry(ctx, ctx->tr, true);
             if (rc) return rc;
             GeomSet &t = ctx->tr;
+            ctx->launches++;
             k_sort_translucent<<<ctx->ntiles, 256, 0, s>>>(t.refs.p, t.tile_offset.p, t.avgz.p, t.clip_ext.p, t.counters.p);
             ForwardParams fp{};
             fill_shade_params(ctx, t, fp.sh);
             fp.refs = t.refs.p;
             fp.offset = t.tile_offset.p;
             fp.counters = t.counters.p;
+            ctx->launches++;
             k_forward_translucent<<<grid, SHADE_BLOCK, 0, s>>>(fp);
             CK(cudaMemcpyAsync(t.h_counters, t.counters.p, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
             ctx->cur->tr_ran = true;
         }
         const int t0 = rb * ctx->tiles_x, t1 = re * ctx->tiles_x;
+        ctx->launches++;
         k_luminance<<<(t1 - t0 + 127) / 128, 128, 0, s>>>(ctx->color.p, ctx->lum.p, sp.Wp, sp.Hp, ctx->tiles_x, ctx->ntiles, t0, t1);
     }
     CK(cudaEventRecord(ctx->cur->ev[3], s));
@@ -998,6 +1015,7 @@ int swr_keys_to_global(swr_ctx *ctx) {
     int rc;
     if ((rc = finish_frame(ctx))) return rc;
     const size_t n = (size_t)ctx->ntiles * SWR_TILE_PIXELS;
+    ctx->launches++;
     k_keys_to_global<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->keys.p, n, ctx->op.records.p, ctx->op.clip_ext.p);
     CK(cudaGetLastError());
     return SWR_OK;
@@ -1009,6 +1027,7 @@ int swr_keys_localize(swr_ctx *ctx) {
     if ((rc = finish_frame(ctx))) return rc;
     if (ctx->bary.reserve((size_t)ctx->W * ctx->H) != cudaSuccess) return SWR_ERR_OOM;
     dim3 blk(32, 8), grid((ctx->W + 31) / 32, (ctx->H + 7) / 8);
+    ctx->launches++;
     k_keys_localize<<<grid, blk, 0, ctx->stream>>>(ctx->keys.p, ctx->tiles_x, ctx->W, ctx->H, ctx->op.records.p, ctx->op.clip_ext.p, ctx->op.draws.p,
                                                    ctx->op.tri_prefix.p, ctx->op.ndraws, ctx->scene.prims, ctx->bary.p);
     CK(cudaGetLastError());
@@ -1046,6 +1065,7 @@ static int resolve_into(swr_ctx *ctx, uint32_t *dst, float exposure) {
         const int idx = dst == ctx->pixels_alt.p ? 1 : 0;
         dim3 grid((unsigned)((W + 255) / 256), (unsigned)((y1 - y0 + 3) / 4));
         if (ctx->copy_pending[idx]) CK(cudaStreamWaitEvent(s, ctx->ev_copied[idx], 0));
+        ctx->launches++;
         k_resolve<<<grid, 256, 0, s>>>(ctx->color.p, ctx->tiles_x * SWR_TILE, dst, ctx->W, (int)y0, (int)y1, exposure);
     }
     CK(cudaEventRecord(ctx->ev_res[1], s));
@@ -1155,9 +1175,11 @@ int swr_resolve_peer(swr_ctx *ctx, float exposure, uint32_t frame) {
     if (y1 > (size_t)ctx->H) y1 = ctx->H;
     uint32_t *ctrl = ctx->peer_pixels + (size_t)ctx->W * ctx->H;
     CK(cudaEventRecord(ctx->ev_res[0], s));
+    ctx->launches++;
     k_peer_wait<<<1, 1, 0, s>>>(ctrl + SWR_PEER_FREE, frame, ctx->peer_local.p + 1);
     // an empty band still contributes (one CTA that only signals) so the assembler's count stays in step
     dim3 grid((unsigned)((W + 255) / 256), (unsigned)(y1 > y0 ? (y1 - y0 + 3) / 4 : 1));
+    ctx->launches++;
     k_resolve_peer<<<grid, 256, 0, s>>>(ctx->color.p, ctx->tiles_x * SWR_TILE, ctx->peer_pixels, ctrl, ctx->W, (int)y0, (int)(y1 > y0 ? y1 : y0), exposure,
                                         ctx->peer_local.p, ctx->peer_local.p + 1);
     CK(cudaEventRecord(ctx->ev_res[1], s));
@@ -1173,7 +1195,10 @@ int swr_peer_collect(swr_ctx *ctx, uint32_t frame, int contributors) {
     }
     CK(cudaSetDevice(ctx->device));
     uint32_t *ctrl = ctx->pixels.p + (size_t)ctx->W * ctx->H;
-    if (contributors > 0) k_peer_wait<<<1, 1, 0, ctx->stream>>>(ctrl + SWR_PEER_DONE, frame * (uint32_t)contributors, ctx->peer_local.p + 1);
+    if (contributors > 0) {
+        ctx->launches++;
+        k_peer_wait<<<1, 1, 0, ctx->stream>>>(ctrl + SWR_PEER_DONE, frame * (uint32_t)contributors, ctx->peer_local.p + 1);
+    }
     CK(cudaGetLastError());
     return SWR_OK;
 }
@@ -1185,6 +1210,7 @@ int swr_peer_release(swr_ctx *ctx, uint32_t frame) {
         return SWR_ERR_INVALID;
     }
     CK(cudaSetDevice(ctx->device));
+    ctx->launches++;
     k_peer_release<<<1, 1, 0, ctx->stream>>>(ctx->pixels.p + (size_t)ctx->W * ctx->H, frame + 1u);
     CK(cudaGetLastError());
     return SWR_OK;
@@ -1200,6 +1226,7 @@ static int issue_resolve_copy(swr_ctx *ctx, int idx, float exposure, uint32_t *h
     if (ctx->copy_pending[idx]) CK(cudaStreamWaitEvent(s, ctx->ev_copied[idx], 0));  // the previous copy out of this buffer
     if (y1 > y0) {
         dim3 grid((unsigned)((W + 255) / 256), (unsigned)((y1 - y0 + 3) / 4));
+        ctx->launches++;
         k_resolve<<<grid, 256, 0, s>>>(ctx->color.p, ctx->tiles_x * SWR_TILE, dst, ctx->W, (int)y0, (int)y1, exposure);
     }
     CK(cudaEventRecord(ctx->ev_resolved[idx], s));
@@ -1300,6 +1327,7 @@ int swr_read_visbuffer(swr_ctx *ctx, uint32_t *depth_bits, uint32_t *seq, float 
     vp.H = ctx->H;
     vp.tiles_x = ctx->tiles_x;
     dim3 blk(32, 8), grid((ctx->W + 31) / 32, (ctx->H + 7) / 8);
+    ctx->launches++;
     k_read_vis<<<grid, blk, 0, ctx->stream>>>(vp, d, d + n, (float *)(d + 2 * n), (float *)(d + 3 * n));
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess && depth_bits) e = cudaMemcpy(depth_bits, d, n * 4, cudaMemcpyDeviceToHost);
@@ -1337,6 +1365,8 @@ int swr_get_stats(swr_ctx *ctx, swr_frame_stats *out) {
     *out = ctx->stats;
     return SWR_OK;
 }
+
+uint64_t swr_launch_count(swr_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 void *swr_device_pixels(swr_ctx *ctx) { return ctx ? (ctx->pix_cur ? ctx->pixels_alt.p : ctx->pixels.p) : nullptr; }
 void *swr_device_keys(swr_ctx *ctx) { return ctx ? ctx->keys.p : nullptr; }

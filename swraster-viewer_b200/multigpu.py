@@ -103,6 +103,74 @@ class PeerAssembly:
             self.r.peer_release(self.f)
 
 
+class SharedHostFrame:
+    """The caller's W*H u32 frame as ONE host buffer shared by the rank processes of a box: a /dev/shm segment every rank
+    maps and page-locks (cudaHostRegister). Sort-first ranks then read their own rows back over their own PCIe links,
+    in parallel, straight into the final frame (Renderer.blit_to_buffer copies only the rows a renderer owns), instead of
+    funnelling 4*W*H bytes through rank 0's link. Behind the pixels: one u64 arrival counter per rank
+    (arrive / wait_all) so the consumer knows when frame f is complete without a collective."""
+
+    MAX_RANKS = 64
+
+    def __init__(self, width, height, tag):
+        import mmap
+        import os
+        import torch
+        import torch.distributed as dist
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.nbytes_pix = width * height * 4
+        n = self.nbytes_pix + self.MAX_RANKS * 8
+        self.path = f"/dev/shm/{tag}"
+        if self.rank == 0:
+            fd = os.open(self.path, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
+            os.ftruncate(fd, n)
+        if dist.is_initialized():
+            dist.barrier()
+        if self.rank != 0:
+            fd = os.open(self.path, os.O_RDWR)
+        self.mm = mmap.mmap(fd, n)
+        os.close(fd)
+        buf = np.frombuffer(self.mm, dtype=np.uint8)
+        self.pixels = buf[:self.nbytes_pix].view(np.uint32)
+        self.flags = buf[self.nbytes_pix:].view(np.uint64)
+        self._rt = torch.cuda.cudart()
+        rc = self._rt.cudaHostRegister(self.pixels.ctypes.data, self.nbytes_pix, 0)
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaHostRegister failed: {rc}")
+        self._registered = True
+        if dist.is_initialized():
+            dist.barrier()
+
+    def reset(self):
+        self.flags[self.rank] = 0
+
+    def arrive(self, rank, frame):
+        self.flags[rank] = frame
+
+    def wait_all(self, world, frame, timeout_s=10.0):
+        import time
+        t0 = time.perf_counter()
+        while int(self.flags[:world].min()) < frame:
+            if time.perf_counter() - t0 > timeout_s:
+                raise RuntimeError("SharedHostFrame.wait_all timed out")
+
+    def close(self, unlink=False):
+        import os
+        if self._registered:
+            self._rt.cudaHostUnregister(self.pixels.ctypes.data)
+            self._registered = False
+        self.pixels = self.flags = None
+        try:
+            self.mm.close()
+        except BufferError:
+            pass
+        if unlink:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
 def composite_keys_min(keys):
     """keys: int64 torch tensor holding the UNSIGNED 64-bit visibility keys of this rank (empty = all ones).
     All-reduce with unsigned MIN: flip the sign bit so signed order == unsigned order, reduce, flip back."""

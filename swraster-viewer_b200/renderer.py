@@ -71,6 +71,8 @@ def load_libraries():
     core.swr_resolve_peer.argtypes = [vp, f32, C.c_uint32]
     core.swr_peer_collect.argtypes = [vp, C.c_uint32, i32]
     core.swr_peer_release.argtypes = [vp, C.c_uint32]
+    core.swr_launch_count.restype = C.c_uint64
+    core.swr_launch_count.argtypes = [vp]
     core.swr_sizeof.restype = C.c_size_t
     core.swr_sizeof.argtypes = [i32]
 
@@ -310,6 +312,11 @@ class Renderer:
         st = abi.FrameStats()
         self._check_core(self.core.swr_get_stats(self.ctx, C.byref(st)))
         return st.as_dict()
+
+    @property
+    def launch_count(self):
+        """CUDA kernels launched by this renderer's context so far (swr_launch_count)."""
+        return int(self.core.swr_launch_count(self.ctx))
 
     def device_pixels_ptr(self):
         return self.core.swr_device_pixels(self.ctx)

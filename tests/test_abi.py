@@ -125,7 +125,7 @@ for name in abi.EXPORTS:
     if name in skip:
         continue
     r = getattr(core, name)(*args.get(name, (None,)))
-    ok = r is None or r == 0 if name in ("swr_destroy", "swr_device_pixels", "swr_device_keys", "swr_device_keys_bytes", "swr_device_bary", "swr_cuda_stream") else r < 0
+    ok = r is None or r == 0 if name in ("swr_destroy", "swr_device_pixels", "swr_device_keys", "swr_device_keys_bytes", "swr_device_bary", "swr_cuda_stream", "swr_launch_count") else r < 0
     assert ok, (name, r)
 print("NULL-SAFE", len(abi.EXPORTS) - len(skip))
 ''' % ROOT

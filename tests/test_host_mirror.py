@@ -205,3 +205,32 @@ def test_scene_ranges_are_validated_before_they_are_indexed():
         with pytest.raises(RuntimeError, match=msg):
             build_draws(variant(edit), cam)
     assert build_draws(variant(lambda n, m, p: setattr(n[0], "mesh_index", -1)), cam)[1] == 0  # a node without a mesh draws nothing
+
+
+def test_bench_camera_fixture_matches_the_host_mirror():
+    """bench.py --impl reference takes its swr_camera blocks from tests/golden/bench_cameras.json (so the CPU arm never maps
+    the product libraries); the host mirror must still reproduce every one of them bit for bit from the recorded spec."""
+    import json
+    import os
+    from swraster_viewer_b200 import scenes
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fx = json.load(open(os.path.join(root, "tests", "golden", "bench_cameras.json")))
+    assert set(fx) == {"c1", "c2", "c3", "c4", "c5"}
+    for name, e in fx.items():
+        spec = scenes.CameraSpec(tuple(e["position"]), tuple(e["look_at"]), e["fov"], e["far_plane"])
+        cam = swr.RenderCamera.from_spec(spec, e["width"], e["height"])
+        assert bytes(cam.abi).hex() == e["camera_hex"], name
+
+
+def test_reference_arm_does_not_map_the_product_libraries():
+    """the CPU arm's process must not load libswr_b200.so / libswr_host.so (only the checker)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, os; sys.argv=['bench.py','--impl','reference','--config','c1','--steps','1','--warmup','0'];"
+            "sys.path.insert(0, %r); import bench; bench.main();"
+            "maps=open('/proc/self/maps').read(); print('MAPPED', 'libswr_b200' in maps or 'libswr_host' in maps, 'liboracle' in maps)") % root
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert "MAPPED False True" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    assert '"impl": "reference"' in out.stdout
