@@ -297,6 +297,32 @@ int swr_resolve_peer(swr_ctx *ctx, float exposure, uint32_t frame);
 int swr_peer_collect(swr_ctx *ctx, uint32_t frame, int contributors);
 int swr_peer_release(swr_ctx *ctx, uint32_t frame);
 
+/* ---- several devices of one process behind one handle ------------------------------------------------------------
+ * What a single `Renderer` (renderer.rs:145-355; SURVEY 8b: "swr_create(w, h, devices, ndev, mode)") needs to drive all
+ * GPUs of a box: the scene is replicated, device i owns a contiguous range of tile rows whose measured cost is 1/ndev of
+ * the frame's (probed on the first frame after an upload), every device culls the same draw list against its band, and
+ * the frame is assembled in devices[0]'s pixel buffer by the other devices' resolve kernels storing over NVLink peer
+ * memory (the swr_peer_* protocol with direct peer pointers: no IPC, no collective). One persistent host thread per
+ * device does the enqueueing. Same call order as the single-device API:
+ *   swr_multi_upload_scene; per frame swr_multi_render, [swr_multi_read_tile_luminance -> update_auto_exposure on the
+ *   host], swr_multi_resolve(exposure, host pixels or NULL). ndev = 1 is the single-device path through the same calls.
+ * Sort-last (shard by primitive + depth composite) keeps one context per rank: swr_keys_to_global / swr_keys_localize. */
+#define SWR_MULTI_SORT_FIRST 1
+typedef struct swr_multi swr_multi;
+swr_multi *swr_multi_create(int width, int height, const int *devices, int ndev, int mode);
+void swr_multi_destroy(swr_multi *m);
+const char *swr_multi_last_error(const swr_multi *m); /* m may be NULL: last create error */
+int swr_multi_device_count(const swr_multi *m);
+swr_ctx *swr_multi_context(swr_multi *m, int i); /* the per-device context (parity read-back, statistics) */
+int swr_multi_tile_rows(const swr_multi *m, int i, int *row_begin, int *row_end);
+int swr_multi_set_rsqrt_table(swr_multi *m, const uint32_t *table, int mantissa_bits);
+int swr_multi_upload_scene(swr_multi *m, const swr_scene_desc *scene);
+int swr_multi_render(swr_multi *m, const swr_camera *camera, const swr_draw *draws, int ndraws);
+int swr_multi_resolve(swr_multi *m, float exposure, uint32_t *out_pixels);
+int swr_multi_read_tile_luminance(swr_multi *m, float *out_per_tile);
+int swr_multi_get_stats(swr_multi *m, swr_frame_stats *out); /* counters summed over the bands, phase times = slowest device */
+int swr_multi_synchronize(swr_multi *m);
+
 /* Device pointers for zero-copy interop (NCCL gather / composite from the host
  * language): RGBA8 image (W*H u32, row-major) and the 64-bit visibility keys
  * (tile-major: tile (ty*tiles_x+tx) owns 4096 consecutive keys, y*64+x inside the

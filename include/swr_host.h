@@ -20,6 +20,11 @@ int swrh_camera_build_rotated(const float pos[3], const float look_at_level[3], 
 
 /* Renderer::new(width, height) (renderer.rs:165) on CUDA device `device`; NULL on error (no CPU fallback) */
 void *swrh_renderer_new(int width, int height, int device);
+/* the same Renderer over several CUDA devices of this process (sort-first; include/swr.h swr_multi_*): one frame, one
+ * blit, every method below works on it except swrh_set_tile_rows (it assigns its own cost-balanced bands, readable
+ * with swrh_renderer_tile_rows) and shard / nshards of swrh_render_scene */
+void *swrh_renderer_new_multi(int width, int height, const int *devices, int ndev);
+int swrh_renderer_tile_rows(void *renderer, int device_index, int *row_begin, int *row_end);
 void swrh_renderer_free(void *renderer);
 swr_ctx *swrh_renderer_ctx(void *renderer); /* the device context underneath, for the swr_* calls of swr.h */
 /* Renderer::render_scene(&scene, &camera) (renderer.rs:201): uploads the scene on first sight, builds the draw list on

@@ -106,4 +106,7 @@ EXPORTS = [
     "swr_synchronize", "swr_get_stats", "swr_device_pixels", "swr_device_keys", "swr_device_keys_bytes",
     "swr_cuda_stream", "swr_sizeof", "swr_launch_count",
     "swr_peer_export", "swr_peer_open", "swr_peer_attach", "swr_resolve_peer", "swr_peer_collect", "swr_peer_release",
+    "swr_multi_create", "swr_multi_destroy", "swr_multi_last_error", "swr_multi_device_count", "swr_multi_context", "swr_multi_tile_rows",
+    "swr_multi_set_rsqrt_table", "swr_multi_upload_scene", "swr_multi_render", "swr_multi_resolve", "swr_multi_read_tile_luminance",
+    "swr_multi_get_stats", "swr_multi_synchronize",
 ]

@@ -8,6 +8,10 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include "../../include/swr.h"
 #include "swr_shade.cuh"
 
@@ -1372,5 +1376,7 @@ void *swr_device_pixels(swr_ctx *ctx) { return ctx ? (ctx->pix_cur ? ctx->pixels
 void *swr_device_keys(swr_ctx *ctx) { return ctx ? ctx->keys.p : nullptr; }
 size_t swr_device_keys_bytes(swr_ctx *ctx) { return ctx ? (size_t)ctx->ntiles * SWR_TILE_PIXELS * 8 : 0; }
 void *swr_cuda_stream(swr_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+#include "swr_multi.inl"
 
 }  // extern "C"

@@ -382,21 +382,35 @@ class Renderer {
         auto_exposure_ev_ = std::log2(SWR_DEFAULT_EXPOSURE);
         set_reference_rsqrt(true);
     }
+    // Renderer::new over several GPUs of this process (sort-first, include/swr.h swr_multi_*): same methods, one frame.
+    Renderer(int width, int height, const std::vector<int> &devices) : width_(width), height_(height) {
+        multi_ = swr_multi_create(width, height, devices.data(), (int)devices.size(), SWR_MULTI_SORT_FIRST);
+        if (!multi_) throw std::runtime_error(std::string("swr_multi_create: ") + swr_multi_last_error(nullptr));
+        ctx_ = swr_multi_context(multi_, 0);
+        auto_exposure_ = auto_exposure_target_ = SWR_DEFAULT_EXPOSURE;
+        auto_exposure_ev_ = std::log2(SWR_DEFAULT_EXPOSURE);
+        set_reference_rsqrt(true);
+    }
     // Match the reference's normalize() on this host (default), or use the device's own rsqrtf().
     void set_reference_rsqrt(bool on) {
         static std::vector<uint32_t> table;
         static int bits = -1;
         if (bits < 0) bits = probe_host_rsqrt_table(table);
-        if (on && bits > 0)
-            check(swr_set_rsqrt_table(ctx_, table.data(), bits), "swr_set_rsqrt_table");
+        const uint32_t *t = (on && bits > 0) ? table.data() : nullptr;
+        if (multi_)
+            check(swr_multi_set_rsqrt_table(multi_, t, t ? bits : 0), "swr_multi_set_rsqrt_table");
         else
-            check(swr_set_rsqrt_table(ctx_, nullptr, 0), "swr_set_rsqrt_table");
+            check(swr_set_rsqrt_table(ctx_, t, t ? bits : 0), "swr_set_rsqrt_table");
         rsqrt_bits_ = on ? bits : 0;
     }
     int reference_rsqrt_bits() const { return rsqrt_bits_; }
     ~Renderer() {
-        if (ctx_) swr_destroy(ctx_);
+        if (multi_)
+            swr_multi_destroy(multi_);
+        else if (ctx_)
+            swr_destroy(ctx_);
     }
+    swr_multi *multi() const { return multi_; }
     Renderer(const Renderer &) = delete;
     Renderer &operator=(const Renderer &) = delete;
 
@@ -404,6 +418,7 @@ class Renderer {
     float auto_exposure() const { return auto_exposure_; }
     const std::vector<swr_draw> &draws() const { return draws_; }
     void set_tile_rows(int r0, int r1) {
+        if (multi_) throw std::runtime_error("set_tile_rows: a multi-device renderer assigns its own row bands");
         check(swr_set_tile_rows(ctx_, r0, r1), "swr_set_tile_rows");
         row0_ = r0;
         row1_ = r1;
@@ -417,8 +432,17 @@ class Renderer {
     void render_scene(const Scene &scene, const swr_camera &cam, bool shade = true, int shard = 0, int nshards = 1) {
         if (scene.desc != uploaded_) {  // immutable scene: upload on first sight (SURVEY §8b ownership)
             validate_scene_ranges(*scene.desc);
-            check(swr_upload_scene(ctx_, scene.desc), "swr_upload_scene");
+            if (multi_)
+                check(swr_multi_upload_scene(multi_, scene.desc), "swr_multi_upload_scene");
+            else
+                check(swr_upload_scene(ctx_, scene.desc), "swr_upload_scene");
             uploaded_ = scene.desc;
+        }
+        if (multi_) {  // every device culls the full draw list against its own band (k_cull)
+            if (!shade || nshards != 1) throw std::runtime_error("multi-device renderer: sort-first only (shade = 1, no shards)");
+            build_draw_list(*scene.desc, cam, draws_);
+            check(swr_multi_render(multi_, &cam, draws_.data(), (int)draws_.size()), "swr_multi_render");
+            return;
         }
         const int tiles_y = (height_ + SWR_TILE_SIZE - 1) / SWR_TILE_SIZE;
         const bool band = row1_ > row0_ && (row0_ > 0 || row1_ < tiles_y);  // sort-first: drop draws that cannot reach my rows
@@ -429,10 +453,10 @@ class Renderer {
     // update_auto_exposure(&mut self, delta_time) — renderer.rs:258-290
     void update_auto_exposure(float delta_time) {
         swr_frame_stats st;
-        check(swr_get_stats(ctx_, &st), "swr_get_stats");
+        check(multi_ ? swr_multi_get_stats(multi_, &st) : swr_get_stats(ctx_, &st), "swr_get_stats");
         if (st.tiles == 0) return;
         std::vector<float> lum(st.tiles);
-        check(swr_read_tile_luminance(ctx_, lum.data()), "swr_read_tile_luminance");
+        check(multi_ ? swr_multi_read_tile_luminance(multi_, lum.data()) : swr_read_tile_luminance(ctx_, lum.data()), "swr_read_tile_luminance");
         // sort-first: only the tiles of the rows this renderer owns were shaded; the others hold no metering value
         if (row1_ > row0_) {
             const size_t tiles_x = (size_t)(width_ + SWR_TILE_SIZE - 1) / SWR_TILE_SIZE;
@@ -463,7 +487,10 @@ class Renderer {
     // blit_to_buffer(&self, buffer) — renderer.rs:293-355
     void blit_to_buffer(RenderBuffer &buffer) {
         if ((int)buffer.width != width_ || (int)buffer.height < height_) throw std::runtime_error("RenderBuffer size mismatch");
-        check(swr_resolve(ctx_, auto_exposure_, buffer.pixels), "swr_resolve");
+        if (multi_)
+            check(swr_multi_resolve(multi_, auto_exposure_, buffer.pixels), "swr_multi_resolve");
+        else
+            check(swr_resolve(ctx_, auto_exposure_, buffer.pixels), "swr_resolve");
     }
 
     // Pipelined blit (the reference's App overlaps present(N-1) with render(N), main.rs:526-597): starts resolve + read-back
@@ -471,19 +498,26 @@ class Renderer {
     int blit_to_buffer_async(RenderBuffer &buffer) {
         if ((int)buffer.width != width_ || (int)buffer.height < height_) throw std::runtime_error("RenderBuffer size mismatch");
         int ticket = -1;
+        if (multi_) {  // the assembled frame lives on device 0 and is handed back by the peer protocol: synchronous form
+            check(swr_multi_resolve(multi_, auto_exposure_, buffer.pixels), "swr_multi_resolve");
+            return 0;
+        }
         check(swr_resolve_async(ctx_, auto_exposure_, buffer.pixels, &ticket), "swr_resolve_async");
         return ticket;
     }
-    void wait_blit(int ticket) { check(swr_wait_pixels(ctx_, ticket), "swr_wait_pixels"); }
+    void wait_blit(int ticket) {
+        if (!multi_) check(swr_wait_pixels(ctx_, ticket), "swr_wait_pixels");
+    }
 
    private:
     void check(int rc, const char *what) {
-        if (rc != 0) throw std::runtime_error(std::string(what) + ": " + swr_last_error(ctx_));
+        if (rc != 0) throw std::runtime_error(std::string(what) + ": " + (multi_ && std::strncmp(what, "swr_multi", 9) == 0 ? swr_multi_last_error(multi_) : swr_last_error(ctx_)));
     }
     int width_, height_;
     int rsqrt_bits_ = 0;
     int row0_ = 0, row1_ = 0;
-    swr_ctx *ctx_ = nullptr;
+    swr_ctx *ctx_ = nullptr;        // single device; with multi_: the context of devices[0] (owned by multi_)
+    swr_multi *multi_ = nullptr;
     const swr_scene_desc *uploaded_ = nullptr;
     std::vector<swr_draw> draws_;
     float auto_exposure_, auto_exposure_target_, auto_exposure_ev_;

@@ -54,6 +54,19 @@ void *swrh_renderer_new(int width, int height, int device) {
         return nullptr;
     }
 }
+void *swrh_renderer_new_multi(int width, int height, const int *devices, int ndev) {
+    try {
+        if (!devices || ndev < 1) throw std::runtime_error("swrh_renderer_new_multi: device list is empty");
+        return new swr::Renderer(width, height, std::vector<int>(devices, devices + ndev));
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+int swrh_renderer_tile_rows(void *r, int device_index, int *row_begin, int *row_end) {
+    SWRH_TRY(swr::Renderer &R = need(r); if (!R.multi()) throw std::runtime_error("not a multi-device renderer");
+             if (swr_multi_tile_rows(R.multi(), device_index, &need_ptr(row_begin, "row_begin"), &need_ptr(row_end, "row_end")) != 0) throw std::runtime_error("device index out of range"));
+}
 void swrh_renderer_free(void *r) { delete (swr::Renderer *)r; }
 swr_ctx *swrh_renderer_ctx(void *r) { return r ? ((swr::Renderer *)r)->ctx() : nullptr; }
 

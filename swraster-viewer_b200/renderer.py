@@ -81,6 +81,9 @@ def load_libraries():
     host.swrh_camera_build_rotated.argtypes = [C.POINTER(f32), C.POINTER(f32), f32, f32, f32, f32, f32, f32, C.POINTER(abi.Camera)]
     host.swrh_renderer_new.restype = vp
     host.swrh_renderer_new.argtypes = [i32, i32, i32]
+    host.swrh_renderer_new_multi.restype = vp
+    host.swrh_renderer_new_multi.argtypes = [i32, i32, C.POINTER(i32), i32]
+    host.swrh_renderer_tile_rows.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     host.swrh_renderer_free.argtypes = [vp]
     host.swrh_renderer_ctx.restype = vp
     host.swrh_renderer_ctx.argtypes = [vp]
@@ -161,12 +164,18 @@ class RenderBuffer:
 class Renderer:
     """renderer.rs:145-355 behind the CUDA path. One Renderer per GPU."""
 
-    def __init__(self, width, height, device=0):
+    def __init__(self, width, height, device=0, devices=None):
+        """device: one CUDA ordinal; devices=[...]: one Renderer over several GPUs of this process (sort-first)."""
         self.core, self.host = load_libraries()
         self.width, self.height = width, height
         self.tiles_x = (width + abi.TILE_SIZE - 1) // abi.TILE_SIZE
         self.tiles_y = (height + abi.TILE_SIZE - 1) // abi.TILE_SIZE
-        self._h = self.host.swrh_renderer_new(width, height, device)
+        self.devices = list(devices) if devices is not None else None
+        if self.devices is not None:
+            arr = (C.c_int * len(self.devices))(*self.devices)
+            self._h = self.host.swrh_renderer_new_multi(width, height, arr, len(self.devices))
+        else:
+            self._h = self.host.swrh_renderer_new(width, height, device)
         if not self._h:
             raise RuntimeError("Renderer::new failed: " + self.host.swrh_last_error().decode())
         self.ctx = self.host.swrh_renderer_ctx(self._h)
@@ -312,6 +321,12 @@ class Renderer:
         st = abi.FrameStats()
         self._check_core(self.core.swr_get_stats(self.ctx, C.byref(st)))
         return st.as_dict()
+
+    def device_tile_rows(self, i):
+        """Rows [begin, end) device i of a multi-device renderer owns."""
+        a, b = C.c_int(), C.c_int()
+        self._check(self.host.swrh_renderer_tile_rows(self._h, i, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     @property
     def launch_count(self):

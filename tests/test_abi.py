@@ -119,13 +119,17 @@ args = {"swr_set_rsqrt_table": (None, None, 10), "swr_set_tile_rows": (None, 0, 
         "swr_wait_pixels": (None, 0), "swr_read_tile_luminance": (None, None), "swr_read_tile_costs": (None, None, None),
         "swr_read_visbuffer": (None, None, None, None, None), "swr_read_color": (None, None), "swr_get_stats": (None, None), "swr_peer_export": (None, None),
         "swr_peer_open": (None, None), "swr_peer_attach": (None, None), "swr_resolve_peer": (None, 2.0, 1), "swr_peer_collect": (None, 1, 1),
-        "swr_peer_release": (None, 1)}
-skip = {"swr_abi_version", "swr_last_error", "swr_create", "swr_sizeof"}
+        "swr_peer_release": (None, 1), "swr_multi_tile_rows": (None, 0, None, None), "swr_multi_set_rsqrt_table": (None, None, 10), "swr_multi_upload_scene": (None, None),
+        "swr_multi_render": (None, None, None, 0), "swr_multi_resolve": (None, 2.0, None), "swr_multi_read_tile_luminance": (None, None), "swr_multi_get_stats": (None, None),
+        "swr_multi_context": (None, 0)}
+core.swr_multi_resolve.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+skip = {"swr_abi_version", "swr_last_error", "swr_create", "swr_sizeof", "swr_multi_create", "swr_multi_last_error"}
 for name in abi.EXPORTS:
     if name in skip:
         continue
     r = getattr(core, name)(*args.get(name, (None,)))
-    ok = r is None or r == 0 if name in ("swr_destroy", "swr_device_pixels", "swr_device_keys", "swr_device_keys_bytes", "swr_device_bary", "swr_cuda_stream", "swr_launch_count") else r < 0
+    ok = r is None or r == 0 if name in ("swr_destroy", "swr_device_pixels", "swr_device_keys", "swr_device_keys_bytes", "swr_device_bary", "swr_cuda_stream", "swr_launch_count", "swr_multi_destroy", "swr_multi_device_count",
+                                     "swr_multi_context") else r < 0
     assert ok, (name, r)
 print("NULL-SAFE", len(abi.EXPORTS) - len(skip))
 ''' % ROOT

@@ -1,0 +1,95 @@
+"""One Renderer over several devices of one process (include/swr.h swr_multi_*, host mirror Renderer(devices=[...])) and
+the two-frames-in-flight / buffer-growth replay logic of the single-device context. The multi-device frame must be the
+single-device frame, pixel for pixel; both must match the oracle (visibility bit-exact through the per-device contexts,
+RGBA8 within 1 LSB)."""
+import numpy as np
+import pytest
+
+import swraster_viewer_b200 as swr
+from helpers import small_configs, render_gpu, render_oracle, rgba_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+def device_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+def render_multi(scene, cam, W, H, devices, frames=2):
+    r = swr.Renderer(W, H, devices=devices)
+    buf = swr.RenderBuffer(W, H)
+    outs = []
+    for _ in range(frames):
+        r.render_scene(scene, cam)
+        r.update_auto_exposure(0.0)
+        r.blit_to_buffer(buf)
+        outs.append(buf.pixels.copy())
+    rows = [r.device_tile_rows(i) for i in range(len(devices))]
+    st = r.stats()
+    r.close()
+    return outs, rows, st
+
+
+@pytest.mark.parametrize("idx", [2, 5])
+def test_multi_with_one_device_is_the_single_device_path(idx):
+    name, scene, spec, W, H = small_configs()[idx]
+    cam = swr.RenderCamera.from_spec(spec, W, H)
+    outs, rows, st = render_multi(scene, cam, W, H, [0])
+    g = render_gpu(scene, cam, W, H)
+    assert rows == [(0, (H + 63) // 64)]
+    for p in outs:
+        assert np.array_equal(p, g["pixels"]), name
+    o = render_oracle(scene, cam, W, H)
+    assert np.abs(rgba_bytes(outs[-1]) - rgba_bytes(o["pixels"])).max() <= 1
+    assert st["triangles_binned"] == o["stats"]["triangles_binned"] and st["tile_refs"] == o["stats"]["tile_refs"]
+
+
+@pytest.mark.parametrize("idx", [2, 6, 1])
+def test_multi_devices_assemble_the_single_device_frame(idx):
+    n = device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs in the box")
+    name, scene, spec, W, H = small_configs()[idx]
+    cam = swr.RenderCamera.from_spec(spec, W, H)
+    g = render_gpu(scene, cam, W, H)
+    for ndev in sorted({2, min(n, 4), n}):
+        outs, rows, st = render_multi(scene, cam, W, H, list(range(ndev)), frames=3)
+        assert rows[0][0] == 0 and rows[-1][1] == (H + 63) // 64 and all(rows[i][1] == rows[i + 1][0] for i in range(ndev - 1)), rows
+        for f, p in enumerate(outs):
+            assert np.array_equal(p, g["pixels"]), f"{name}: {ndev} devices, frame {f}: {np.count_nonzero(p != g['pixels'])} pixels differ"
+
+
+def test_buffer_growth_is_replayed_with_frames_in_flight():
+    """A renderer that has sized its buffers on a small scene is handed a much larger one: tile lists / clip buffers
+    overflow on the device, the frame (and the resolve + read-back queued behind it) must be replayed transparently —
+    also when the next frame was already enqueued (two frames in flight)."""
+    from swraster_viewer_b200 import scenes
+    from helpers import SMALL
+    cfgs = small_configs()
+    _, small, spec_s, _, _ = cfgs[0]
+    W, H = 512, 288
+    # ~400 K triangles, heavy clipping: far more tile refs and clip vertices than the 4.6 K-triangle sphere sized the buffers for
+    big, spec_b = scenes.scene_c3_instanced(400000, ico_subdiv=3, torus_n=16, box_n=4, **SMALL)
+    cam_s = swr.RenderCamera.from_spec(spec_s, W, H)
+    cam_b = swr.RenderCamera.from_spec(spec_b, W, H)
+    ref = render_gpu(big, cam_b, W, H)["pixels"]
+    r = swr.Renderer(W, H)
+    bufs = [swr.RenderBuffer(W, H, pinned=False), swr.RenderBuffer(W, H, pinned=False)]
+    for _ in range(2):
+        r.render_scene(small, cam_s)
+        r.blit_to_buffer(bufs[0])
+    # pipelined: frame 0 (big, overflows) and frame 1 are both enqueued before anything is waited for
+    r.render_scene(big, cam_b)
+    t0 = r.blit_to_buffer_async(bufs[0])
+    r.render_scene(big, cam_b)
+    t1 = r.blit_to_buffer_async(bufs[1])
+    r.wait_blit(t0)
+    assert np.array_equal(bufs[0].pixels, ref), f"{np.count_nonzero(bufs[0].pixels != ref)} pixels differ after the replay"
+    r.wait_blit(t1)
+    assert np.array_equal(bufs[1].pixels, ref)
+    # and the device-only resolve form
+    r.render_scene(big, cam_b)
+    r.resolve_device_only(2.0)
+    r.synchronize()
+    r.close()
