@@ -37,6 +37,9 @@ int swrh_invalidate_scene(void *renderer);
 /* Renderer::update_auto_exposure(delta_time) (renderer.rs:258) and the exposure blit_to_buffer applies */
 int swrh_update_auto_exposure(void *renderer, float delta_time);
 float swrh_auto_exposure(void *renderer);
+/* the metering maths of update_auto_exposure on its own (no device): state = {auto_exposure, auto_exposure_target,
+ * auto_exposure_ev}, updated in place from `ntiles` per-tile center_luminance values (tilerasterizer.rs:103-106) */
+int swrh_auto_exposure_step(float state[3], const float *tile_luminance, int ntiles, float delta_time);
 /* Renderer::blit_to_buffer(&mut RenderBuffer) (renderer.rs:293): W*H u32, row-major, (R<<24)|(G<<16)|(B<<8)|A */
 int swrh_blit_to_buffer(void *renderer, uint32_t *pixels, size_t width, size_t height);
 /* pipelined form: resolve + read-back into pinned `pixels` in the background; swrh_wait_blit(ticket) completes it */

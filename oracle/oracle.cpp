@@ -1409,6 +1409,45 @@ int orc_resolve(void *h, float exposure, int nthreads, uint32_t *out_pixels, orc
     return 0;
 }
 
+// update_auto_exposure (renderer.rs:258-290) on a caller-supplied list of per-tile center_luminance values.
+// state = {auto_exposure, auto_exposure_target, auto_exposure_ev} (renderer.rs:194-196 start: 2.0, 2.0, log2(2.0)).
+int orc_update_auto_exposure(float *state, const float *center_luminance, int sample_count, float delta_time) {
+    if (sample_count == 0) return 0;  // :260-262
+    std::vector<float> tile_log_luminance((size_t)sample_count);
+    for (int i = 0; i < sample_count; i++) {  // :264-267  f32::max ignores a NaN operand, like fmaxf
+        tile_log_luminance[i] = log2f(fmaxf(center_luminance[i], 1e-4f));
+    }
+    // :269-270 sort_unstable_by(total_cmp): IEEE totalOrder (-NaN < -inf < ... < -0 < +0 < ... < +inf < +NaN)
+    auto total_key = [](float f) {
+        int32_t b;
+        memcpy(&b, &f, 4);
+        return b ^ (int32_t)(((uint32_t)(b >> 31)) >> 1);
+    };
+    std::sort(tile_log_luminance.begin(), tile_log_luminance.end(), [&](float a, float b) { return total_key(a) < total_key(b); });
+    // :272-276
+    size_t trim_count = (size_t)floorf((float)sample_count * 0.10f);
+    trim_count = std::min(trim_count, (size_t)(sample_count - 1) / 2);
+    float sum = 0.0f;  // iter().sum::<f32>() adds left to right starting from 0.0
+    for (size_t i = trim_count; i < (size_t)sample_count - trim_count; i++) sum += tile_log_luminance[i];
+    const float mean_log_luminance = sum / (float)((size_t)sample_count - 2 * trim_count);
+    // :279 tonemap_inverse_scalar(0.45) (util.rs:43-47), TONEMAP_K = 0.2
+    const float y = std::min(std::max(0.45f, 0.0f), 1.0f);
+    const float denom = fmaxf(1.0f + 0.2f - y, 1e-6f);
+    const float meter_key = fmaxf((y * 0.2f) / denom, 1e-4f);
+    // :280-283
+    float target_ev = log2f(meter_key) - mean_log_luminance;
+    float target = powf(2.0f, target_ev);
+    target = target < 0.05f ? 0.05f : (target > 32.0f ? 32.0f : target);  // clamp(AUTO_EXPOSURE_MIN, AUTO_EXPOSURE_MAX); NaN passes through
+    state[1] = target;
+    // :285-289
+    target_ev = log2f(state[1]);
+    const float tau = fmaxf(1.0f, 1e-4f);
+    const float alpha = 1.0f - expf(-(fmaxf(delta_time, 0.0f) / tau));
+    state[2] += (target_ev - state[2]) * alpha;
+    state[0] = powf(2.0f, state[2]);
+    return 0;
+}
+
 // Host-side draw list exactly as the oracle builds it (for cross-checking the product's host mirror).
 int orc_build_draws(const swr_scene_desc *scene, const swr_camera *cam, swr_draw *out, int max_draws) {
     Oracle o;

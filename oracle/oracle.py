@@ -51,6 +51,7 @@ def load():
         _lib.orc_resolve.argtypes = [vp, C.c_float, C.c_int, vp, C.POINTER(OrcStats)]
         _lib.orc_build_draws.argtypes = [vp, vp, vp, C.c_int]
         _lib.orc_set_exact_rsqrt.argtypes = [C.c_int]
+        _lib.orc_update_auto_exposure.argtypes = [vp, vp, C.c_int, C.c_float]
         _lib.orc_num_threads.restype = C.c_int
     return _lib
 
@@ -103,3 +104,12 @@ def set_exact_rsqrt(on):
 
 def num_threads():
     return load().orc_num_threads()
+
+
+def update_auto_exposure(state, center_luminance, delta_time):
+    """renderer.rs:258-290 on a list of per-tile metering values; state = [auto_exposure, target, ev] (float32), returns the new state."""
+    import numpy as np
+    st = np.array(state, np.float32)
+    lum = np.ascontiguousarray(center_luminance, np.float32)
+    load().orc_update_auto_exposure(st.ctypes.data, lum.ctypes.data, len(lum), float(delta_time))
+    return st

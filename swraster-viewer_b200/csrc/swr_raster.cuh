@@ -1265,7 +1265,9 @@ __global__ void k_read_vis(VisParams P, uint32_t *depth_bits, uint32_t *seq, flo
         uint32_t slot = 0xFFFFFFFFu - (uint32_t)key;
         TriRecord r = P.records[record_of_id(slot, P.clip_ext)];
         float z;
-        if (resolve_pixel(r, P.W, P.H, px, py, b1, b2, z)) {
+        // the owner must cover the pixel AND the depth it re-derives must be the depth the rasteriser ranked it by: a
+        // raster-vs-read-back disagreement shows up as a poisoned depth word, not as a silently different winner
+        if (resolve_pixel(r, P.W, P.H, px, py, b1, b2, z) && depth_orderable(z) == (uint32_t)(key >> 32)) {
             db = __float_as_uint(z);
             sq = r.seq;
         } else {

@@ -371,6 +371,38 @@ inline int probe_host_rsqrt_table(std::vector<uint32_t> &table) {
     return 0;
 }
 
+// renderer.rs:258-290 on a given set of per-tile metering values (tile.center_luminance): trimmed mean of log2 luminance,
+// target exposure from the post-tonemap mid grey, exponential smoothing over delta_time.
+// state = {auto_exposure, auto_exposure_target, auto_exposure_ev}, updated in place.
+inline void auto_exposure_step(float state[3], const float *tile_luminance, size_t n, float delta_time) {
+    if (n == 0) return;
+    std::vector<float> lum(tile_luminance, tile_luminance + n);
+    for (float &v : lum) v = std::log2(std::fmax(v, 1e-4f));
+    std::sort(lum.begin(), lum.end(), [](float a, float b) {  // f32::total_cmp
+        int32_t x, y;
+        std::memcpy(&x, &a, 4);
+        std::memcpy(&y, &b, 4);
+        x ^= (int32_t)((uint32_t)(x >> 31) >> 1);
+        y ^= (int32_t)((uint32_t)(y >> 31) >> 1);
+        return x < y;
+    });
+    size_t trim = (size_t)std::floor((float)n * 0.10f);
+    trim = std::min(trim, (n - 1) / 2);
+    float sum = 0.0f;
+    for (size_t i = trim; i < n - trim; i++) sum += lum[i];
+    const float mean_log = sum / (float)(n - 2 * trim);
+    // tonemap_inverse_scalar(0.45) (util.rs:43-47)
+    const float y = 0.45f, denom = std::fmax(1.0f + 0.2f - y, 1e-6f);
+    const float meter_key = std::fmax((y * 0.2f) / denom, 1e-4f);
+    const float target_ev = std::log2(meter_key) - mean_log;
+    const float target = std::fmin(std::fmax(std::pow(2.0f, target_ev), 0.05f), 32.0f);
+    state[1] = target;
+    const float tev = std::log2(target);
+    const float alpha = 1.0f - std::exp(-(std::fmax(delta_time, 0.0f) / 1.0f));
+    state[2] += (tev - state[2]) * alpha;
+    state[0] = std::pow(2.0f, state[2]);
+}
+
 // ---- renderer.rs:145-355 --------------------------------------------------------------
 class Renderer {
    public:
@@ -463,25 +495,11 @@ class Renderer {
             const size_t t0 = std::min((size_t)row0_ * tiles_x, lum.size()), t1 = std::min((size_t)row1_ * tiles_x, lum.size());
             lum = std::vector<float>(lum.begin() + t0, lum.begin() + t1);
         }
-        const size_t n = lum.size();
-        if (n == 0) return;
-        for (float &v : lum) v = std::log2(std::fmax(v, 1e-4f));
-        std::sort(lum.begin(), lum.end());
-        size_t trim = (size_t)std::floor((float)n * 0.10f);
-        trim = std::min(trim, (n - 1) / 2);
-        float sum = 0.0f;
-        for (size_t i = trim; i < n - trim; i++) sum += lum[i];
-        float mean_log = sum / (float)(n - 2 * trim);
-        // tonemap_inverse_scalar(0.45) (util.rs:43-47)
-        float y = 0.45f, denom = std::fmax(1.0f + 0.2f - y, 1e-6f);
-        float meter_key = std::fmax((y * 0.2f) / denom, 1e-4f);
-        float target_ev = std::log2(meter_key) - mean_log;
-        float target = std::fmin(std::fmax(std::pow(2.0f, target_ev), 0.05f), 32.0f);
-        auto_exposure_target_ = target;
-        float tev = std::log2(auto_exposure_target_);
-        float alpha = 1.0f - std::exp(-(std::fmax(delta_time, 0.0f) / 1.0f));
-        auto_exposure_ev_ += (tev - auto_exposure_ev_) * alpha;
-        auto_exposure_ = std::pow(2.0f, auto_exposure_ev_);
+        float state[3] = {auto_exposure_, auto_exposure_target_, auto_exposure_ev_};
+        auto_exposure_step(state, lum.data(), lum.size(), delta_time);
+        auto_exposure_ = state[0];
+        auto_exposure_target_ = state[1];
+        auto_exposure_ev_ = state[2];
     }
 
     // blit_to_buffer(&self, buffer) — renderer.rs:293-355

@@ -92,6 +92,10 @@ int swrh_build_draws_band(const swr_scene_desc *scene, const swr_camera *cam, sw
 }
 int swrh_invalidate_scene(void *r) { SWRH_TRY(need(r).invalidate_scene()); }
 int swrh_num_draws(void *r) { return r ? (int)((swr::Renderer *)r)->draws().size() : -1; }
+int swrh_auto_exposure_step(float state[3], const float *tile_luminance, int ntiles, float delta_time) {
+    SWRH_TRY(if (ntiles < 0) throw std::runtime_error("negative tile count");
+             swr::auto_exposure_step(&need_ptr(state, "state"), ntiles ? &need_ptr(tile_luminance, "tile luminance") : nullptr, (size_t)ntiles, delta_time));
+}
 int swrh_update_auto_exposure(void *r, float dt) { SWRH_TRY(need(r).update_auto_exposure(dt)); }
 float swrh_auto_exposure(void *r) { return r ? ((swr::Renderer *)r)->auto_exposure() : 0.0f; }
 

@@ -94,6 +94,7 @@ def load_libraries():
     host.swrh_render_scene.argtypes = [vp, C.POINTER(abi.SceneDesc), C.POINTER(abi.Camera), i32, i32, i32]
     host.swrh_update_auto_exposure.argtypes = [vp, f32]
     host.swrh_num_draws.argtypes = [vp]
+    host.swrh_auto_exposure_step.argtypes = [vp, vp, i32, f32]
     host.swrh_auto_exposure.restype = f32
     host.swrh_auto_exposure.argtypes = [vp]
     host.swrh_blit_to_buffer.argtypes = [vp, vp, C.c_size_t, C.c_size_t]

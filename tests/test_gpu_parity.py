@@ -112,6 +112,29 @@ def test_exposure_and_auto_exposure_state(configs):
     r.update_auto_exposure(0.5)
     assert 0.05 <= r.auto_exposure <= 32.0 and r.auto_exposure != pytest.approx(2.0)
     r.close()
+    # R14 end to end: a 5-frame sequence (render, meter, blit) against the oracle's update_auto_exposure restatement
+    # (renderer.rs:258-290) fed with the device's per-tile metering values — bit for bit — and against the oracle's own
+    # frame (its metering values, its resolve at the metered exposure): RGBA8 within 1 LSB.
+    import oracle as orc
+    r = swr.Renderer(W, H)
+    o = orc.Oracle(W, H)
+    state = np.array([2.0, 2.0, 1.0], np.float32)
+    ostate = state.copy()
+    buf = swr.RenderBuffer(W, H)
+    for f, dt in enumerate([0.0, 1 / 60, 0.25, 1.0, 1 / 60]):
+        r.render_scene(scene, cam)
+        lum = r.read_tile_luminance()
+        state = orc.update_auto_exposure(state, lum, dt)
+        r.update_auto_exposure(dt)
+        assert np.float32(r.auto_exposure).view(np.uint32) == state[0].view(np.uint32), (f, r.auto_exposure, state)
+        r.blit_to_buffer(buf)
+        ref = o.render(scene, cam.abi, nthreads=1)
+        ostate = orc.update_auto_exposure(ostate, ref["luminance"], dt)
+        assert ostate[0] == pytest.approx(state[0], rel=1e-5)
+        opix = o.resolve(float(ostate[0]))
+        assert np.abs(rgba_bytes(buf.pixels) - rgba_bytes(opix)).max() <= 1, f
+    assert state[0] != np.float32(2.0)
+    r.close()
 
 
 def test_create_rejects_bad_arguments():

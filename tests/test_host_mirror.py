@@ -234,3 +234,29 @@ def test_reference_arm_does_not_map_the_product_libraries():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert "MAPPED False True" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
     assert '"impl": "reference"' in out.stdout
+
+
+def test_auto_exposure_matches_the_oracle_restatement_over_a_frame_sequence():
+    """R14: update_auto_exposure (renderer.rs:258-290). The host mirror's metering maths against the oracle's restatement,
+    bit for bit, over 5-frame sequences of per-tile luminances (state carried from frame to frame), for several tile
+    counts (trim 10 %, min((n-1)/2)) and time steps, including dt = 0 (exposure must stay exactly 2.0) and odd values."""
+    import oracle as orc
+    _, host = swr.load_libraries()
+    rng = np.random.default_rng(1234)
+    for ntiles in (1, 2, 3, 9, 510, 2040, 8160):
+        for dts in ([0.0] * 5, [1 / 60] * 5, [0.5, 0.0, 2.0, 1e-3, 10.0], [-1.0, 0.016, 0.016, 0.016, 0.016]):
+            host_state = np.array([2.0, 2.0, 1.0], np.float32)
+            orc_state = host_state.copy()
+            for f, dt in enumerate(dts):
+                lum = (rng.random(ntiles, dtype=np.float32) ** 3 * np.float32(8.0)).astype(np.float32)
+                if f == 2:
+                    lum[: max(1, ntiles // 7)] = 0.0  # unlit tiles: clamped to 1e-4 before the log
+                if f == 3 and ntiles > 2:
+                    lum[1] = np.float32("inf")
+                    lum[2] = np.float32("nan")  # f32::max drops the NaN operand
+                assert host.swrh_auto_exposure_step(host_state.ctypes.data, lum.ctypes.data, ntiles, float(dt)) == 0
+                orc_state = orc.update_auto_exposure(orc_state, lum, dt)
+                assert np.array_equal(host_state.view(np.uint32), orc_state.view(np.uint32)), (ntiles, dts, f, host_state, orc_state)
+            if all(d == 0.0 for d in dts):
+                assert host_state[0] == np.float32(2.0) and host_state[2] == np.float32(1.0)  # alpha = 1 - e^0 = 0
+            assert 0.05 <= host_state[1] <= 32.0
