@@ -1409,6 +1409,56 @@ int orc_resolve(void *h, float exposure, int nthreads, uint32_t *out_pixels, orc
     return 0;
 }
 
+// Per-tile digests of the tile state left by the last orc_render (serial schedule), in the reference's own storage order
+// (tilerasterizer.rs:25-38: 2x2 quads, lane = 2*(y&1) + (x&1)), so that tools/reference_digest.rs — a few lines a
+// maintainer adds to the reference crate — can print the same numbers from the real Rust renderer and pin this oracle:
+//   out[3*t + 0] = FNV-1a-64 over, per quad and lane: depth bits, and for lanes with depth != +INF also packet_index
+//                  (the tile queue's index: equals the reference's when it runs with RAYON_NUM_THREADS=1), bary1, bary2 bits;
+//   out[3*t + 1] = number of lanes with depth != +INF;
+//   out[3*t + 2] = FNV-1a-64 over the colour quads (x, y, z lanes) — depends on the host's _mm_rsqrt_ps and libm.
+static inline void fnv_u32(uint64_t &h, uint32_t w) {
+    for (int k = 0; k < 4; k++) {
+        h ^= (w >> (8 * k)) & 0xFFu;
+        h *= 0x100000001b3ull;
+    }
+}
+int orc_tile_digests(void *hnd, uint64_t *out) {
+    Oracle &o = *(Oracle *)hnd;
+    for (size_t ti = 0; ti < o.tiles.size(); ti++) {
+        const Tile &t = *o.tiles[ti];
+        uint64_t hv = 0xcbf29ce484222325ull, hc = 0xcbf29ce484222325ull, covered = 0;
+        for (size_t q = 0; q < t.depth.size(); q++) {
+            for (int l = 0; l < 4; l++) {
+                float d = t.depth[q][l];
+                uint32_t db;
+                memcpy(&db, &d, 4);
+                fnv_u32(hv, db);
+                if (db != 0x7F800000u) {
+                    covered++;
+                    float b1 = t.bary1[q][l], b2 = t.bary2[q][l];
+                    uint32_t u1, u2;
+                    memcpy(&u1, &b1, 4);
+                    memcpy(&u2, &b2, 4);
+                    fnv_u32(hv, t.packet_index[q][l]);
+                    fnv_u32(hv, u1);
+                    fnv_u32(hv, u2);
+                }
+            }
+            for (int c = 0; c < 3; c++)
+                for (int l = 0; l < 4; l++) {
+                    float v = c == 0 ? t.color[q].x[l] : (c == 1 ? t.color[q].y[l] : t.color[q].z[l]);
+                    uint32_t u;
+                    memcpy(&u, &v, 4);
+                    fnv_u32(hc, u);
+                }
+        }
+        out[3 * ti + 0] = hv;
+        out[3 * ti + 1] = covered;
+        out[3 * ti + 2] = hc;
+    }
+    return (int)o.tiles.size();
+}
+
 // update_auto_exposure (renderer.rs:258-290) on a caller-supplied list of per-tile center_luminance values.
 // state = {auto_exposure, auto_exposure_target, auto_exposure_ev} (renderer.rs:194-196 start: 2.0, 2.0, log2(2.0)).
 int orc_update_auto_exposure(float *state, const float *center_luminance, int sample_count, float delta_time) {

@@ -52,6 +52,7 @@ def load():
         _lib.orc_build_draws.argtypes = [vp, vp, vp, C.c_int]
         _lib.orc_set_exact_rsqrt.argtypes = [C.c_int]
         _lib.orc_update_auto_exposure.argtypes = [vp, vp, C.c_int, C.c_float]
+        _lib.orc_tile_digests.argtypes = [vp, vp]
         _lib.orc_num_threads.restype = C.c_int
     return _lib
 
@@ -90,6 +91,16 @@ class Oracle:
         px = np.zeros(self.width * self.height, np.uint32)
         self.lib.orc_resolve(self.h, exposure, nthreads, px.ctypes.data, C.byref(self.stats))
         return px
+
+    def tile_digests(self):
+        """(ntiles, 3) uint64: visibility digest, covered lanes, colour digest of every tile after the last render
+        (tools/reference_digest.rs prints the same from the Rust renderer)."""
+        import numpy as np
+        n = ((self.width + 63) // 64) * ((self.height + 63) // 64)
+        out = np.zeros((n, 3), np.uint64)
+        got = self.lib.orc_tile_digests(self.h, out.ctypes.data)
+        assert got == n
+        return out
 
     def build_draws(self, scene, camera_abi, draw_type, max_draws=1 << 20):
         n = self.lib.orc_build_draws(C.addressof(scene.desc()), C.addressof(camera_abi), None, 0)
