@@ -998,6 +998,8 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long unit_t0 = clock64();
     FragQueue &fq = fqs[wid];
+    uint32_t fq_addr;  // shared-window address of fq.pkpix[0]; w1 / w2 follow at FRAGQ_CAP * 4 / * 8 bytes
+    asm volatile("mov.u32 %0, %1;" : "=r"(fq_addr) : "r"((uint32_t)__cvta_generic_to_shared(&fq.pkpix[0])));
     unsigned lt_mask;  // one S2R when the compiler rematerialises it (it does, at 64 registers)
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
 
@@ -1166,6 +1168,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
                     }
                 }
                 const int phys = st.ybase + (st.x ^ st.swz);  // key index of lane 0; lane 1 = +1, lanes 2,3 = +64
+                const uint32_t pkbase = (uint32_t)st.pk << 16;
                 if (m4) {
                     // early-Z: the packet's depth lower bound is already behind what the pixel holds -> it cannot win
                     const uint4 k0 = lds_volatile_v4(skeys + phys), k1 = lds_volatile_v4(skeys + phys + SWR_TILE);
@@ -1183,10 +1186,13 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
                             // lazy drain: only when this plane's fragments would not fit, so drains run (nearly) 32 wide
                             if (qn + __popc(m) > FRAGQ_CAP) qn = drain_queue(P, skeys, tb, fq, qn, lane);
                             if (cov) {
-                                const int pos = qn + __popc(m & lt_mask);
-                                fq.pkpix[pos] = ((uint32_t)st.pk << 16) | (uint32_t)(phys + (l & 1) + (l >> 1) * SWR_TILE);
-                                fq.w1[pos] = st.v[l][1];
-                                fq.w2[pos] = st.v[l][2];
+                                // explicit shared-window address kept in a register: the compiler would otherwise rebuild the
+                                // queue's base (warp id, dynamic-smem window) at every one of the four push sites
+                                const uint32_t a = fq_addr + 4u * (uint32_t)(qn + __popc(m & lt_mask));
+                                const uint32_t pp = pkbase + (uint32_t)(phys + (l & 1) + (l >> 1) * SWR_TILE);
+                                asm volatile("st.shared.u32 [%0], %1;\n\tst.shared.f32 [%0+%4], %2;\n\tst.shared.f32 [%0+%5], %3;" ::"r"(a), "r"(pp), "f"(st.v[l][1]),
+                                             "f"(st.v[l][2]), "n"(FRAGQ_CAP * 4), "n"(FRAGQ_CAP * 8)
+                                             : "memory");
                             }
                             qn += __popc(m);
 #ifdef SWR_PROFILE_COUNTERS
