@@ -325,8 +325,9 @@ int swr_multi_synchronize(swr_multi *m);
 
 /* Device pointers for zero-copy interop (NCCL gather / composite from the host
  * language): RGBA8 image (W*H u32, row-major) and the 64-bit visibility keys
- * (tile-major: tile (ty*tiles_x+tx) owns 4096 consecutive keys, y*64+x inside the
- * tile; key = orderable(depth)<<32 | ~record id, empty = all ones). Valid until the
+ * (tile-major: tile (ty*tiles_x+tx) owns 4096 consecutive keys; inside the tile pixel
+ * (x, y) is entry y*64 + (x ^ (((y >> 1) & 7) << 1)) — the rasteriser's bank-conflict-free shared-memory order, kept so
+ * that a tile leaves the SM as one bulk copy; key = orderable(depth)<<32 | ~record id, empty = all ones). Valid until the
  * next swr_render that grows buffers, or swr_destroy. */
 void *swr_device_pixels(swr_ctx *ctx);
 void *swr_device_keys(swr_ctx *ctx);

@@ -689,13 +689,13 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
     }
     if (translucent) {
         ctx->launches++;
-        k_scan_simple<<<1, 1024, 0, s>>>(g.tile_count.p, g.tile_offset.p, g.tile_cursor.p, ctx->ntiles, g.counters.p, (uint32_t)g.refs.cap);
+        k_scan_simple<<<1, 1024, 0, s>>>(g.tile_count.p, g.tile_offset.p, g.tile_cursor.p, ctx->ntiles, g.counters.p, (uint32_t)(g.refs.cap - 16));
     } else {
         const size_t unit_cap = (size_t)ctx->ntiles + g.refs.cap / RASTER_UNIT_MIN + 1;
         const uint32_t cta_slots = (uint32_t)ctx->num_sms * 4u;  // k_raster_tiles: 4 CTAs per SM
         if (ctx->unit_list.reserve(unit_cap) != cudaSuccess) return SWR_ERR_OOM;
         ctx->launches++;
-        k_scan_tiles<<<1, 1024, 0, s>>>(g.tile_count.p, g.tile_offset.p, g.tile_cursor.p, ctx->ntiles, g.counters.p, (uint32_t)g.refs.cap, ctx->unit_list.p,
+        k_scan_tiles<<<1, 1024, 0, s>>>(g.tile_count.p, g.tile_offset.p, g.tile_cursor.p, ctx->ntiles, g.counters.p, (uint32_t)(g.refs.cap - 16), ctx->unit_list.p,
                                         (uint32_t)unit_cap, rb * ctx->tiles_x, re * ctx->tiles_x, cta_slots, ctx->tile_unit.p, ctx->tile_count_prev.p,
                                         ctx->tile_cycles_prev.p, ctx->have_history ? 1 : 0);
         ctx->have_history = true;

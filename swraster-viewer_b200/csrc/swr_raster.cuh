@@ -731,11 +731,18 @@ struct RasterParams {
 // One batch of up to 256 packets of the tile, structure of arrays in shared memory. Work is then re-distributed
 // over the CTA at the granularity of one quad row inside one 16x16 block ("item"), so a triangle that fills the
 // tile (128 items of 8 quads) is shared by all warps instead of serialising one of them.
+#define REF_STAGES 3
+#define REF_STAGE_WORDS (RASTER_THREADS + 4)  // one batch of refs + up to 3 leading words (16-byte alignment of the bulk copy)
 struct TileBatch {
-    int a[3][RASTER_THREADS], b[3][RASTER_THREADS], c[3][RASTER_THREADS];
+    // edge 0 is not stored: a12 + a20 + a01 == 0 and b12 + b20 + b01 == 0 in wrapping i32 arithmetic, so a[0] = -(a[1] + a[2])
+    int a[2][RASTER_THREADS], b[2][RASTER_THREADS], c[3][RASTER_THREADS];
     // region origin in quads relative to the tile (5 + 5 bits) | nqx << 10 | nqy << 16 | coarse << 22 | exact << 23 | alpha-tested << 24
     uint32_t geom[RASTER_THREADS];
-    uint32_t slot[RASTER_THREADS];
+    // The unit's ref list is contiguous in global memory: each batch's 1 KiB chunk is brought in by ONE bulk async copy
+    // (cp.async.bulk, the TMA engine: no LSU instructions, no registers) two batches ahead, completion on an mbarrier.
+    // refs[s][lead + k] is the record id of packet k of the batch staged in s (it doubles as the fragment's id).
+    __align__(16) uint32_t refs[REF_STAGES][REF_STAGE_WORDS];
+    __align__(8) unsigned long long mbar[REF_STAGES];
     float ooa[RASTER_THREADS], iw0[RASTER_THREADS], iwda[RASTER_THREADS], iwdb[RASTER_THREADS];
     float zw0[RASTER_THREADS], zwda[RASTER_THREADS], zwdb[RASTER_THREADS];
     uint32_t zmin_hi[RASTER_THREADS];  // orderable lower bound of every fragment depth of the packet (0 = unknown)
@@ -757,9 +764,40 @@ __device__ __forceinline__ uint4 lds_volatile_v4(const void *p) {
     return v;
 }
 
+// ---- bulk async copies (TMA engine) + mbarrier, sm_90+ PTX ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared, completion counted in bytes on `bar`; src, dst and bytes are multiples of 16
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes),
+                 "r"(smem_addr(bar))
+                 : "memory");
+}
+// shared -> global; the caller orders its generic-proxy writes first (fence.proxy.async) and waits before reusing the source
+__device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("fence.proxy.async.shared::cta;\n\tcp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;" ::"l"(dst_gmem),
+                 "r"(smem_addr(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // Per-warp queue of covered pixels waiting for the depth computation: coverage is found by lanes walking different
 // quad rows (divergent by nature); the expensive part — perspective depth, 64-bit min — then runs up to 32 wide.
-#define FRAGQ_CAP 44  // a drain takes min(qn, 32) entries, leaving <= 12: the next plane of <= 32 fragments always fits
+#define FRAGQ_CAP 42  // a drain takes min(qn, 32) entries, leaving <= 10: the next plane of <= 32 fragments always fits
 struct FragQueue {
     uint32_t pkpix[FRAGQ_CAP];  // packet index in the batch << 16 | pixel index in the tile
     float w1[FRAGQ_CAP], w2[FRAGQ_CAP];
@@ -829,7 +867,7 @@ __device__ __noinline__ bool alpha_test_fragment(const TriRecord *records, const
 // The alpha test does not depend on the depth state, so dropping alpha-failed fragments before the min is equivalent to
 // the reference's "depth test, then mask, then conditional depth write" for any packet order.
 template <typename RP>
-__device__ __forceinline__ void shade_fragment(const RP &P, unsigned long long *skeys, const TileBatch &tb, uint32_t pkpix, float w1, float w2) {
+__device__ __forceinline__ void shade_fragment(const RP &P, unsigned long long *skeys, const TileBatch &tb, const uint32_t *ids, uint32_t pkpix, float w1, float w2) {
     const int pk = pkpix >> 16, pix = pkpix & 0xFFFF;
     const float ooa = tb.ooa[pk];
     float b1 = fmul(w1, ooa), b2 = fmul(w2, ooa);
@@ -838,7 +876,7 @@ __device__ __forceinline__ void shade_fragment(const RP &P, unsigned long long *
     float zz = fadd(fadd(tb.zw0[pk], fmul(b1, tb.zwda[pk])), fmul(b2, tb.zwdb[pk]));
     float z = fmul(zz, wpix);
     if (z == z) {  // NaN never passes `z <= current` (tilerasterizer.rs:516)
-        const uint32_t id = tb.slot[pk];
+        const uint32_t id = ids[pk];
         unsigned long long key = ((unsigned long long)depth_orderable(z) << 32) | (0xFFFFFFFFu - id);
         // keys only ever decrease, so a (possibly stale) read that is already <= key proves the atomic would be a no-op;
         // the shared-memory 64-bit min is a CAS loop (ATOMS.CAST.SPIN.64), worth skipping for occluded fragments
@@ -853,10 +891,10 @@ __device__ __forceinline__ void shade_fragment(const RP &P, unsigned long long *
 
 // Drain up to 32 fragments from the tail of the warp's queue; returns the new count.
 template <typename RP>
-__device__ __forceinline__ int drain_queue(const RP &P, unsigned long long *skeys, const TileBatch &tb, const FragQueue &fq, int qn, int lane) {
+__device__ __forceinline__ int drain_queue(const RP &P, unsigned long long *skeys, const TileBatch &tb, const uint32_t *ids, const FragQueue &fq, int qn, int lane) {
     const int n = min(qn, 32);
     __syncwarp();
-    if (lane < n) shade_fragment(P, skeys, tb, fq.pkpix[qn - n + lane], fq.w1[qn - n + lane], fq.w2[qn - n + lane]);
+    if (lane < n) shade_fragment(P, skeys, tb, ids, fq.pkpix[qn - n + lane], fq.w1[qn - n + lane], fq.w2[qn - n + lane]);
     __syncwarp();
     return qn - n;
 }
@@ -896,11 +934,16 @@ __device__ __forceinline__ void row_setup(const TileBatch &tb, int pk, uint32_t 
     int a[3], b[3], c[3];
 #pragma unroll
     for (int e = 0; e < 3; e++) {
-        a[e] = tb.a[e][pk];
-        b[e] = tb.b[e][pk];
+        if (e > 0) {
+            a[e] = tb.a[e - 1][pk];
+            b[e] = tb.b[e - 1][pk];
+        }
         c[e] = tb.c[e][pk];
-        st.step[e] = i2f(wmul(a[e], 32));
     }
+    a[0] = wsub(0, wadd(a[1], a[2]));  // the three edge vectors of a triangle sum to zero (wrapping i32, like the reference's)
+    b[0] = wsub(0, wadd(b[1], b[2]));
+#pragma unroll
+    for (int e = 0; e < 3; e++) st.step[e] = i2f(wmul(a[e], 32));
     st.ybase = (yq + qy) * 2 * SWR_TILE;
     st.x = (xq + qx0) * 2;
     st.swz = key_swz((yq + qy) * 2);
@@ -984,6 +1027,12 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
     if (P.counters->overflow_refs || P.counters->overflow_ext) return;  // lists incomplete; the host replays the frame
     __shared__ uint32_t s_unit_index;
     const uint32_t nunits = P.counters->raster_units;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < REF_STAGES; s++) mbar_init(&tb.mbar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t mphase = 0;  // bit s: parity of the next completion of stage s (every thread waits on every stage, so all agree)
   // persistent CTA: fetch work units (heaviest first) until the list is drained
   for (;;) {
     __syncthreads();  // everybody is done with the previous unit's shared memory
@@ -1014,20 +1063,41 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
 #endif
 
     const uint32_t beg = tile_beg + chunk * unit_refs, end = min(beg + unit_refs, tile_end);
-    // software pipeline over batches: the record of batch n+1 and the ref of batch n+2 are in flight while batch n is rasterised
-    uint32_t slot_next = 0, slot_next2 = 0;
-    uint4 rq0 = make_uint4(0, 0, 0, 0), rq1 = rq0, rq2 = rq0, rq3 = rq0;
-    if (beg + tid < end) {
-        slot_next = __ldg(P.refs + beg + tid);
-        const uint4 *src = reinterpret_cast<const uint4 *>(P.records + record_of_id(slot_next, P.clip_ext));
-        rq0 = __ldg(src);
-        rq1 = __ldg(src + 1);
-        rq2 = __ldg(src + 2);
-        rq3 = __ldg(src + 3);
+    // Ref staging: batch k of the unit (refs [beg + 256k, ...)) is copied by one bulk async copy into stage k % 3, two
+    // batches ahead of its use. The copy starts at the 16-byte boundary below `beg` (`lead` extra words in front) and is
+    // rounded up to 16 bytes (the ref buffer carries that much slack behind its last entry).
+    const uint32_t lead = beg & 3u;
+    const uint32_t nb = (end - beg + RASTER_THREADS - 1) / RASTER_THREADS;
+    auto issue = [&](uint32_t k) {
+        const uint32_t count = min((uint32_t)RASTER_THREADS, end - beg - k * RASTER_THREADS) + lead;
+        const uint32_t bytes = (count * 4u + 15u) & ~15u;
+        unsigned long long *bar = &tb.mbar[k % REF_STAGES];
+        mbar_expect_tx(bar, bytes);
+        bulk_load(tb.refs[k % REF_STAGES], P.refs + (beg - lead + k * RASTER_THREADS), bytes, bar);
+    };
+    if (tid == 0) {  // the __syncthreads at the top of the unit loop ordered every read of the previous unit's stages before this
+        if (nb > 0) issue(0);
+        if (nb > 1) issue(1);
     }
-    if (beg + RASTER_THREADS + tid < end) slot_next2 = __ldg(P.refs + beg + RASTER_THREADS + tid);
-    for (uint32_t base = beg; base < end; base += RASTER_THREADS) {
+    // software pipeline over batches: the record of batch n+1 is in flight (registers) while batch n is rasterised
+    uint32_t slot_next = 0;
+    uint4 rq0 = make_uint4(0, 0, 0, 0), rq1 = rq0, rq2 = rq0, rq3 = rq0;
+    if (nb > 0) {
+        mbar_wait(&tb.mbar[0], mphase & 1u);
+        mphase ^= 1u;
+        if (beg + tid < end) {
+            slot_next = tb.refs[0][lead + tid];
+            const uint4 *src = reinterpret_cast<const uint4 *>(P.records + record_of_id(slot_next, P.clip_ext));
+            rq0 = __ldg(src);
+            rq1 = __ldg(src + 1);
+            rq2 = __ldg(src + 2);
+            rq3 = __ldg(src + 3);
+        }
+    }
+    uint32_t bn = 0;  // batch number inside the unit
+    for (uint32_t base = beg; base < end; base += RASTER_THREADS, bn++) {
         __syncthreads();  // previous batch fully consumed (and key init done)
+        if (tid == 0 && bn + 2 < nb) issue(bn + 2);  // into the stage batch bn - 1 has just released
         if (base != beg) {
             // Hi-Z refresh: warp w takes blocks 8w..8w+7 (one band), two pixels per lane. Nobody writes keys until the item
             // phase, and readers of zmax in the packet phase below may see the old or the new value: both are upper bounds.
@@ -1043,7 +1113,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
         }
         const uint32_t ri = base + tid;
         uint32_t nitems = 0;
-        const uint32_t slot = slot_next;
+        const uint32_t *ids = &tb.refs[bn % REF_STAGES][lead];  // ids[k] = record id of packet k of this batch
         TriRecord r;
         {
             uint4 *dst = reinterpret_cast<uint4 *>(&r);
@@ -1052,15 +1122,19 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
             dst[2] = rq2;
             dst[3] = rq3;
         }
-        slot_next = slot_next2;
-        if (ri + RASTER_THREADS < end) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(P.records + record_of_id(slot_next, P.clip_ext));
-            rq0 = __ldg(src);
-            rq1 = __ldg(src + 1);
-            rq2 = __ldg(src + 2);
-            rq3 = __ldg(src + 3);
+        if (bn + 1 < nb) {
+            const uint32_t s1 = (bn + 1) % REF_STAGES;
+            mbar_wait(&tb.mbar[s1], (mphase >> s1) & 1u);
+            mphase ^= 1u << s1;
+            if (ri + RASTER_THREADS < end) {
+                slot_next = tb.refs[s1][lead + tid];
+                const uint4 *src = reinterpret_cast<const uint4 *>(P.records + record_of_id(slot_next, P.clip_ext));
+                rq0 = __ldg(src);
+                rq1 = __ldg(src + 1);
+                rq2 = __ldg(src + 2);
+                rq3 = __ldg(src + 3);
+            }
         }
-        if (ri + 2 * RASTER_THREADS < end) slot_next2 = __ldg(P.refs + ri + 2 * RASTER_THREADS);
         if (ri < end) {
             PacketSetup ps;
             packet_setup(r, P.W, P.H, tile_x0, tile_y0, ps);
@@ -1068,13 +1142,14 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
                 nitems = (uint32_t)((ps.coarse ? ((ps.nqx + 7) >> 3) : 1) * ps.nqy);
 #pragma unroll
                 for (int e = 0; e < 3; e++) {
-                    tb.a[e][tid] = ps.a[e];
-                    tb.b[e][tid] = ps.b[e];
+                    if (e > 0) {
+                        tb.a[e - 1][tid] = ps.a[e];
+                        tb.b[e - 1][tid] = ps.b[e];
+                    }
                     tb.c[e][tid] = ps.c[e];
                 }
                 tb.geom[tid] = (uint32_t)((ps.xs >> 5) - tile_x0 / 2) | ((uint32_t)((ps.ys >> 5) - tile_y0 / 2) << 5) | ((uint32_t)ps.nqx << 10) |
                                ((uint32_t)ps.nqy << 16) | (ps.coarse ? 1u << 22 : 0u) | (ps.exact ? 1u << 23 : 0u) | ((r.draw & SWR_REC_ALPHA) ? 1u << 24 : 0u);
-                tb.slot[tid] = slot;
                 tb.ooa[tid] = r.ooa;
                 tb.iw0[tid] = r.iw0;
                 tb.iwda[tid] = fsub(r.iw1, r.iw0);
@@ -1184,7 +1259,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
                         const unsigned m = __ballot_sync(0xFFFFFFFFu, cov);
                         if (m) {
                             // lazy drain: only when this plane's fragments would not fit, so drains run (nearly) 32 wide
-                            if (qn + __popc(m) > FRAGQ_CAP) qn = drain_queue(P, skeys, tb, fq, qn, lane);
+                            if (qn + __popc(m) > FRAGQ_CAP) qn = drain_queue(P, skeys, tb, ids, fq, qn, lane);
                             if (cov) {
                                 // explicit shared-window address kept in a register: the compiler would otherwise rebuild the
                                 // queue's base (warp id, dynamic-smem window) at every one of the four push sites
@@ -1208,7 +1283,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
                 st.x += 2;
             }
         }
-        while (qn > 0) qn = drain_queue(P, skeys, tb, fq, qn, lane);  // fragments reference this batch's packets
+        while (qn > 0) qn = drain_queue(P, skeys, tb, ids, fq, qn, lane);  // fragments reference this batch's packets
 #ifdef SWR_PROFILE_COUNTERS
         atomicAdd((unsigned long long *)&P.counters->dbg[2], dbg_steps);      // quads stepped (useful lanes)
         if (lane == 0) {
@@ -1219,11 +1294,16 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams
     }
     __syncthreads();
     unsigned long long *out = P.keys + (size_t)tile * SWR_TILE_PIXELS;
+    // the global key buffer uses the same swizzled in-tile order as shared memory (key_index), so a finished tile leaves
+    // as ONE 32 KiB bulk async store issued by one thread
     if (!split) {
-        for (int i = tid; i < SWR_TILE_PIXELS; i += RASTER_THREADS) out[i] = skeys[key_index(i & (SWR_TILE - 1), i >> 6)];
+        if (tid == 0) {
+            bulk_store(out, skeys, SWR_TILE_PIXELS * 8);
+            bulk_store_wait_read();  // the source may be overwritten once it has been read (next unit's key init)
+        }
     } else {  // the key buffer was reset to EMPTY before the launch
         for (int i = tid; i < SWR_TILE_PIXELS; i += RASTER_THREADS) {
-            const unsigned long long k = skeys[key_index(i & (SWR_TILE - 1), i >> 6)];
+            const unsigned long long k = skeys[i];
             if (k != SWR_KEY_EMPTY) atomicMin(&out[i], k);
         }
     }
@@ -1253,7 +1333,7 @@ struct VisParams {
 
 __device__ __forceinline__ unsigned long long load_key(const unsigned long long *keys, int tiles_x, int px, int py) {
     int tile = (py >> 6) * tiles_x + (px >> 6);
-    return keys[(size_t)tile * SWR_TILE_PIXELS + (py & 63) * SWR_TILE + (px & 63)];
+    return keys[(size_t)tile * SWR_TILE_PIXELS + key_index(px & 63, py & 63)];
 }
 
 __global__ void k_read_vis(VisParams P, uint32_t *depth_bits, uint32_t *seq, float *bary1, float *bary2) {

@@ -754,7 +754,7 @@ __global__ void k_keys_localize(unsigned long long *keys, int tiles_x, int W, in
                                 const DevDraw *draws, const uint32_t *tri_prefix, uint32_t ndraws, const DevPrim *prims, float2 *bary) {
     int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
     if (px >= W || py >= H) return;
-    const size_t ki = (size_t)((py >> 6) * tiles_x + (px >> 6)) * SWR_TILE_PIXELS + (py & 63) * SWR_TILE + (px & 63);
+    const size_t ki = (size_t)((py >> 6) * tiles_x + (px >> 6)) * SWR_TILE_PIXELS + key_index(px & 63, py & 63);
     unsigned long long k = keys[ki];
     float2 b = make_float2(0.0f, 0.0f);
     if (k != SWR_KEY_EMPTY) {
