@@ -323,6 +323,44 @@ int swr_multi_read_tile_luminance(swr_multi *m, float *out_per_tile);
 int swr_multi_get_stats(swr_multi *m, swr_frame_stats *out); /* counters summed over the bands, phase times = slowest device */
 int swr_multi_synchronize(swr_multi *m);
 
+/* ---- load-time bakes on the device ---------------------------------------------------------------
+ * The inputs of the shading kernel the reference derives when a scene is loaded, computed on the GPU. Stateless calls
+ * (device < 0: the current device); host pointers in and out; no CPU fallback. The cheap glue around them (cross -> six
+ * faces, mip chains, hierarchy build, voxel marking) stays on the host (swr_gltf.h, like R1/R2 of the frame path).
+ *   swr_bake_brdf_lut            generate_brdf_lut texels, size x size                          texture.rs:167-235
+ *   swr_bake_irradiance_sh4      compute_irradiance_sh4: 4 coefficients x rgb                   texture.rs:289-328
+ *   swr_bake_prefilter_specular  generate_prefiltered_specular_cubemap: num_mips x 6 x h x w texels, every mip at full
+ *                                resolution; returns num_mips = floor(log2(max(w, h))) + 1        texture.rs:330-420
+ *   swr_bake_sun_visibility      one ray per active voxel towards the light through the caller's hierarchy, opaque hit
+ *                                -> 0, translucent hits multiply, then the 3x3x3 blur, squared   gi.rs:267-314,
+ *                                raytracer.rs:177-259, voxelgrid.rs:371-419
+ * cubemap_faces: mip 0 of the sky, six faces of w x h RGBA8 texels (R in bits 31..24), face-major (+X -X +Y -Y +Z -Z). */
+typedef struct swr_bvh_node {
+    float lo[3], hi[3];
+    uint32_t first, count; /* leaf: order[first .. first + count); inner (count = 0): children first and first + 1 */
+} swr_bvh_node;
+typedef struct swr_sun_triangle {
+    float p0[3], p1[3], p2[3]; /* world space */
+    float transmission;        /* material transmission of a translucent surface; < 0 = opaque */
+} swr_sun_triangle;
+typedef struct swr_sunvis_desc {
+    const swr_bvh_node *nodes; /* node 0 = root; nnodes = 0: no geometry */
+    uint32_t nnodes;
+    const uint32_t *order; /* triangle indices referenced by the leaves */
+    uint32_t norder;
+    const swr_sun_triangle *triangles;
+    uint32_t ntriangles;
+    const uint8_t *active; /* per voxel (z*W*H + y*W + x): cast a ray from this voxel */
+    uint32_t dims[3];
+    float world_min[3], world_max[3];
+    float light_direction[3];
+} swr_sunvis_desc;
+int swr_bake_brdf_lut(int device, uint32_t size, uint32_t *out_texels);
+int swr_bake_irradiance_sh4(int device, const uint32_t *cubemap_faces, uint32_t w, uint32_t h, float *out12);
+int swr_bake_prefilter_specular(int device, const uint32_t *cubemap_faces, uint32_t w, uint32_t h, uint32_t sample_count, uint32_t *out_texels);
+int swr_bake_sun_visibility(int device, const swr_sunvis_desc *desc, float *out_per_voxel);
+const char *swr_bake_last_error(void);
+
 /* Device pointers for zero-copy interop (NCCL gather / composite from the host
  * language): RGBA8 image (W*H u32, row-major) and the 64-bit visibility keys
  * (tile-major: tile (ty*tiles_x+tx) owns 4096 consecutive keys; inside the tile pixel

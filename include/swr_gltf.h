@@ -53,7 +53,9 @@ const char *swrh_gltf_texture_uri(void *doc, uint32_t slot);
  * looked up by the exact `uri` string of the glTF image. rgba == NULL removes the entry. */
 int swrh_gltf_register_image(const char *uri, const uint8_t *rgba, uint32_t width, uint32_t height);
 
-/* Load-time environment bakes, on the host like the reference's (scene.rs:151-231 + main.rs:228-281): from a sky image in
+/* Load-time environment bakes (scene.rs:151-231 + main.rs:228-281). The three integrals (BRDF LUT, irradiance SH4, GGX
+ * prefilter) run on the CURRENT CUDA device (include/swr.h swr_bake_*; there is no CPU fallback), the glue (faces, mip chains,
+ * voxel fill) on the host. From a sky image in
  * the reference's cross layout (+Y on top; -X +Z +X -Z in the middle row; -Y below; face size = width/4 x height/3) build
  * the sky cubemap with mips (texture.rs:922-959, :45-128), the GGX-prefiltered specular cubemap (texture.rs:330-420, every
  * mip at full face resolution, `specular_samples` = 64 in the reference), the irradiance SH4 (texture.rs:289-328), the
@@ -66,14 +68,13 @@ void *swrh_env_bake(const uint8_t *cross_rgba, uint32_t width, uint32_t height, 
 int swrh_env_get(void *env, swrh_gltf_env *out, float irradiance_sh_out[12]);
 void swrh_env_free(void *env);
 /* Voxel sun visibility as the reference's default load path computes it (main.rs:237-246; gi.rs:151-314, raytracer.rs,
- * voxelgrid.rs:371-419): voxels near geometry cast one ray towards scene->light_direction, opaque hits give 0, translucent
+ * voxelgrid.rs:371-419); triangles, hierarchy and active-voxel mask are built on the host, the rays and the blur run on the
+ * current CUDA device (swr_bake_sun_visibility, no CPU fallback): voxels near geometry cast one ray towards scene->light_direction, opaque hits give 0, translucent
  * hits multiply their transmission, the grid is blurred (3x3x3 mean, squared). out_per_voxel receives dims[0]*dims[1]*dims[2]
  * floats (index z*w*h + y*w + x); the value belongs into gi_sh4[voxel][0].w. swrh_gltf_bake_sun_visibility does that for
  * a loaded document in place (call it before the scene is first rendered: uploads are once per scene). */
 int swrh_compute_sun_visibility(const swr_scene_desc *scene, float *out_per_voxel);
 int swrh_gltf_bake_sun_visibility(void *doc);
-/* one texel's worth of integrate_brdf (texture.rs:167-197): out = (scale, bias) */
-int swrh_integrate_brdf(float ndotv, float roughness, float out[2]);
 
 /* The pieces of the loader that are useful on their own (and are what the tests pin): */
 int swrh_compute_smooth_normals(const float *positions4, uint32_t nverts, const uint32_t *indices, uint32_t nindices, float *normals4_out);

@@ -124,3 +124,72 @@ def update_auto_exposure(state, center_luminance, delta_time):
     lum = np.ascontiguousarray(center_luminance, np.float32)
     load().orc_update_auto_exposure(st.ctypes.data, lum.ctypes.data, len(lum), float(delta_time))
     return st
+
+
+# ---- load-time bakes (oracle_bake.cpp, oracle_sunvis.cpp): the checkers of the device bakes ----------------------------------
+def integrate_brdf(ndotv, roughness):
+    """One texel's worth of integrate_brdf (texture.rs:167-197): (scale, bias)."""
+    out = (C.c_float * 2)()
+    lib = load()
+    lib.orc_integrate_brdf.argtypes = [C.c_float, C.c_float, C.c_void_p]
+    lib.orc_integrate_brdf(ndotv, roughness, C.addressof(out))
+    return float(out[0]), float(out[1])
+
+
+def bake_brdf_lut(size):
+    import numpy as np
+    out = np.zeros((size, size), np.uint32)
+    lib = load()
+    lib.orc_bake_brdf_lut.argtypes = [C.c_uint32, C.c_void_p]
+    lib.orc_bake_brdf_lut(size, out.ctypes.data)
+    return out
+
+
+def bake_irradiance_sh4(faces):
+    """faces: (6, h, w) uint32 RGBA8 (R in bits 31..24). Returns (4, 3) float32."""
+    import numpy as np
+    f = np.ascontiguousarray(faces, np.uint32)
+    out = np.zeros(12, np.float32)
+    lib = load()
+    lib.orc_bake_irradiance_sh4.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.orc_bake_irradiance_sh4(f.ctypes.data, f.shape[2], f.shape[1], out.ctypes.data)
+    return out.reshape(4, 3)
+
+
+def bake_prefilter_specular(faces, sample_count):
+    """faces: (6, h, w) uint32. Returns (num_mips, 6, h, w) uint32."""
+    import numpy as np
+    f = np.ascontiguousarray(faces, np.uint32)
+    h, w = f.shape[1], f.shape[2]
+    nm = int(max(w, h)).bit_length()
+    out = np.zeros((nm, 6, h, w), np.uint32)
+    lib = load()
+    lib.orc_bake_prefilter_specular.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    got = lib.orc_bake_prefilter_specular(f.ctypes.data, w, h, sample_count, out.ctypes.data)
+    assert got == nm
+    return out
+
+
+def sun_visibility(scene):
+    """compute_sun_visibility + blur of a scenes.SceneData / loaded glTF (anything with .desc()): (D, H, W) float32."""
+    import numpy as np
+    d = scene.desc()
+    w, h, dd = d.voxel_grid.dims[:]
+    out = np.zeros(w * h * dd, np.float32)
+    lib = load()
+    lib.orc_sun_visibility.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    light = (C.c_float * 3)(*d.light_direction[:])
+    rc = lib.orc_sun_visibility(C.addressof(d), C.addressof(d.voxel_grid), C.addressof(light), out.ctypes.data)
+    assert rc == 0
+    return out.reshape(dd, h, w)
+
+
+def sunvis_active_mask(scene):
+    import numpy as np
+    d = scene.desc()
+    w, h, dd = d.voxel_grid.dims[:]
+    out = np.zeros(w * h * dd, np.uint8)
+    lib = load()
+    lib.orc_sunvis_active_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.orc_sunvis_active_mask(C.addressof(d), C.addressof(d.voxel_grid), out.ctypes.data)
+    return out.reshape(dd, h, w)

@@ -141,6 +141,34 @@ pub struct swr_frame_stats {
     pub ms_resolve: f32,
 }
 #[repr(C)]
+pub struct swr_bvh_node {
+    pub lo: [f32; 3],
+    pub hi: [f32; 3],
+    pub first: u32,
+    pub count: u32,
+}
+#[repr(C)]
+pub struct swr_sun_triangle {
+    pub p0: [f32; 3],
+    pub p1: [f32; 3],
+    pub p2: [f32; 3],
+    pub transmission: f32,
+}
+#[repr(C)]
+pub struct swr_sunvis_desc {
+    pub nodes: *const swr_bvh_node,
+    pub nnodes: u32,
+    pub order: *const u32,
+    pub norder: u32,
+    pub triangles: *const swr_sun_triangle,
+    pub ntriangles: u32,
+    pub active: *const u8,
+    pub dims: [u32; 3],
+    pub world_min: [f32; 3],
+    pub world_max: [f32; 3],
+    pub light_direction: [f32; 3],
+}
+#[repr(C)]
 pub struct swr_ctx {
     _private: [u8; 0],
 }
@@ -194,6 +222,11 @@ extern "C" {
     pub fn swr_multi_read_tile_luminance(m: *mut swr_multi, out_per_tile: *mut f32) -> c_int;
     pub fn swr_multi_get_stats(m: *mut swr_multi, out: *mut swr_frame_stats) -> c_int;
     pub fn swr_multi_synchronize(m: *mut swr_multi) -> c_int;
+    pub fn swr_bake_brdf_lut(device: c_int, size: u32, out_texels: *mut u32) -> c_int;
+    pub fn swr_bake_irradiance_sh4(device: c_int, cubemap_faces: *const u32, w: u32, h: u32, out12: *mut f32) -> c_int;
+    pub fn swr_bake_prefilter_specular(device: c_int, cubemap_faces: *const u32, w: u32, h: u32, sample_count: u32, out_texels: *mut u32) -> c_int;
+    pub fn swr_bake_sun_visibility(device: c_int, desc: *const swr_sunvis_desc, out_per_voxel: *mut f32) -> c_int;
+    pub fn swr_bake_last_error() -> *const c_char;
     pub fn swr_device_pixels(ctx: *mut swr_ctx) -> *mut c_void;
     pub fn swr_device_keys(ctx: *mut swr_ctx) -> *mut c_void;
     pub fn swr_device_keys_bytes(ctx: *mut swr_ctx) -> usize;

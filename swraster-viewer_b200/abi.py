@@ -109,4 +109,5 @@ EXPORTS = [
     "swr_multi_create", "swr_multi_destroy", "swr_multi_last_error", "swr_multi_device_count", "swr_multi_context", "swr_multi_tile_rows",
     "swr_multi_set_rsqrt_table", "swr_multi_upload_scene", "swr_multi_render", "swr_multi_resolve", "swr_multi_read_tile_luminance",
     "swr_multi_get_stats", "swr_multi_synchronize",
+    "swr_bake_brdf_lut", "swr_bake_irradiance_sh4", "swr_bake_prefilter_specular", "swr_bake_sun_visibility", "swr_bake_last_error",
 ]

@@ -14,6 +14,7 @@
 #include <thread>
 #include "../../include/swr.h"
 #include "swr_shade.cuh"
+#include "swr_bake.cuh"
 
 static thread_local std::string g_create_error;
 
@@ -1378,5 +1379,6 @@ size_t swr_device_keys_bytes(swr_ctx *ctx) { return ctx ? (size_t)ctx->ntiles * 
 void *swr_cuda_stream(swr_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 #include "swr_multi.inl"
+#include "swr_bake_api.inl"
 
 }  // extern "C"

@@ -187,7 +187,7 @@ def decode_png(file_bytes):
 
 
 class BakedEnvironment:
-    """Host-side bakes of everything the viewer derives from its sky image (include/swr_gltf.h swrh_env_bake):
+    """Bakes of everything the viewer derives from its sky image (include/swr_gltf.h swrh_env_bake; the three integrals run on the GPU):
     sky cubemap + mips, GGX-prefiltered cubemap, irradiance SH4, BRDF LUT, SH-initialised voxel grid."""
 
     def __init__(self, cross_rgba_u8, lut_size=128, specular_samples=64, voxel_dim=16, irradiance_scale=0.25, sky_visibility=1.0, light_intensity=1.0):
@@ -270,11 +270,3 @@ def bake_sun_visibility(gltf_scene):
     host = _host()
     host.swrh_gltf_bake_sun_visibility.argtypes = [C.c_void_p]
     _check(host.swrh_gltf_bake_sun_visibility(gltf_scene._h), host)
-
-
-def integrate_brdf(ndotv, roughness):
-    host = _host()
-    host.swrh_integrate_brdf.argtypes = [C.c_float, C.c_float, C.POINTER(C.c_float * 2)]
-    out = (C.c_float * 2)()
-    _check(host.swrh_integrate_brdf(ndotv, roughness, C.byref(out)), host)
-    return float(out[0]), float(out[1])

@@ -293,11 +293,6 @@ int swrh_env_get(void *env, swrh_gltf_env *out, float irradiance_sh_out[12]) {
     return 0;
 }
 void swrh_env_free(void *env) { delete (swr::bake::EnvironmentBake *)env; }
-int swrh_integrate_brdf(float ndotv, float roughness, float out[2]) {
-    if (!out) return -1;
-    swr::bake::integrate_brdf(ndotv, roughness, out[0], out[1]);
-    return 0;
-}
 
 // ---- voxel sun visibility (include/swr_gltf.h, host/swr_sunvis.hpp) ------------------------------------------------------
 int swrh_compute_sun_visibility(const swr_scene_desc *scene, float *out_per_voxel) {

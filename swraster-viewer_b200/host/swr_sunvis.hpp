@@ -1,6 +1,9 @@
-// swr_sunvis.hpp — voxel sun visibility on the host (the part the default load path runs: main.rs:237-246).
+// swr_sunvis.hpp — voxel sun visibility (the part the default load path runs: main.rs:237-246).
 // The reference marks the voxels near geometry, casts one ray per such voxel towards the sun through a BVH and blurs the
 // result; the value lands in gi_sh4[voxel][0].w and is what the shader uses to shadow the direct light.
+// Here the ray cast and the blur run on the GPU (include/swr.h swr_bake_sun_visibility, csrc/swr_bake.cuh); the host builds
+// what they consume: world-space triangles, the hierarchy, the active-voxel mask. No CPU fallback for the trace (the CPU
+// restatement the tests check against is hierarchy-free and lives outside this package).
 //   RayTracer::new            src/raytracer.rs:71-132   world-space triangles, degenerate ones skipped, AABB padded by 1e-5
 //   ray_triangle_intersect    src/raytracer.rs:223-259  Moeller-Trumbore, |det| <= 1e-8 rejected, u in [0,1], v >= 0, u+v <= 1
 //   trace_transmittance       src/raytracer.rs:177-211  every hit in [t_min, t_max], sorted by t; opaque -> 0, translucent multiplies
@@ -48,25 +51,6 @@ inline std::vector<Triangle> collect_triangles(const swr_scene_desc &sc) {
     return tris;
 }
 
-// raytracer.rs:223-259
-inline bool ray_triangle_intersect(V3 origin, V3 direction, const Triangle &tri, float t_min, float t_max, float &t_out) {
-    const V3 edge1 = tri.p1 - tri.p0, edge2 = tri.p2 - tri.p0;
-    const V3 pvec = gltf::cross(direction, edge2);
-    const float det = gltf::dot(edge1, pvec);
-    if (std::fabs(det) <= 1.0e-8f) return false;
-    const float inv_det = 1.0f / det;
-    const V3 tvec = origin - tri.p0;
-    const float u = gltf::dot(tvec, pvec) * inv_det;
-    if (!(u >= 0.0f && u <= 1.0f)) return false;
-    const V3 qvec = gltf::cross(tvec, edge1);
-    const float v = gltf::dot(direction, qvec) * inv_det;
-    if (v < 0.0f || (u + v) > 1.0f) return false;
-    const float t = gltf::dot(edge2, qvec) * inv_det;
-    if (t < t_min || t > t_max) return false;
-    t_out = t;
-    return true;
-}
-
 class Bvh {
    public:
     explicit Bvh(const std::vector<Triangle> &tris) : tris_(tris) {
@@ -87,44 +71,16 @@ class Bvh {
         }
     }
 
-    // every triangle whose padded box the ray (t >= 0) touches, give or take a conservative margin
-    template <typename F>
-    void traverse(V3 o, V3 d, F &&visit) const {
-        if (nodes_.empty()) return;
-        const float inv[3] = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
-        const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
-        uint32_t stack[64];
-        int sp = 0;
-        stack[sp++] = 0;
-        while (sp) {
-            const Node &nd = nodes_[stack[--sp]];
-            const float lo[3] = {nd.lo.x, nd.lo.y, nd.lo.z}, hi[3] = {nd.hi.x, nd.hi.y, nd.hi.z};
-            float t0 = 0.0f, t1 = INFINITY;
-            bool miss = false;
-            for (int a = 0; a < 3 && !miss; a++) {
-                if (dd[a] == 0.0f) {
-                    miss = oo[a] < lo[a] || oo[a] > hi[a];
-                } else {
-                    float ta = (lo[a] - oo[a]) * inv[a], tb = (hi[a] - oo[a]) * inv[a];
-                    if (ta > tb) std::swap(ta, tb);
-                    // widen by a few ulps so rounding can only add candidates
-                    ta -= std::fabs(ta) * 4.0e-7f;
-                    tb += std::fabs(tb) * 4.0e-7f;
-                    t0 = std::fmax(t0, ta);
-                    t1 = std::fmin(t1, tb);
-                    miss = t0 > t1;
-                }
-            }
-            if (miss) continue;
-            if (nd.count) {
-                for (uint32_t k = 0; k < nd.count; k++) visit(order_[nd.first + k]);
-            } else {
-                if (sp + 2 > 64) throw std::runtime_error("BVH traversal stack overflow");
-                stack[sp++] = nd.first;
-                stack[sp++] = nd.first + 1;
-            }
+    // flat tables for the device traversal (swr_bvh_node: leaf = order[first, first + count); inner = children first, first + 1)
+    std::vector<swr_bvh_node> flat_nodes() const {
+        std::vector<swr_bvh_node> out(nodes_.size());
+        for (size_t i = 0; i < nodes_.size(); i++) {
+            const Node &n = nodes_[i];
+            out[i] = swr_bvh_node{{n.lo.x, n.lo.y, n.lo.z}, {n.hi.x, n.hi.y, n.hi.z}, n.first, n.count};
         }
+        return out;
     }
+    const std::vector<uint32_t> &order() const { return order_; }
 
    private:
     struct Node {
@@ -164,26 +120,6 @@ class Bvh {
     }
 };
 
-// raytracer.rs:177-211
-inline float trace_transmittance(const Bvh &bvh, const std::vector<Triangle> &tris, const swr_scene_desc &sc, V3 origin, V3 direction, float t_min,
-                                 float t_max) {
-    std::vector<std::pair<float, uint32_t>> hits;
-    bvh.traverse(origin, direction, [&](uint32_t ti) {
-        float t;
-        if (ray_triangle_intersect(origin, direction, tris[ti], t_min, t_max, t)) hits.emplace_back(t, ti);
-    });
-    // sort_by partial_cmp on t; ties keep candidate order in the reference (unknowable without its BVH) — broken here by index
-    std::sort(hits.begin(), hits.end());
-    float transmittance = 1.0f;
-    for (const auto &h : hits) {
-        const swr_material_desc &m = sc.materials[tris[h.second].material_index];
-        if (!(m.flags & SWR_MAT_TRANSLUCENT)) return 0.0f;
-        transmittance *= m.transmission;
-        if (transmittance <= 0.0001f) return 0.0f;
-    }
-    return transmittance;
-}
-
 // gi.rs:151-265 (the mask only; surface normals / albedo feed the full GI bake, which is not built)
 inline std::vector<uint8_t> build_active_voxel_mask(const std::vector<Triangle> &tris, const swr_voxel_grid_desc &g) {
     const size_t W = g.dims[0], H = g.dims[1], D = g.dims[2], total = W * H * D;
@@ -222,46 +158,38 @@ inline std::vector<uint8_t> build_active_voxel_mask(const std::vector<Triangle> 
     return dilated;
 }
 
-// gi.rs:267-314 + voxelgrid.rs:371-419. Returns the blurred light intensity per voxel (index = z*W*H + y*W + x).
+// gi.rs:267-314 + voxelgrid.rs:371-419. Returns the blurred light intensity per voxel (index = z*W*H + y*W + x): triangles,
+// hierarchy and active mask from the host, rays and blur on the device.
 inline std::vector<float> compute_sun_visibility(const swr_scene_desc &sc, const swr_voxel_grid_desc &g, const float light_direction[3]) {
     const size_t W = g.dims[0], H = g.dims[1], D = g.dims[2], total = W * H * D;
     if (!total) throw std::runtime_error("Invalid data: empty voxel grid");
     const std::vector<Triangle> tris = collect_triangles(sc);
     const Bvh bvh(tris);
     const std::vector<uint8_t> active = build_active_voxel_mask(tris, g);
-    const V3 L = gltf::normalize(V3{light_direction[0], light_direction[1], light_direction[2]});
-    const V3 vs{(g.world_max[0] - g.world_min[0]) / (float)W, (g.world_max[1] - g.world_min[1]) / (float)H, (g.world_max[2] - g.world_min[2]) / (float)D};
-    const V3 center_min = V3{g.world_min[0], g.world_min[1], g.world_min[2]} + vs * 0.5f;
-    const float bias = gltf::length(vs) * 3.0f;
-    std::vector<float> out(total, 1.0f);
-    size_t nactive = 0;
-    for (uint8_t a : active) nactive += a;
-    if (nactive) {
-#pragma omp parallel for schedule(dynamic, 64)
-        for (int64_t index = 0; index < (int64_t)total; index++) {
-            if (!active[(size_t)index]) continue;
-            const size_t z = (size_t)index / (W * H), rem = (size_t)index % (W * H), y = rem / W, x = rem % W;
-            const V3 c = center_min + V3{(float)x * vs.x, (float)y * vs.y, (float)z * vs.z};
-            out[(size_t)index] = trace_transmittance(bvh, tris, sc, c + L * bias, L, 1.0e-4f, INFINITY);
-        }
-        std::vector<float> blurred(total, 0.0f);  // blur_grid: 3x3x3 mean of what lies inside the grid, squared
-        for (size_t z = 0; z < D; z++)
-            for (size_t y = 0; y < H; y++)
-                for (size_t x = 0; x < W; x++) {
-                    float sum = 0.0f;
-                    int count = 0;
-                    for (int dz = -1; dz <= 1; dz++)
-                        for (int dy = -1; dy <= 1; dy++)
-                            for (int dx = -1; dx <= 1; dx++) {
-                                const int64_t nx = (int64_t)x + dx, ny = (int64_t)y + dy, nz = (int64_t)z + dz;
-                                if (nx < 0 || ny < 0 || nz < 0 || nx >= (int64_t)W || ny >= (int64_t)H || nz >= (int64_t)D) continue;
-                                sum += out[((size_t)nz * H + (size_t)ny) * W + (size_t)nx];
-                                count++;
-                            }
-                    blurred[(z * H + y) * W + x] = count ? std::pow(sum / (float)count, 2.0f) : 0.0f;
-                }
-        out.swap(blurred);
+    std::vector<swr_sun_triangle> flat(tris.size());
+    for (size_t i = 0; i < tris.size(); i++) {
+        const Triangle &t = tris[i];
+        const swr_material_desc &m = sc.materials[t.material_index];
+        flat[i] = swr_sun_triangle{{t.p0.x, t.p0.y, t.p0.z}, {t.p1.x, t.p1.y, t.p1.z}, {t.p2.x, t.p2.y, t.p2.z},
+                                   (m.flags & SWR_MAT_TRANSLUCENT) ? std::fmax(m.transmission, 0.0f) : -1.0f};
     }
+    const std::vector<swr_bvh_node> nodes = bvh.flat_nodes();
+    swr_sunvis_desc d{};
+    d.nodes = nodes.data();
+    d.nnodes = (uint32_t)nodes.size();
+    d.order = bvh.order().data();
+    d.norder = (uint32_t)bvh.order().size();
+    d.triangles = flat.data();
+    d.ntriangles = (uint32_t)flat.size();
+    d.active = active.data();
+    for (int k = 0; k < 3; k++) {
+        d.dims[k] = g.dims[k];
+        d.world_min[k] = g.world_min[k];
+        d.world_max[k] = g.world_max[k];
+        d.light_direction[k] = light_direction[k];
+    }
+    std::vector<float> out(total, 1.0f);
+    if (swr_bake_sun_visibility(-1, &d, out.data()) != SWR_OK) throw std::runtime_error(std::string("swr_bake_sun_visibility: ") + swr_bake_last_error());
     return out;
 }
 

@@ -121,9 +121,10 @@ args = {"swr_set_rsqrt_table": (None, None, 10), "swr_set_tile_rows": (None, 0, 
         "swr_peer_open": (None, None), "swr_peer_attach": (None, None), "swr_resolve_peer": (None, 2.0, 1), "swr_peer_collect": (None, 1, 1),
         "swr_peer_release": (None, 1), "swr_multi_tile_rows": (None, 0, None, None), "swr_multi_set_rsqrt_table": (None, None, 10), "swr_multi_upload_scene": (None, None),
         "swr_multi_render": (None, None, None, 0), "swr_multi_resolve": (None, 2.0, None), "swr_multi_read_tile_luminance": (None, None), "swr_multi_get_stats": (None, None),
-        "swr_multi_context": (None, 0)}
+        "swr_multi_context": (None, 0), "swr_bake_brdf_lut": (0, 0, None), "swr_bake_irradiance_sh4": (0, None, 4, 4, None),
+        "swr_bake_prefilter_specular": (0, None, 4, 4, 8, None), "swr_bake_sun_visibility": (0, None, None)}
 core.swr_multi_resolve.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
-skip = {"swr_abi_version", "swr_last_error", "swr_create", "swr_sizeof", "swr_multi_create", "swr_multi_last_error"}
+skip = {"swr_abi_version", "swr_last_error", "swr_create", "swr_sizeof", "swr_multi_create", "swr_multi_last_error", "swr_bake_last_error"}
 for name in abi.EXPORTS:
     if name in skip:
         continue
@@ -159,7 +160,7 @@ neg = {"swrh_camera_build": (None, None, f(1), f(64), f(64), f(10), None), "swrh
        "swrh_blit_to_buffer": (None, None, 64, 64), "swrh_blit_to_buffer_async": (None, None, 64, 64, None), "swrh_wait_blit": (None, 0),
        "swrh_build_draws": (None, None, None, 0, 0, 1), "swrh_build_draws_band": (None, None, None, 0, 0, 64, 64),
        "swrh_gltf_get_info": (None, None), "swrh_gltf_get_camera": (None, 0, None), "swrh_gltf_register_image": (None, None, 0, 0),
-       "swrh_gltf_bake_sun_visibility": (None,), "swrh_compute_sun_visibility": (None, None), "swrh_env_get": (None, None, None), "swrh_integrate_brdf": (f(0.5), f(0.5), None)}
+       "swrh_gltf_bake_sun_visibility": (None,), "swrh_compute_sun_visibility": (None, None), "swrh_env_get": (None, None, None)}
 for name, a in neg.items():
     r = getattr(h, name)(*a)
     assert r < 0, (name, r)

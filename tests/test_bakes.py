@@ -1,14 +1,14 @@
-"""Host-side environment bakes (host/swr_bake.hpp, SURVEY 8f N3 host side) against analytic properties and independent
-restatements of texture.rs:135-420 / gi.rs:123-149 written here in float64 numpy / scalar Python. CPU only.
+"""The CHECKER of the device environment bakes (oracle/oracle_bake.cpp: CPU restatement of texture.rs:135-420) against
+analytic properties and independent restatements written here in float64 numpy / scalar Python. CPU only: this is what pins
+the oracle that tests/test_gpu_bakes.py then holds the CUDA bakes (csrc/swr_bake.cuh) to.
 Tolerances are stated where float32-vs-float64 evaluation or libm differences can move a value across an 8-bit boundary."""
 import math
 
 import numpy as np
 import pytest
 
-from swraster_viewer_b200 import abi, gltf, scenes
-from helpers import SMALL, render_oracle
-import swraster_viewer_b200 as swr
+import oracle as orc
+from swraster_viewer_b200 import scenes
 
 F32 = np.float32
 
@@ -85,30 +85,12 @@ def sample_linear(faces_f, d):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def test_cross_layout_mips_and_structure():
-    rng = np.random.default_rng(2)
-    faces = rng.integers(0, 256, (6, 8, 8, 4), dtype=np.uint8)
-    env = gltf.BakedEnvironment(cross_from_faces(faces), lut_size=8, specular_samples=4, voxel_dim=2)
-    data, offs, ws, hs, st, typ = env.texture("cubemap")
-    assert typ == abi.TEX_CUBEMAP and list(ws) == [8, 4, 2, 1] and list(st) == [64, 16, 4, 1] and list(offs) == [0, 384, 480, 504]
-    assert np.array_equal(data[:384], scenes.pack_rgba8(faces).reshape(-1))  # faces in the order +X -X +Y -Y +Z -Z
-    ref = scenes.make_texture(scenes.pack_rgba8(faces), 8, 8, abi.TEX_CUBEMAP, abi.WRAP_CLAMP_TO_EDGE, slices=6)  # plain 2x2 average per face
-    assert np.array_equal(data, ref.data)
-    sdata, soffs, sws, shs, sst, styp = env.texture("cubemap_specular")
-    assert styp == abi.TEX_LINEAR and list(sws) == [8] * 4 and list(sst) == [64] * 4 and list(soffs) == [0, 384, 768, 1152] and len(sdata) == 1536
-    ldata, loffs, lws, _, lst, ltyp = env.texture("brdf_lut")
-    assert ltyp == abi.TEX_LINEAR and list(lws) == [8, 4, 2, 1] and list(lst) == [0, 16, 4, 1]
-    with pytest.raises(gltf.GltfError, match="smaller than 4x3"):
-        gltf.BakedEnvironment(np.zeros((2, 3, 4), np.uint8))
-
-
 def test_brdf_lut_against_the_float64_restatement_and_limits():
-    assert gltf.integrate_brdf(1.0, 1e-4) == (1.0, 0.0)  # mirror, head on: all energy in the scale term
-    a, b = gltf.integrate_brdf(0.5, 0.5)
+    assert orc.integrate_brdf(1.0, 1e-4) == (1.0, 0.0)  # mirror, head on: all energy in the scale term
+    a, b = orc.integrate_brdf(0.5, 0.5)
     assert 0 < b < a < 1 and a + b <= 1.0
     N = 16
-    env = gltf.BakedEnvironment(np.full((3, 4, 4), 128, np.uint8), lut_size=N, specular_samples=2, voxel_dim=1)
-    got = env.texture("brdf_lut")[0][:N * N]
+    got = orc.bake_brdf_lut(N).reshape(-1)
     # float64 restatement of integrate_brdf / generate_brdf_lut (texture.rs:167-235) INCLUDING the tangent frame of
     # importance_sample_ggx: with n = +Z the frame is (Y, -X, Z), and the 128-sample sum is not rotation invariant
     # (scenes.brdf_lut, which builds the test inputs, ignores the frame and differs by up to 8 LSB)
@@ -139,17 +121,17 @@ def test_brdf_lut_against_the_float64_restatement_and_limits():
 
 def test_irradiance_sh_of_a_constant_sky_and_against_the_restatement():
     c = 180
-    env = gltf.BakedEnvironment(np.full((3 * 16, 4 * 16, 4), c, np.uint8), lut_size=4, specular_samples=2, voxel_dim=1)
+    sh = orc.bake_irradiance_sh4(scenes.pack_rgba8(np.full((6, 16, 16, 4), c, np.uint8)))
     L = float(s2l(c / 255.0))
     # constant radiance L: sum of the texel solid angles is 4 pi, and 4 pi * 0.282095^2 = 1, so coefficient 0 is pi * L; the rest vanish
-    assert np.allclose(env.irradiance_sh[0], math.pi * L, rtol=2e-3)
-    assert np.abs(env.irradiance_sh[1:]).max() < 1e-4
+    assert np.allclose(sh[0], math.pi * L, rtol=2e-3)
+    assert np.abs(sh[1:]).max() < 1e-4
     # a smooth sky: against the float64 nearest-texel restatement in scenes.py (bilinear at a texel centre returns that texel)
     tex, col = scenes.sky_cubemap(16, 5)
     faces = unpack(tex.data[:6 * 256]).reshape(6, 16, 16, 4).astype(np.uint8)
-    env = gltf.BakedEnvironment(cross_from_faces(faces), lut_size=4, specular_samples=2, voxel_dim=1)
+    sh = orc.bake_irradiance_sh4(scenes.pack_rgba8(faces))
     want = scenes.irradiance_sh4(faces[..., :3].astype(np.float32) / np.float32(255.0))
-    assert np.allclose(env.irradiance_sh, want, rtol=2e-4, atol=2e-5), (env.irradiance_sh, want)
+    assert np.allclose(sh, want, rtol=2e-4, atol=2e-5), (sh, want)
 
 
 def test_prefiltered_cubemap_against_the_restatement():
@@ -157,10 +139,10 @@ def test_prefiltered_cubemap_against_the_restatement():
     faces = rng.integers(0, 256, (6, 8, 8, 4), dtype=np.uint8)
     faces[..., 3] = 255
     S = 16
-    env = gltf.BakedEnvironment(cross_from_faces(faces), lut_size=4, specular_samples=S, voxel_dim=1)
-    data, offs, ws, hs, st, _ = env.texture("cubemap_specular")
+    pre = orc.bake_prefilter_specular(scenes.pack_rgba8(faces), S)
+    nm = pre.shape[0]
+    data, offs, st = pre.reshape(-1), [m * 384 for m in range(nm)], [64] * nm
     faces_f = faces[..., :3].astype(np.float64) / 255.0
-    nm = len(offs)
     t = ((np.arange(8) + 0.5) / 8) * 2 - 1
     worst = 0
     for mip, face, y, x in [(0, 0, 0, 0), (0, 3, 5, 2), (1, 1, 3, 4), (1, 4, 7, 7), (2, 2, 0, 6), (3, 5, 4, 1), (3, 0, 2, 2), (2, 3, 6, 0)]:
@@ -186,31 +168,6 @@ def test_prefiltered_cubemap_against_the_restatement():
     spread = [unpack(data[offs[m]:offs[m] + 384])[:, :3].std() for m in range(nm)]
     assert max(spread[1:]) < 0.5 * spread[0], spread
     # a constant sky stays constant at every roughness
-    env = gltf.BakedEnvironment(np.full((3 * 4, 4 * 4, 4), 90, np.uint8), lut_size=4, specular_samples=8, voxel_dim=1)
-    cdata = unpack(env.texture("cubemap_specular")[0])
+    cdata = unpack(orc.bake_prefilter_specular(scenes.pack_rgba8(np.full((6, 4, 4, 4), 90, np.uint8)), 8).reshape(-1))
     lin = int(math.floor(float(s2l(90 / 255.0)) * 255.0))
     assert np.abs(cdata[:, :3] - lin).max() <= 1 and (cdata[:, 3] == 255).all()
-
-
-def test_voxel_grid_initialisation_and_use_as_loader_environment(tmp_path):
-    tex, _ = scenes.sky_cubemap(8, 3)
-    faces = unpack(tex.data[:6 * 64]).reshape(6, 8, 8, 4).astype(np.uint8)
-    env = gltf.BakedEnvironment(cross_from_faces(faces), lut_size=16, specular_samples=8, voxel_dim=3, irradiance_scale=0.25, sky_visibility=1.0, light_intensity=0.5)
-    vox = env.voxels()
-    assert vox.shape == (27, 4, 4)
-    assert np.array_equal(vox[:, :, :3], np.broadcast_to(env.irradiance_sh * F32(0.25), (27, 4, 3)))  # gi.rs:137-144
-    assert (vox[:, 0, 3] == 0.5).all() and (vox[:, 1, 3] == 1.0).all() and (vox[:, 2:, 3] == 0.0).all()  # gi.rs:145-146
-    # the baked environment completes a loaded glTF file into a renderable scene (oracle, CPU): lit, sky visible, grid spans the bounds
-    sc, spec = scenes.scene_c1_sphere(segments=24, bands=16, **SMALL)
-    scenes.export_gltf(sc, str(tmp_path / "s"))
-    g = gltf.load_gltf(tmp_path / "s.gltf", environment=env)
-    d = g.desc()
-    assert d.ntextures == 3 and (d.cubemap, d.cubemap_specular, d.brdf_lut) == (0, 1, 2)
-    assert np.allclose(d.voxel_grid.world_min[:], g.bounds_min) and np.allclose(d.voxel_grid.world_max[:], g.bounds_max)
-    W, H = 160, 96
-    cam = swr.RenderCamera.from_spec(spec, W, H)
-    o = render_oracle(g, cam, W, H)
-    px = np.stack([(o["pixels"] >> 24) & 255, (o["pixels"] >> 16) & 255, (o["pixels"] >> 8) & 255], -1).reshape(H, W, 3)
-    covered = (o["seq"] != 0xFFFFFFFF).reshape(H, W)
-    assert covered.any() and (~covered).any()
-    assert px[covered].mean() > 20 and px[~covered].mean() > 60  # the sphere is lit, the sky is the bright procedural sky

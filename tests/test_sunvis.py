@@ -1,14 +1,13 @@
-"""Host-side voxel sun visibility (host/swr_sunvis.hpp, SURVEY 8f N4, default load path) against a brute-force float32
-restatement of gi.rs:151-314 / raytracer.rs:177-259 / voxelgrid.rs:371-419 written here (no hierarchy: every triangle is
-tested for every ray), and end to end: the shadow shows up in the frame. CPU only."""
+"""The CHECKER of the device sun-visibility bake (oracle/oracle_sunvis.cpp) against a brute-force float32
+restatement of gi.rs:151-314 / raytracer.rs:177-259 / voxelgrid.rs:371-419 written here in numpy. CPU only: this pins the
+oracle that tests/test_gpu_bakes.py then holds the CUDA ray cast (csrc/swr_bake.cuh) to, end to end included."""
 import math
 
 import numpy as np
 import pytest
 
-from swraster_viewer_b200 import abi, gltf, scenes
-from helpers import SMALL, render_oracle
-import swraster_viewer_b200 as swr
+import oracle as orc
+from swraster_viewer_b200 import abi, scenes
 
 F32 = np.float32
 
@@ -120,8 +119,9 @@ def brute_force(sc):
 @pytest.mark.parametrize("lid", [False, True])
 def test_sun_visibility_matches_the_brute_force_restatement(lid):
     sc, _ = shadow_scene(lid, voxel_dim=32)
-    got = gltf.compute_sun_visibility(sc)
+    got = orc.sun_visibility(sc)
     want, active = brute_force(sc)
+    assert np.array_equal(orc.sunvis_active_mask(sc).astype(bool), active)
     assert active.any() and not active.all() and got.shape == (32, 32, 32)
     assert np.allclose(got, want, rtol=0, atol=1e-5), np.abs(got - want).max()
     assert got.min() < 0.05 and got.max() == 1.0  # some voxels sit in the box's shadow, some see the sun
@@ -135,64 +135,4 @@ def test_empty_scene_keeps_every_voxel_lit():
     sc.nodes = []
     sc._desc = None
     sc.node_spheres = []
-    assert np.array_equal(gltf.compute_sun_visibility(sc), np.ones((4, 4, 4), F32))  # no active voxel: no rays, no blur (gi.rs:281-284)
-
-
-def test_shadow_reaches_the_frame_through_the_loader(tmp_path):
-    sc, spec = shadow_scene(False, voxel_dim=40)
-    scenes.export_gltf(sc, str(tmp_path / "s"))
-    W, H = 256, 160
-    cam = swr.RenderCamera.from_spec(spec, W, H)
-    lit = gltf.load_gltf(tmp_path / "s.gltf", environment=sc)
-    vis = gltf.compute_sun_visibility(lit)
-    shadowed = gltf.load_gltf(tmp_path / "s.gltf", environment=sc)
-    gltf.bake_sun_visibility(shadowed)
-    d = shadowed.desc()
-    nv = int(np.prod(d.voxel_grid.dims[:]))
-    w0 = np.ctypeslib.as_array(d.voxel_grid.gi_sh4, (nv * 16,)).reshape(nv, 16)[:, 3]
-    assert np.array_equal(w0, vis.reshape(-1))
-    a, b = render_oracle(lit, cam, W, H), render_oracle(shadowed, cam, W, H)
-    assert np.array_equal(a["seq"], b["seq"])  # visibility is untouched, only the lighting changes
-    lum = lambda o: ((o["pixels"] >> 24) & 255).astype(np.int32) + ((o["pixels"] >> 16) & 255) + ((o["pixels"] >> 8) & 255)
-    darker = (lum(a) - lum(b)) > 30
-    assert 0.005 < darker.mean() < 0.5, darker.mean()  # a shadow patch on the ground, not the whole frame
-
-
-def test_load_scene_is_the_viewers_load_path_in_one_call(tmp_path):
-    """gltf.load_scene = parse + environment bake + voxel grid over the bounds + SH initialisation + sun visibility
-    (main.rs:100-291); the result renders (oracle) with the default camera of main.rs:210-224."""
-    from test_bakes import cross_from_faces, unpack
-    sc, _ = shadow_scene(False, voxel_dim=4)
-    scenes.export_gltf(sc, str(tmp_path / "s"))
-    tex, _ = scenes.sky_cubemap(8, 3)
-    faces = unpack(tex.data[:6 * 64]).reshape(6, 8, 8, 4).astype(np.uint8)
-    scene, (pos, look, fov, far) = gltf.load_scene(tmp_path / "s.gltf", cross_from_faces(faces), grid_size=24, lut_size=16, specular_samples=8)
-    d = scene.desc()
-    assert tuple(d.voxel_grid.dims[:]) == (24, 24, 24) and np.allclose(d.voxel_grid.world_min[:], scene.bounds_min)
-    vox = np.ctypeslib.as_array(d.voxel_grid.gi_sh4, (24 ** 3 * 16,)).reshape(-1, 4, 4)
-    assert vox[:, 0, 3].min() < 0.1 and vox[:, 0, 3].max() == 1.0 and (vox[:, 1, 3] == 1.0).all()  # sun visibility in, sky visibility 1
-    assert np.array_equal(vox[0, :, :3], vox[-1, :, :3]) and np.abs(vox[0, 0, :3]).min() > 0  # the same scaled SH everywhere
-    assert pos[2] == pytest.approx(float(scene.bounds_center[2]) + float(scene.bounds_diagonal)) and far == pytest.approx(2 * float(scene.bounds_diagonal))
-    W, H = 160, 96
-    cam = swr.RenderCamera(pos, look, fov, W, H, far)
-    o = render_oracle(scene, cam, W, H)
-    assert (o["seq"] != 0xFFFFFFFF).mean() > 0.02
-
-
-def test_load_scene_camera_rules(tmp_path):
-    """main.rs:198-224: the first glTF camera wins and only its yfov is used; orthographic is a load error; none -> default."""
-    import json
-    from test_bakes import cross_from_faces
-    sc, _ = shadow_scene(False, voxel_dim=4)
-    scenes.export_gltf(sc, str(tmp_path / "s"))
-    sky = cross_from_faces(np.full((6, 4, 4, 4), 200, np.uint8))
-    doc = json.load(open(tmp_path / "s.gltf"))
-    doc["cameras"] = [{"type": "perspective", "perspective": {"yfov": 0.6, "znear": 0.1, "zfar": 50.0}}, {"type": "orthographic", "orthographic": {"xmag": 1, "ymag": 1, "znear": 0.1, "zfar": 5}}]
-    doc["nodes"].append({"camera": 0, "translation": [3, 4, 5]})
-    json.dump(doc, open(tmp_path / "p.gltf", "w"))
-    _, cam = gltf.load_scene(tmp_path / "p.gltf", sky, grid_size=4, lut_size=4, specular_samples=2)
-    assert cam == ((0.0, 0.0, 5.0), (0.0, 0.0, 0.0), pytest.approx(0.6), 1000.0)
-    doc["cameras"].reverse()
-    json.dump(doc, open(tmp_path / "o.gltf", "w"))
-    with pytest.raises(gltf.GltfError, match="unsupported camera type"):
-        gltf.load_scene(tmp_path / "o.gltf", sky, grid_size=4, lut_size=4, specular_samples=2)
+    assert np.array_equal(orc.sun_visibility(sc), np.ones((4, 4, 4), F32))  # no active voxel: no rays, no blur (gi.rs:281-284)
