@@ -1,5 +1,7 @@
 """Parity at BASELINE.json's FULL sizes. C1-C3: the whole frame against the serial oracle (seconds of CPU time).
 C4 (50 M triangles): size-independent properties — determinism, sort-first band union == full frame, full coverage."""
+import os
+
 import numpy as np
 import pytest
 
@@ -38,6 +40,13 @@ def test_c2_terrain_1m_1080p():
 def test_c3_instanced_10m_4k():
     g = full_compare(*scenes.scene_c3_instanced(**BIG), 3840, 2160)
     assert g["stats"]["triangles_submitted"] > 7_000_000 and g["stats"]["triangles_clipped"] > 10_000
+
+
+@pytest.mark.skipif(os.environ.get("SWR_FULLSIZE_ORACLE") != "1", reason="about two minutes of CPU and ~20 GB of host memory: set SWR_FULLSIZE_ORACLE=1")
+def test_c4_micro_50m_4k_against_the_oracle():
+    """the full-size C4 frame (50 M micro-triangles) against the serial oracle, not only through properties."""
+    g = full_compare(*scenes.scene_c4_micro(**BIG), 3840, 2160)
+    assert g["stats"]["triangles_submitted"] == 50_000_000
 
 
 def test_c4_micro_50m_4k_properties():
