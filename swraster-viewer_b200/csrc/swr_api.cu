@@ -94,7 +94,9 @@ struct FrameSlot {
     swr_camera cam{};
     int shade = 0;
     bool tr_ran = false;      // the translucent geometry pass was launched (its counters are valid)
-    int resolve_kind = 0;     // queued behind the frame: 0 nothing, 1 device-only resolve, 2 resolve + read-back (swr_resolve_async)
+    int resolve_kind = 0;     // queued behind the frame: 0 nothing, 1 device-only resolve, 2 resolve + read-back (swr_resolve_async),
+                              // 3 peer resolve (swr_resolve_peer, frame number in resolve_frame)
+    uint32_t resolve_frame = 0;
     int resolve_idx = 0;
     float resolve_exposure = 0.0f;
     uint32_t *resolve_host = nullptr;
@@ -831,6 +833,7 @@ static void set_camera(swr_ctx *ctx, const swr_camera *cam) {
 static int issue_resolve_copy(swr_ctx *ctx, int idx, float exposure, uint32_t *host);
 
 static int resolve_into(swr_ctx *ctx, uint32_t *dst, float exposure);
+static int launch_peer_resolve(swr_ctx *ctx, float exposure, uint32_t frame, bool tr_ran);
 
 // Enqueue (or re-enqueue) everything a slot describes: opaque pass, shading, and the resolve that was queued behind it.
 static int enqueue_slot(swr_ctx *ctx, FrameSlot &f) {
@@ -850,6 +853,7 @@ static int enqueue_slot(swr_ctx *ctx, FrameSlot &f) {
     CK(cudaEventRecord(f.done, ctx->stream));
     if (f.resolve_kind == 1) return resolve_into(ctx, f.resolve_idx ? ctx->pixels_alt.p : ctx->pixels.p, f.resolve_exposure);
     if (f.resolve_kind == 2) return issue_resolve_copy(ctx, f.resolve_idx, f.resolve_exposure, f.resolve_host);
+    if (f.resolve_kind == 3) return launch_peer_resolve(ctx, f.resolve_exposure, f.resolve_frame, f.tr_ran);
     return SWR_OK;
 }
 
@@ -1162,18 +1166,7 @@ int swr_peer_open(swr_ctx *ctx, const void *handle) {
     return SWR_OK;
 }
 
-int swr_resolve_peer(swr_ctx *ctx, float exposure, uint32_t frame) {
-    if (!ctx) return SWR_ERR_INVALID;
-    if (!ctx->peer_pixels || ctx->peer_exported) {
-        ctx->err = "swr_resolve_peer needs swr_peer_open / swr_peer_attach first (and is for contributing ranks)";
-        return SWR_ERR_INVALID;
-    }
-    CK(cudaSetDevice(ctx->device));
-    // A contribution cannot be taken back once it is signalled, so the frame must be known good first: wait for its
-    // counters (one event wait, no full drain) and replay it here if a buffer had to grow.
-    int rc;
-    while (ctx->slots_pending > 0)
-        if ((rc = settle_oldest(ctx))) return rc;
+static int launch_peer_resolve(swr_ctx *ctx, float exposure, uint32_t frame, bool tr_ran) {
     cudaStream_t s = ctx->stream;
     const size_t W = ctx->W;
     size_t y0 = (size_t)ctx->row_begin * SWR_TILE, y1 = (size_t)ctx->row_end * SWR_TILE;
@@ -1186,10 +1179,34 @@ int swr_resolve_peer(swr_ctx *ctx, float exposure, uint32_t frame) {
     dim3 grid((unsigned)((W + 255) / 256), (unsigned)(y1 > y0 ? (y1 - y0 + 3) / 4 : 1));
     ctx->launches++;
     k_resolve_peer<<<grid, 256, 0, s>>>(ctx->color.p, ctx->tiles_x * SWR_TILE, ctx->peer_pixels, ctrl, ctx->W, (int)y0, (int)(y1 > y0 ? y1 : y0), exposure,
-                                        ctx->peer_local.p, ctx->peer_local.p + 1);
+                                        ctx->peer_local.p, ctx->peer_local.p + 1, ctx->op.counters.p, tr_ran ? ctx->tr.counters.p : nullptr);
     CK(cudaEventRecord(ctx->ev_res[1], s));
     CK(cudaGetLastError());
     return SWR_OK;
+}
+
+int swr_resolve_peer(swr_ctx *ctx, float exposure, uint32_t frame) {
+    if (!ctx) return SWR_ERR_INVALID;
+    if (!ctx->peer_pixels || ctx->peer_exported) {
+        ctx->err = "swr_resolve_peer needs swr_peer_open / swr_peer_attach first (and is for contributing ranks)";
+        return SWR_ERR_INVALID;
+    }
+    CK(cudaSetDevice(ctx->device));
+    // A contribution cannot be taken back once it is signalled. The frame in front of this resolve is guarded on the device
+    // (k_resolve_peer neither stores nor signals when the frame's buffers overflowed; the replay re-issues it), so the host
+    // does not have to wait for it here. Older frames are settled first: at most one unsettled frame carries a peer
+    // resolve, which is what keeps a replay from queueing behind a device-side wait for its own contribution.
+    int rc;
+    while (ctx->slots_pending > 1)
+        if ((rc = settle_oldest(ctx))) return rc;
+    bool tr_ran = false;
+    if (FrameSlot *f = newest_pending(ctx)) {
+        f->resolve_kind = 3;
+        f->resolve_exposure = exposure;
+        f->resolve_frame = frame;
+        tr_ran = f->tr_ran;
+    }
+    return launch_peer_resolve(ctx, exposure, frame, tr_ran);
 }
 
 int swr_peer_collect(swr_ctx *ctx, uint32_t frame, int contributors) {

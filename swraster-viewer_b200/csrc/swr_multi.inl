@@ -249,6 +249,17 @@ int swr_multi_resolve(swr_multi *m, float exposure, uint32_t *out_pixels) {
     if (m->ndev == 1) return swr_resolve(m->ctx[0], exposure, out_pixels);
     const uint32_t f = ++m->frame;
     int rc = multi_run(m, [=](int i) {
+        // When the frame is about to be handed to the host, every device first makes sure ITS part is good (a buffer-growth
+        // replay re-renders it): nobody else would look at a contributor's counters while the assembler waits for it.
+        // Without host output the contributors only guard themselves on the device (k_resolve_peer stays silent on a
+        // frame that overflowed) and the next call that settles the frame replays it.
+        if (out_pixels) {
+            cudaSetDevice(m->ctx[i]->device);
+            while (m->ctx[i]->slots_pending > 0) {
+                int rs = settle_oldest(m->ctx[i]);
+                if (rs) return rs;
+            }
+        }
         if (i > 0) return swr_resolve_peer(m->ctx[i], exposure, f);
         int r = swr_resolve(m->ctx[0], exposure, nullptr);
         return r ? r : swr_peer_collect(m->ctx[0], f, m->ndev - 1);

@@ -518,9 +518,16 @@ __device__ __forceinline__ bool peer_wait(const uint32_t *ctr, uint32_t target) 
 // k_resolve into the assembling rank's buffer: store this rank's rows over NVLink and let the last CTA publish the
 // contribution (fence + system-scope atomic on the assembler's counter). The buffer-reuse guard (k_peer_wait) runs
 // as a one-thread kernel in front so that only one remote poll is in flight instead of one per CTA.
+// A frame whose tile lists / clip buffers overflowed holds no valid image: it contributes nothing and does NOT signal — the
+// host replays the frame (and this resolve with it) when it next looks at the frame's counters, and the assembler simply
+// keeps waiting for that contribution.
+__device__ __forceinline__ bool frame_overflowed(const FrameCounters *c) { return c != nullptr && (c->overflow_refs | c->overflow_clip | c->overflow_ext) != 0u; }
+
 __global__ void __launch_bounds__(256) k_resolve_peer(const float4 *color, int Wp, uint32_t *pixels, uint32_t *ctrl, int W, int y0, int y1, float exposure,
-                                                      uint32_t *local_done, const uint32_t *timeout_flag) {
-    if (*timeout_flag == 0u) {  // after a timeout the buffer may still be in use: contribute nothing but still signal
+                                                      uint32_t *local_done, const uint32_t *timeout_flag, const FrameCounters *op_counters,
+                                                      const FrameCounters *tr_counters) {
+    const bool bad = frame_overflowed(op_counters) || frame_overflowed(tr_counters);
+    if (*timeout_flag == 0u && !bad) {  // after a timeout the buffer may still be in use: contribute nothing but still signal
         const int x = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
         const int y = y0 + blockIdx.y * 4 + (threadIdx.x >> 6);
         if (y < y1 && x < W) {
@@ -545,7 +552,7 @@ __global__ void __launch_bounds__(256) k_resolve_peer(const float4 *color, int W
         if (atomicAdd(local_done, 1u) == n - 1u) {
             *local_done = 0u;  // next frame
             __threadfence_system();
-            atomicAdd_system(ctrl + SWR_PEER_DONE, 1u);
+            if (!bad) atomicAdd_system(ctrl + SWR_PEER_DONE, 1u);
         }
     }
 }

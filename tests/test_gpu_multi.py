@@ -93,3 +93,29 @@ def test_buffer_growth_is_replayed_with_frames_in_flight():
     r.resolve_device_only(2.0)
     r.synchronize()
     r.close()
+
+
+def test_multi_devices_replay_a_frame_that_outgrew_its_buffers():
+    """a contributing device whose tile lists overflow must not deliver (or signal) a sky-only strip. Its resolve
+    kernel checks the frame's overflow flags on the device, stays silent, and the host replays frame + peer resolve."""
+    n = device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs in the box")
+    from swraster_viewer_b200 import scenes
+    from helpers import SMALL
+    _, small, spec_s, _, _ = small_configs()[0]
+    W, H = 512, 288
+    big, spec_b = scenes.scene_c3_instanced(400000, ico_subdiv=3, torus_n=16, box_n=4, **SMALL)
+    cam_s = swr.RenderCamera.from_spec(spec_s, W, H)
+    cam_b = swr.RenderCamera.from_spec(spec_b, W, H)
+    ref = render_gpu(big, cam_b, W, H)["pixels"]
+    r = swr.Renderer(W, H, devices=[0, 1])
+    buf = swr.RenderBuffer(W, H)
+    for _ in range(2):  # every device sizes its buffers on the small scene
+        r.render_scene(small, cam_s)
+        r.blit_to_buffer(buf)
+    for f in range(3):
+        r.render_scene(big, cam_b)
+        r.blit_to_buffer(buf)
+        assert np.array_equal(buf.pixels, ref), f"frame {f}: {np.count_nonzero(buf.pixels != ref)} pixels differ"
+    r.close()
