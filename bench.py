@@ -234,11 +234,11 @@ def run_gpu(args):
     pa = PeerAssembly(r, dst=0) if (world > 1 and not sort_last) else None
     # host frame(s) of the e2e path: pinned; shared between the ranks at N > 1
     if world > 1:
-        hosts = [SharedHostFrame(W, H, tag=f"swr_bench_{os.environ.get('MASTER_PORT', '0')}_{k}") for k in range(2)]
+        hosts = [SharedHostFrame(W, H, tag=f"swr_bench_{os.environ.get('MASTER_PORT', '0')}_{k}") for k in range(4)]
         bufs = [swr.RenderBuffer(W, H, pixels=h.pixels) for h in hosts]
     else:
         hosts = None
-        bufs = [swr.RenderBuffer(W, H, pinned=True), swr.RenderBuffer(W, H, pinned=True)]
+        bufs = [swr.RenderBuffer(W, H, pinned=True) for _ in range(4)]
 
     def step_device():
         if sort_last:
@@ -293,41 +293,47 @@ def run_gpu(args):
             barrier()
         e2e_mode = "sort-last composite over NCCL, then D2H of the composited frame on rank 0 (synchronous)"
     else:
+        # the pipelined renderer: frames alternate between two contexts of the device (two streams, two sets of per-frame
+        # buffers, one scene), so frame N+1's geometry pass overlaps frame N's raster tail and shading
+        re = swr.Renderer(W, H, device=local, lanes=2)
+        if world > 1:
+            re.set_tile_rows(*ranges[rank])
+
         def e2e_loop(n):
             # pipelined like the reference's App (present N-1 || render N, main.rs:526-597): every step still uploads its draw
             # table and reads its own pixels back into pinned host memory; the read-back of frame N overlaps frame N+1.
             # N > 1: each rank's rows go over its own PCIe link into the host frame all ranks share; the frame is complete
             # when every rank has waited for its copy (hosts[k].arrive / wait_all: flags in the same shared segment).
-            prev = None
+            def complete(p):
+                re.wait_blit(p[0])
+                if hosts:
+                    hosts[p[1]].arrive(rank, p[2])
+                    if rank == 0:
+                        hosts[p[1]].wait_all(world, p[2])
+            pend = []
             for i in range(n):
-                r.render_scene(scene, cam)
-                tk = r.blit_to_buffer_async(bufs[i & 1])
-                if prev is not None:
-                    r.wait_blit(prev[0])
-                    if hosts:
-                        hosts[prev[1]].arrive(rank, prev[2])
-                        if rank == 0:
-                            hosts[prev[1]].wait_all(world, prev[2])
-                prev = (tk, i & 1, i + 1)
-            r.wait_blit(prev[0])
-            if hosts:
-                hosts[prev[1]].arrive(rank, prev[2])
-                if rank == 0:
-                    hosts[prev[1]].wait_all(world, prev[2])
-        e2e_mode = ("pipelined: read-back of frame N overlaps frame N+1 (swr_resolve_async)" if world == 1 else
-                    "pipelined; every rank reads its own rows back over its own PCIe link into one page-locked host frame shared by all ranks")
+                re.render_scene(scene, cam)
+                tk = re.blit_to_buffer_async(bufs[i % len(bufs)])
+                pend.append((tk, i % len(bufs), i // len(bufs) + 1))
+                if len(pend) > 2:  # two frames stay in flight behind the one just enqueued
+                    complete(pend.pop(0))
+            for p in pend:
+                complete(p)
+        e2e_mode = ("pipelined, Renderer(lanes=2): frames alternate between two contexts (streams) of the device, read-back of frame N overlaps frames N+1, N+2 (swr_resolve_async)" if world == 1 else
+                    "pipelined, Renderer(lanes=2); every rank reads its own rows back over its own PCIe link into one page-locked host frame shared by all ranks")
     for h in hosts or []:
         h.reset()
     e2e_loop(2)
     for h in hosts or []:
         h.reset()
     barrier()
-    launches1 = r.launch_count
+    rl = r if sort_last else re
+    launches1 = rl.launch_count
     t0 = time.perf_counter()
     e2e_loop(K)
     barrier()
     e2e_s = time.perf_counter() - t0
-    launches2 = r.launch_count
+    launches2 = rl.launch_count
     e2e_sync_s = None
     if world == 1:
         # the strictly synchronous form (render, blit, wait) for reference
@@ -422,6 +428,8 @@ def run_gpu(args):
     torch.cuda.synchronize()
     del ev, flush, stream
     e2e_loop = step_device = None  # closures hold tensors that live on the library's stream
+    if not sort_last:
+        re.close()
     if sort_last:
         del pix_host
     bufs = None

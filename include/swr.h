@@ -222,6 +222,12 @@ int swr_set_rsqrt_table(swr_ctx *ctx, const uint32_t *table, int mantissa_bits);
 /* Copies the scene to device memory; the descriptor may be freed afterwards. */
 int swr_upload_scene(swr_ctx *ctx, const swr_scene_desc *scene);
 
+/* A second context on the SAME device renders the scene `owner` uploaded, without a second copy in device memory (the
+ * scene is immutable; `owner` must outlive `ctx` and must not upload again while `ctx` uses the scene). This is how a
+ * pipelined host alternates frames between two contexts — two streams, two sets of per-frame buffers — so that frame
+ * N+1's geometry pass fills the SMs frame N's raster tail and single-block phases leave idle (host mirror: lanes). */
+int swr_share_scene(swr_ctx *ctx, const swr_ctx *owner);
+
 /* Device half of render_scene (renderer.rs:201-220): set-up, clip, bin, raster,
  * shade.  Asynchronous on the context's stream. With shade=0 only the
  * visibility buffer is produced (used by the sort-last composite). */

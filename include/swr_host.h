@@ -20,6 +20,12 @@ int swrh_camera_build_rotated(const float pos[3], const float look_at_level[3], 
 
 /* Renderer::new(width, height) (renderer.rs:165) on CUDA device `device`; NULL on error (no CPU fallback) */
 void *swrh_renderer_new(int width, int height, int device);
+/* the same Renderer with `lanes` (1..4) contexts on one device that frames alternate between (own stream and per-frame
+ * buffers each, one shared scene: swr_share_scene): for callers that pipeline with swrh_blit_to_buffer_async, frame N+1's
+ * geometry pass then overlaps frame N's raster tail and shading. swrh_renderer_ctx returns the lane of the last frame. */
+void *swrh_renderer_new_lanes(int width, int height, int device, int lanes);
+int swrh_renderer_lanes(void *renderer);                  /* 0 for a multi-device renderer */
+swr_ctx *swrh_renderer_lane_ctx(void *renderer, int lane); /* NULL when out of range */
 /* the same Renderer over several CUDA devices of this process (sort-first; include/swr.h swr_multi_*): one frame, one
  * blit, every method below works on it except swrh_set_tile_rows (it assigns its own cost-balanced bands, readable
  * with swrh_renderer_tile_rows) and shard / nshards of swrh_render_scene */

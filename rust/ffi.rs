@@ -187,6 +187,7 @@ extern "C" {
     pub fn swr_set_tile_rows(ctx: *mut swr_ctx, row_begin: c_int, row_end: c_int) -> c_int;
     pub fn swr_set_rsqrt_table(ctx: *mut swr_ctx, table: *const u32, mantissa_bits: c_int) -> c_int;
     pub fn swr_upload_scene(ctx: *mut swr_ctx, scene: *const swr_scene_desc) -> c_int;
+    pub fn swr_share_scene(ctx: *mut swr_ctx, owner: *const swr_ctx) -> c_int;
     pub fn swr_render(ctx: *mut swr_ctx, camera: *const swr_camera, draws: *const swr_draw, ndraws: c_int, shade: c_int) -> c_int;
     pub fn swr_shade(ctx: *mut swr_ctx, camera: *const swr_camera) -> c_int;
     pub fn swr_keys_to_global(ctx: *mut swr_ctx) -> c_int;

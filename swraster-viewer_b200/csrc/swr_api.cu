@@ -123,6 +123,7 @@ struct swr_ctx {
 
     // scene
     bool have_scene = false;
+    bool scene_borrowed = false;  // swr_share_scene: the device scene belongs to another context of the same device
     std::vector<void *> scene_allocs;
     std::vector<cudaTextureObject_t> tex_objs;
     DevScene scene{};
@@ -260,6 +261,13 @@ swr_ctx *swr_create(int width, int height, int device) {
 }
 
 static void free_scene(swr_ctx *ctx) {
+    if (ctx->scene_borrowed) {  // nothing here is ours
+        ctx->tex_objs.clear();
+        ctx->scene_allocs.clear();
+        ctx->scene_borrowed = false;
+        ctx->have_scene = false;
+        return;
+    }
     for (cudaTextureObject_t t : ctx->tex_objs) cudaDestroyTextureObject(t);
     ctx->tex_objs.clear();
     for (void *p : ctx->scene_allocs) cudaFree(p);
@@ -531,6 +539,26 @@ int swr_upload_scene(swr_ctx *ctx, const swr_scene_desc *s) {
     sc.brdf_lut = s->brdf_lut;
     CK(cudaStreamSynchronize(ctx->stream));  // host staging vectors go out of scope
     ctx->have_scene = true;
+    return SWR_OK;
+}
+
+int swr_share_scene(swr_ctx *ctx, const swr_ctx *owner) {
+    if (!ctx || !owner || ctx == owner) return SWR_ERR_INVALID;
+    if (!owner->have_scene || owner->scene_borrowed || owner->device != ctx->device) {
+        ctx->err = "swr_share_scene: the owner must hold an uploaded scene of its own on the same device";
+        return SWR_ERR_INVALID;
+    }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(owner->stream));  // the owner's upload (its own stream) is complete before this context reads it
+    free_scene(ctx);
+    ctx->scene = owner->scene;
+    ctx->prim_ntris = owner->prim_ntris;
+    ctx->prim_nverts = owner->prim_nverts;
+    ctx->scene_borrowed = true;
+    ctx->have_scene = true;
+    ctx->frame_valid = false;
+    ctx->have_history = false;
     return SWR_OK;
 }
 

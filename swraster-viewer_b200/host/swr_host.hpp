@@ -407,9 +407,22 @@ inline void auto_exposure_step(float state[3], const float *tile_luminance, size
 class Renderer {
    public:
     // Renderer::new(width, height); device selects the GPU (one Renderer per GPU).
-    Renderer(int width, int height, int device = 0) : width_(width), height_(height) {
-        ctx_ = swr_create(width, height, device);
-        if (!ctx_) throw std::runtime_error(std::string("swr_create: ") + swr_last_error(nullptr));
+    // lanes > 1: frames alternate between that many contexts of the device (own stream, own per-frame buffers, one shared
+    // scene), so a caller that pipelines (render N+1 before waiting for N's pixels) gets frame N+1's geometry pass
+    // overlapped with frame N's raster tail and shading. Every per-frame query (stats, luminance, blit) goes to the lane of
+    // the frame rendered last. lanes = 1 is the plain single-stream renderer.
+    Renderer(int width, int height, int device = 0, int lanes = 1) : width_(width), height_(height) {
+        if (lanes < 1 || lanes > 4) throw std::runtime_error("Renderer: lanes must be 1..4");
+        for (int l = 0; l < lanes; l++) {
+            swr_ctx *c = swr_create(width, height, device);
+            if (!c) {
+                const std::string msg = std::string("swr_create: ") + swr_last_error(nullptr);
+                for (swr_ctx *o : lanes_) swr_destroy(o);
+                throw std::runtime_error(msg);
+            }
+            lanes_.push_back(c);
+        }
+        ctx_ = lanes_[0];
         auto_exposure_ = auto_exposure_target_ = SWR_DEFAULT_EXPOSURE;  // renderer.rs:194-196
         auto_exposure_ev_ = std::log2(SWR_DEFAULT_EXPOSURE);
         set_reference_rsqrt(true);
@@ -432,16 +445,19 @@ class Renderer {
         if (multi_)
             check(swr_multi_set_rsqrt_table(multi_, t, t ? bits : 0), "swr_multi_set_rsqrt_table");
         else
-            check(swr_set_rsqrt_table(ctx_, t, t ? bits : 0), "swr_set_rsqrt_table");
+            for (swr_ctx *c : lanes_) check(swr_set_rsqrt_table(c, t, t ? bits : 0), "swr_set_rsqrt_table");
         rsqrt_bits_ = on ? bits : 0;
     }
     int reference_rsqrt_bits() const { return rsqrt_bits_; }
     ~Renderer() {
-        if (multi_)
+        if (multi_) {
             swr_multi_destroy(multi_);
-        else if (ctx_)
-            swr_destroy(ctx_);
+        } else {
+            for (size_t l = lanes_.size(); l-- > 0;) swr_destroy(lanes_[l]);  // lane 0 owns the scene: last
+        }
     }
+    int lanes() const { return (int)lanes_.size(); }
+    swr_ctx *lane_ctx(int i) const { return (i >= 0 && i < (int)lanes_.size()) ? lanes_[i] : nullptr; }
     swr_multi *multi() const { return multi_; }
     Renderer(const Renderer &) = delete;
     Renderer &operator=(const Renderer &) = delete;
@@ -451,7 +467,7 @@ class Renderer {
     const std::vector<swr_draw> &draws() const { return draws_; }
     void set_tile_rows(int r0, int r1) {
         if (multi_) throw std::runtime_error("set_tile_rows: a multi-device renderer assigns its own row bands");
-        check(swr_set_tile_rows(ctx_, r0, r1), "swr_set_tile_rows");
+        for (swr_ctx *c : lanes_) check(swr_set_tile_rows(c, r0, r1), "swr_set_tile_rows");
         row0_ = r0;
         row1_ = r1;
     }
@@ -464,11 +480,22 @@ class Renderer {
     void render_scene(const Scene &scene, const swr_camera &cam, bool shade = true, int shard = 0, int nshards = 1) {
         if (scene.desc != uploaded_) {  // immutable scene: upload on first sight (SURVEY §8b ownership)
             validate_scene_ranges(*scene.desc);
-            if (multi_)
+            if (multi_) {
                 check(swr_multi_upload_scene(multi_, scene.desc), "swr_multi_upload_scene");
-            else
-                check(swr_upload_scene(ctx_, scene.desc), "swr_upload_scene");
+            } else {
+                ctx_ = lanes_[0];
+                check(swr_upload_scene(lanes_[0], scene.desc), "swr_upload_scene");
+                for (size_t l = 1; l < lanes_.size(); l++) {
+                    ctx_ = lanes_[l];
+                    check(swr_share_scene(lanes_[l], lanes_[0]), "swr_share_scene");
+                }
+                cur_ = (int)lanes_.size() - 1;  // the next frame goes to lane 0
+            }
             uploaded_ = scene.desc;
+        }
+        if (!multi_) {
+            cur_ = (cur_ + 1) % (int)lanes_.size();
+            ctx_ = lanes_[cur_];
         }
         if (multi_) {  // every device culls the full draw list against its own band (k_cull)
             if (!shade || nshards != 1) throw std::runtime_error("multi-device renderer: sort-first only (shade = 1, no shards)");
@@ -521,10 +548,13 @@ class Renderer {
             return 0;
         }
         check(swr_resolve_async(ctx_, auto_exposure_, buffer.pixels, &ticket), "swr_resolve_async");
-        return ticket;
+        return cur_ * 2 + ticket;  // the lane that holds the frame + its pixel buffer
     }
     void wait_blit(int ticket) {
-        if (!multi_) check(swr_wait_pixels(ctx_, ticket), "swr_wait_pixels");
+        if (multi_) return;
+        if (ticket < 0 || ticket >= 2 * (int)lanes_.size()) throw std::runtime_error("wait_blit: unknown ticket");
+        swr_ctx *c = lanes_[ticket >> 1];
+        if (swr_wait_pixels(c, ticket & 1) != 0) throw std::runtime_error(std::string("swr_wait_pixels: ") + swr_last_error(c));
     }
 
    private:
@@ -534,7 +564,9 @@ class Renderer {
     int width_, height_;
     int rsqrt_bits_ = 0;
     int row0_ = 0, row1_ = 0;
-    swr_ctx *ctx_ = nullptr;        // single device; with multi_: the context of devices[0] (owned by multi_)
+    std::vector<swr_ctx *> lanes_;  // single device: the contexts frames alternate between (lane 0 owns the scene)
+    int cur_ = 0;                   // lane of the frame rendered last
+    swr_ctx *ctx_ = nullptr;        // = lanes_[cur_]; with multi_: the context of devices[0] (owned by multi_)
     swr_multi *multi_ = nullptr;
     const swr_scene_desc *uploaded_ = nullptr;
     std::vector<swr_draw> draws_;

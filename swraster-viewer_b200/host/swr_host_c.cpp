@@ -54,6 +54,16 @@ void *swrh_renderer_new(int width, int height, int device) {
         return nullptr;
     }
 }
+void *swrh_renderer_new_lanes(int width, int height, int device, int lanes) {
+    try {
+        return new swr::Renderer(width, height, device, lanes);
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+int swrh_renderer_lanes(void *r) { return r ? ((swr::Renderer *)r)->lanes() : -1; }
+swr_ctx *swrh_renderer_lane_ctx(void *r, int lane) { return r ? ((swr::Renderer *)r)->lane_ctx(lane) : nullptr; }
 void *swrh_renderer_new_multi(int width, int height, const int *devices, int ndev) {
     try {
         if (!devices || ndev < 1) throw std::runtime_error("swrh_renderer_new_multi: device list is empty");

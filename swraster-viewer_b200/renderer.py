@@ -81,6 +81,11 @@ def load_libraries():
     host.swrh_camera_build_rotated.argtypes = [C.POINTER(f32), C.POINTER(f32), f32, f32, f32, f32, f32, f32, C.POINTER(abi.Camera)]
     host.swrh_renderer_new.restype = vp
     host.swrh_renderer_new.argtypes = [i32, i32, i32]
+    host.swrh_renderer_new_lanes.restype = vp
+    host.swrh_renderer_new_lanes.argtypes = [i32, i32, i32, i32]
+    host.swrh_renderer_lanes.argtypes = [vp]
+    host.swrh_renderer_lane_ctx.restype = vp
+    host.swrh_renderer_lane_ctx.argtypes = [vp, i32]
     host.swrh_renderer_new_multi.restype = vp
     host.swrh_renderer_new_multi.argtypes = [i32, i32, C.POINTER(i32), i32]
     host.swrh_renderer_tile_rows.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
@@ -165,8 +170,9 @@ class RenderBuffer:
 class Renderer:
     """renderer.rs:145-355 behind the CUDA path. One Renderer per GPU."""
 
-    def __init__(self, width, height, device=0, devices=None):
-        """device: one CUDA ordinal; devices=[...]: one Renderer over several GPUs of this process (sort-first)."""
+    def __init__(self, width, height, device=0, devices=None, lanes=1):
+        """device: one CUDA ordinal; devices=[...]: one Renderer over several GPUs of this process (sort-first);
+        lanes=2: frames alternate between two contexts of the device (for pipelined callers: blit_to_buffer_async)."""
         self.core, self.host = load_libraries()
         self.width, self.height = width, height
         self.tiles_x = (width + abi.TILE_SIZE - 1) // abi.TILE_SIZE
@@ -175,12 +181,18 @@ class Renderer:
         if self.devices is not None:
             arr = (C.c_int * len(self.devices))(*self.devices)
             self._h = self.host.swrh_renderer_new_multi(width, height, arr, len(self.devices))
+        elif lanes != 1:
+            self._h = self.host.swrh_renderer_new_lanes(width, height, device, lanes)
         else:
             self._h = self.host.swrh_renderer_new(width, height, device)
         if not self._h:
             raise RuntimeError("Renderer::new failed: " + self.host.swrh_last_error().decode())
-        self.ctx = self.host.swrh_renderer_ctx(self._h)
         self._scene = None
+
+    @property
+    def ctx(self):
+        """The device context of the frame rendered last (the lanes of a pipelined renderer alternate)."""
+        return self.host.swrh_renderer_ctx(self._h)
 
     def close(self):
         if self._h:
@@ -331,8 +343,11 @@ class Renderer:
 
     @property
     def launch_count(self):
-        """CUDA kernels launched by this renderer's context so far (swr_launch_count)."""
-        return int(self.core.swr_launch_count(self.ctx))
+        """CUDA kernels launched by this renderer's context(s) so far (swr_launch_count, summed over the lanes)."""
+        n = self.host.swrh_renderer_lanes(self._h)
+        if n <= 0:
+            return int(self.core.swr_launch_count(self.ctx))
+        return sum(int(self.core.swr_launch_count(self.host.swrh_renderer_lane_ctx(self._h, i))) for i in range(n))
 
     def device_pixels_ptr(self):
         return self.core.swr_device_pixels(self.ctx)

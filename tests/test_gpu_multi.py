@@ -119,3 +119,42 @@ def test_multi_devices_replay_a_frame_that_outgrew_its_buffers():
         r.blit_to_buffer(buf)
         assert np.array_equal(buf.pixels, ref), f"frame {f}: {np.count_nonzero(buf.pixels != ref)} pixels differ"
     r.close()
+
+
+def test_two_lanes_alternate_frames_and_share_one_scene():
+    """Renderer(lanes=2): frames alternate between two contexts (streams) of the device that share one uploaded scene
+    (swr_share_scene); pipelined blits come back complete and identical to the single-lane frames, per-frame queries follow
+    the lane of the last frame, and a second scene re-uploads on lane 0 and is shared again."""
+    cfgs = small_configs()
+    name, scene, spec, W, H = cfgs[2]
+    _, scene2, spec2, _, _ = cfgs[5]
+    cam = swr.RenderCamera.from_spec(spec, W, H)
+    cam2 = swr.RenderCamera.from_spec(spec2, W, H)
+    ref = render_gpu(scene, cam, W, H)
+    ref2 = render_gpu(scene2, cam2, W, H)
+    r = swr.Renderer(W, H, lanes=2)
+    bufs = [swr.RenderBuffer(W, H) for _ in range(4)]
+    pend = []
+    ctxs = set()
+    for i in range(7):
+        r.render_scene(scene, cam)
+        ctxs.add(r.ctx)
+        pend.append((r.blit_to_buffer_async(bufs[i % 4]), i % 4))
+        if len(pend) > 2:
+            t, b = pend.pop(0)
+            r.wait_blit(t)
+            assert np.array_equal(bufs[b].pixels, ref["pixels"]), f"frame {i - 2}"
+    for t, b in pend:
+        r.wait_blit(t)
+        assert np.array_equal(bufs[b].pixels, ref["pixels"])
+    assert len(ctxs) == 2
+    st = r.stats()
+    assert st["triangles_binned"] == ref["stats"]["triangles_binned"] and st["tile_refs"] == ref["stats"]["tile_refs"]
+    d, s, _, _ = r.read_visbuffer()
+    assert np.array_equal(d, ref["depth"]) and np.array_equal(s, ref["seq"])
+    for i in range(3):  # another scene: uploaded once, shared with the other lane
+        r.render_scene(scene2, cam2)
+        r.blit_to_buffer(bufs[0])
+        assert np.array_equal(bufs[0].pixels, ref2["pixels"]), i
+    assert r.launch_count > 0
+    r.close()
