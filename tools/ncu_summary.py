@@ -41,6 +41,6 @@ if len(sys.argv) > 4:  # also: per-kernel DRAM traffic and warp-instruction coun
         rd, wr = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
         traffic[k] = int(float(r[rd].replace(",", "")) * scale[rr[1][rd]] + float(r[wr].replace(",", "")) * scale[rr[1][wr]])
         winst[k] = int(float(r[h.index("smsp__inst_executed.sum")].replace(",", "")))
-    json.dump(traffic, open(os.path.join(sys.argv[4], "r01_traffic.json"), "w"), indent=1)
-    json.dump(winst, open(os.path.join(sys.argv[4], "r01_warp_inst.json"), "w"), indent=1)
+    json.dump(traffic, open(os.path.join(sys.argv[4], "r02_traffic.json"), "w"), indent=1)
+    json.dump(winst, open(os.path.join(sys.argv[4], "r02_warp_inst.json"), "w"), indent=1)
 print("\n".join(lines))
