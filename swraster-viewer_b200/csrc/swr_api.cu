@@ -62,12 +62,13 @@ struct GeomSet {
     DevBuf<DevDraw> draws_alt;
     DevBuf<uint32_t> tri_prefix_alt;
     DevBuf<uint32_t> cull;  // k_cull output: keep mask, per-block counts and offsets, draw of every cluster
-    DevBuf<uint2> work;     // k_compact output: surviving (draw, cluster) pairs in submission order
+    DevBuf<uint4> work;     // k_compact output: surviving clusters in submission order (draw, cluster, dense base, triangles)
     DevBuf<TriRecord> records;
     DevBuf<uint32_t> rects;
     DevBuf<float> avgz;  // translucent set only: packet.avg_z per record (renderer.rs:765-775)
     DevBuf<ClipVertex> clip_verts;
-    DevBuf<uint32_t> clip_queue, clip_ext, clip_list;
+    DevBuf<uint2> clip_queue;  // (dense triangle, draw) pairs waiting for k_clip
+    DevBuf<uint32_t> clip_ext, clip_list;
     size_t ext_cap = 0;
     DevBuf<uint32_t> tile_count, tile_offset, tile_cursor;
     DevBuf<uint32_t> refs;
@@ -723,7 +724,7 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
         k_scan_simple<<<1, 1024, 0, s>>>(g.tile_count.p, g.tile_offset.p, g.tile_cursor.p, ctx->ntiles, g.counters.p, (uint32_t)(g.refs.cap - 16));
     } else {
         const size_t unit_cap = (size_t)ctx->ntiles + g.refs.cap / RASTER_UNIT_MIN + 1;
-        const uint32_t cta_slots = (uint32_t)ctx->num_sms * 4u;  // k_raster_tiles: 4 CTAs per SM
+        const uint32_t cta_slots = (uint32_t)ctx->num_sms * RASTER_MINB;  // k_raster_tiles: resident CTAs per SM
         if (ctx->unit_list.reserve(unit_cap) != cudaSuccess) return SWR_ERR_OOM;
         ctx->launches++;
         k_scan_tiles<<<1, 1024, 0, s>>>(g.tile_count.p, g.tile_offset.p, g.tile_cursor.p, ctx->ntiles, g.counters.p, (uint32_t)(g.refs.cap - 16), ctx->unit_list.p,
@@ -733,11 +734,7 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
     }
     if (tris > 0) {
         ctx->launches++;
-        k_scatter<<<g.geom_grid, SWR_CLUSTER_TRIS, 0, s>>>(sp, g.tile_cursor.p, g.refs.p);
-        if (clip_tris > 0) {
-            ctx->launches++;
-            k_scatter_list<<<148, 256, 0, s>>>(g.rects.p, g.clip_list.p, g.clip_ext.p, g.tile_cursor.p, g.refs.p, g.counters.p, ctx->tiles_x);
-        }
+        k_scatter<<<g.geom_grid + (clip_tris > 0 ? SCATTER_LIST_BLOCKS : 0u), SWR_CLUSTER_TRIS, 0, s>>>(sp, g.tile_cursor.p, g.refs.p, g.geom_grid);
     }
     CK(cudaGetLastError());
     return SWR_OK;
@@ -754,7 +751,7 @@ static int launch_frame(swr_ctx *ctx) {
     int rc = launch_geometry(ctx, g, false);
     if (rc) return rc;
     const int rb = ctx->row_begin, re = ctx->row_end;
-    const uint32_t cta_slots = (uint32_t)ctx->num_sms * 4u;
+    const uint32_t cta_slots = (uint32_t)ctx->num_sms * RASTER_MINB;
     CK(cudaEventRecord(ctx->cur->ev[1], s));
     if (re > rb) {
         RasterParams rp{};

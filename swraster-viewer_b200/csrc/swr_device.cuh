@@ -127,6 +127,33 @@ __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b)
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ float frcp(float a) { return __frcp_rn(a); }  // correctly rounded 1/a == IEEE 1.0f / a
 __device__ __forceinline__ float i2f(int a) { return __int2float_rn(a); }
+
+// Packed fp32 pairs (sm_100+: add/mul/fma.rn.f32x2 -> FADD2 / FMUL2 / FFMA2). Each half is an ordinary IEEE round-to-nearest
+// operation, so a packed operation is bit-identical to its two scalar ones; it just costs one issue slot instead of two.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long pack2(float v) { return pack2(v, v); }
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ ulonglong2 ldg_pairs(const float4 *p) { return __ldg(reinterpret_cast<const ulonglong2 *>(p)); }  // (xy, zw)
+
 __device__ __forceinline__ int wmul(int a, int b) { return (int)((unsigned)a * (unsigned)b); }
 __device__ __forceinline__ int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
 __device__ __forceinline__ int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }

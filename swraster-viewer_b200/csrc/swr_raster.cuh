@@ -23,7 +23,10 @@ struct SetupParams {
     // every cluster, and per k_cull block (256 clusters = 8 mask words) the exclusive prefix of survivors.
     uint32_t *cl_mask, *cl_blk, *cl_blk_off, *cl_draw;
     uint32_t ncull_blocks;
-    uint2 *work;                 // k_compact: the surviving (draw, cluster-in-draw) pairs, in submission order; counters->work_n entries
+    // k_compact: the surviving clusters in submission order, counters->work_n entries of (draw, cluster in draw, dense index of
+    // the cluster's first triangle, triangles in the cluster): everything k_setup / k_scatter need to address their
+    // triangle without walking draws -> prims first
+    uint4 *work;
     float band_lo, band_hi;      // NDC y range of this rank's rows (widened by 2 px); used when use_band != 0 (sort-first)
     int use_band;
     uint32_t ndraws;
@@ -35,9 +38,9 @@ struct SetupParams {
     float *avgz;  // translucent set: packet.avg_z per record (renderer.rs:765-775), else NULL
     ClipVertex *clip_verts;
     uint32_t clip_capacity;
-    uint32_t *clip_queue;  // dense triangle ids that need the clipper
+    uint2 *clip_queue;     // (dense triangle id, draw) of the triangles that need the clipper
     uint32_t *clip_ext;    // per dense triangle: first extension record of its fans 1..n-3 (written by k_clip)
-    uint32_t *clip_list;   // ids (tri*8+fan, fan >= 1) of clipped fan triangles that survived, for k_scatter_list
+    uint32_t *clip_list;   // ids (tri*8+fan, fan >= 1) of clipped fan triangles that survived, for the list blocks of k_scatter
     uint32_t ext_capacity; // extension records available after the total_tris dense ones
     uint32_t *tile_count;
     FrameCounters *counters;
@@ -314,7 +317,9 @@ __global__ void __launch_bounds__(256) k_compact(SetupParams P) {
     uint32_t pos = __ldg(P.cl_blk_off + blockIdx.x) + (uint32_t)__popc(m & ((1u << lane) - 1u));
     for (uint32_t w = 0; w < wid; w++) pos += (uint32_t)__popc(__ldg(P.cl_mask + blockIdx.x * 8u + w));
     const uint32_t d = __ldg(P.cl_draw + i);
-    P.work[pos] = make_uint2(d, i - __ldg(P.cl_prefix + d));
+    const uint32_t cl = i - __ldg(P.cl_prefix + d);
+    const uint32_t ntris = P.prims[P.draws[d].prim].ntris;
+    P.work[pos] = make_uint4(d, cl, __ldg(P.tri_prefix + d) + cl * SWR_CLUSTER_TRIS, min((uint32_t)SWR_CLUSTER_TRIS, ntris - cl * SWR_CLUSTER_TRIS));
 }
 
 // K1: persistent over the surviving clusters; one block iteration = one cluster, one thread = one triangle.
@@ -324,15 +329,15 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams P) {
     const unsigned lane = tid & 31;
     const uint32_t nwork = P.counters->work_n;
     for (uint32_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
-        const uint2 w = P.work[wi];
+        const uint4 w = P.work[wi];
         const uint32_t d = w.x;
         const DevDraw &dr = P.draws[d];
         const DevPrim &pr = P.prims[dr.prim];
         const uint32_t tri = w.y * SWR_CLUSTER_TRIS + tid;
-        const uint32_t g = P.tri_prefix[d] + tri;
+        const uint32_t g = w.z + tid;
         uint32_t rect = 0;
         bool queued = false, nocover = false;
-        if (tri < pr.ntris) {
+        if (tid < w.w) {
             const bool clip = (dr.flags & 1u) != 0;
             const uint32_t dflag = d | ((P.mats[pr.material].flags & 1u) ? SWR_REC_ALPHA : 0u);
             const uint32_t slot = g;  // record of fan 0 = dense triangle index; id = g * 8 + fan
@@ -372,7 +377,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams P) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(&P.counters->clip_queue_n, (uint32_t)__popc(qm));
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (queued) P.clip_queue[base + __popc(qm & ((1u << lane) - 1u))] = g;
+            if (queued) P.clip_queue[base + __popc(qm & ((1u << lane) - 1u))] = make_uint2(g, d);
         }
     }
 }
@@ -395,8 +400,8 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip(SetupParams P) {
         uint32_t rect_out = 0;
         bool nocover_out = false;
         if (e < qn) {
-            const uint32_t gg = P.clip_queue[e];
-            const uint32_t dd = find_draw(P.tri_prefix, P.ndraws, gg);
+            const uint2 qe = P.clip_queue[e];
+            const uint32_t gg = qe.x, dd = qe.y;
             const uint32_t ttri = gg - P.tri_prefix[dd];
             const DevDraw &dr = P.draws[dd];
             const DevPrim &pr = P.prims[dr.prim];
@@ -509,6 +514,9 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip(SetupParams P) {
 // keys are merged with a global 64-bit atomicMin), so one hot tile cannot become the long pole of the frame.
 // Units are ordered heaviest-first (bit-length buckets of their ref count).
 // ---------------------------------------------------------------------------------------------
+#ifndef SWR_UNITS_PER_SLOT
+#define SWR_UNITS_PER_SLOT 3u  // target number of raster units per resident CTA slot (measured on C3: 2-3 best, 4 +4 %, 6 +12 %: every extra split costs a key init and a global min-merge)
+#endif
 #define RASTER_UNIT_MAX 2048u
 #define RASTER_UNIT_MIN 32u
 
@@ -588,7 +596,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
         uint32_t u = s_carry / (3u * cta_slots);
         u = ((u + 255u) / 256u) * 256u;
         s_unit = min(max(u, 256u), RASTER_UNIT_MAX);
-        s_target = have_history ? s_cyc / (float)(4u * cta_slots) : 0.0f;
+        s_target = have_history ? s_cyc / (float)(SWR_UNITS_PER_SLOT * cta_slots) : 0.0f;
     }
     __syncthreads();
     if (counters->overflow_refs) return;
@@ -650,7 +658,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
 
 // ---------------------------------------------------------------------------------------------
 // K3 pass 2: scatter refs (ids = dense triangle * 8 + fan). k_scatter: one thread per dense triangle (fan 0);
-// k_scatter_list: the surviving fans >= 1 of clipped polygons.
+// the grid's last blocks: the surviving fans >= 1 of clipped polygons.
 // ---------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ void scatter_rect(uint32_t rect, uint32_t id, uint32_t *tile_cursor, uint32_t *refs, int tiles_x) {
@@ -673,32 +681,33 @@ __device__ __forceinline__ void scatter_rect(uint32_t rect, uint32_t id, uint32_
     }
 }
 
-// fan-0 records of the surviving clusters (same ordered work list as k_setup): persistent, one cluster per block iteration
-__global__ void __launch_bounds__(SWR_CLUSTER_TRIS) k_scatter(SetupParams P, uint32_t *tile_cursor, uint32_t *refs) {
+// fan-0 records of the surviving clusters (same ordered work list as k_setup): persistent, one cluster per block iteration.
+// The last SCATTER_LIST_BLOCKS blocks of the grid take the surviving fans >= 1 of clipped polygons instead (k_clip's list), so
+// the short, latency-bound list pass runs beside the cluster pass instead of behind it.
+#define SCATTER_LIST_BLOCKS 148u
+__global__ void __launch_bounds__(SWR_CLUSTER_TRIS) k_scatter(SetupParams P, uint32_t *tile_cursor, uint32_t *refs, uint32_t cluster_blocks) {
     if (P.counters->overflow_refs) return;  // lists would not fit: the host grows the buffer and replays the frame
-    const uint32_t nwork = P.counters->work_n;
-    for (uint32_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
-        const uint2 w = P.work[wi];
-        const uint32_t d = w.x;
-        const uint32_t tri = w.y * SWR_CLUSTER_TRIS + threadIdx.x;
-        const uint32_t t = P.tri_prefix[d] + tri;
-        const uint32_t rect = tri < P.prims[P.draws[d].prim].ntris ? __ldg(P.rects + t) : 0u;
-        scatter_rect(rect, t * 8u, tile_cursor, refs, P.tiles_x);
-    }
-}
-
-__global__ void __launch_bounds__(256) k_scatter_list(const uint32_t *rects, const uint32_t *clip_list, const uint32_t *clip_ext,
-                                                      uint32_t *tile_cursor, uint32_t *refs, const FrameCounters *counters, int tiles_x) {
-    if (counters->overflow_refs || counters->overflow_ext) return;
-    const uint32_t n = counters->clip_list_n;
-    for (uint32_t base = blockIdx.x * 256; base < n; base += gridDim.x * 256) {  // uniform trip count per block
-        uint32_t i = base + threadIdx.x;
-        uint32_t id = 0, rect = 0;
-        if (i < n) {
-            id = clip_list[i];
-            rect = __ldg(rects + record_of_id(id, clip_ext));
+    if (blockIdx.x >= cluster_blocks) {
+        if (P.counters->overflow_ext) return;
+        const uint32_t n = P.counters->clip_list_n;
+        const uint32_t nb = gridDim.x - cluster_blocks;
+        for (uint32_t base = (blockIdx.x - cluster_blocks) * SWR_CLUSTER_TRIS; base < n; base += nb * SWR_CLUSTER_TRIS) {  // uniform trip count per block
+            const uint32_t i = base + threadIdx.x;
+            uint32_t id = 0, rect = 0;
+            if (i < n) {
+                id = P.clip_list[i];
+                rect = __ldg(P.rects + record_of_id(id, P.clip_ext));
+            }
+            scatter_rect(rect, id, tile_cursor, refs, P.tiles_x);
         }
-        scatter_rect(rect, id, tile_cursor, refs, tiles_x);
+        return;
+    }
+    const uint32_t nwork = P.counters->work_n;
+    for (uint32_t wi = blockIdx.x; wi < nwork; wi += cluster_blocks) {
+        const uint4 w = P.work[wi];
+        const uint32_t t = w.z + threadIdx.x;
+        const uint32_t rect = threadIdx.x < w.w ? __ldg(P.rects + t) : 0u;
+        scatter_rect(rect, t * 8u, tile_cursor, refs, P.tiles_x);
     }
 }
 
@@ -706,6 +715,9 @@ __global__ void __launch_bounds__(256) k_scatter_list(const uint32_t *rects, con
 // K4: tile rasteriser
 // ---------------------------------------------------------------------------------------------
 #define RASTER_THREADS 256
+#ifndef RASTER_MINB
+#define RASTER_MINB 3  // resident CTAs per SM: 80 registers (no spills in the row loop) beat 4 x 64 (C3: 0.61 -> 0.57 ms)
+#endif
 #define RASTER_WARPS (RASTER_THREADS / 32)
 
 struct RasterParams {
@@ -1018,7 +1030,7 @@ __device__ __forceinline__ void row_setup(const TileBatch &tb, int pk, uint32_t 
     }
 }
 
-__global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster_tiles(RasterParams P) {
+__global__ void __launch_bounds__(RASTER_THREADS, RASTER_MINB) k_raster_tiles(RasterParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *skeys = reinterpret_cast<unsigned long long *>(smem_raw);
     TileBatch &tb = *reinterpret_cast<TileBatch *>(smem_raw + SWR_TILE_PIXELS * 8);

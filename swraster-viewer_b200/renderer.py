@@ -13,7 +13,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(_HERE, "lib")
+LIB_DIR = os.environ.get("SWR_LIB_DIR") or os.path.join(_HERE, "lib")  # SWR_LIB_DIR: A/B builds (tools/build_variant.sh)
 
 
 class LibraryMissing(RuntimeError):
