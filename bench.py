@@ -95,6 +95,10 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def mark(self):
+        """The timed region starts here: only samples taken from now on are reported."""
+        self.first = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -103,7 +107,7 @@ class ClockSampler:
         self.t.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "first", 0):]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -251,6 +255,13 @@ def run_gpu(args):
         else:
             r.resolve_device_only(2.0)
 
+    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML initialisation over every GPU of the box, 0.1-0.3 s) stalls
+    # CUDA submissions on all devices for milliseconds, which used to land inside the 15-90 ms timed region (N = 8: 1.4 ms
+    # per frame reported for frames whose phases add up to 0.47 ms). Only samples taken after mark() are reported.
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.5)
     # ---- warm-up (also settles buffer growth) -------------------------------------------------------------
     for _ in range(max(3, args.warmup)):
         step_device()
@@ -258,10 +269,9 @@ def run_gpu(args):
     st0 = r.stats()
 
     # ---- device-resident timing: CUDA events on the launching stream, L2 flushed between frames ------------
-    sampler = ClockSampler(local)
     barrier()
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     K = args.steps
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     phase = {"ms_setup_bin": 0.0, "ms_raster": 0.0, "ms_shade": 0.0}
@@ -278,7 +288,8 @@ def run_gpu(args):
             phase[k] += s[k]
     barrier()
     launches_dev = r.launch_count - launches0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    step_ms = sorted(a.elapsed_time(b) for a, b in ev)
+    dev_ms = sum(step_ms)
     # ---- end-to-end timing: public API, host buffers, wall clock ---------------------------------------------
     if sort_last:
         pix_host = torch.empty(W * H, dtype=torch.int32).pin_memory()
@@ -323,7 +334,9 @@ def run_gpu(args):
                     "pipelined, Renderer(lanes=2); every rank reads its own rows back over its own PCIe link into one page-locked host frame shared by all ranks")
     for h in hosts or []:
         h.reset()
+    barrier()
     e2e_loop(2)
+    barrier()  # rank 0 may still be polling the warm-up frames' arrival flags: nobody resets its flag before everybody is through
     for h in hosts or []:
         h.reset()
     barrier()
@@ -398,6 +411,7 @@ def run_gpu(args):
                     "mode": e2e_mode, "synchronous_value": (K / e2e_sync_s) if e2e_sync_s else None},
             # kernels of ours launched on this rank inside the two timed regions, counted by the library (swr_launch_count)
             "gpu_launches": launches_dev + (launches2 - launches1),
+            "step_ms": {"min": step_ms[0], "median": step_ms[len(step_ms) // 2], "max": step_ms[-1], "note": "device-resident steps on rank 0 (ms_per_step is the mean, max over ranks)"},
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel_ms": dom_ms, "kernel_algorithmic_bytes": kbytes,

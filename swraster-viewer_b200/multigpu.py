@@ -152,7 +152,7 @@ class SharedHostFrame:
         t0 = time.perf_counter()
         while int(self.flags[:world].min()) < frame:
             if time.perf_counter() - t0 > timeout_s:
-                raise RuntimeError("SharedHostFrame.wait_all timed out")
+                raise RuntimeError(f"SharedHostFrame.wait_all timed out waiting for frame {frame}: arrival flags {self.flags[:world].tolist()}")
 
     def close(self, unlink=False):
         import os
