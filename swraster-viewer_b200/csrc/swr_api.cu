@@ -732,9 +732,19 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
                                         ctx->tile_cycles_prev.p, ctx->have_history ? 1 : 0);
         ctx->have_history = true;
     }
-    if (tris > 0) {
-        ctx->launches++;
-        k_scatter<<<g.geom_grid + (clip_tris > 0 ? SCATTER_LIST_BLOCKS : 0u), SWR_CLUSTER_TRIS, 0, s>>>(sp, g.tile_cursor.p, g.refs.p, g.geom_grid);
+    {
+        // cluster blocks (none when nothing was submitted) + the auxiliary blocks: key initialisation of split tiles, clipped fans
+        ScatterAux aux{};
+        if (!translucent) {
+            aux.keys = ctx->keys.p;
+            aux.tile_unit = ctx->tile_unit.p;
+            aux.tile_begin = rb * ctx->tiles_x;
+            aux.tile_end = re * ctx->tiles_x;
+        }
+        if (tris > 0) {  // nothing submitted: no tile is split, no list
+            ctx->launches++;
+            k_scatter<<<g.geom_grid + SCATTER_AUX_BLOCKS, SWR_CLUSTER_TRIS, 0, s>>>(sp, g.tile_cursor.p, g.refs.p, g.geom_grid, aux);
+        }
     }
     CK(cudaGetLastError());
     return SWR_OK;
@@ -778,8 +788,7 @@ static int launch_frame(swr_ctx *ctx) {
         rp.tiles_y = ctx->tiles_y;
         rp.row_begin = rb;
         rp.row_end = re;
-        // keys of the owned rows start EMPTY: tiles split over several CTAs merge into them with atomicMin
-        CK(cudaMemsetAsync(ctx->keys.p + (size_t)rb * ctx->tiles_x * SWR_TILE_PIXELS, 0xFF, (size_t)(re - rb) * ctx->tiles_x * SWR_TILE_PIXELS * 8, s));
+        // (the global keys of split tiles were set to EMPTY by k_scatter's auxiliary blocks; whole tiles are simply overwritten)
         ctx->launches++;
         k_raster_tiles<<<cta_slots, RASTER_THREADS, raster_smem_bytes(), s>>>(rp);  // persistent: one CTA per resident slot
     }
@@ -810,6 +819,7 @@ static void fill_shade_params(swr_ctx *ctx, const GeomSet &g, ShadeParams &sp) {
     sp.ext_bary = ctx->composited ? ctx->bary.p : nullptr;
     sp.sky_row_begin = ctx->sky_r0;
     sp.sky_row_end = ctx->sky_r1;
+    sp.counters = ctx->op.counters.p;
 }
 
 static int launch_shade(swr_ctx *ctx) {

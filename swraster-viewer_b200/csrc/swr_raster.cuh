@@ -682,16 +682,30 @@ __device__ __forceinline__ void scatter_rect(uint32_t rect, uint32_t id, uint32_
 }
 
 // fan-0 records of the surviving clusters (same ordered work list as k_setup): persistent, one cluster per block iteration.
-// The last SCATTER_LIST_BLOCKS blocks of the grid take the surviving fans >= 1 of clipped polygons instead (k_clip's list), so
-// the short, latency-bound list pass runs beside the cluster pass instead of behind it.
-#define SCATTER_LIST_BLOCKS 148u
-__global__ void __launch_bounds__(SWR_CLUSTER_TRIS) k_scatter(SetupParams P, uint32_t *tile_cursor, uint32_t *refs, uint32_t cluster_blocks) {
+// The last SCATTER_AUX_BLOCKS blocks of the grid do two short, latency-bound side jobs beside the cluster pass instead of
+// behind it: (1) tiles that k_scan_tiles split over several raster units get their global keys set to EMPTY (their CTAs
+// merge into them with atomicMin; every other tile is written whole by its one unit, so no frame-wide 67 MB clear is
+// needed), (2) the surviving fans >= 1 of clipped polygons (k_clip's list) are scattered.
+#define SCATTER_AUX_BLOCKS 148u
+struct ScatterAux {
+    unsigned long long *keys;   // NULL: no key initialisation (translucent set)
+    const uint32_t *tile_unit;  // refs per raster unit of each tile (k_scan_tiles)
+    int tile_begin, tile_end;   // owned tiles
+};
+__global__ void __launch_bounds__(SWR_CLUSTER_TRIS) k_scatter(SetupParams P, uint32_t *tile_cursor, uint32_t *refs, uint32_t cluster_blocks, ScatterAux A) {
     if (P.counters->overflow_refs) return;  // lists would not fit: the host grows the buffer and replays the frame
     if (blockIdx.x >= cluster_blocks) {
+        const uint32_t nb = gridDim.x - cluster_blocks, b = blockIdx.x - cluster_blocks;
+        if (A.keys) {
+            for (int t = A.tile_begin + (int)b; t < A.tile_end; t += (int)nb) {
+                if (__ldg(P.tile_count + t) <= __ldg(A.tile_unit + t)) continue;  // one unit: written whole by k_raster_tiles
+                uint4 *dst = reinterpret_cast<uint4 *>(A.keys + (size_t)t * SWR_TILE_PIXELS);
+                for (int i = threadIdx.x; i < SWR_TILE_PIXELS / 2; i += SWR_CLUSTER_TRIS) dst[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            }
+        }
         if (P.counters->overflow_ext) return;
         const uint32_t n = P.counters->clip_list_n;
-        const uint32_t nb = gridDim.x - cluster_blocks;
-        for (uint32_t base = (blockIdx.x - cluster_blocks) * SWR_CLUSTER_TRIS; base < n; base += nb * SWR_CLUSTER_TRIS) {  // uniform trip count per block
+        for (uint32_t base = b * SWR_CLUSTER_TRIS; base < n; base += nb * SWR_CLUSTER_TRIS) {  // uniform trip count per block
             const uint32_t i = base + threadIdx.x;
             uint32_t id = 0, rect = 0;
             if (i < n) {

@@ -29,6 +29,9 @@ struct ShadeParams {
     // winner belongs to another rank carry SWR_ID_FOREIGN and are left unshaded (colour.w = 0); sky only in sky rows.
     const float2 *ext_bary;
     int sky_row_begin, sky_row_end;
+    // opaque pass counters: a frame whose tile lists overflowed left the keys of the previous frame in place (the host grows
+    // the buffers and replays it); such a frame is not shaded
+    const FrameCounters *counters;
 };
 
 // Value-domain arithmetic. The translation unit is built with -fmad=false and everything that decides an ADDRESS (texel,
@@ -411,6 +414,7 @@ __device__ __forceinline__ V3 compute_skybox(const ShadeParams &P, int px, int p
 #define SHADE_BLOCK 128
 #define SHADE_ROWS (SHADE_BLOCK / 32 * 2)
 __global__ void __launch_bounds__(SHADE_BLOCK, SWR_SHADE_MINB) k_shade(ShadeParams P) {
+    if (P.counters->overflow_refs | P.counters->overflow_ext | P.counters->overflow_clip) return;  // stale keys: the frame is replayed
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int quad = lane >> 2, sub = lane & 3;
     const int px = blockIdx.x * 16 + quad * 2 + (sub & 1);
