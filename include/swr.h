@@ -233,6 +233,17 @@ int swr_share_scene(swr_ctx *ctx, const swr_ctx *owner);
  * visibility buffer is produced (used by the sort-last composite). */
 int swr_render(swr_ctx *ctx, const swr_camera *camera, const swr_draw *draws, int ndraws, int shade);
 
+/* Fixed-exposure frames. The reference only changes its exposure in update_auto_exposure (renderer.rs:258-290); a host that
+ * knows the exposure BEFORE the frame is shaded (auto exposure idle, dt = 0, a fixed-exposure capture) says so here, and
+ * shading then applies exposure, tonemap and the RGBA8 pack of blit_to_buffer (renderer.rs:293-355) itself: the 16-byte HDR
+ * colour per pixel is neither written nor read back, and the tile metering values (tilerasterizer.rs:103-106) come from the
+ * same pass. exposure > 0 switches it on for frames rendered from now on, 0 switches it off (default). Plain opaque frames
+ * only: a frame with translucent draws or a sort-last composite is shaded to HDR as before. Such a frame can be resolved
+ * with exactly that exposure; any other exposure (and swr_read_color) fails with SWR_ERR_INVALID — call
+ * swr_set_fixed_exposure(ctx, 0) and swr_shade() to shade the same visibility buffer to HDR (the host mirror does that by
+ * itself when update_auto_exposure moved the exposure between render_scene and blit_to_buffer). */
+int swr_set_fixed_exposure(swr_ctx *ctx, float exposure);
+
 /* Shade the current visibility-key buffer again (same frame, e.g. a different camera block is NOT supported:
  * the records belong to the last swr_render). */
 int swr_shade(swr_ctx *ctx, const swr_camera *camera);

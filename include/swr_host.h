@@ -43,6 +43,13 @@ int swrh_invalidate_scene(void *renderer);
 /* Renderer::update_auto_exposure(delta_time) (renderer.rs:258) and the exposure blit_to_buffer applies */
 int swrh_update_auto_exposure(void *renderer, float delta_time);
 float swrh_auto_exposure(void *renderer);
+/* Fixed-exposure shading (include/swr.h, swr_set_fixed_exposure): while update_auto_exposure leaves the exposure where it
+ * is, swrh_render_scene shades straight to RGBA8 with it. Callers that go to the context directly (swrh_renderer_ctx) say
+ * what they are about to ask of the frame rendered last: swrh_frame_exposure = "resolve it with this exposure",
+ * swrh_frame_hdr = "read its HDR colour". Either shades the frame again to HDR if it has to; swrh_blit_to_buffer(_async)
+ * do this by themselves. */
+int swrh_frame_exposure(void *renderer, float exposure);
+int swrh_frame_hdr(void *renderer);
 /* the metering maths of update_auto_exposure on its own (no device): state = {auto_exposure, auto_exposure_target,
  * auto_exposure_ev}, updated in place from `ntiles` per-tile center_luminance values (tilerasterizer.rs:103-106) */
 int swrh_auto_exposure_step(float state[3], const float *tile_luminance, int ntiles, float delta_time);

@@ -189,6 +189,7 @@ extern "C" {
     pub fn swr_upload_scene(ctx: *mut swr_ctx, scene: *const swr_scene_desc) -> c_int;
     pub fn swr_share_scene(ctx: *mut swr_ctx, owner: *const swr_ctx) -> c_int;
     pub fn swr_render(ctx: *mut swr_ctx, camera: *const swr_camera, draws: *const swr_draw, ndraws: c_int, shade: c_int) -> c_int;
+    pub fn swr_set_fixed_exposure(ctx: *mut swr_ctx, exposure: c_float) -> c_int;
     pub fn swr_shade(ctx: *mut swr_ctx, camera: *const swr_camera) -> c_int;
     pub fn swr_keys_to_global(ctx: *mut swr_ctx) -> c_int;
     pub fn swr_keys_localize(ctx: *mut swr_ctx) -> c_int;

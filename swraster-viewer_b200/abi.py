@@ -102,7 +102,7 @@ PEER_HANDLE_BYTES = 64  # SWR_PEER_HANDLE_BYTES
 
 EXPORTS = [
     "swr_abi_version", "swr_last_error", "swr_create", "swr_destroy", "swr_set_tile_rows", "swr_set_rsqrt_table", "swr_upload_scene", "swr_share_scene",
-    "swr_render", "swr_shade", "swr_keys_to_global", "swr_keys_localize", "swr_shade_composited", "swr_device_bary", "swr_resolve", "swr_resolve_async", "swr_wait_pixels", "swr_read_tile_luminance", "swr_read_tile_costs", "swr_read_visbuffer", "swr_read_color",
+    "swr_render", "swr_set_fixed_exposure", "swr_shade", "swr_keys_to_global", "swr_keys_localize", "swr_shade_composited", "swr_device_bary", "swr_resolve", "swr_resolve_async", "swr_wait_pixels", "swr_read_tile_luminance", "swr_read_tile_costs", "swr_read_visbuffer", "swr_read_color",
     "swr_synchronize", "swr_get_stats", "swr_device_pixels", "swr_device_keys", "swr_device_keys_bytes",
     "swr_cuda_stream", "swr_sizeof", "swr_launch_count",
     "swr_peer_export", "swr_peer_open", "swr_peer_attach", "swr_resolve_peer", "swr_peer_collect", "swr_peer_release",

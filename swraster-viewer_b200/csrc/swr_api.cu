@@ -94,6 +94,7 @@ struct FrameSlot {
     std::vector<swr_draw> op_draws, tr_draws;
     swr_camera cam{};
     int shade = 0;
+    float fixed_exposure = 0.0f;  // > 0: shade straight to RGBA8 with this exposure when the frame allows it (swr_set_fixed_exposure)
     bool tr_ran = false;      // the translucent geometry pass was launched (its counters are valid)
     int resolve_kind = 0;     // queued behind the frame: 0 nothing, 1 device-only resolve, 2 resolve + read-back (swr_resolve_async),
                               // 3 peer resolve (swr_resolve_peer, frame number in resolve_frame)
@@ -144,6 +145,11 @@ struct swr_ctx {
     bool copy_pending[2] = {false, false};
     int pix_cur = 0;
     DevBuf<float> lum;
+    // fixed-exposure frames: k_shade<true> packs RGBA8 itself into `fused_px`; the resolve entry points then only move it
+    float fixed_exposure = 0.0f;   // swr_set_fixed_exposure (applies to frames rendered from now on)
+    DevBuf<uint32_t> fused_px;
+    bool last_fused = false;       // the frame shaded last holds RGBA8 in fused_px (exposure last_fused_exposure) and NO HDR colour
+    float last_fused_exposure = 0.0f;
     DevBuf<float2> bary;
     bool composited = false;
     int sky_r0 = 0, sky_r1 = 0;
@@ -325,6 +331,7 @@ void swr_destroy(swr_ctx *ctx) {
     ctx->bary.release();
     ctx->rsqrt_tab.release();
     ctx->dbg_tiles.release();
+    ctx->fused_px.release();
     for (FrameSlot &f : ctx->slots) {
         for (auto &e : f.ev)
             if (e) cudaEventDestroy(e);
@@ -829,8 +836,29 @@ static int launch_shade(swr_ctx *ctx) {
         ShadeParams sp{};
         fill_shade_params(ctx, ctx->op, sp);
         dim3 grid(sp.Wp / 16, (re - rb) * SWR_TILE / SHADE_ROWS);
+        // Fixed exposure: the frame leaves shading as packed RGBA8 (+ the metering values); only plain opaque frames qualify
+        // (the translucent pass blends over the HDR colour, the sort-last composite sums HDR-resolved strips).
+        const float fx = ctx->cur ? ctx->cur->fixed_exposure : 0.0f;
+        const bool fused = fx > 0.0f && ctx->tr.last_draws.empty() && !ctx->composited;
+        ctx->last_fused = false;
+        if (fused) {
+            if (ctx->fused_px.reserve((size_t)ctx->W * ctx->H) != cudaSuccess) return SWR_ERR_OOM;
+            // a read-back of the previous fixed-exposure frame may still be copying out of fused_px
+            for (int i = 0; i < 2; i++)
+                if (ctx->copy_pending[i]) CK(cudaStreamWaitEvent(s, ctx->ev_copied[i], 0));
+            sp.rgba = ctx->fused_px.p;
+            sp.lum = ctx->lum.p;
+            sp.exposure = fx;
+            ctx->launches++;
+            k_shade<true><<<grid, SHADE_BLOCK, 0, s>>>(sp);
+            ctx->last_fused = true;
+            ctx->last_fused_exposure = fx;
+            CK(cudaEventRecord(ctx->cur->ev[3], s));
+            CK(cudaGetLastError());
+            return SWR_OK;
+        }
         ctx->launches++;
-        k_shade<<<grid, SHADE_BLOCK, 0, s>>>(sp);
+        k_shade<false><<<grid, SHADE_BLOCK, 0, s>>>(sp);
         if (!ctx->tr.last_draws.empty() && !ctx->composited) {
             // translucent pass (tilerasterizer.rs:92-101): own geometry set, per-tile back-to-front sort, forward shading
             int rc = launch_geometry(ctx, ctx->tr, true);
@@ -1035,10 +1063,17 @@ int swr_render(swr_ctx *ctx, const swr_camera *camera, const swr_draw *draws, in
     for (int i = 0; i < ndraws; i++) ((draws[i].flags & SWR_DRAW_TRANSLUCENT) ? f.tr_draws : f.op_draws).push_back(draws[i]);
     f.cam = *camera;
     f.shade = shade;
+    f.fixed_exposure = ctx->fixed_exposure;
     f.resolve_kind = 0;
     f.pending = true;
     ctx->slots_pending++;
     return enqueue_slot(ctx, f);
+}
+
+int swr_set_fixed_exposure(swr_ctx *ctx, float exposure) {
+    if (!ctx || !(exposure >= 0.0f) || exposure > 3.0e38f) return SWR_ERR_INVALID;
+    ctx->fixed_exposure = exposure;
+    return SWR_OK;
 }
 
 int swr_shade(swr_ctx *ctx, const swr_camera *camera) {
@@ -1049,6 +1084,7 @@ int swr_shade(swr_ctx *ctx, const swr_camera *camera) {
     if ((rc = finish_frame(ctx))) return rc;
     set_camera(ctx, camera);
     ctx->cur->shade = 1;  // not pending any more: only its phase events and counter block are reused
+    ctx->cur->fixed_exposure = ctx->fixed_exposure;
     ctx->tr.h_counters = ctx->cur->h_tr;
     CK(cudaEventRecord(ctx->cur->ev[2], ctx->stream));
     return launch_shade(ctx);
@@ -1110,10 +1146,20 @@ static int resolve_into(swr_ctx *ctx, uint32_t *dst, float exposure) {
         dim3 grid((unsigned)((W + 255) / 256), (unsigned)((y1 - y0 + 3) / 4));
         if (ctx->copy_pending[idx]) CK(cudaStreamWaitEvent(s, ctx->ev_copied[idx], 0));
         ctx->launches++;
-        k_resolve<<<grid, 256, 0, s>>>(ctx->color.p, ctx->tiles_x * SWR_TILE, dst, ctx->W, (int)y0, (int)y1, exposure);
+        k_resolve<<<grid, 256, 0, s>>>(ctx->color.p, ctx->tiles_x * SWR_TILE, dst, ctx->W, (int)y0, (int)y1, exposure, ctx->last_fused ? ctx->fused_px.p : nullptr);
     }
     CK(cudaEventRecord(ctx->ev_res[1], s));
     CK(cudaGetLastError());
+    return SWR_OK;
+}
+
+// A frame shaded with a fixed exposure holds packed RGBA8 only: it can be handed out with that exposure and no other.
+static int check_fused_exposure(swr_ctx *ctx, float exposure) {
+    if (ctx->last_fused && exposure != ctx->last_fused_exposure) {
+        ctx->err = "the frame was shaded with a fixed exposure (swr_set_fixed_exposure) and holds no HDR colour: resolve it with that exposure, or "
+                   "call swr_set_fixed_exposure(ctx, 0) and swr_shade() to shade it again";
+        return SWR_ERR_INVALID;
+    }
     return SWR_OK;
 }
 
@@ -1127,6 +1173,7 @@ int swr_resolve(swr_ctx *ctx, float exposure, uint32_t *out_pixels) {
     int rc;
     // The host form settles the frame first (a buffer-growth replay must happen before pixels are handed out). The
     // device-only form stays asynchronous: it is noted in the frame's slot so that a replay re-issues it.
+    if ((rc = check_fused_exposure(ctx, exposure))) return rc;
     if (out_pixels && (rc = finish_frame(ctx))) return rc;
     uint32_t *dst = (uint32_t *)swr_device_pixels(ctx);
     if (!out_pixels) {
@@ -1214,7 +1261,8 @@ static int launch_peer_resolve(swr_ctx *ctx, float exposure, uint32_t frame, boo
     dim3 grid((unsigned)((W + 255) / 256), (unsigned)(y1 > y0 ? (y1 - y0 + 3) / 4 : 1));
     ctx->launches++;
     k_resolve_peer<<<grid, 256, 0, s>>>(ctx->color.p, ctx->tiles_x * SWR_TILE, ctx->peer_pixels, ctrl, ctx->W, (int)y0, (int)(y1 > y0 ? y1 : y0), exposure,
-                                        ctx->peer_local.p, ctx->peer_local.p + 1, ctx->op.counters.p, tr_ran ? ctx->tr.counters.p : nullptr);
+                                        ctx->peer_local.p, ctx->peer_local.p + 1, ctx->op.counters.p, tr_ran ? ctx->tr.counters.p : nullptr,
+                                        ctx->last_fused ? ctx->fused_px.p : nullptr);
     CK(cudaEventRecord(ctx->ev_res[1], s));
     CK(cudaGetLastError());
     return SWR_OK;
@@ -1232,6 +1280,7 @@ int swr_resolve_peer(swr_ctx *ctx, float exposure, uint32_t frame) {
     // does not have to wait for it here. Older frames are settled first: at most one unsettled frame carries a peer
     // resolve, which is what keeps a replay from queueing behind a device-side wait for its own contribution.
     int rc;
+    if ((rc = check_fused_exposure(ctx, exposure))) return rc;
     while (ctx->slots_pending > 1)
         if ((rc = settle_oldest(ctx))) return rc;
     bool tr_ran = false;
@@ -1281,10 +1330,12 @@ static int issue_resolve_copy(swr_ctx *ctx, int idx, float exposure, uint32_t *h
     if (y1 > (size_t)ctx->H) y1 = ctx->H;
     uint32_t *dst = idx ? ctx->pixels_alt.p : ctx->pixels.p;
     if (ctx->copy_pending[idx]) CK(cudaStreamWaitEvent(s, ctx->ev_copied[idx], 0));  // the previous copy out of this buffer
-    if (y1 > y0) {
+    if (ctx->last_fused) {
+        dst = ctx->fused_px.p;  // already packed: read back straight from where k_shade wrote it (the next fixed-exposure frame waits for this copy)
+    } else if (y1 > y0) {
         dim3 grid((unsigned)((W + 255) / 256), (unsigned)((y1 - y0 + 3) / 4));
         ctx->launches++;
-        k_resolve<<<grid, 256, 0, s>>>(ctx->color.p, ctx->tiles_x * SWR_TILE, dst, ctx->W, (int)y0, (int)y1, exposure);
+        k_resolve<<<grid, 256, 0, s>>>(ctx->color.p, ctx->tiles_x * SWR_TILE, dst, ctx->W, (int)y0, (int)y1, exposure, nullptr);
     }
     CK(cudaEventRecord(ctx->ev_resolved[idx], s));
     CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_resolved[idx], 0));
@@ -1307,8 +1358,9 @@ int swr_resolve_async(swr_ctx *ctx, float exposure, uint32_t *out_pixels, int *t
         if (ctx->pixels_alt.reserve((size_t)ctx->W * ctx->H) != cudaSuccess) return SWR_ERR_OOM;
     }
     const int idx = ctx->pix_cur ^ 1;
-    int rc = issue_resolve_copy(ctx, idx, exposure, out_pixels);
+    int rc = check_fused_exposure(ctx, exposure);
     if (rc) return rc;
+    if ((rc = issue_resolve_copy(ctx, idx, exposure, out_pixels))) return rc;
     ctx->pix_cur = idx;
     if (FrameSlot *f = newest_pending(ctx)) {  // re-issued if the frame has to be replayed
         f->resolve_kind = 2;
@@ -1400,6 +1452,10 @@ int swr_read_color(swr_ctx *ctx, float *rgb) {
     if (!ctx || !rgb) return SWR_ERR_INVALID;
     int rc;
     if ((rc = finish_frame(ctx))) return rc;
+    if (ctx->last_fused) {
+        ctx->err = "swr_read_color: the frame was shaded with a fixed exposure and holds no HDR colour (swr_set_fixed_exposure(ctx, 0) + swr_shade())";
+        return SWR_ERR_INVALID;
+    }
     const size_t Wp = (size_t)ctx->tiles_x * SWR_TILE, n = Wp * ctx->tiles_y * SWR_TILE;
     std::vector<float4> tmp(n);
     CK(cudaMemcpy(tmp.data(), ctx->color.p, n * sizeof(float4), cudaMemcpyDeviceToHost));

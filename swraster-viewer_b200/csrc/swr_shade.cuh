@@ -29,6 +29,12 @@ struct ShadeParams {
     // winner belongs to another rank carry SWR_ID_FOREIGN and are left unshaded (colour.w = 0); sky only in sky rows.
     const float2 *ext_bary;
     int sky_row_begin, sky_row_end;
+    // Fixed-exposure frames (swr_set_fixed_exposure): k_shade<true> applies exposure, tonemap and the RGBA8 pack itself
+    // (renderer.rs:293-355) and writes `rgba` (W x H) plus the tile's metering value `lum` (tilerasterizer.rs:103-106); the
+    // 16-byte HDR value never goes to memory.
+    uint32_t *rgba;
+    float *lum;
+    float exposure;
     // opaque pass counters: a frame whose tile lists overflowed left the keys of the previous frame in place (the host grows
     // the buffers and replays it); such a frame is not shaded
     const FrameCounters *counters;
@@ -408,11 +414,14 @@ __device__ __forceinline__ V3 compute_skybox(const ShadeParams &P, int px, int p
     return srgb_to_linear_fast(sample_cubemap_rgb(P.scene.texs[P.scene.cubemap], normalize(d, rq), 0u));
 }
 
+__device__ __forceinline__ uint32_t resolve_pixel_rgba(float4 c, float exposure);
+
 #ifndef SWR_SHADE_MINB
 #define SWR_SHADE_MINB 8  // 64 registers: measured best (0.75 ms vs 0.95 ms at 4 blocks/SM on C3)
 #endif
 #define SHADE_BLOCK 128
 #define SHADE_ROWS (SHADE_BLOCK / 32 * 2)
+template <bool FUSED>
 __global__ void __launch_bounds__(SHADE_BLOCK, SWR_SHADE_MINB) k_shade(ShadeParams P) {
     if (P.counters->overflow_refs | P.counters->overflow_ext | P.counters->overflow_clip) return;  // stale keys: the frame is replayed
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -477,7 +486,18 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SWR_SHADE_MINB) k_shade(ShadePara
             wrote = true;
         }
     }
-    if (inside) P.color[(size_t)py * P.Wp + px] = make_float4(out.x, out.y, out.z, wrote ? 1.0f : 0.0f);
+    if (!FUSED) {
+        if (inside) P.color[(size_t)py * P.Wp + px] = make_float4(out.x, out.y, out.z, wrote ? 1.0f : 0.0f);
+    } else {
+        if (px < P.W && py < P.H) P.rgba[(size_t)py * P.W + px] = resolve_pixel_rgba(make_float4(out.x, out.y, out.z, wrote ? 1.0f : 0.0f), P.exposure);
+        // metering quad of the tile = pixels (0..1, 32..33): k_luminance's sum, in its order, inside the quad's four lanes
+        if ((px & (SWR_TILE - 1)) < 2 && ((py & (SWR_TILE - 1)) >> 1) == 16 && inside) {  // quad-uniform (and the whole quad is inside)
+            const float l = out.x * 0.2126f + out.y * 0.7152f + out.z * 0.0722f;
+            const float l0 = __shfl_sync(qmask, l, (lane & ~3)), l1 = __shfl_sync(qmask, l, (lane & ~3) + 1);
+            const float l2 = __shfl_sync(qmask, l, (lane & ~3) + 2), l3 = __shfl_sync(qmask, l, (lane & ~3) + 3);
+            if (sub == 0) P.lum[(py >> 6) * P.tiles_x + (px >> 6)] = (l0 + l1 + l2 + l3) * 0.25f;
+        }
+    }
 }
 
 // tilerasterizer.rs:103-106: quad #512 of the tile = pixels (0..1, 32..33)
@@ -506,12 +526,22 @@ __device__ __forceinline__ uint32_t resolve_pixel_rgba(float4 c, float exposure)
     b = b / (b + k) * opk;
     return (f2u8(r * 255.0f) << 24) | (f2u8(g * 255.0f) << 16) | (f2u8(b * 255.0f) << 8) | 0xFFu;
 }
-__global__ void __launch_bounds__(256) k_resolve(const float4 *color, int Wp, uint32_t *pixels, int W, int y0, int y1, float exposure) {
+// `rgba` != NULL: the frame was shaded with a fixed exposure and is already packed: the kernel only moves it.
+__global__ void __launch_bounds__(256) k_resolve(const float4 *color, int Wp, uint32_t *pixels, int W, int y0, int y1, float exposure, const uint32_t *rgba) {
     const int x = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
     const int y = y0 + blockIdx.y * 4 + (threadIdx.x >> 6);
     if (y >= y1 || x >= W) return;
     const float4 *c = color + (size_t)y * Wp + x;
     uint32_t *o = pixels + (size_t)y * W + x;
+    if (rgba) {
+        const uint32_t *src = rgba + (size_t)y * W + x;
+        if (x + 3 < W && (W & 3) == 0) {
+            *reinterpret_cast<uint4 *>(o) = *reinterpret_cast<const uint4 *>(src);
+        } else {
+            for (int k = 0; k < 4 && x + k < W; k++) o[k] = src[k];
+        }
+        return;
+    }
     if (x + 3 < W && (W & 3) == 0) {
         uint4 v;
         v.x = resolve_pixel_rgba(c[0], exposure);
@@ -561,7 +591,7 @@ __device__ __forceinline__ bool frame_overflowed(const FrameCounters *c) { retur
 
 __global__ void __launch_bounds__(256) k_resolve_peer(const float4 *color, int Wp, uint32_t *pixels, uint32_t *ctrl, int W, int y0, int y1, float exposure,
                                                       uint32_t *local_done, const uint32_t *timeout_flag, const FrameCounters *op_counters,
-                                                      const FrameCounters *tr_counters) {
+                                                      const FrameCounters *tr_counters, const uint32_t *rgba) {
     const bool bad = frame_overflowed(op_counters) || frame_overflowed(tr_counters);
     if (*timeout_flag == 0u && !bad) {  // after a timeout the buffer may still be in use: contribute nothing but still signal
         const int x = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
@@ -569,7 +599,14 @@ __global__ void __launch_bounds__(256) k_resolve_peer(const float4 *color, int W
         if (y < y1 && x < W) {
             const float4 *c = color + (size_t)y * Wp + x;
             uint32_t *o = pixels + (size_t)y * W + x;
-            if (x + 3 < W && (W & 3) == 0) {
+            if (rgba) {  // fixed-exposure frame: already packed
+                const uint32_t *src = rgba + (size_t)y * W + x;
+                if (x + 3 < W && (W & 3) == 0) {
+                    *reinterpret_cast<uint4 *>(o) = *reinterpret_cast<const uint4 *>(src);
+                } else {
+                    for (int k = 0; k < 4 && x + k < W; k++) o[k] = src[k];
+                }
+            } else if (x + 3 < W && (W & 3) == 0) {
                 uint4 v;
                 v.x = resolve_pixel_rgba(c[0], exposure);
                 v.y = resolve_pixel_rgba(c[1], exposure);

@@ -506,7 +506,30 @@ class Renderer {
         const int tiles_y = (height_ + SWR_TILE_SIZE - 1) / SWR_TILE_SIZE;
         const bool band = row1_ > row0_ && (row0_ > 0 || row1_ < tiles_y);  // sort-first: drop draws that cannot reach my rows
         build_draw_list(*scene.desc, cam, draws_, shard, nshards, band ? row0_ * SWR_TILE_SIZE : 0, band ? row1_ * SWR_TILE_SIZE : 0, height_);
+        // The exposure blit_to_buffer will use is the one held now unless update_auto_exposure moves it in between
+        // (renderer.rs:258-290 is the only writer). While the meter is idle the frame is shaded straight to RGBA8 with it
+        // (swr_set_fixed_exposure); if the exposure does move, frame_exposure() shades the frame again to HDR and later
+        // frames take the HDR path until the meter has settled.
+        const float fixed = (shade && nshards == 1 && !meter_live_) ? auto_exposure_ : 0.0f;
+        check(swr_set_fixed_exposure(ctx_, fixed), "swr_set_fixed_exposure");
         check(swr_render(ctx_, &cam, draws_.data(), (int)draws_.size(), shade ? 1 : 0), "swr_render");
+        if (fused_.size() != lanes_.size()) fused_.assign(lanes_.size(), 0.0f);
+        fused_[cur_] = fixed;
+        last_cam_ = cam;
+    }
+
+    // The frame rendered last must be resolvable with `exposure`: a frame that was shaded to RGBA8 with another exposure is
+    // shaded again from its visibility buffer, this time to HDR.
+    void frame_exposure(float exposure) {
+        if (multi_ || fused_.empty() || fused_[cur_] == 0.0f || fused_[cur_] == exposure) return;
+        frame_hdr();
+    }
+    // The frame rendered last must hold HDR colour (read_color, a caller that wants to meter before it picks an exposure).
+    void frame_hdr() {
+        if (multi_ || fused_.empty() || fused_[cur_] == 0.0f) return;
+        check(swr_set_fixed_exposure(ctx_, 0.0f), "swr_set_fixed_exposure");
+        check(swr_shade(ctx_, &last_cam_), "swr_shade");
+        fused_[cur_] = 0.0f;
     }
 
     // update_auto_exposure(&mut self, delta_time) — renderer.rs:258-290
@@ -524,6 +547,7 @@ class Renderer {
         }
         float state[3] = {auto_exposure_, auto_exposure_target_, auto_exposure_ev_};
         auto_exposure_step(state, lum.data(), lum.size(), delta_time);
+        meter_live_ = state[0] != auto_exposure_;  // the exposure is moving: frames are shaded to HDR until it holds still
         auto_exposure_ = state[0];
         auto_exposure_target_ = state[1];
         auto_exposure_ev_ = state[2];
@@ -532,6 +556,7 @@ class Renderer {
     // blit_to_buffer(&self, buffer) — renderer.rs:293-355
     void blit_to_buffer(RenderBuffer &buffer) {
         if ((int)buffer.width != width_ || (int)buffer.height < height_) throw std::runtime_error("RenderBuffer size mismatch");
+        frame_exposure(auto_exposure_);
         if (multi_)
             check(swr_multi_resolve(multi_, auto_exposure_, buffer.pixels), "swr_multi_resolve");
         else
@@ -547,6 +572,7 @@ class Renderer {
             check(swr_multi_resolve(multi_, auto_exposure_, buffer.pixels), "swr_multi_resolve");
             return 0;
         }
+        frame_exposure(auto_exposure_);
         check(swr_resolve_async(ctx_, auto_exposure_, buffer.pixels, &ticket), "swr_resolve_async");
         return cur_ * 2 + ticket;  // the lane that holds the frame + its pixel buffer
     }
@@ -562,6 +588,9 @@ class Renderer {
         if (rc != 0) throw std::runtime_error(std::string(what) + ": " + (multi_ && std::strncmp(what, "swr_multi", 9) == 0 ? swr_multi_last_error(multi_) : swr_last_error(ctx_)));
     }
     int width_, height_;
+    std::vector<float> fused_;  // per lane: the fixed exposure its last frame was shaded with (0 = HDR)
+    bool meter_live_ = false;   // update_auto_exposure changed the exposure last time it ran
+    swr_camera last_cam_{};
     int rsqrt_bits_ = 0;
     int row0_ = 0, row1_ = 0;
     std::vector<swr_ctx *> lanes_;  // single device: the contexts frames alternate between (lane 0 owns the scene)

@@ -107,6 +107,8 @@ int swrh_auto_exposure_step(float state[3], const float *tile_luminance, int nti
              swr::auto_exposure_step(&need_ptr(state, "state"), ntiles ? &need_ptr(tile_luminance, "tile luminance") : nullptr, (size_t)ntiles, delta_time));
 }
 int swrh_update_auto_exposure(void *r, float dt) { SWRH_TRY(need(r).update_auto_exposure(dt)); }
+int swrh_frame_exposure(void *r, float exposure) { SWRH_TRY(need(r).frame_exposure(exposure)); }
+int swrh_frame_hdr(void *r) { SWRH_TRY(need(r).frame_hdr()); }
 float swrh_auto_exposure(void *r) { return r ? ((swr::Renderer *)r)->auto_exposure() : 0.0f; }
 
 int swrh_blit_to_buffer(void *r, uint32_t *pixels, size_t width, size_t height) {

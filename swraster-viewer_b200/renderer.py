@@ -47,6 +47,7 @@ def load_libraries():
     core.swr_set_rsqrt_table.argtypes = [vp, vp, i32]
     core.swr_upload_scene.argtypes = [vp, C.POINTER(abi.SceneDesc)]
     core.swr_render.argtypes = [vp, C.POINTER(abi.Camera), C.POINTER(abi.Draw), i32, i32]
+    core.swr_set_fixed_exposure.argtypes = [vp, f32]
     core.swr_shade.argtypes = [vp, C.POINTER(abi.Camera)]
     core.swr_keys_to_global.argtypes = [vp]
     core.swr_keys_localize.argtypes = [vp]
@@ -98,6 +99,8 @@ def load_libraries():
     host.swrh_reference_rsqrt_bits.argtypes = [vp]
     host.swrh_render_scene.argtypes = [vp, C.POINTER(abi.SceneDesc), C.POINTER(abi.Camera), i32, i32, i32]
     host.swrh_update_auto_exposure.argtypes = [vp, f32]
+    host.swrh_frame_exposure.argtypes = [vp, f32]
+    host.swrh_frame_hdr.argtypes = [vp]
     host.swrh_num_draws.argtypes = [vp]
     host.swrh_auto_exposure_step.argtypes = [vp, vp, i32, f32]
     host.swrh_auto_exposure.restype = f32
@@ -259,6 +262,7 @@ class Renderer:
 
     # ---- C-ABI extras used by tests / bench -----------------------------------------------
     def resolve_device_only(self, exposure=abi.DEFAULT_EXPOSURE):
+        self._check(self.host.swrh_frame_exposure(self._h, exposure))
         self._check_core(self.core.swr_resolve(self.ctx, exposure, None))
 
     def shade(self, camera):
@@ -289,6 +293,7 @@ class Renderer:
         self._check_core(self.core.swr_peer_attach(self.ctx, device_ptr))
 
     def resolve_peer(self, exposure, frame):
+        self._check(self.host.swrh_frame_exposure(self._h, exposure))
         self._check_core(self.core.swr_resolve_peer(self.ctx, exposure, frame))
 
     def peer_collect(self, frame, contributors):
@@ -312,6 +317,7 @@ class Renderer:
 
     def read_color(self):
         rgb = np.empty(self.width * self.height * 3, np.float32)
+        self._check(self.host.swrh_frame_hdr(self._h))
         self._check_core(self.core.swr_read_color(self.ctx, rgb.ctypes.data))
         return rgb.reshape(self.height, self.width, 3)
 

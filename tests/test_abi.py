@@ -115,7 +115,7 @@ core, _ = swr.load_libraries()
 core.swr_resolve_async.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
 core.swr_wait_pixels.argtypes = [C.c_void_p, C.c_int]
 args = {"swr_set_rsqrt_table": (None, None, 10), "swr_set_tile_rows": (None, 0, 1), "swr_upload_scene": (None, None), "swr_share_scene": (None, None), "swr_render": (None, None, None, 0, 1),
-        "swr_shade": (None, None), "swr_shade_composited": (None, None, 0, 0), "swr_resolve": (None, 2.0, None), "swr_resolve_async": (None, 2.0, None, None),
+        "swr_set_fixed_exposure": (None, 2.0), "swr_shade": (None, None), "swr_shade_composited": (None, None, 0, 0), "swr_resolve": (None, 2.0, None), "swr_resolve_async": (None, 2.0, None, None),
         "swr_wait_pixels": (None, 0), "swr_read_tile_luminance": (None, None), "swr_read_tile_costs": (None, None, None),
         "swr_read_visbuffer": (None, None, None, None, None), "swr_read_color": (None, None), "swr_get_stats": (None, None), "swr_peer_export": (None, None),
         "swr_peer_open": (None, None), "swr_peer_attach": (None, None), "swr_resolve_peer": (None, 2.0, 1), "swr_peer_collect": (None, 1, 1),
