@@ -9,6 +9,7 @@
 // ("fancy") chroma upsampling for 2:1 horizontal and 2:1 x 2:1, replication otherwise, and the 16-bit fixed-point
 // YCbCr -> RGB tables. tests/test_jpeg.py checks it bit for bit against libjpeg-turbo (through Pillow).
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <stdexcept>
@@ -62,6 +63,7 @@ class Decoder {
    private:
     const uint8_t *p_;
     size_t n_, pos_ = 0;
+    int scans_ = 0;
     std::string name_;
 
     struct Component {
@@ -99,6 +101,8 @@ class Decoder {
         if (o + 2 > n_) fail("truncated file");
         return ((uint32_t)p_[o] << 8) | p_[o + 1];
     }
+    // DC predictors of a conforming stream stay inside 16 bits; a hostile one must not walk an int into overflow
+    static int clamp_pred(int v) { return std::min(std::max(v, -32768), 32767); }
     size_t seg_len() const {
         const size_t len = be16(pos_);
         if (len < 2 || pos_ + len > n_) fail("truncated segment");
@@ -307,7 +311,7 @@ class Decoder {
         const Huff &hd = dc_[c.td], &ha = ac_[c.ta];
         const int t = decode_huff(hd);
         if (t > 11) fail("corrupt data: bad DC size");
-        c.pred += receive_extend(t);
+        c.pred = clamp_pred(c.pred + receive_extend(t));
         blk[0] = (int16_t)c.pred;
         for (int k = 1; k < 64;) {
             const int rs = decode_huff(ha), r = rs >> 4, s = rs & 15;
@@ -324,7 +328,7 @@ class Decoder {
     void decode_dc_first(Component &c, int16_t *blk, int al) {
         const int t = decode_huff(dc_[c.td]);
         if (t > 11) fail("corrupt data: bad DC size");
-        c.pred += receive_extend(t);
+        c.pred = clamp_pred(c.pred + receive_extend(t));
         blk[0] = (int16_t)(c.pred * (1 << al));
     }
     void decode_dc_refine(int16_t *blk, int al) {
@@ -401,6 +405,8 @@ class Decoder {
     void read_scan() {
         if (!have_frame_) fail("scan before frame header");
         const size_t len = seg_len();
+        if (len < 6) fail("bad scan header");  // seg_len only guarantees the two length bytes
+        if (++scans_ > 1000) fail("too many scans");  // a hostile file could make every 10-byte scan header cost a pass over all blocks
         const int ns = p_[pos_ + 2];
         if (ns < 1 || ns > (int)comp_.size() || len != 6 + 2 * (size_t)ns) fail("bad scan header");
         std::vector<int> sel((size_t)ns);
