@@ -65,6 +65,7 @@ struct GeomSet {
     DevBuf<uint4> work;     // k_compact output: surviving clusters in submission order (draw, cluster, dense base, triangles)
     DevBuf<TriRecord> records;
     DevBuf<uint32_t> rects;
+    DevBuf<uint8_t> zb;  // depth bucket per record (tile lists are bucket-major)
     DevBuf<float> avgz;  // translucent set only: packet.avg_z per record (renderer.rs:765-775)
     DevBuf<ClipVertex> clip_verts;
     DevBuf<uint2> clip_queue;  // (dense triangle, draw) pairs waiting for k_clip
@@ -245,8 +246,8 @@ swr_ctx *swr_create(int width, int height, int device) {
     ctx->cur = &ctx->slots[0];
     for (int i = 0; ok && i < 2; i++) ok = cudaEventCreate(&ctx->ev_res[i]) == cudaSuccess;
     for (int i = 0; ok && i < 4; i++) ok = cudaEventCreateWithFlags(&ctx->op.staging[i].done, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && ctx->op.tile_count.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->op.tile_offset.reserve(ctx->ntiles + 1) == cudaSuccess &&
-         ctx->op.tile_cursor.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_cycles.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_cycles_prev.reserve(ctx->ntiles + 1) == cudaSuccess &&
+    ok = ok && ctx->op.tile_count.reserve((size_t)(ctx->ntiles + 1) * SWR_ZBUCKETS) == cudaSuccess && ctx->op.tile_offset.reserve(ctx->ntiles + 1) == cudaSuccess &&
+         ctx->op.tile_cursor.reserve((size_t)(ctx->ntiles + 1) * SWR_ZBUCKETS) == cudaSuccess && ctx->tile_cycles.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_cycles_prev.reserve(ctx->ntiles + 1) == cudaSuccess &&
          ctx->tile_count_prev.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->tile_unit.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->unit_list.reserve(ctx->ntiles + 1) == cudaSuccess && ctx->keys.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess &&
          ctx->color.reserve((size_t)ctx->ntiles * SWR_TILE_PIXELS) == cudaSuccess && ctx->pixels.reserve((size_t)width * height + SWR_PEER_WORDS) == cudaSuccess && ctx->peer_local.reserve(16) == cudaSuccess &&
          ctx->lum.reserve(ctx->ntiles) == cudaSuccess && ctx->op.counters.reserve(1) == cudaSuccess;
@@ -296,6 +297,7 @@ void swr_destroy(swr_ctx *ctx) {
         g->work.release();
         g->records.release();
         g->rects.release();
+        g->zb.release();
         g->avgz.release();
         g->clip_verts.release();
         g->clip_queue.release();
@@ -634,8 +636,8 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
     g.clusters = (uint32_t)clusters;
     g.total_verts = verts;
     bool ok = g.draws.reserve(nd + 1) == cudaSuccess && g.tri_prefix.reserve(2 * (size_t)nd + 4) == cudaSuccess && g.cull.reserve(((clusters + 255) / 256) * 10 + clusters + 16) == cudaSuccess && g.work.reserve(clusters + 1) == cudaSuccess && g.records.reserve(slots + 1) == cudaSuccess &&
-              g.rects.reserve(slots + 1) == cudaSuccess && g.tile_count.reserve(ctx->ntiles + 1) == cudaSuccess &&
-              g.tile_offset.reserve(ctx->ntiles + 1) == cudaSuccess && g.tile_cursor.reserve(ctx->ntiles + 1) == cudaSuccess &&
+              g.rects.reserve(slots + 1) == cudaSuccess && g.zb.reserve(slots + 16) == cudaSuccess && g.tile_count.reserve((size_t)(ctx->ntiles + 1) * SWR_ZBUCKETS) == cudaSuccess &&
+              g.tile_offset.reserve(ctx->ntiles + 1) == cudaSuccess && g.tile_cursor.reserve((size_t)(ctx->ntiles + 1) * SWR_ZBUCKETS) == cudaSuccess &&
               g.counters.reserve(1) == cudaSuccess && (!translucent || g.avgz.reserve(slots + 1) == cudaSuccess);
     if (!ok) {
         ctx->err = "out of device memory for per-frame triangle records";
@@ -664,7 +666,7 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
     CK(cudaMemcpyAsync(g.tri_prefix.p, hp, 2 * (size_t)(nd + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->upload_stream));
     CK(cudaEventRecord(st.done, ctx->upload_stream));
     CK(cudaStreamWaitEvent(s, st.done, 0));
-    CK(cudaMemsetAsync(g.tile_count.p, 0, (ctx->ntiles + 1) * sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(g.tile_count.p, 0, (size_t)(ctx->ntiles + 1) * SWR_ZBUCKETS * sizeof(uint32_t), s));
     CK(cudaMemsetAsync(g.counters.p, 0, sizeof(FrameCounters), s));
 
     const int rb = ctx->row_begin, re = ctx->row_end;
@@ -690,6 +692,7 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
         sp.mats = ctx->scene.mats;
         sp.records = g.records.p;
         sp.rects = g.rects.p;
+        sp.zb = g.zb.p;
         sp.avgz = translucent ? g.avgz.p : nullptr;
         sp.clip_verts = g.clip_verts.p;
         sp.clip_capacity = (uint32_t)g.clip_verts.cap;
@@ -745,6 +748,7 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
         if (!translucent) {
             aux.keys = ctx->keys.p;
             aux.tile_unit = ctx->tile_unit.p;
+            aux.tile_offset = g.tile_offset.p;
             aux.tile_begin = rb * ctx->tiles_x;
             aux.tile_end = re * ctx->tiles_x;
         }
@@ -1402,7 +1406,11 @@ int swr_read_tile_costs(swr_ctx *ctx, uint32_t *refs, uint32_t *cycles) {
     if (!ctx) return SWR_ERR_INVALID;
     int rc;
     if ((rc = finish_frame(ctx))) return rc;
-    if (refs) CK(cudaMemcpy(refs, ctx->op.tile_count.p, ctx->ntiles * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (refs) {  // refs per tile = difference of the scanned offsets (the counters themselves are per depth bucket)
+        std::vector<uint32_t> off((size_t)ctx->ntiles + 1);
+        CK(cudaMemcpy(off.data(), ctx->op.tile_offset.p, off.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < ctx->ntiles; i++) refs[i] = off[(size_t)i + 1] - off[(size_t)i];
+    }
     if (cycles) CK(cudaMemcpy(cycles, ctx->tile_cycles.p, ctx->ntiles * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return SWR_OK;
 }

@@ -35,6 +35,7 @@ struct SetupParams {
     const DevMat *mats;
     TriRecord *records;
     uint32_t *rects;
+    uint8_t *zb;  // depth bucket of every record with a rectangle (tile lists are bucket-major: near buckets first)
     float *avgz;  // translucent set: packet.avg_z per record (renderer.rs:765-775), else NULL
     ClipVertex *clip_verts;
     uint32_t clip_capacity;
@@ -67,29 +68,45 @@ __device__ __forceinline__ uint32_t record_of_id(uint32_t id, const uint32_t *cl
     return fan == 0 ? t : __ldg(clip_ext + t) + fan - 1u;
 }
 
+// Depth-bucketed tile lists. The per-tile counters and cursors are SWR_ZBUCKETS wide: a triangle is counted / scattered under
+// (tile, bucket of its nearest vertex), the scan lays a tile's buckets out one after the other, so the raster kernel — which
+// just walks the tile's ref range — meets near geometry first and its Hi-Z / early-Z tests reject most of what lies behind
+// (C3: fragments that reach the depth test 19.8 M -> 11.4 M of 8.3 M visible; raster 0.54 -> 0.46 ms). The order of a list
+// never changes a result (the 64-bit min is order-independent), only the work. Buckets are octaves of 1 - z/w, which is
+// proportional to 1/w away from the far plane: bucket = exponent distance of (1 - z_ndc) from 1.0.
+#ifndef SWR_ZBUCKET_SHIFT
+#define SWR_ZBUCKET_SHIFT 0  // buckets per octave = 1 << shift
+#endif
+#define SWR_ZBUCKETS (8 << SWR_ZBUCKET_SHIFT)
+__device__ __forceinline__ uint32_t depth_bucket(float zmin_ndc) {
+    const float t = fminf(fmaxf(1.0f - zmin_ndc, 1.0e-30f), 1.0f);  // NaN -> far bucket
+    return min((uint32_t)SWR_ZBUCKETS - 1u, (0x3F800000u - __float_as_uint(t)) >> (23 - SWR_ZBUCKET_SHIFT));
+}
+
 // Count one triangle's tile rectangle into tile_count. Single-tile rectangles (the common case) are
 // aggregated across the warp with match.any so each distinct tile costs one atomic. Must be called by
 // all 32 lanes of the warp.
-__device__ __forceinline__ void count_tiles(uint32_t rect, uint32_t *tile_count, int tiles_x) {
+__device__ __forceinline__ void count_tiles(uint32_t rect, uint32_t bucket, uint32_t *tile_count, int tiles_x) {
     int tx0 = rect & 0xFF, ty0 = (rect >> 8) & 0xFF, tx1 = (rect >> 16) & 0xFF, ty1 = rect >> 24;
     bool valid = rect != 0;
     bool single = valid && (tx1 - tx0 == 1) && (ty1 - ty0 == 1);
     unsigned sm = __ballot_sync(0xFFFFFFFFu, single);
     if (single) {
-        int tile = ty0 * tiles_x + tx0;
+        int tile = (ty0 * tiles_x + tx0) * SWR_ZBUCKETS + (int)bucket;
         unsigned peers = __match_any_sync(sm, tile);
         if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&tile_count[tile], (uint32_t)__popc(peers));
     } else if (valid) {
         for (int ty = ty0; ty < ty1; ty++)
-            for (int tx = tx0; tx < tx1; tx++) atomicAdd(&tile_count[ty * tiles_x + tx], 1u);
+            for (int tx = tx0; tx < tx1; tx++) atomicAdd(&tile_count[(ty * tiles_x + tx) * SWR_ZBUCKETS + (int)bucket], 1u);
     }
 }
 
 // renderer.rs:668-760 minus attribute set-up (deferred to shading). Returns the packed tile rectangle
 // (0 = culled / off-screen / not owned) and writes the record when it survives.
 __device__ __forceinline__ uint32_t emit_triangle(const SetupParams &P, float4 c0, float4 c1, float4 c2, uint32_t slot,
-                                                  uint32_t draw, uint32_t seq, uint32_t clipref, bool &nocover) {
+                                                  uint32_t draw, uint32_t seq, uint32_t clipref, bool &nocover, uint32_t &bucket) {
     nocover = false;
+    bucket = 0;
     float Wf = (float)P.W, Hf = (float)P.H;
     TriRecord r;
     snap_vertex(c0, Wf, Hf, r.X0, r.Y0);
@@ -143,6 +160,8 @@ __device__ __forceinline__ uint32_t emit_triangle(const SetupParams &P, float4 c
     r.seq = seq;
     r.clip = clipref;
     if (P.avgz) P.avgz[slot] = fdiv(fadd(fadd(c0.z, c1.z), c2.z), 3.0f);
+    else bucket = depth_bucket(fminf(r.zw0, fminf(r.zw1, r.zw2)));  // translucent lists are sorted per tile anyway: one bucket
+    P.zb[slot] = (uint8_t)bucket;
     uint4 *dst = reinterpret_cast<uint4 *>(&P.records[slot]);
     const uint4 *src = reinterpret_cast<const uint4 *>(&r);
     dst[0] = src[0];
@@ -335,7 +354,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams P) {
         const DevPrim &pr = P.prims[dr.prim];
         const uint32_t tri = w.y * SWR_CLUSTER_TRIS + tid;
         const uint32_t g = w.z + tid;
-        uint32_t rect = 0;
+        uint32_t rect = 0, bucket = 0;
         bool queued = false, nocover = false;
         if (tid < w.w) {
             const bool clip = (dr.flags & 1u) != 0;
@@ -362,15 +381,15 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams P) {
                             state = 2;
                     }
                 }
-                if (state == 0) rect = emit_triangle(P, c0, c1, c2, slot, dflag, seq, SWR_NO_CLIP, nocover);
+                if (state == 0) rect = emit_triangle(P, c0, c1, c2, slot, dflag, seq, SWR_NO_CLIP, nocover, bucket);
                 queued = state == 2;
             } else {
-                rect = emit_triangle(P, c0, c1, c2, slot, dflag, seq, SWR_NO_CLIP, nocover);
+                rect = emit_triangle(P, c0, c1, c2, slot, dflag, seq, SWR_NO_CLIP, nocover, bucket);
             }
             P.rects[slot] = nocover ? 0u : rect;  // k_clip overwrites it when fan 0 of a clipped polygon survives
         }
         rect = account_block(rect, nocover, P.counters, &s_unc);
-        count_tiles(rect, P.tile_count, P.tiles_x);
+        count_tiles(rect, bucket, P.tile_count, P.tiles_x);
         // warp-aggregated append to the clip queue
         unsigned qm = __ballot_sync(0xFFFFFFFFu, queued);
         if (qm) {
@@ -397,7 +416,7 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip(SetupParams P) {
     const unsigned gmask = 0xFFFFu << (tid & 16);  // the 16 lanes of my group inside the warp
     for (uint32_t base = blockIdx.x * CLIP_GROUPS; base < qn; base += gridDim.x * CLIP_GROUPS) {
         const uint32_t e = base + grp;
-        uint32_t rect_out = 0;
+        uint32_t rect_out = 0, bucket_out = 0;
         bool nocover_out = false;
         if (e < qn) {
             const uint2 qe = P.clip_queue[e];
@@ -497,14 +516,14 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip(SetupParams P) {
                     const uint32_t sl = fan == 0 ? gg : P.total_tris + ext + fan - 1;
                     rect_out = emit_triangle(P, make_float4(v0[0], v0[1], v0[2], v0[3]), make_float4(v1[0], v1[1], v1[2], v1[3]),
                                              make_float4(v2[0], v2[1], v2[2], v2[3]), sl, dd | ((P.mats[pr.material].flags & 1u) ? SWR_REC_ALPHA : 0u),
-                                             (dr.first_tri + ttri) * 8u + fan, vbase, nocover_out);
+                                             (dr.first_tri + ttri) * 8u + fan, vbase, nocover_out, bucket_out);
                     P.rects[sl] = nocover_out ? 0u : rect_out;
                     if (fan > 0 && rect_out != 0 && !nocover_out) P.clip_list[atomicAdd(&P.counters->clip_list_n, 1u)] = gg * 8u + fan;
                 }
             }
         }
         rect_out = account_block(rect_out, nocover_out, P.counters, &s_unc);  // block-uniform loop: safe to use block barriers
-        count_tiles(rect_out, P.tile_count, P.tiles_x);
+        count_tiles(rect_out, bucket_out, P.tile_count, P.tiles_x);
     }
 }
 
@@ -533,6 +552,30 @@ __device__ __forceinline__ uint32_t tile_unit_refs(uint32_t refs, uint32_t prev_
     return min(max(u, RASTER_UNIT_MIN), RASTER_UNIT_MAX);
 }
 
+// One tile's SWR_ZBUCKETS counters (32 bytes) -> total; and its cursors: bucket b starts at base + (counts of buckets < b).
+__device__ __forceinline__ uint32_t load_tile_counts(const uint32_t *tile_count, int i, uint32_t c[SWR_ZBUCKETS]) {
+    uint32_t sum = 0;
+#pragma unroll
+    for (int q = 0; q < SWR_ZBUCKETS / 4; q++) {
+        const uint4 a = reinterpret_cast<const uint4 *>(tile_count)[(SWR_ZBUCKETS / 4) * i + q];
+        c[4 * q] = a.x; c[4 * q + 1] = a.y; c[4 * q + 2] = a.z; c[4 * q + 3] = a.w;
+        sum += (a.x + a.y) + (a.z + a.w);
+    }
+    return sum;
+}
+__device__ __forceinline__ void store_tile_cursors(uint32_t *tile_cursor, int i, uint32_t base, const uint32_t c[SWR_ZBUCKETS]) {
+#pragma unroll
+    for (int q = 0; q < SWR_ZBUCKETS / 4; q++) {
+        uint4 a;
+        a.x = base;
+        a.y = a.x + c[4 * q];
+        a.z = a.y + c[4 * q + 1];
+        a.w = a.z + c[4 * q + 2];
+        base = a.w + c[4 * q + 3];
+        reinterpret_cast<uint4 *>(tile_cursor)[(SWR_ZBUCKETS / 4) * i + q] = a;
+    }
+}
+
 __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count, uint32_t *tile_offset, uint32_t *tile_cursor, int ntiles,
                                                      FrameCounters *counters, uint32_t ref_capacity, uint32_t *unit_list, uint32_t unit_capacity,
                                                      int tile_begin, int tile_end, uint32_t cta_slots, uint32_t *tile_unit,
@@ -552,7 +595,8 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
     __syncthreads();
     for (int base = 0; base < ntiles; base += 1024) {
         int i = base + tid;
-        uint32_t v = i < ntiles ? tile_count[i] : 0u;
+        uint32_t cb[SWR_ZBUCKETS];
+        uint32_t v = i < ntiles ? load_tile_counts(tile_count, i, cb) : 0u;
         uint32_t incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -574,7 +618,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
         uint32_t excl = s_carry + s_warp[wid] + incl - v;
         if (i < ntiles) {
             tile_offset[i] = excl;
-            tile_cursor[i] = excl;
+            store_tile_cursors(tile_cursor, i, excl, cb);
             if (have_history && i >= tile_begin && i < tile_end && prev_count[i] >= 16u) {
                 // expected cycles of this tile now = cycles per ref last frame x refs now
                 my_cyc += (float)prev_cycles[i] / (float)prev_count[i] * (float)v;
@@ -603,7 +647,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
     const uint32_t U = s_unit;
     const float target = s_target;
     for (int i = tile_begin + tid; i < tile_end; i += 1024) {
-        const uint32_t v = tile_count[i];
+        const uint32_t v = tile_offset[i + 1] - tile_offset[i];
         const uint32_t ut = tile_unit_refs(v, have_history ? prev_count[i] : 0u, have_history ? prev_cycles[i] : 0u, target, U);
         tile_unit[i] = ut;
         const uint32_t nfull = v / ut, rem = v % ut;
@@ -626,7 +670,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
     if (counters->overflow_refs) return;
     // one thread per tile; a tile split into many units (a hot tile has hundreds) is left to a whole warp afterwards
     for (int i = tile_begin + tid; i < tile_end; i += 1024) {
-        const uint32_t v = tile_count[i];
+        const uint32_t v = tile_offset[i + 1] - tile_offset[i];
         const uint32_t ut = tile_unit[i];
         const uint32_t nfull = v / ut, rem = v % ut;
         prev_count[i] = v;  // history for the next frame
@@ -641,7 +685,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
         uint32_t nfull = 0, ut = 1;
         if (i < tile_end) {
             ut = tile_unit[i];
-            nfull = tile_count[i] / ut;
+            nfull = (tile_offset[i + 1] - tile_offset[i]) / ut;
         }
         unsigned big = __ballot_sync(0xFFFFFFFFu, nfull > 8u);
         while (big) {
@@ -661,13 +705,13 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
 // the grid's last blocks: the surviving fans >= 1 of clipped polygons.
 // ---------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ void scatter_rect(uint32_t rect, uint32_t id, uint32_t *tile_cursor, uint32_t *refs, int tiles_x) {
+__device__ __forceinline__ void scatter_rect(uint32_t rect, uint32_t bucket, uint32_t id, uint32_t *tile_cursor, uint32_t *refs, int tiles_x) {
     int tx0 = rect & 0xFF, ty0 = (rect >> 8) & 0xFF, tx1 = (rect >> 16) & 0xFF, ty1 = rect >> 24;
     bool valid = rect != 0;
     bool single = valid && (tx1 - tx0 == 1) && (ty1 - ty0 == 1);
     unsigned sm = __ballot_sync(0xFFFFFFFFu, single);
     if (single) {
-        int tile = ty0 * tiles_x + tx0;
+        int tile = (ty0 * tiles_x + tx0) * SWR_ZBUCKETS + (int)bucket;
         unsigned peers = __match_any_sync(sm, tile);
         int leader = __ffs(peers) - 1;
         uint32_t base = 0;
@@ -677,7 +721,7 @@ __device__ __forceinline__ void scatter_rect(uint32_t rect, uint32_t id, uint32_
         refs[base + rank] = id;
     } else if (valid) {
         for (int ty = ty0; ty < ty1; ty++)
-            for (int tx = tx0; tx < tx1; tx++) refs[atomicAdd(&tile_cursor[ty * tiles_x + tx], 1u)] = id;
+            for (int tx = tx0; tx < tx1; tx++) refs[atomicAdd(&tile_cursor[(ty * tiles_x + tx) * SWR_ZBUCKETS + (int)bucket], 1u)] = id;
     }
 }
 
@@ -690,6 +734,7 @@ __device__ __forceinline__ void scatter_rect(uint32_t rect, uint32_t id, uint32_
 struct ScatterAux {
     unsigned long long *keys;   // NULL: no key initialisation (translucent set)
     const uint32_t *tile_unit;  // refs per raster unit of each tile (k_scan_tiles)
+    const uint32_t *tile_offset;
     int tile_begin, tile_end;   // owned tiles
 };
 __global__ void __launch_bounds__(SWR_CLUSTER_TRIS) k_scatter(SetupParams P, uint32_t *tile_cursor, uint32_t *refs, uint32_t cluster_blocks, ScatterAux A) {
@@ -698,7 +743,7 @@ __global__ void __launch_bounds__(SWR_CLUSTER_TRIS) k_scatter(SetupParams P, uin
         const uint32_t nb = gridDim.x - cluster_blocks, b = blockIdx.x - cluster_blocks;
         if (A.keys) {
             for (int t = A.tile_begin + (int)b; t < A.tile_end; t += (int)nb) {
-                if (__ldg(P.tile_count + t) <= __ldg(A.tile_unit + t)) continue;  // one unit: written whole by k_raster_tiles
+                if (__ldg(A.tile_offset + t + 1) - __ldg(A.tile_offset + t) <= __ldg(A.tile_unit + t)) continue;  // one unit: written whole by k_raster_tiles
                 uint4 *dst = reinterpret_cast<uint4 *>(A.keys + (size_t)t * SWR_TILE_PIXELS);
                 for (int i = threadIdx.x; i < SWR_TILE_PIXELS / 2; i += SWR_CLUSTER_TRIS) dst[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
             }
@@ -707,12 +752,14 @@ __global__ void __launch_bounds__(SWR_CLUSTER_TRIS) k_scatter(SetupParams P, uin
         const uint32_t n = P.counters->clip_list_n;
         for (uint32_t base = b * SWR_CLUSTER_TRIS; base < n; base += nb * SWR_CLUSTER_TRIS) {  // uniform trip count per block
             const uint32_t i = base + threadIdx.x;
-            uint32_t id = 0, rect = 0;
+            uint32_t id = 0, rect = 0, bucket = 0;
             if (i < n) {
                 id = P.clip_list[i];
-                rect = __ldg(P.rects + record_of_id(id, P.clip_ext));
+                const uint32_t slot = record_of_id(id, P.clip_ext);
+                rect = __ldg(P.rects + slot);
+                bucket = __ldg(P.zb + slot);
             }
-            scatter_rect(rect, id, tile_cursor, refs, P.tiles_x);
+            scatter_rect(rect, bucket, id, tile_cursor, refs, P.tiles_x);
         }
         return;
     }
@@ -721,7 +768,8 @@ __global__ void __launch_bounds__(SWR_CLUSTER_TRIS) k_scatter(SetupParams P, uin
         const uint4 w = P.work[wi];
         const uint32_t t = w.z + threadIdx.x;
         const uint32_t rect = threadIdx.x < w.w ? __ldg(P.rects + t) : 0u;
-        scatter_rect(rect, t * 8u, tile_cursor, refs, P.tiles_x);
+        const uint32_t bucket = rect ? __ldg(P.zb + t) : 0u;
+        scatter_rect(rect, bucket, t * 8u, tile_cursor, refs, P.tiles_x);
     }
 }
 

@@ -653,7 +653,8 @@ __global__ void __launch_bounds__(1024) k_scan_simple(const uint32_t *count, uin
     __syncthreads();
     for (int base = 0; base < ntiles; base += 1024) {
         int i = base + tid;
-        uint32_t v = i < ntiles ? count[i] : 0u;
+        uint32_t cb[SWR_ZBUCKETS];
+        uint32_t v = i < ntiles ? load_tile_counts(count, i, cb) : 0u;
         uint32_t incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -675,7 +676,7 @@ __global__ void __launch_bounds__(1024) k_scan_simple(const uint32_t *count, uin
         uint32_t excl = s_carry + s_warp[wid] + incl - v;
         if (i < ntiles) {
             offset[i] = excl;
-            cursor[i] = excl;
+            store_tile_cursors(cursor, i, excl, cb);
         }
         __syncthreads();
         if (tid == 1023) s_carry = excl + v;
