@@ -153,7 +153,10 @@ __device__ __forceinline__ uint32_t f2usize_clamped(float f, uint32_t hi) { retu
 __device__ __forceinline__ void sample_gi(const DevScene &s, V3 pos, V3 rgb[4], float w[4]) {
     const uint32_t W = s.gdim[0], H = s.gdim[1], D = s.gdim[2];
     const float vsx = s.gvs[0], vsy = s.gvs[1], vsz = s.gvs[2];  // (world_max - world_min) / dims, voxelgrid.rs:154-161
-    float vx = (pos.x - s.gmin[0]) / vsx, vy = (pos.y - s.gmin[1]) / vsy, vz = (pos.z - s.gmin[2]) / vsz;
+    // value-domain quotients although they pick the voxel: the trilinear blend is continuous across cell boundaries (a cell
+    // flip by a last-bit difference swaps (cell k, weight ~1) for (cell k+1, weight ~0)), so 2 ulp in the grid coordinate is
+    // 2 ulp in the colour, nothing more
+    float vx = vdiv(pos.x - s.gmin[0], vsx), vy = vdiv(pos.y - s.gmin[1], vsy), vz = vdiv(pos.z - s.gmin[2], vsz);
     float x0f = floorf(vx), y0f = floorf(vy), z0f = floorf(vz);
     uint32_t x0 = f2usize_clamped(x0f, W - 1), y0 = f2usize_clamped(y0f, H - 1), z0 = f2usize_clamped(z0f, D - 1);
     uint32_t x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1), z1 = min(z0 + 1, D - 1);
@@ -521,9 +524,9 @@ __device__ __forceinline__ uint32_t resolve_pixel_rgba(float4 c, float exposure)
     if (c.w == 0.0f) return 0u;  // not shaded by this rank (sort-last): contributes nothing to the sum-combine
     float r = c.x * exposure, g = c.y * exposure, b = c.z * exposure;
     const float k = 0.2f, opk = 1.0f + 0.2f;  // util.rs:37-41
-    r = r / (r + k) * opk;
-    g = g / (g + k) * opk;
-    b = b / (b + k) * opk;
+    r = vdiv(r, r + k) * opk;  // value domain: a 2-ulp quotient moves a byte only when the product sits on an integer
+    g = vdiv(g, g + k) * opk;
+    b = vdiv(b, b + k) * opk;
     return (f2u8(r * 255.0f) << 24) | (f2u8(g * 255.0f) << 16) | (f2u8(b * 255.0f) << 8) | 0xFFu;
 }
 // `rgba` != NULL: the frame was shaded with a fixed exposure and is already packed: the kernel only moves it.
