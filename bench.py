@@ -195,7 +195,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     import swraster_viewer_b200 as swr
-    from swraster_viewer_b200.multigpu import (tile_row_ranges, balanced_row_ranges, PeerAssembly, SharedHostFrame, device_tensor,
+    from swraster_viewer_b200.multigpu import (tile_row_ranges, balanced_row_ranges, rebalance_row_ranges, PeerAssembly, SharedHostFrame, device_tensor,
                                                sort_last_frame)
 
     cfg = CONFIGS[args.config]
@@ -223,8 +223,24 @@ def run_gpu(args):
             r.render_scene(scene, cam, shade=False)
         cyc = torch.from_numpy(r.read_tile_costs()[1].astype(np.int64)).to(dev)
         dist.broadcast(cyc, src=0)  # measured cycles differ slightly per rank: everybody uses rank 0's
-        ranges = balanced_row_ranges(cyc.cpu().numpy(), world)
+        cost = cyc.cpu().numpy()
+        ranges = balanced_row_ranges(cost, world)
         r.set_tile_rows(*ranges[rank])
+        # feedback: the probe only knows raster cycles; two rounds of "render the band, measure all its phases, cut again"
+        # (set-up time, untimed) level what set-up and shading add per band
+        row_cost = cost.sum(axis=1).astype(np.float64) + 0.9 * cost.mean() * cost.shape[1]
+        for _ in range(2):
+            acc = 0.0
+            for _ in range(4):
+                r.render_scene(scene, cam)
+                r.synchronize()
+                st = r.stats()
+                acc += st["ms_setup_bin"] + st["ms_raster"] + st["ms_shade"]
+            t = torch.tensor([0.0] * world, dtype=torch.float64, device=dev)
+            t[rank] = acc / 4
+            dist.all_reduce(t)
+            ranges = rebalance_row_ranges(ranges, t.cpu().numpy(), row_cost)
+            r.set_tile_rows(*ranges[rank])
     stream = torch.cuda.ExternalStream(r.cuda_stream(), device=local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -357,6 +373,10 @@ def run_gpu(args):
         e2e_sync_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
 
+    per_rank = torch.zeros(world, 3, dtype=torch.float64, device=dev)
+    per_rank[rank] = torch.tensor([phase[k] / K for k in ("ms_setup_bin", "ms_raster", "ms_shade")], dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(per_rank)
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
     cnt = torch.tensor([st0["tile_refs"], st0["triangles_binned"]], dtype=torch.float64, device=dev)
     if world > 1:
@@ -412,6 +432,7 @@ def run_gpu(args):
             # kernels of ours launched on this rank inside the two timed regions, counted by the library (swr_launch_count)
             "gpu_launches": launches_dev + (launches2 - launches1),
             "step_ms": {"min": step_ms[0], "median": step_ms[len(step_ms) // 2], "max": step_ms[-1], "note": "device-resident steps on rank 0 (ms_per_step is the mean, max over ranks)"},
+            "per_rank_phase_ms": [[round(float(x), 4) for x in row] for row in per_rank.cpu().tolist()],
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel_ms": dom_ms, "kernel_algorithmic_bytes": kbytes,

@@ -148,6 +148,7 @@ struct swr_ctx {
     DevBuf<float> lum;
     // fixed-exposure frames: k_shade<true> packs RGBA8 itself into `fused_px`; the resolve entry points then only move it
     float fixed_exposure = 0.0f;   // swr_set_fixed_exposure (applies to frames rendered from now on)
+    float units_floor = 1.0f;      // least raster units per CTA slot (development knob: SWR_UNITS_FLOOR)
     DevBuf<uint32_t> fused_px;
     bool last_fused = false;       // the frame shaded last holds RGBA8 in fused_px (exposure last_fused_exposure) and NO HDR colour
     float last_fused_exposure = 0.0f;
@@ -224,6 +225,7 @@ swr_ctx *swr_create(int width, int height, int device) {
     swr_ctx *ctx = new swr_ctx();
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
+    if (const char *e = getenv("SWR_UNITS_FLOOR")) ctx->units_floor = (float)atof(e) > 0.0f ? (float)atof(e) : 1.0f;  // development knob
     ctx->W = width;
     ctx->H = height;
     ctx->tiles_x = (width + SWR_TILE - 1) / SWR_TILE;
@@ -735,10 +737,13 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
     } else {
         const size_t unit_cap = (size_t)ctx->ntiles + g.refs.cap / RASTER_UNIT_MIN + 1;
         const uint32_t cta_slots = (uint32_t)ctx->num_sms * RASTER_MINB;  // k_raster_tiles: resident CTAs per SM
+        // a band's tiles are cut no finer than a full frame's would be (floor: one unit per slot)
+        float units_per_slot = SWR_UNITS_PER_SLOT * (float)(re - rb) / (float)(ctx->tiles_y > 0 ? ctx->tiles_y : 1);
+        if (units_per_slot < ctx->units_floor) units_per_slot = ctx->units_floor;
         if (ctx->unit_list.reserve(unit_cap) != cudaSuccess) return SWR_ERR_OOM;
         ctx->launches++;
         k_scan_tiles<<<1, 1024, 0, s>>>(g.tile_count.p, g.tile_offset.p, g.tile_cursor.p, ctx->ntiles, g.counters.p, (uint32_t)(g.refs.cap - 16), ctx->unit_list.p,
-                                        (uint32_t)unit_cap, rb * ctx->tiles_x, re * ctx->tiles_x, cta_slots, ctx->tile_unit.p, ctx->tile_count_prev.p,
+                                        (uint32_t)unit_cap, rb * ctx->tiles_x, re * ctx->tiles_x, cta_slots, units_per_slot, ctx->tile_unit.p, ctx->tile_count_prev.p,
                                         ctx->tile_cycles_prev.p, ctx->have_history ? 1 : 0);
         ctx->have_history = true;
     }

@@ -534,7 +534,9 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip(SetupParams P) {
 // Units are ordered heaviest-first (bit-length buckets of their ref count).
 // ---------------------------------------------------------------------------------------------
 #ifndef SWR_UNITS_PER_SLOT
-#define SWR_UNITS_PER_SLOT 3u  // target number of raster units per resident CTA slot (measured on C3: 2-3 best, 4 +4 %, 6 +12 %: every extra split costs a key init and a global min-merge)
+#define SWR_UNITS_PER_SLOT 3.0f  // raster units per resident CTA slot for a FULL frame (measured on C3: 1-3 the same, 4 +4 %, 6 +12 %: every extra split
+                                  // costs a key init, a global min-merge and the occlusion the other chunks would have provided); a sort-first band
+                                  // scales it by its share of the screen (swr_api.cu) so that its tiles are not cut finer than a full frame's
 #endif
 #define RASTER_UNIT_MAX 2048u
 #define RASTER_UNIT_MIN 32u
@@ -578,7 +580,7 @@ __device__ __forceinline__ void store_tile_cursors(uint32_t *tile_cursor, int i,
 
 __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count, uint32_t *tile_offset, uint32_t *tile_cursor, int ntiles,
                                                      FrameCounters *counters, uint32_t ref_capacity, uint32_t *unit_list, uint32_t unit_capacity,
-                                                     int tile_begin, int tile_end, uint32_t cta_slots, uint32_t *tile_unit,
+                                                     int tile_begin, int tile_end, uint32_t cta_slots, float units_per_slot, uint32_t *tile_unit,
                                                      uint32_t *prev_count, const uint32_t *prev_cycles, int have_history) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry, s_unit;
@@ -637,10 +639,10 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *tile_count,
         counters->tile_refs = s_carry;
         if (s_carry > ref_capacity) counters->overflow_refs = 1;
         // default unit: ~3 units per resident CTA slot, so the tail stays short even when this context owns only a band
-        uint32_t u = s_carry / (3u * cta_slots);
+        uint32_t u = (uint32_t)((float)s_carry / (units_per_slot * (float)cta_slots));
         u = ((u + 255u) / 256u) * 256u;
         s_unit = min(max(u, 256u), RASTER_UNIT_MAX);
-        s_target = have_history ? s_cyc / (float)(SWR_UNITS_PER_SLOT * cta_slots) : 0.0f;
+        s_target = have_history ? s_cyc / (units_per_slot * (float)cta_slots) : 0.0f;
     }
     __syncthreads();
     if (counters->overflow_refs) return;

@@ -43,6 +43,28 @@ def balanced_row_ranges(tile_cost, world, pixel_cost=None):
     return [(cuts[i], cuts[i + 1]) for i in range(world)]
 
 
+def rebalance_row_ranges(ranges, band_ms, row_cost):
+    """One feedback step of the sort-first split: `band_ms[k]` is what rank k's band (ranges[k]) really took per frame (all
+    phases: the probe's raster cycles know nothing of a band's set-up or shading share); the rows of a band keep their relative
+    `row_cost` (tiles_y values) but the band as a whole is re-weighted to its measured time, and the cuts are laid again so that
+    every band gets the same share. Returns the new ranges (contiguous, every band at least one row)."""
+    world, tiles_y = len(ranges), len(row_cost)
+    w = np.asarray(row_cost, np.float64) + 1e-9
+    dens = np.zeros(tiles_y)
+    for (r0, r1), ms in zip(ranges, band_ms):
+        if r1 > r0:
+            dens[r0:r1] = w[r0:r1] / w[r0:r1].sum() * max(float(ms), 1e-6)
+    cum = np.concatenate([[0.0], np.cumsum(dens)])
+    cuts = [0]
+    for k in range(1, world):
+        target = cum[-1] * k / world
+        r = int(np.searchsorted(cum, target))
+        r = r if abs(cum[min(r, tiles_y)] - target) <= abs(cum[max(r - 1, 0)] - target) else r - 1
+        cuts.append(min(max(r, cuts[-1] + 1), tiles_y - (world - k)))
+    cuts.append(tiles_y)
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
 def gather_strips(image, ranges, height, dst=0):
     """image: (H, W) int32 torch tensor whose rows [64*r0, 64*r1) are valid on this rank.
     Returns the assembled image on `dst` (in place in `image`), None elsewhere. Uses send/recv so strips of

@@ -11,7 +11,7 @@ import pytest
 import swraster_viewer_b200 as swr
 from swraster_viewer_b200 import abi, scenes
 from swraster_viewer_b200.renderer import build_draws
-from swraster_viewer_b200.multigpu import tile_row_ranges, balanced_row_ranges
+from swraster_viewer_b200.multigpu import tile_row_ranges, balanced_row_ranges, rebalance_row_ranges
 from helpers import small_configs, SMALL
 
 
@@ -85,6 +85,27 @@ def test_balanced_row_ranges_partition_and_balance():
             band = [cost[a:b].sum() for a, b in r]
             even = [cost[a:b].sum() for a, b in tile_row_ranges(tiles_y, world)]
             assert max(band) <= max(even) * 1.001  # never worse than the even split
+
+
+def test_rebalance_row_ranges_converges_on_the_measured_time():
+    """Feedback step of the sort-first split: bands are re-cut from what they really took. Model: a band's time is its
+    raster cost plus a per-row term the probe does not know (set-up + shading); a few steps level the bands."""
+    rng = np.random.default_rng(5)
+    tiles_y = 34
+    raster = rng.random(tiles_y) ** 3 * 100 + 5
+    hidden = np.linspace(30, 5, tiles_y)  # what the probe cannot see: heavier at the top of the screen
+    true_ms = raster + hidden
+    for world in (2, 4, 8):
+        ranges = tile_row_ranges(tiles_y, world)
+        first = max(true_ms[a:b].sum() for a, b in ranges)
+        for _ in range(3):
+            band = [true_ms[a:b].sum() for a, b in ranges]
+            ranges = rebalance_row_ranges(ranges, band, raster)
+            assert ranges[0][0] == 0 and ranges[-1][1] == tiles_y
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:])) and all(b > a for a, b in ranges)
+        worst = max(true_ms[a:b].sum() for a, b in ranges)
+        assert worst <= first * 1.001, (world, worst, first)
+        assert worst <= true_ms.sum() / world + true_ms.max()  # within one row of the ideal split
 
 
 def test_band_culling_is_conservative():
