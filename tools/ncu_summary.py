@@ -1,12 +1,18 @@
 """Turn an ncu launch list (csv) and a full .ncu-rep into the short text summaries kept under profiles/."""
 import collections, csv, subprocess, sys
 launch_csv, rep, out = sys.argv[1], sys.argv[2], sys.argv[3]
+import re
+def kname(full):
+    """`void k_shade<1>(ShadeParams)` -> `k_shade`: templated kernels are printed with their return type and arguments"""
+    n = full.split("(")[0].strip()
+    n = n[5:] if n.startswith("void ") else n
+    return re.sub(r"<.*>$", "", n)
 rows = [r for r in csv.reader(open(launch_csv)) if len(r) > 10]
 hdr = rows[0]
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
 agg = collections.OrderedDict()
 for r in rows[1:]:
-    agg.setdefault(r[ki].split("(")[0][:60], []).append(float(r[vi].replace(",", "")))
+    agg.setdefault(kname(r[ki])[:60], []).append(float(r[vi].replace(",", "")))
 lines = ["# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare SHARES)", ""]
 own = {k: v for k, v in agg.items() if k.startswith("k_")}
 per_frame = sum(sum(v) / len(v) for v in own.values())
@@ -37,7 +43,7 @@ if len(sys.argv) > 4:  # also: per-kernel DRAM traffic and warp-instruction coun
     traffic, winst = {}, {}
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for r in rr[2:]:
-        k = r[h.index("Kernel Name")].split("(")[0]
+        k = kname(r[h.index("Kernel Name")])
         rd, wr = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
         traffic[k] = int(float(r[rd].replace(",", "")) * scale[rr[1][rd]] + float(r[wr].replace(",", "")) * scale[rr[1][wr]])
         winst[k] = int(float(r[h.index("smsp__inst_executed.sum")].replace(",", "")))

@@ -20,7 +20,7 @@ pipes = ["smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_execut
          "smsp__thread_inst_executed_per_inst_executed.ratio", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "launch__registers_per_thread"]
 seen = set()
 for r in rr[2:]:
-    k = r[h.index("Kernel Name")].split("(")[0]
+    k = r[h.index("Kernel Name")].split("(")[0].replace("void ", "")
     if k in seen:
         continue
     seen.add(k)
