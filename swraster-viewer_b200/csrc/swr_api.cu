@@ -759,7 +759,8 @@ static int launch_geometry(swr_ctx *ctx, GeomSet &g, bool translucent) {
         }
         if (tris > 0) {  // nothing submitted: no tile is split, no list
             ctx->launches++;
-            k_scatter<<<g.geom_grid + SCATTER_AUX_BLOCKS, SWR_CLUSTER_TRIS, 0, s>>>(sp, g.tile_cursor.p, g.refs.p, g.geom_grid, aux);
+            const unsigned sc_blocks = (g.geom_grid + SCATTER_BATCH - 1) / SCATTER_BATCH;
+            k_scatter<<<sc_blocks + SCATTER_AUX_BLOCKS, SWR_CLUSTER_TRIS, 0, s>>>(sp, g.tile_cursor.p, g.refs.p, sc_blocks, aux);
         }
     }
     CK(cudaGetLastError());

@@ -6,6 +6,7 @@
 // reference's f32 arithmetic bit for bit. The translation unit is also
 // compiled with -fmad=false as a second guard.
 #pragma once
+#include <cstddef>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -17,6 +18,10 @@
 #define SWR_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define SWR_INF_BITS 0x7F800000u
 #define SWR_REC_ALPHA 0x80000000u  // TriRecord.draw bit 31: the triangle's material is alpha-tested (shader.rs:40-43)
+// TriRecord.draw bit 30: the f32 edge chain of this triangle is exact over the WHOLE padded screen (|a| x + |b| y + |c| < 2^24 at
+// the largest coordinates any tile region can reach), hence over every tile region: packet_setup() need not bound it again
+#define SWR_REC_EXACT 0x40000000u
+#define SWR_REC_DRAW_MASK 0x3FFFFFFFu
 #define SWR_ID_FOREIGN 0xFFFFFFFEu  // sort-last: the pixel's winner belongs to another rank
 
 // One surviving (post cull/clip) triangle: 64 bytes, 4 x 128-bit.
@@ -102,11 +107,12 @@ struct FrameCounters {
     // statistics spread over 32 slots (block index & 31) so that the per-block atomics do not serialise on one address
     unsigned long long tris_binned[32];
     unsigned long long refs_uncovered[32];  // refs of triangles that provably cover no pixel: counted, not emitted
-    uint32_t clip_verts;      // bump allocator for ClipVertex
+    // the two bump allocators of k_clip sit in one aligned 64-bit word so that a polygon takes both with ONE atomic
+    uint32_t clip_verts;      // bump allocator for ClipVertex (low word)
+    uint32_t ext_records;     // bump allocator for the records of fans >= 1 (high word)
     uint32_t overflow_refs;   // tile_refs exceeded the ref buffer
     uint32_t overflow_clip;   // clip vertex buffer exhausted
     uint32_t clip_queue_n;    // triangles queued for k_clip
-    uint32_t ext_records;     // bump allocator for the records of fans >= 1
     uint32_t overflow_ext;    // extension records exhausted
     uint32_t clip_list_n;     // surviving fans >= 1
     uint32_t raster_units;    // entries of the raster work list
@@ -117,6 +123,7 @@ struct FrameCounters {
     uint32_t overflow_sort;   // a tile holds more translucent packets than the in-kernel sort supports
     unsigned long long dbg[8];  // SWR_PROFILE_COUNTERS builds only
 };
+static_assert(offsetof(FrameCounters, clip_verts) % 8 == 0 && offsetof(FrameCounters, ext_records) == offsetof(FrameCounters, clip_verts) + 4, "k_clip's paired allocator");
 
 // ---------------------------------------------------------------------------------------------
 // exact float helpers
@@ -219,6 +226,16 @@ __device__ __forceinline__ void tri_bbox_pixels(const TriRecord &r, int W, int H
     bmaxy = wadd(mxy, 16) >> 4;
 }
 
+// |a| * xhi + |b| * yhi + |c| < 2^24. Fast path in 32 bits: xhi, yhi < 2^18 + 256 (screens up to 255 tiles of 1024 sub-pixel
+// units), so with |a|, |b| < 2^12 and |c| < 2^24 the sum stays below 2^32; anything larger takes the 64-bit form (same value).
+__device__ __forceinline__ bool edge_bound_ok(int a, int b, int c, uint32_t xhi, uint32_t yhi) {
+    const uint32_t ua = (uint32_t)(a < 0 ? -(long long)a : a), ub = (uint32_t)(b < 0 ? -(long long)b : b), uc = (uint32_t)(c < 0 ? -(long long)c : c);
+    if ((ua | ub) >= 4096u || uc >= (1u << 24)) {
+        return (long long)ua * xhi + (long long)ub * yhi + (long long)uc < (1ll << 24);
+    }
+    return ua * xhi + ub * yhi + uc < (1u << 24);
+}
+
 __device__ __forceinline__ void packet_setup(const TriRecord &r, int W, int H, int tile_x0, int tile_y0, PacketSetup &p) {
     int bminx, bminy, bmaxx, bmaxy;
     tri_bbox_pixels(r, W, H, bminx, bminy, bmaxx, bmaxy);
@@ -246,15 +263,27 @@ __device__ __forceinline__ void packet_setup(const TriRecord &r, int W, int H, i
     // Exactness bound: all evaluated coordinates are positive and <= (xhi, yhi); every partial sum of the f32
     // chain is then bounded by |a|*xhi + |b|*yhi + |c|. Below 2^24 all of them are exact integers, so the chain
     // equals the integer edge function and the coarse reject can never drop a covered pixel.
+    if (r.draw & SWR_REC_EXACT) {  // bounded once per triangle over the whole screen (k_setup): a fortiori here
+        p.exact = true;
+        return;
+    }
     int xhi = p.coarse ? p.xs + (((p.xe - p.xs) + 255) >> 8) * 256 : p.xs + p.nqx * 32;
     int yhi = p.coarse ? p.ys + (((p.ye - p.ys) + 255) >> 8) * 256 : p.ys + p.nqy * 32;
     bool ex = true;
 #pragma unroll
-    for (int e = 0; e < 3; e++) {
-        long long bound = (long long)abs((long long)p.a[e]) * xhi + (long long)abs((long long)p.b[e]) * yhi + abs((long long)p.c[e]);
-        ex = ex && (bound < (1ll << 24));
-    }
+    for (int e = 0; e < 3; e++) ex = ex && edge_bound_ok(p.a[e], p.b[e], p.c[e], (uint32_t)xhi, (uint32_t)yhi);
     p.exact = ex;
+}
+
+// The same bound over the whole padded screen plus the 255 sub-pixel units a coarse block may reach past a region's end: every
+// (xhi, yhi) packet_setup() can come up with is below these, and the bound is monotonic in both.
+__device__ __forceinline__ bool exact_on_screen(const TriRecord &r, int tiles_x, int tiles_y) {
+    const uint32_t xhi = (uint32_t)tiles_x * SWR_TILE * 16 + 256, yhi = (uint32_t)tiles_y * SWR_TILE * 16 + 256;
+    const int a01 = wsub(r.Y1, r.Y0), b01 = wsub(r.X0, r.X1), a12 = wsub(r.Y2, r.Y1), b12 = wsub(r.X1, r.X2), a20 = wsub(r.Y0, r.Y2), b20 = wsub(r.X2, r.X0);
+    const int c01 = wadd(wsub(wmul(r.X1, r.Y0), wmul(r.X0, r.Y1)), top_left_bias(a01, b01));
+    const int c12 = wadd(wsub(wmul(r.X2, r.Y1), wmul(r.X1, r.Y2)), top_left_bias(a12, b12));
+    const int c20 = wadd(wsub(wmul(r.X0, r.Y2), wmul(r.X2, r.Y0)), top_left_bias(a20, b20));
+    return edge_bound_ok(a01, b01, c01, xhi, yhi) && edge_bound_ok(a12, b12, c12, xhi, yhi) && edge_bound_ok(a20, b20, c20, xhi, yhi);
 }
 
 // Edge value of one pixel of a NON-exact packet, replaying the reference's f32 chain:
@@ -327,17 +356,21 @@ __device__ __forceinline__ void eval_chain_owner(const PacketSetup &p, int qx, i
         j = qy & 7;
     }
     const float x = i2f(bx + 8 + 16 * lx), y = i2f(by + 8 + 16 * ly);
-    float v[2];
-#pragma unroll
-    for (int e = 1; e < 3; e++) {
-        float t = fadd(fadd(fmul(i2f(p.a[e]), x), fmul(i2f(p.b[e]), y)), i2f(p.c[e]));
-        const float sy = i2f(wmul(p.b[e], 32)), sx = i2f(wmul(p.a[e], 32));
-        for (int k = 0; k < j; k++) t = fadd(t, sy);
-        for (int k = 0; k < i; k++) t = fadd(t, sx);
-        v[e - 1] = t;
+    // both edges walk the same j row steps and i column steps: one loop each (the per-edge order of additions is the reference's)
+    float t1 = fadd(fadd(fmul(i2f(p.a[1]), x), fmul(i2f(p.b[1]), y)), i2f(p.c[1]));
+    float t2 = fadd(fadd(fmul(i2f(p.a[2]), x), fmul(i2f(p.b[2]), y)), i2f(p.c[2]));
+    const float sy1 = i2f(wmul(p.b[1], 32)), sx1 = i2f(wmul(p.a[1], 32));
+    const float sy2 = i2f(wmul(p.b[2], 32)), sx2 = i2f(wmul(p.a[2], 32));
+    for (int k = 0; k < j; k++) {
+        t1 = fadd(t1, sy1);
+        t2 = fadd(t2, sy2);
     }
-    w1 = v[0];
-    w2 = v[1];
+    for (int k = 0; k < i; k++) {
+        t1 = fadd(t1, sx1);
+        t2 = fadd(t2, sx2);
+    }
+    w1 = t1;
+    w2 = t2;
 }
 
 // Barycentrics and depth of a pixel for the record that owns its key (shading): no coverage re-test.

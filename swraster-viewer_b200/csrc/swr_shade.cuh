@@ -219,7 +219,7 @@ struct ShadePacket {
 };
 
 __device__ __forceinline__ void build_shade_packet(const ShadeParams &P, const TriRecord &r, ShadePacket &sp) {
-    const DevDraw &dr = P.draws[r.draw & ~SWR_REC_ALPHA];
+    const DevDraw &dr = P.draws[r.draw & SWR_REC_DRAW_MASK];
     const DevPrim &pr = P.scene.prims[dr.prim];
     V3 n[3], t[3], pw[3];
     float tw[3], uu[3], vv[3];
