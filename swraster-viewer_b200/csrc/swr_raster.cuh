@@ -161,7 +161,6 @@ __device__ __forceinline__ uint32_t emit_triangle(const SetupParams &P, float4 c
     r.clip = clipref;
     if (P.avgz) P.avgz[slot] = fdiv(fadd(fadd(c0.z, c1.z), c2.z), 3.0f);
     else bucket = depth_bucket(fminf(r.zw0, fminf(r.zw1, r.zw2)));  // translucent lists are sorted per tile anyway: one bucket
-    P.zb[slot] = (uint8_t)bucket;
     uint4 *dst = reinterpret_cast<uint4 *>(&P.records[slot]);
     const uint4 *src = reinterpret_cast<const uint4 *>(&r);
     dst[0] = src[0];
@@ -401,6 +400,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams P) {
                 rect = emit_triangle(P, c0, c1, c2, slot, dflag, seq, SWR_NO_CLIP, nocover, bucket);
             }
             P.rects[slot] = nocover ? 0u : rect;  // k_clip overwrites it when fan 0 of a clipped polygon survives
+            P.zb[slot] = (uint8_t)bucket;         // written for every submitted triangle: k_scatter loads it beside the rectangle
         }
         rect = account_block(rect, nocover, P.counters, &s_unc);
         count_tiles(rect, bucket, P.tile_count, P.tiles_x);
@@ -532,6 +532,7 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip(SetupParams P) {
                                              make_float4(v2[0], v2[1], v2[2], v2[3]), sl, dd | ((P.mats[pr.material].flags & 1u) ? SWR_REC_ALPHA : 0u),
                                              (dr.first_tri + ttri) * 8u + fan, vbase, nocover_out, bucket_out);
                     P.rects[sl] = nocover_out ? 0u : rect_out;
+                    P.zb[sl] = (uint8_t)bucket_out;
                     if (fan > 0 && rect_out != 0 && !nocover_out) P.clip_list[atomicAdd(&P.counters->clip_list_n, 1u)] = gg * 8u + fan;
                 }
             }
