@@ -18,10 +18,7 @@
 #define SWR_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define SWR_INF_BITS 0x7F800000u
 #define SWR_REC_ALPHA 0x80000000u  // TriRecord.draw bit 31: the triangle's material is alpha-tested (shader.rs:40-43)
-// TriRecord.draw bit 30: the f32 edge chain of this triangle is exact over the WHOLE padded screen (|a| x + |b| y + |c| < 2^24 at
-// the largest coordinates any tile region can reach), hence over every tile region: packet_setup() need not bound it again
-#define SWR_REC_EXACT 0x40000000u
-#define SWR_REC_DRAW_MASK 0x3FFFFFFFu
+#define SWR_REC_DRAW_MASK 0x7FFFFFFFu
 #define SWR_ID_FOREIGN 0xFFFFFFFEu  // sort-last: the pixel's winner belongs to another rank
 
 // One surviving (post cull/clip) triangle: 64 bytes, 4 x 128-bit.
@@ -263,27 +260,12 @@ __device__ __forceinline__ void packet_setup(const TriRecord &r, int W, int H, i
     // Exactness bound: all evaluated coordinates are positive and <= (xhi, yhi); every partial sum of the f32
     // chain is then bounded by |a|*xhi + |b|*yhi + |c|. Below 2^24 all of them are exact integers, so the chain
     // equals the integer edge function and the coarse reject can never drop a covered pixel.
-    if (r.draw & SWR_REC_EXACT) {  // bounded once per triangle over the whole screen (k_setup): a fortiori here
-        p.exact = true;
-        return;
-    }
     int xhi = p.coarse ? p.xs + (((p.xe - p.xs) + 255) >> 8) * 256 : p.xs + p.nqx * 32;
     int yhi = p.coarse ? p.ys + (((p.ye - p.ys) + 255) >> 8) * 256 : p.ys + p.nqy * 32;
     bool ex = true;
 #pragma unroll
     for (int e = 0; e < 3; e++) ex = ex && edge_bound_ok(p.a[e], p.b[e], p.c[e], (uint32_t)xhi, (uint32_t)yhi);
     p.exact = ex;
-}
-
-// The same bound over the whole padded screen plus the 255 sub-pixel units a coarse block may reach past a region's end: every
-// (xhi, yhi) packet_setup() can come up with is below these, and the bound is monotonic in both.
-__device__ __forceinline__ bool exact_on_screen(const TriRecord &r, int tiles_x, int tiles_y) {
-    const uint32_t xhi = (uint32_t)tiles_x * SWR_TILE * 16 + 256, yhi = (uint32_t)tiles_y * SWR_TILE * 16 + 256;
-    const int a01 = wsub(r.Y1, r.Y0), b01 = wsub(r.X0, r.X1), a12 = wsub(r.Y2, r.Y1), b12 = wsub(r.X1, r.X2), a20 = wsub(r.Y0, r.Y2), b20 = wsub(r.X2, r.X0);
-    const int c01 = wadd(wsub(wmul(r.X1, r.Y0), wmul(r.X0, r.Y1)), top_left_bias(a01, b01));
-    const int c12 = wadd(wsub(wmul(r.X2, r.Y1), wmul(r.X1, r.Y2)), top_left_bias(a12, b12));
-    const int c20 = wadd(wsub(wmul(r.X0, r.Y2), wmul(r.X2, r.Y0)), top_left_bias(a20, b20));
-    return edge_bound_ok(a01, b01, c01, xhi, yhi) && edge_bound_ok(a12, b12, c12, xhi, yhi) && edge_bound_ok(a20, b20, c20, xhi, yhi);
 }
 
 // Edge value of one pixel of a NON-exact packet, replaying the reference's f32 chain:

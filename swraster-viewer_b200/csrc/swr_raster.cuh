@@ -156,7 +156,7 @@ __device__ __forceinline__ uint32_t emit_triangle(const SetupParams &P, float4 c
     r.zw0 = fmul(c0.z, r.iw0);
     r.zw1 = fmul(c1.z, r.iw1);
     r.zw2 = fmul(c2.z, r.iw2);
-    r.draw = draw | (exact_on_screen(r, P.tiles_x, P.tiles_y) ? SWR_REC_EXACT : 0u);
+    r.draw = draw;
     r.seq = seq;
     r.clip = clipref;
     if (P.avgz) P.avgz[slot] = fdiv(fadd(fadd(c0.z, c1.z), c2.z), 3.0f);
