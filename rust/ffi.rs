@@ -105,6 +105,7 @@ pub struct swr_scene_desc {
     pub light_color: [f32; 3],
 }
 #[repr(C)]
+#[derive(Clone, Copy)]
 pub struct swr_camera {
     pub position: [f32; 4],
     pub view_matrix: [f32; 16],

@@ -293,6 +293,12 @@ pub struct Renderer {
     auto_exposure: f32,
     auto_exposure_target: f32,
     auto_exposure_ev: f32,
+    // Fixed-exposure shading (include/swr.h swr_set_fixed_exposure): the exposure the frame rendered last was shaded with
+    // (0.0 = HDR), whether update_auto_exposure moved the exposure the last time it ran, and that frame's camera block
+    // (shading the same visibility buffer again needs it). Cell: blit_to_buffer takes &self, like the reference's.
+    frame_fixed: std::cell::Cell<f32>,
+    meter_live: bool,
+    last_cam: Option<swr_camera>,
 }
 // App holds Mutex<Renderer> and calls from a rayon worker (main.rs:526-543): one call at a time, any thread.
 unsafe impl Send for Renderer {}
@@ -335,6 +341,9 @@ impl Renderer {
             auto_exposure: DEFAULT_EXPOSURE,
             auto_exposure_target: DEFAULT_EXPOSURE,
             auto_exposure_ev: DEFAULT_EXPOSURE.log2(),
+            frame_fixed: std::cell::Cell::new(0.0),
+            meter_live: false,
+            last_cam: None,
         }
     }
 
@@ -399,6 +408,15 @@ impl Renderer {
             }
         }
         let cam = camera_pod(camera);
+        // renderer.rs:258-290 is the only writer of the exposure: while it leaves it alone, blit_to_buffer will use the value
+        // held now, and shading can pack RGBA8 with it (no HDR round trip); frame_exposure() below covers the other case
+        let fixed = if self.meter_live { 0.0 } else { self.auto_exposure };
+        if let Backend::Single(ctx) = self.backend {
+            let rc = unsafe { swr_set_fixed_exposure(ctx, fixed) };
+            self.check(rc, "swr_set_fixed_exposure");
+            self.frame_fixed.set(fixed);
+        }
+        self.last_cam = Some(cam);
         let rc = match self.backend {
             Backend::Single(ctx) => unsafe { swr_render(ctx, &cam, self.draws.as_ptr(), self.draws.len() as c_int, 1) },
             Backend::Multi(m) => unsafe { swr_multi_render(m, &cam, self.draws.as_ptr(), self.draws.len() as c_int) },
@@ -438,12 +456,31 @@ impl Renderer {
         let tau = AUTO_EXPOSURE_TIME_CONSTANT_SECONDS.max(1e-4);
         let alpha = 1.0 - (-(delta_time.max(0.0) / tau)).exp();
         self.auto_exposure_ev += (target_ev - self.auto_exposure_ev) * alpha;
-        self.auto_exposure = 2.0f32.powf(self.auto_exposure_ev);
+        let moved = 2.0f32.powf(self.auto_exposure_ev);
+        self.meter_live = moved != self.auto_exposure; // moving: the next frames are shaded to HDR until it holds still
+        self.auto_exposure = moved;
+    }
+
+    // The frame rendered last must be resolvable with `exposure`: one that was packed with another exposure is shaded again
+    // from its visibility buffer, to HDR (swr::Renderer::frame_exposure in host/swr_host.hpp is the tested twin of this).
+    fn frame_exposure(&self, exposure: f32) {
+        let fixed = self.frame_fixed.get();
+        if fixed == 0.0 || fixed == exposure {
+            return;
+        }
+        if let (Backend::Single(ctx), Some(cam)) = (&self.backend, self.last_cam.as_ref()) {
+            let rc = unsafe { swr_set_fixed_exposure(*ctx, 0.0) };
+            self.check(rc, "swr_set_fixed_exposure");
+            let rc = unsafe { swr_shade(*ctx, cam) };
+            self.check(rc, "swr_shade");
+            self.frame_fixed.set(0.0);
+        }
     }
 
     // Copy the frame to the backbuffer (renderer.rs:293): exposure, tonemap, RGBA8 pack on the device, then W*H u32 to the host
     pub fn blit_to_buffer(&self, buffer: &mut RenderBuffer) {
         assert!(buffer.width == self.width as usize && buffer.pixels.len() >= (self.width * self.height) as usize, "RenderBuffer size mismatch");
+        self.frame_exposure(self.auto_exposure);
         let rc = match self.backend {
             Backend::Single(ctx) => unsafe { swr_resolve(ctx, self.auto_exposure, buffer.pixels.as_mut_ptr()) },
             Backend::Multi(m) => unsafe { swr_multi_resolve(m, self.auto_exposure, buffer.pixels.as_mut_ptr()) },
