@@ -65,6 +65,12 @@ int swrh_gltf_register_image(const char *uri, const uint8_t *rgba, uint32_t widt
  * caller's); they stay valid until swrh_env_free. */
 void *swrh_env_bake(const uint8_t *cross_rgba, uint32_t width, uint32_t height, uint32_t lut_size, uint32_t specular_samples, uint32_t voxel_dim,
                     float irradiance_scale, float sky_visibility, float light_intensity);
+/* The same with the reference's `.ggx` cache (scene.rs:164-206, texture.rs:426-552): when `ggx_cache_path` names a cache of the
+ * sky's face size the prefiltered cubemap is read from it; otherwise it is baked on the device and the cache is written.
+ * swrh_env_specular_from_cache says which happened. */
+void *swrh_env_bake_cached(const uint8_t *cross_rgba, uint32_t width, uint32_t height, uint32_t lut_size, uint32_t specular_samples, uint32_t voxel_dim,
+                           float irradiance_scale, float sky_visibility, float light_intensity, const char *ggx_cache_path);
+int swrh_env_specular_from_cache(void *env);
 int swrh_env_get(void *env, swrh_gltf_env *out, float irradiance_sh_out[12]);
 void swrh_env_free(void *env);
 /* Voxel sun visibility as the reference's default load path computes it (main.rs:237-246; gi.rs:151-314, raytracer.rs,
@@ -75,6 +81,17 @@ void swrh_env_free(void *env);
  * a loaded document in place (call it before the scene is first rendered: uploads are once per scene). */
 int swrh_compute_sun_visibility(const swr_scene_desc *scene, float *out_per_voxel);
 int swrh_gltf_bake_sun_visibility(void *doc);
+
+/* The reference's bake caches on their own. `.ggx` (texture.rs:12-17, 426-552): "GGX0", version 1, width, height, mips, then the
+ * brotli stream of width*height*6*mips RGBA8 texels (every mip at full face resolution, mips = 1 + ilog2(max(w, h))). `.gi`
+ * (gi.rs:17-22, 30-122): "VGI0", version 8, w, h, d, then the brotli stream of w*h*d x 4 coefficients x (r, g, b, w) f32 — the
+ * layout of swr_voxel_grid.gi_sh4. Loads return 1 = read, 0 = no usable cache (missing file, other magic / version / size, payload
+ * of another length: the reference then bakes and saves), -1 = error (swrh_last_error). Brotli is the system's libbrotlidec /
+ * libbrotlienc, bound at run time; without them the calls fail. */
+int swrh_ggx_cache_load(const char *path, uint32_t width, uint32_t height, uint32_t *out_texels);
+int swrh_ggx_cache_save(const char *path, uint32_t width, uint32_t height, uint32_t mips, const uint32_t *texels);
+int swrh_gi_cache_load(const char *path, uint32_t w, uint32_t h, uint32_t d, float *gi_sh4_out);
+int swrh_gi_cache_save(const char *path, uint32_t w, uint32_t h, uint32_t d, const float *gi_sh4);
 
 /* The pieces of the loader that are useful on their own (and are what the tests pin): */
 int swrh_compute_smooth_normals(const float *positions4, uint32_t nverts, const uint32_t *indices, uint32_t nindices, float *normals4_out);

@@ -1,6 +1,7 @@
 """ctypes face of the native glTF / GLB loader (include/swr_gltf.h, host/swr_gltf.hpp): the step in front of the hot path
 (SURVEY 8f N2). `load_gltf` returns a scene object that Renderer.render_scene and the oracle accept like a SceneData."""
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -190,19 +191,24 @@ class BakedEnvironment:
     """Bakes of everything the viewer derives from its sky image (include/swr_gltf.h swrh_env_bake; the three integrals run on the GPU):
     sky cubemap + mips, GGX-prefiltered cubemap, irradiance SH4, BRDF LUT, SH-initialised voxel grid."""
 
-    def __init__(self, cross_rgba_u8, lut_size=128, specular_samples=64, voxel_dim=16, irradiance_scale=0.25, sky_visibility=1.0, light_intensity=1.0):
+    def __init__(self, cross_rgba_u8, lut_size=128, specular_samples=64, voxel_dim=16, irradiance_scale=0.25, sky_visibility=1.0, light_intensity=1.0,
+                 ggx_cache=None):
+        """ggx_cache: path of the reference's `.ggx` cache (scene.rs:164-206): read when it matches the sky's face size, else written
+        after the prefiltered cubemap has been baked; `specular_from_cache` says which."""
         host = _host()
-        host.swrh_env_bake.restype = C.c_void_p
-        host.swrh_env_bake.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float]
+        host.swrh_env_bake_cached.restype = C.c_void_p
+        host.swrh_env_bake_cached.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_char_p]
+        host.swrh_env_specular_from_cache.argtypes = [C.c_void_p]
         host.swrh_env_get.argtypes = [C.c_void_p, C.POINTER(GltfEnv), C.POINTER(C.c_float * 12)]
         host.swrh_env_free.argtypes = [C.c_void_p]
         a = np.ascontiguousarray(cross_rgba_u8, np.uint8)
         assert a.ndim == 3 and a.shape[2] == 4
         self._host = host
-        self._h = host.swrh_env_bake(a.ctypes.data, a.shape[1], a.shape[0], lut_size, specular_samples, voxel_dim, irradiance_scale, sky_visibility,
-                                     light_intensity)
+        self._h = host.swrh_env_bake_cached(a.ctypes.data, a.shape[1], a.shape[0], lut_size, specular_samples, voxel_dim, irradiance_scale, sky_visibility,
+                                            light_intensity, os.fsencode(ggx_cache) if ggx_cache else None)
         if not self._h:
             raise GltfError(host.swrh_last_error().decode())
+        self.specular_from_cache = bool(host.swrh_env_specular_from_cache(self._h))
         self.env = GltfEnv()
         sh = (C.c_float * 12)()
         _check(host.swrh_env_get(self._h, C.byref(self.env), C.byref(sh)), host)
@@ -232,14 +238,59 @@ class BakedEnvironment:
             pass
 
 
-def load_scene(path, sky_cross_rgba, grid_size=128, lut_size=128, specular_samples=64):
+def ggx_cache_load(path, width, height):
+    """The reference's `.ggx` cache (texture.rs:426-514): (mips, 6, height, width) uint32 texels, or None when the file is missing
+    or is a cache of something else (the reference then bakes and writes one)."""
+    host = _host()
+    host.swrh_ggx_cache_load.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    mips = 1 + int(max(width, height)).bit_length() - 1
+    out = np.zeros(width * height * 6 * mips, np.uint32)
+    rc = host.swrh_ggx_cache_load(os.fsencode(path), width, height, out.ctypes.data)
+    if rc < 0:
+        raise GltfError(host.swrh_last_error().decode())
+    return out.reshape(mips, 6, height, width) if rc == 1 else None
+
+
+def ggx_cache_save(path, texels):
+    """texels: (mips, 6, height, width) uint32 (texture.rs:516-552)."""
+    host = _host()
+    host.swrh_ggx_cache_save.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    t = np.ascontiguousarray(texels, np.uint32)
+    assert t.ndim == 4 and t.shape[1] == 6
+    _check(host.swrh_ggx_cache_save(os.fsencode(path), t.shape[3], t.shape[2], t.shape[0], t.ctypes.data), host)
+
+
+def gi_cache_load(path, dims):
+    """The reference's `.gi` cache (gi.rs:30-83) for a (w, h, d) voxel grid: (w*h*d, 4, 4) float32 SH4 coefficients (r, g, b, w), or
+    None when there is no usable cache."""
+    host = _host()
+    host.swrh_gi_cache_load.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    w, h, d = (int(x) for x in dims)
+    out = np.zeros(w * h * d * 16, np.float32)
+    rc = host.swrh_gi_cache_load(os.fsencode(path), w, h, d, out.ctypes.data)
+    if rc < 0:
+        raise GltfError(host.swrh_last_error().decode())
+    return out.reshape(w * h * d, 4, 4) if rc == 1 else None
+
+
+def gi_cache_save(path, dims, gi_sh4):
+    """gi.rs:85-118."""
+    host = _host()
+    host.swrh_gi_cache_save.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    w, h, d = (int(x) for x in dims)
+    g = np.ascontiguousarray(gi_sh4, np.float32)
+    assert g.size == w * h * d * 16
+    _check(host.swrh_gi_cache_save(os.fsencode(path), w, h, d, g.ctypes.data), host)
+
+
+def load_scene(path, sky_cross_rgba, grid_size=128, lut_size=128, specular_samples=64, ggx_cache=None):
     """What the viewer's load_scene does before the first frame (main.rs:100-291), for the fields the renderer consumes:
     parse the glTF / GLB file, bake the environment from the sky image (scene.rs:151-231), span a grid_size^3 voxel grid over
     the scene bounds (main.rs:228-235), initialise it from the irradiance SH with GI_FALLBACK_SCENE_SH_SCALE = 0.25 and sky
     visibility 1 (main.rs:54, :280; gi.rs:123-149) and fill in the ray-cast sun visibility (main.rs:237-246).
     Returns (scene, default camera spec as main.rs:210-224 builds it: (position, look_at, fov, far_plane))."""
     env = BakedEnvironment(sky_cross_rgba, lut_size=lut_size, specular_samples=specular_samples, voxel_dim=grid_size, irradiance_scale=0.25,
-                           sky_visibility=1.0, light_intensity=1.0)
+                           sky_visibility=1.0, light_intensity=1.0, ggx_cache=ggx_cache)
     scene = load_gltf(path, environment=env)
     bake_sun_visibility(scene)
     if scene.cameras:

@@ -15,6 +15,7 @@
 // call on Linux. f32::powi(5) is compiler-rt's square-and-multiply: x * ((x*x) * (x*x)).
 #pragma once
 #include "swr_gltf.hpp"
+#include "swr_cache.hpp"
 
 namespace swr {
 namespace bake {
@@ -107,12 +108,38 @@ struct EnvironmentBake {
     uint32_t voxel_dims[3];
     // flat views
     swr_texture_desc descs[3];
+    bool specular_from_cache = false;
 
     static std::unique_ptr<EnvironmentBake> from_cross(const gltf::Image &cross, uint32_t lut_size, uint32_t specular_samples, uint32_t voxel_dim,
-                                                       float irradiance_scale, float sky_visibility, float light_intensity) {
+                                                       float irradiance_scale, float sky_visibility, float light_intensity,
+                                                       const char *ggx_cache_path = nullptr) {
         std::unique_ptr<EnvironmentBake> e(new EnvironmentBake());
         e->cubemap = cubemap_from_cross(cross);
-        e->cubemap_specular = generate_prefiltered_specular_cubemap(e->cubemap, specular_samples);
+        // scene.rs:164-206: the prefiltered cubemap comes from `assets/cubemap.ggx` when that file matches the sky's face size,
+        // otherwise it is baked (here: on the device) and the cache is written; a cache that cannot be written is not an error
+        std::vector<uint32_t> cached;
+        if (ggx_cache_path && cache::ggx_load(ggx_cache_path, e->cubemap.width, e->cubemap.height, cached)) {
+            TextureData &t = e->cubemap_specular;
+            const uint32_t bw = e->cubemap.width, bh = e->cubemap.height, mips = cache::ggx_mips(bw, bh);
+            t.width = bw, t.height = bh, t.type = SWR_TEX_LINEAR;
+            t.data = std::move(cached);
+            for (uint32_t mip = 0; mip < mips; mip++) {
+                t.mip_offsets.push_back(mip * bw * bh * 6);
+                t.mip_widths.push_back(bw);
+                t.mip_heights.push_back(bh);
+                t.array_stride.push_back(bw * bh);
+            }
+            e->specular_from_cache = true;
+        } else {
+            e->cubemap_specular = generate_prefiltered_specular_cubemap(e->cubemap, specular_samples);
+            if (ggx_cache_path) {
+                try {
+                    const TextureData &t = e->cubemap_specular;
+                    cache::ggx_save(ggx_cache_path, t.width, t.height, (uint32_t)t.mip_offsets.size(), t.data.data(), t.data.size());
+                } catch (const std::exception &) {
+                }
+            }
+        }
         compute_irradiance_sh4(e->cubemap, e->irradiance_sh);
         e->brdf_lut = generate_brdf_lut(lut_size);
         e->voxel_dims[0] = e->voxel_dims[1] = e->voxel_dims[2] = voxel_dim;

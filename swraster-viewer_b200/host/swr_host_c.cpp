@@ -293,6 +293,67 @@ void *swrh_env_bake(const uint8_t *cross_rgba, uint32_t width, uint32_t height, 
         return nullptr;
     }
 }
+void *swrh_env_bake_cached(const uint8_t *cross_rgba, uint32_t width, uint32_t height, uint32_t lut_size, uint32_t specular_samples, uint32_t voxel_dim,
+                           float irradiance_scale, float sky_visibility, float light_intensity, const char *ggx_cache_path) {
+    try {
+        if (!cross_rgba || !lut_size || !specular_samples || !voxel_dim) throw std::runtime_error("Invalid data: null image or zero size");
+        if (lut_size > 4096 || voxel_dim > 1024 || width > 32768 || height > 32768) throw std::runtime_error("Invalid data: bake size out of range");
+        swr::gltf::Image img;
+        img.width = width;
+        img.height = height;
+        img.rgba.assign(cross_rgba, cross_rgba + (size_t)width * height * 4);
+        return swr::bake::EnvironmentBake::from_cross(img, lut_size, specular_samples, voxel_dim, irradiance_scale, sky_visibility, light_intensity, ggx_cache_path)
+            .release();
+    } catch (const std::exception &ex) {
+        g_err = ex.what();
+        return nullptr;
+    }
+}
+int swrh_env_specular_from_cache(void *env) { return env ? (((swr::bake::EnvironmentBake *)env)->specular_from_cache ? 1 : 0) : -1; }
+
+// ---- bake caches (include/swr_gltf.h, host/swr_cache.hpp) -----------------------------------------------------------------
+int swrh_ggx_cache_load(const char *path, uint32_t width, uint32_t height, uint32_t *out_texels) {
+    try {
+        if (!path || !out_texels) throw std::runtime_error("Invalid data: null argument");
+        std::vector<uint32_t> t;
+        if (!swr::cache::ggx_load(path, width, height, t)) return 0;
+        std::memcpy(out_texels, t.data(), t.size() * sizeof(uint32_t));
+        return 1;
+    } catch (const std::exception &ex) {
+        g_err = ex.what();
+        return -1;
+    }
+}
+int swrh_ggx_cache_save(const char *path, uint32_t width, uint32_t height, uint32_t mips, const uint32_t *texels) {
+    try {
+        if (!path || !texels) throw std::runtime_error("Invalid data: null argument");
+        swr::cache::ggx_save(path, width, height, mips, texels, (size_t)width * height * 6 * mips);
+        return 0;
+    } catch (const std::exception &ex) {
+        g_err = ex.what();
+        return -1;
+    }
+}
+int swrh_gi_cache_load(const char *path, uint32_t w, uint32_t h, uint32_t d, float *gi_sh4_out) {
+    try {
+        if (!path || !gi_sh4_out) throw std::runtime_error("Invalid data: null argument");
+        return swr::cache::gi_load(path, w, h, d, gi_sh4_out) ? 1 : 0;
+    } catch (const std::exception &ex) {
+        g_err = ex.what();
+        return -1;
+    }
+}
+int swrh_gi_cache_save(const char *path, uint32_t w, uint32_t h, uint32_t d, const float *gi_sh4) {
+    try {
+        if (!path || !gi_sh4) throw std::runtime_error("Invalid data: null argument");
+        swr::cache::gi_save(path, w, h, d, gi_sh4);
+        return 0;
+    } catch (const std::exception &ex) {
+        g_err = ex.what();
+        return -1;
+    }
+}
+
 int swrh_env_get(void *env, swrh_gltf_env *out, float irradiance_sh_out[12]) {
     if (!env || !out) return -1;
     swr::bake::EnvironmentBake &e = *(swr::bake::EnvironmentBake *)env;

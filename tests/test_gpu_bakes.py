@@ -178,3 +178,25 @@ def test_load_scene_camera_rules(tmp_path):
     json.dump(doc, open(tmp_path / "o.gltf", "w"))
     with pytest.raises(gltf.GltfError, match="unsupported camera type"):
         gltf.load_scene(tmp_path / "o.gltf", sky, grid_size=4, lut_size=4, specular_samples=2)
+
+
+def test_prefiltered_cubemap_through_the_ggx_cache(tmp_path):
+    """scene.rs:164-206: no cache -> bake (on the device) and write `cubemap.ggx`; a cache of the sky's face size -> read it,
+    no bake; a cache of another size is not this sky's and is replaced."""
+    rng = np.random.default_rng(9)
+    faces = rng.integers(0, 256, size=(6, 8, 8, 4), dtype=np.uint8)
+    cross = cross_from_faces(faces)
+    p = tmp_path / "cubemap.ggx"
+    first = gltf.BakedEnvironment(cross, lut_size=4, specular_samples=4, voxel_dim=1, ggx_cache=p)
+    assert not first.specular_from_cache and p.exists()
+    baked = first.texture("cubemap_specular")[0]
+    assert np.array_equal(gltf.ggx_cache_load(p, 8, 8).ravel(), baked)
+    # poison the file's texels: a second load must take them from the cache, not bake again
+    marked = gltf.ggx_cache_load(p, 8, 8) ^ np.uint32(0x01000000)
+    gltf.ggx_cache_save(p, marked)
+    second = gltf.BakedEnvironment(cross, lut_size=4, specular_samples=4, voxel_dim=1, ggx_cache=p)
+    assert second.specular_from_cache and np.array_equal(second.texture("cubemap_specular")[0], marked.ravel())
+    # another sky size: the cache is not used and is rewritten for this sky
+    small = cross_from_faces(faces[:, :4, :4])
+    third = gltf.BakedEnvironment(small, lut_size=4, specular_samples=4, voxel_dim=1, ggx_cache=p)
+    assert not third.specular_from_cache and gltf.ggx_cache_load(p, 4, 4) is not None and gltf.ggx_cache_load(p, 8, 8) is None
