@@ -842,6 +842,7 @@ static void fill_shade_params(swr_ctx *ctx, const GeomSet &g, ShadeParams &sp) {
 static int launch_shade(swr_ctx *ctx) {
     cudaStream_t s = ctx->stream;
     const int rb = ctx->row_begin, re = ctx->row_end;
+    ctx->last_fused = false;  // also for an empty band: the state always describes the frame shaded last
     if (re > rb) {
         ShadeParams sp{};
         fill_shade_params(ctx, ctx->op, sp);
@@ -850,7 +851,6 @@ static int launch_shade(swr_ctx *ctx) {
         // (the translucent pass blends over the HDR colour, the sort-last composite sums HDR-resolved strips).
         const float fx = ctx->cur ? ctx->cur->fixed_exposure : 0.0f;
         const bool fused = fx > 0.0f && ctx->tr.last_draws.empty() && !ctx->composited;
-        ctx->last_fused = false;
         if (fused) {
             if (ctx->fused_px.reserve((size_t)ctx->W * ctx->H) != cudaSuccess) return SWR_ERR_OOM;
             // a read-back of the previous fixed-exposure frame may still be copying out of fused_px
@@ -919,6 +919,7 @@ static int enqueue_slot(swr_ctx *ctx, FrameSlot &f) {
     f.tr_ran = false;
     int rc;
     if ((rc = launch_frame(ctx))) return rc;
+    if (!f.shade) ctx->last_fused = false;  // a visibility-only frame holds neither HDR colour nor packed pixels
     if (f.shade && (rc = launch_shade(ctx))) return rc;
     f.total_tris = ctx->op.total_tris;
     f.total_verts = ctx->op.total_verts;
