@@ -113,3 +113,43 @@ def test_save_rejects_a_texture_of_the_wrong_size(tmp_path):
     assert host.swrh_ggx_cache_save(None, 4, 4, 3, None) != 0  # NULL arguments are errors, not crashes
     with pytest.raises(gltf.GltfError):
         gltf.ggx_cache_save(tmp_path / "no" / "such" / "dir" / "x.ggx", np.zeros((3, 6, 4, 4), np.uint32))
+
+
+def test_mutated_caches_never_crash_the_reader(tmp_path):
+    """Hostile / damaged files: every byte-flipped or truncated cache is either rejected ("no cache") or decodes to a payload of
+    exactly the expected size — never a crash, never an error the reference would not raise (its decoder errors are I/O errors,
+    ours are folded into "no cache" because the one-shot decoder does not tell them from a short stream)."""
+    rng = np.random.default_rng(7)
+    w, h, mips = 8, 4, 4
+    tex = rng.integers(0, 2**32, size=(mips, 6, h, w), dtype=np.uint64).astype(np.uint32)
+    good = tmp_path / "good.ggx"
+    gltf.ggx_cache_save(good, tex)
+    blob = bytearray(good.read_bytes())
+    p = tmp_path / "m.ggx"
+    accepted = 0
+    for trial in range(300):
+        b = bytearray(blob)
+        kind = trial % 3
+        if kind == 0:
+            for _ in range(int(rng.integers(1, 4))):
+                b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:
+            b = b[:int(rng.integers(0, len(b)))]
+        else:
+            i = int(rng.integers(20, len(b)))
+            b[i:i] = bytes(rng.integers(0, 256, size=int(rng.integers(1, 9)), dtype=np.uint8))
+        p.write_bytes(bytes(b))
+        got = gltf.ggx_cache_load(p, w, h)
+        if got is not None:
+            assert got.shape == tex.shape
+            accepted += 1
+    assert accepted < 300  # most damage is caught by the header checks, the brotli decoder or the exact-length rule
+    gi = rng.standard_normal((2 * 2 * 2, 4, 4)).astype(np.float32)
+    gltf.gi_cache_save(tmp_path / "g.gi", (2, 2, 2), gi)
+    gb = bytearray((tmp_path / "g.gi").read_bytes())
+    for trial in range(100):
+        b = bytearray(gb)
+        b[int(rng.integers(0, len(b)))] ^= 0xFF
+        (tmp_path / "mg.gi").write_bytes(bytes(b[:int(rng.integers(1, len(b) + 1))]))
+        got = gltf.gi_cache_load(tmp_path / "mg.gi", (2, 2, 2))
+        assert got is None or got.shape == gi.shape
