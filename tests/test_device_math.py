@@ -47,8 +47,25 @@ static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f
 extern "C" int t_edge_bound_ok(int a, int b, int c, uint32_t xhi, uint32_t yhi) { return edge_bound_ok(a, b, c, xhi, yhi) ? 1 : 0; }
 extern "C" uint32_t t_depth_bucket(float z) { return depth_bucket(z); }
 extern "C" uint32_t t_nbuckets() { return SWR_ZBUCKETS; }
+#define SWR_TILE 64
+struct uint4 { uint32_t x, y, z, w; };
+%s
+%s
+%s
+%s
+extern "C" int t_key_index(int x, int y) { return key_index(x, y); }
+extern "C" uint32_t t_counts_to_cursors(const uint32_t *count, uint32_t *cursor, int tile, uint32_t base) {
+    uint32_t c[SWR_ZBUCKETS];
+    const uint32_t total = load_tile_counts(count, tile, c);
+    store_tile_cursors(cursor, tile, base, c);
+    return total;
+}
 """ % (shift, cut(os.path.join(CSRC, "swr_device.cuh"), "__device__ __forceinline__ bool edge_bound_ok("),
-       cut(os.path.join(CSRC, "swr_raster.cuh"), "__device__ __forceinline__ uint32_t depth_bucket("))
+       cut(os.path.join(CSRC, "swr_raster.cuh"), "__device__ __forceinline__ uint32_t depth_bucket("),
+       cut(os.path.join(CSRC, "swr_raster.cuh"), "__device__ __forceinline__ int key_swz("),
+       cut(os.path.join(CSRC, "swr_raster.cuh"), "__device__ __forceinline__ int key_index("),
+       cut(os.path.join(CSRC, "swr_raster.cuh"), "__device__ __forceinline__ uint32_t load_tile_counts("),
+       cut(os.path.join(CSRC, "swr_raster.cuh"), "__device__ __forceinline__ void store_tile_cursors("))
     src = d / "devmath.cpp"
     src.write_text(code)
     so = d / "devmath.so"
@@ -58,6 +75,8 @@ extern "C" uint32_t t_nbuckets() { return SWR_ZBUCKETS; }
     lib.t_depth_bucket.argtypes = [C.c_float]
     lib.t_depth_bucket.restype = C.c_uint32
     lib.t_nbuckets.restype = C.c_uint32
+    lib.t_counts_to_cursors.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]
+    lib.t_counts_to_cursors.restype = C.c_uint32
     return lib
 
 
@@ -105,3 +124,30 @@ def test_depth_bucket_is_monotonic_and_covers_the_range(lib):
     if nb == 8:
         for k in range(0, 7):
             assert lib.t_depth_bucket(float(np.float32(1.0) - np.float32(2.0 ** -k))) == min(k, nb - 1)
+
+
+def test_key_swizzle_is_a_bijection_that_keeps_quad_rows_paired(lib):
+    """Shared-memory / global key layout of a tile: every pixel has its own slot, a row stays inside its 64 slots, and the two pixels
+    of a quad row (even x, x + 1) stay an aligned pair (one 16-byte access) — k_raster_tiles and load_key rely on all three."""
+    idx = np.array([[lib.t_key_index(x, y) for x in range(64)] for y in range(64)])
+    assert sorted(idx.ravel().tolist()) == list(range(4096))
+    assert (idx // 64 == np.arange(64)[:, None]).all()
+    assert (idx[:, 0::2] % 2 == 0).all() and (idx[:, 1::2] == idx[:, 0::2] + 1).all()
+    # rows two apart map the same x to different banks (what the swizzle is for): 8 consecutive quad rows, 8 distinct offsets
+    for x in (0, 2, 30):
+        assert len({int(idx[y, x]) % 64 for y in range(0, 16, 2)}) == 8
+
+
+def test_bucket_counters_become_consecutive_cursors(lib):
+    nb = lib.t_nbuckets()
+    rng = np.random.default_rng(3)
+    ntiles = 37
+    count = rng.integers(0, 5000, size=ntiles * nb, dtype=np.uint32)
+    cursor = np.zeros_like(count)
+    base = 0
+    for t in range(ntiles):
+        total = lib.t_counts_to_cursors(count.ctypes.data, cursor.ctypes.data, t, base)
+        c = count[t * nb:(t + 1) * nb].astype(np.int64)
+        assert total == c.sum()
+        assert np.array_equal(cursor[t * nb:(t + 1) * nb], base + np.concatenate([[0], np.cumsum(c)[:-1]]))
+        base += int(total)
